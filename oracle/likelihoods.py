@@ -1,0 +1,126 @@
+"""GPLikelihoods 0.4 / Distributions semantics (oracle; test infrastructure).
+
+``expected_loglikelihood(quadrature, lik, q_f, y)`` is imported by the reference at
+src/SparseVariationalApproximationModule.jl:25 and called at :355; ``logpdf(dist_y_given_f(f), y)``
+is called at src/LaplaceApproximationModule.jl:231.  GPLikelihoods / Distributions /
+FastGaussQuadrature are not vendored (Project.toml:30-34, compat ranges only), so this restates
+their published behaviour:
+
+* ``DefaultExpectationMethod`` -> analytic for ``GaussianLikelihood`` and
+  ``PoissonLikelihood{ExpLink}``, else ``GaussHermiteExpectation(20)``.
+* Gauss-Hermite: per point ``(1/sqrt(pi)) * sum_k w_k * loglikelihood(lik(mu + sqrt2*sigma*x_k), y)``
+  with ``(x_k, w_k) = gausshermite(n)`` == ``numpy.polynomial.hermite.hermgauss(n)``.
+* ``BernoulliLikelihood`` -> ``Bernoulli(logistic(f))`` with ``logpdf = y ? log(p) : log(1-p)``;
+  ``PoissonLikelihood`` -> ``Poisson(exp(f))`` with ``logpdf = xlogy(y, lam) - lam - loggamma(y+1)``;
+  ``GaussianLikelihood(s2)`` -> ``Normal(f, sqrt(s2))``.
+
+Every function returns per-point values and the derivatives of the *finite quadrature sum*
+(that is what Zygote differentiates in the reference), so a caller gets
+(E_i, dE_i/dmu_i, dE_i/dvar_i, dE_i/dlik_param).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+from scipy.special import gammaln, xlogy
+
+GAUSSIAN, BERNOULLI_LOGIT, POISSON_EXP = "gaussian", "bernoulli_logit", "poisson_exp"
+ANALYTIC, GAUSS_HERMITE = "analytic", "gauss_hermite"
+
+_LOG2PI = np.log(2.0 * np.pi)
+_INVSQRTPI = 1.0 / np.sqrt(np.pi)
+_SQRT2 = np.sqrt(2.0)
+
+
+@dataclass
+class Likelihood:
+    kind: str = GAUSSIAN
+    sigma2: float = 1.0  # GaussianLikelihood only
+
+
+@dataclass
+class Expectation:
+    """``method == 'default'`` resolves like ``DefaultExpectationMethod()``."""
+
+    method: str = "default"
+    n_points: int = 20
+
+    def resolve(self, lik: Likelihood) -> "Expectation":
+        if self.method != "default":
+            return self
+        if lik.kind in (GAUSSIAN, POISSON_EXP):
+            return Expectation(ANALYTIC, 0)
+        return Expectation(GAUSS_HERMITE, 20)
+
+
+def gausshermite(n: int):
+    """FastGaussQuadrature.gausshermite(n): physicists' nodes/weights (weight exp(-x^2))."""
+    return np.polynomial.hermite.hermgauss(n)
+
+
+def logistic(f):
+    f = np.asarray(f, dtype=np.float64)
+    out = np.empty_like(f)
+    pos = f >= 0
+    out[pos] = 1.0 / (1.0 + np.exp(-f[pos]))
+    e = np.exp(f[~pos])
+    out[~pos] = e / (1.0 + e)
+    return out
+
+
+def loglik_and_derivs(lik: Likelihood, f, y):
+    """Pointwise log p(y|f), d/df, d2/df2 (closed forms of what
+    src/LaplaceApproximationModule.jl:230-241 obtains with nested ForwardDiff)."""
+    f = np.asarray(f, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    if lik.kind == GAUSSIAN:
+        r = y - f
+        return -0.5 * (_LOG2PI + np.log(lik.sigma2)) - 0.5 * r * r / lik.sigma2, r / lik.sigma2, np.full_like(f, -1.0 / lik.sigma2)
+    if lik.kind == BERNOULLI_LOGIT:
+        p = logistic(f)
+        with np.errstate(divide="ignore"):
+            ll = np.where(y > 0.5, np.log(p), np.log(1.0 - p))  # Distributions.logpdf(Bernoulli(p), y)
+        return ll, y - p, -p * (1.0 - p)
+    if lik.kind == POISSON_EXP:
+        lam = np.exp(f)
+        return xlogy(y, lam) - lam - gammaln(y + 1.0), y - lam, -lam
+    raise ValueError(lik.kind)
+
+
+def expected_loglik_terms(exp_: Expectation, lik: Likelihood, mu, var, y):
+    """Per-point expected log-likelihood under N(mu, var) and its derivatives.
+
+    Returns (E, dE/dmu, dE/dvar, dE/dsigma2_lik); arrays of len(y).  ``var`` is the marginal
+    variance *including* the 1e-18 jitter of ``f_post(x)`` (SVA.jl:354): the reference builds
+    ``Normal(mu, sqrt(var))`` so GH uses ``std = sqrt(var)`` and the analytic forms use ``std^2``.
+    """
+    exp_ = exp_.resolve(lik)
+    mu = np.asarray(mu, dtype=np.float64)
+    var = np.asarray(var, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    std = np.sqrt(var)
+    if exp_.method == ANALYTIC:
+        v = std * std
+        if lik.kind == GAUSSIAN:
+            s2 = lik.sigma2
+            r = y - mu
+            E = -0.5 * (_LOG2PI + np.log(s2) + (r * r + v) / s2)
+            return E, r / s2, np.full_like(mu, -0.5 / s2), -0.5 / s2 + 0.5 * (r * r + v) / (s2 * s2)
+        if lik.kind == POISSON_EXP:
+            e = np.exp(mu + v / 2.0)
+            return y * mu - e - gammaln(y + 1.0), y - e, -0.5 * e, np.zeros_like(mu)
+        raise ValueError(f"no analytic expectation for {lik.kind}")
+    xs, ws = gausshermite(exp_.n_points)
+    f = mu[:, None] + (_SQRT2 * std)[:, None] * xs[None, :]
+    ll, dll, _ = loglik_and_derivs(lik, f, y[:, None])
+    E = _INVSQRTPI * (ll @ ws)
+    dmu = _INVSQRTPI * (dll @ ws)
+    dstd = _INVSQRTPI * ((dll * (_SQRT2 * xs)[None, :]) @ ws)
+    dvar = dstd / (2.0 * std)
+    if lik.kind == GAUSSIAN:
+        r = y[:, None] - f
+        ds2 = _INVSQRTPI * ((-0.5 / lik.sigma2 + 0.5 * r * r / lik.sigma2**2) @ ws)
+    else:
+        ds2 = np.zeros_like(mu)
+    return E, dmu, dvar, ds2
