@@ -1,0 +1,1132 @@
+// agp.cu -- host orchestration and the C ABI (include/agp.h) of the B200 SVGP / Laplace hot path.
+//
+// One translation unit: the device code lives in the headers included below.  Build:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC \
+//        -o libagp_b200.so agp.cu -ldl
+// The library links neither torch nor cuBLAS/cuSOLVER; NCCL is dlopen'ed on agp_comm_init.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/agp.h"
+#include "dense.cuh"
+#include "gemm.cuh"
+#include "kfun.cuh"
+#include "laplace.cuh"
+#include "sweep.cuh"
+
+using namespace agp;
+
+// ---------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int32_t fail(int32_t code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(x)                                                                                        \
+  do {                                                                                               \
+    cudaError_t e_ = (x);                                                                            \
+    if (e_ != cudaSuccess) return fail(AGP_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define OK(x)                      \
+  do {                             \
+    int32_t s_ = (x);              \
+    if (s_ != AGP_OK) return s_;   \
+  } while (0)
+
+extern "C" const char* agp_last_error_string(void) { return g_err.c_str(); }
+extern "C" int32_t agp_build_arch(void) { return 100; }
+
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+struct DevBuf {
+  double* p = nullptr;
+  int64_t n = 0;
+  int32_t ensure(int64_t need) {
+    if (need <= n) return AGP_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMalloc(&p, sizeof(double) * need);
+    if (e != cudaSuccess) return fail(AGP_ERR_ALLOC, "cudaMalloc of %lld doubles failed: %s", (long long)need, cudaGetErrorString(e));
+    n = need;
+    return AGP_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int32_t load_nccl() {
+  if (g_nccl.lib) return AGP_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) return fail(AGP_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+    return fail(AGP_ERR_NCCL, "libnccl is missing a required symbol");
+  return AGP_OK;
+}
+
+// Everything the sweep needs that depends on one agp_svgp_params (uploaded once per step).
+struct SvgpState {
+  bool valid = false;
+  int M = 0, Mp = 0, D = 0, nb = 0;
+  int n_scale = 1;
+  bool centered = false;
+  double mean_const = 0, jitter = 0, scale = 1;
+  int want_grad = 0;
+  KernelParams kp;
+  LikParams lp;
+  std::vector<double> h_m, h_Lq;  // padded host copies (Lq column-major Mp x Mp)
+};
+
+struct agp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sms = 148;
+  int64_t launches = 0;
+  int64_t chunk_cols = 0;  // capacity of the per-chunk scratch (columns)
+  int nslab = 0, nsplit = 0;
+  // once-per-step M x M operands (column-major, ld = Mp unless noted)
+  DevBuf z, zs, zn, mvec, mt, Lq, Kw, Lk, Lt, Ut, Bt_cm, Bt_rm, W1, W2, W3, W4, vec64, vec64b;
+  // per-chunk scratch [Mp][chunk_cols]
+  DevBuf A, C, Ab, As, saa, sam, scc_part, dmu, dv, sc_part;
+  // accumulators
+  DevBuf gpart, Gpart, kpart, red, small;
+  int* d_flags = nullptr;  // [0] potrf info, [1] domain flag
+  SvgpState st;
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+  // prediction outputs
+  DevBuf mu_out, var_out;
+};
+
+struct agp_dataset {
+  agp_ctx* ctx = nullptr;
+  int64_t cap = 0, N = 0;
+  int D = 0;
+  double* X = nullptr;  // point-major [cap][D]
+  double* y = nullptr;
+  DevBuf stage;
+};
+
+#define LAUNCHED(ctx) ((ctx)->launches++)
+#define KCHECK()                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = cudaGetLastError();                                                           \
+    if (e_ != cudaSuccess) return fail(AGP_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" int32_t agp_ctx_create(int32_t device, agp_ctx** out) {
+  if (!out) return fail(AGP_ERR_INVALID, "agp_ctx_create: out is NULL");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(AGP_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(AGP_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(AGP_ERR_UNSUPPORTED, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+  agp_ctx* c = new agp_ctx();
+  c->device = device;
+  c->sms = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaMalloc(&c->d_flags, 4 * sizeof(int)));
+  CU(cudaMemset(c->d_flags, 0, 4 * sizeof(int)));
+  *out = c;
+  return AGP_OK;
+}
+
+extern "C" int32_t agp_ctx_destroy(agp_ctx* c) {
+  if (!c) return AGP_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  DevBuf* bufs[] = {&c->z, &c->zs, &c->zn, &c->mvec, &c->mt, &c->Lq, &c->Kw, &c->Lk, &c->Lt, &c->Ut, &c->Bt_cm, &c->Bt_rm,
+                    &c->W1, &c->W2, &c->W3, &c->W4, &c->vec64, &c->vec64b, &c->A, &c->C, &c->Ab, &c->As, &c->saa, &c->sam,
+                    &c->scc_part, &c->dmu, &c->dv, &c->sc_part, &c->gpart, &c->Gpart, &c->kpart, &c->red, &c->small,
+                    &c->mu_out, &c->var_out};
+  for (DevBuf* b : bufs) b->release();
+  if (c->d_flags) cudaFree(c->d_flags);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return AGP_OK;
+}
+
+extern "C" int32_t agp_ctx_stream(agp_ctx* c, void** s) {
+  if (!c || !s) return fail(AGP_ERR_INVALID, "agp_ctx_stream: NULL argument");
+  *s = (void*)c->stream;
+  return AGP_OK;
+}
+extern "C" int32_t agp_ctx_launch_count(agp_ctx* c, int64_t* out) {
+  if (!c || !out) return fail(AGP_ERR_INVALID, "agp_ctx_launch_count: NULL argument");
+  *out = c->launches;
+  return AGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// communicator
+// ---------------------------------------------------------------------------------------------------
+extern "C" int32_t agp_comm_unique_id(void* id128) {
+  if (!id128) return fail(AGP_ERR_INVALID, "agp_comm_unique_id: NULL");
+  OK(load_nccl());
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) return fail(AGP_ERR_NCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  memcpy(id128, &id, 128);
+  return AGP_OK;
+}
+extern "C" int32_t agp_comm_init(agp_ctx* c, int32_t nranks, int32_t rank, const void* id128) {
+  if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(AGP_ERR_INVALID, "agp_comm_init: bad arguments");
+  OK(load_nccl());
+  CU(cudaSetDevice(c->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+  if (r != ncclSuccess) return fail(AGP_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  c->nranks = nranks;
+  c->rank = rank;
+  return AGP_OK;
+}
+extern "C" int32_t agp_comm_destroy(agp_ctx* c) {
+  if (c && c->comm) {
+    g_nccl.CommDestroy(c->comm);
+    c->comm = nullptr;
+    c->nranks = 1;
+    c->rank = 0;
+  }
+  return AGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// datasets
+// ---------------------------------------------------------------------------------------------------
+__global__ void feature_to_point_major_kernel(const double* in, int64_t ldx, double* out, int64_t N, int D) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N * D; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / D;
+    const int d = (int)(i % D);
+    out[i] = in[(int64_t)d * ldx + n];
+  }
+}
+template <typename T>
+__global__ void convert_y_kernel(const T* in, double* out, int64_t N) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) out[i] = (double)in[i];
+}
+
+extern "C" int32_t agp_dataset_create(agp_ctx* c, int64_t capacity, int32_t D, agp_dataset** out) {
+  if (!c || !out || capacity < 1 || D < 1) return fail(AGP_ERR_INVALID, "agp_dataset_create: bad arguments");
+  if (D > MAXD) return fail(AGP_ERR_UNSUPPORTED, "input dimension %d > %d is not supported on device", D, MAXD);
+  CU(cudaSetDevice(c->device));
+  agp_dataset* ds = new agp_dataset();
+  ds->ctx = c;
+  ds->cap = capacity;
+  ds->D = D;
+  // one tile of slack so a partially filled last column tile can be staged without reading out of bounds
+  cudaError_t e = cudaMalloc(&ds->X, sizeof(double) * (capacity + BN) * D);
+  if (e == cudaSuccess) e = cudaMalloc(&ds->y, sizeof(double) * (capacity + BN));
+  if (e != cudaSuccess) {
+    delete ds;
+    return fail(AGP_ERR_ALLOC, "dataset allocation failed: %s", cudaGetErrorString(e));
+  }
+  *out = ds;
+  return AGP_OK;
+}
+
+extern "C" int32_t agp_dataset_upload(agp_dataset* ds, const void* X, int64_t N, int64_t ldx, int32_t layout, const void* y,
+                                      int32_t ytype, int32_t location) {
+  if (!ds || !X || N < 0 || N > ds->cap) return fail(AGP_ERR_INVALID, "agp_dataset_upload: bad arguments (N=%lld, cap=%lld)", (long long)N, ds ? (long long)ds->cap : -1LL);
+  agp_ctx* c = ds->ctx;
+  CU(cudaSetDevice(c->device));
+  const int D = ds->D;
+  const cudaMemcpyKind kind = location == AGP_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (layout == AGP_POINT_MAJOR) {
+    if (ldx <= 0) ldx = D;
+    if (ldx == D)
+      CU(cudaMemcpyAsync(ds->X, X, sizeof(double) * N * D, kind, c->stream));
+    else
+      CU(cudaMemcpy2DAsync(ds->X, sizeof(double) * D, X, sizeof(double) * ldx, sizeof(double) * D, N, kind, c->stream));
+  } else if (layout == AGP_FEATURE_MAJOR) {
+    if (ldx <= 0) ldx = N;
+    const double* src = (const double*)X;
+    if (location == AGP_HOST) {
+      OK(ds->stage.ensure(ldx * D));
+      CU(cudaMemcpyAsync(ds->stage.p, X, sizeof(double) * ldx * D, cudaMemcpyHostToDevice, c->stream));
+      src = ds->stage.p;
+    }
+    feature_to_point_major_kernel<<<1024, 256, 0, c->stream>>>(src, ldx, ds->X, N, D);
+    LAUNCHED(c);
+    KCHECK();
+  } else {
+    return fail(AGP_ERR_INVALID, "unknown layout %d", layout);
+  }
+  if (y) {
+    if (ytype == AGP_Y_F64) {
+      CU(cudaMemcpyAsync(ds->y, y, sizeof(double) * N, kind, c->stream));
+    } else {
+      const size_t esz = ytype == AGP_Y_F32 ? 4 : ytype == AGP_Y_I64 ? 8 : ytype == AGP_Y_U8 ? 1 : 0;
+      if (!esz) return fail(AGP_ERR_INVALID, "unknown ytype %d", ytype);
+      const void* src = y;
+      if (location == AGP_HOST) {
+        OK(ds->stage.ensure((int64_t)((esz * N + 7) / 8) + 1));
+        CU(cudaMemcpyAsync(ds->stage.p, y, esz * N, cudaMemcpyHostToDevice, c->stream));
+        src = ds->stage.p;
+      }
+      if (ytype == AGP_Y_F32) convert_y_kernel<float><<<1024, 256, 0, c->stream>>>((const float*)src, ds->y, N);
+      if (ytype == AGP_Y_I64) convert_y_kernel<long long><<<1024, 256, 0, c->stream>>>((const long long*)src, ds->y, N);
+      if (ytype == AGP_Y_U8) convert_y_kernel<unsigned char><<<1024, 256, 0, c->stream>>>((const unsigned char*)src, ds->y, N);
+      LAUNCHED(c);
+      KCHECK();
+    }
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  ds->N = N;
+  return AGP_OK;
+}
+
+extern "C" int32_t agp_dataset_size(agp_dataset* ds, int64_t* N, int32_t* D) {
+  if (!ds) return fail(AGP_ERR_INVALID, "agp_dataset_size: NULL");
+  if (N) *N = ds->N;
+  if (D) *D = ds->D;
+  return AGP_OK;
+}
+extern "C" int32_t agp_dataset_destroy(agp_dataset* ds) {
+  if (!ds) return AGP_OK;
+  cudaSetDevice(ds->ctx->device);
+  if (ds->X) cudaFree(ds->X);
+  if (ds->y) cudaFree(ds->y);
+  ds->stage.release();
+  delete ds;
+  return AGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------------
+template <int MODE>
+static int32_t launch_trsm(agp_ctx* c, const TrsmArgs& a, int tiles_n) {
+  using Cfg = StageCfg<A_KM, B_KN>;
+  const int smem = Cfg::smem_bytes + ((MODE == TR_KUF_FWD) ? a.kp.D * 64 * 8 : 0) + 64 * 8 + 16;
+  CU(cudaFuncSetAttribute(trsm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  trsm_kernel<MODE><<<tiles_n, NTHREADS, smem, c->stream>>>(a);
+  LAUNCHED(c);
+  KCHECK();
+  return AGP_OK;
+}
+
+template <int LA, int LB, class Epi>
+static int32_t run_gemm(agp_ctx* c, int tiles_m, int tiles_n, const double* A, int64_t lda, const double* B, int64_t ldb, int K,
+                        int kmode, int tmode, const Epi& epi) {
+  using Cfg = StageCfg<LA, LB>;
+  GemmArgs g{A, lda, B, ldb, K, kmode, tmode};
+  CU(cudaFuncSetAttribute(gemm_kernel<LA, LB, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes));
+  dim3 grid(tiles_m, tiles_n);
+  gemm_kernel<LA, LB, Epi><<<grid, NTHREADS, Cfg::smem_bytes, c->stream>>>(g, epi);
+  LAUNCHED(c);
+  KCHECK();
+  return AGP_OK;
+}
+
+static EpiStore epi_store(double* C, int64_t ldc, bool rowmajor, double alpha = 1.0, double beta = 0.0, int mask = MASK_NONE,
+                          double diag_add = 0.0, const double* u = nullptr, const double* v = nullptr, double r1 = 0.0) {
+  EpiStore e;
+  e.C = C;
+  e.ldc = ldc;
+  e.rowmajor = rowmajor ? 1 : 0;
+  e.alpha = alpha;
+  e.beta = beta;
+  e.mask = mask;
+  e.diag_add = diag_add;
+  e.r1u = u;
+  e.r1v = v;
+  e.r1 = r1;
+  return e;
+}
+
+static int32_t fill(agp_ctx* c, double* p, int64_t n, double v) {
+  if (n <= 0) return AGP_OK;
+  if (v == 0.0) {
+    CU(cudaMemsetAsync(p, 0, sizeof(double) * n, c->stream));
+    return AGP_OK;
+  }
+  fill_kernel<<<(int)std::min<int64_t>(1024, (n + 255) / 256), 256, 0, c->stream>>>(p, n, v);
+  LAUNCHED(c);
+  KCHECK();
+  return AGP_OK;
+}
+
+static int32_t transpose(agp_ctx* c, const double* in, double* out, int n, int64_t ld) {
+  dim3 grid(n / 32, n / 32), block(32, 8);
+  transpose_kernel<<<grid, block, 0, c->stream>>>(in, out, n, ld);
+  LAUNCHED(c);
+  KCHECK();
+  return AGP_OK;
+}
+
+// Blocked right-looking Cholesky of the n x n (n = nb*128) matrix Kw (column-major, lower triangle read,
+// destroyed) into L; also produces the inverse diagonal blocks in the diagonal blocks of Lt (inv) and Ut (inv^T).
+static int32_t blocked_cholesky(agp_ctx* c, double* Kw, double* L, double* Lt, double* Ut, int nb, int64_t ld, int* info) {
+  const int smem_potrf = 128 * 129 * 8, smem_trinv = 2 * 128 * 129 * 8;
+  CU(cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_potrf));
+  CU(cudaFuncSetAttribute(trinv128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_trinv));
+  for (int J = 0; J < nb; J++) {
+    const int64_t djj = (int64_t)J * BM * ld + (int64_t)J * BM;
+    potrf128_kernel<<<1, 256, smem_potrf, c->stream>>>(Kw + djj, L + djj, ld, J * BM, info);
+    LAUNCHED(c);
+    KCHECK();
+    trinv128_kernel<<<1, 128, smem_trinv, c->stream>>>(L + djj, ld, Lt + djj, Ut + djj, ld);
+    LAUNCHED(c);
+    KCHECK();
+    const int rem = nb - 1 - J;
+    if (rem == 0) break;
+    const int64_t pnl = (int64_t)J * BM * ld + (int64_t)(J + 1) * BM;  // block column J, rows below the diagonal block
+    // panel: L[>J, J] = Kw[>J, J] * inv(L_JJ)^T ;  B(k, n) = inv[n][k] = Lt[djj + n + k*ld]
+    OK((run_gemm<A_KM, B_KN>(c, rem, 2, Kw + pnl, ld, Lt + djj, ld, BM, KR_FULL, TS_ALL, epi_store(L + pnl, ld, false))));
+    // trailing update (lower tiles): Kw[>J, >J] -= P P^T
+    const int64_t trl = (int64_t)(J + 1) * BM * ld + (int64_t)(J + 1) * BM;
+    OK((run_gemm<A_KM, B_KN>(c, rem, 2 * rem, L + pnl, ld, L + pnl, ld, BM, KR_FULL, TS_NBLK_LE,
+                             epi_store(Kw + trl, ld, false, -1.0, 1.0))));
+  }
+  return AGP_OK;
+}
+
+// Lt off-diagonal blocks: Lt[J][L<J] = -inv(L_JJ) L[J][L];  Ut[J][L>J] = -(L[L][J] inv(L_JJ))^T
+static int32_t build_block_scaled(agp_ctx* c, const double* L, double* Lt, double* Ut, int nb, int64_t ld) {
+  if (nb < 2) return AGP_OK;
+  // A(m,k) = Lt diag block (column-major, KM); B(k,n) = L[(J*128+k) + n*ld]  (k contiguous: NK)
+  OK((run_gemm<A_KM, B_NK>(c, nb, 2 * nb, Lt, ld, L, ld, nb * BM, KR_DIAG, TS_NBLK_LT, epi_store(Lt, ld, false, -1.0))));
+  // A(m,k) = Ut diag block = inv^T (KM); B(k,n) = L[n + (J*128+k)*ld]  (n contiguous: KN)
+  OK((run_gemm<A_KM, B_KN>(c, nb, 2 * nb, Ut, ld, L, ld, nb * BM, KR_DIAG, TS_NBLK_GT, epi_store(Ut, ld, false, -1.0))));
+  return AGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small element-wise kernels of the SVGP epilogue
+// ---------------------------------------------------------------------------------------------------
+// out[0] = KL(q || p) from (mt, Bt row-major, Lk, Lq), cf. SVA.jl:362-373 (see DESIGN.md for the whitened form)
+__global__ void __launch_bounds__(256) kl_kernel(const double* mt, const double* Bt_cm, const double* Lk, const double* Lq, int M,
+                                                 int Mp, int centered, double* out) {
+  __shared__ double sred[8];
+  double tr = 0.0, mm = 0.0, ldq = 0.0, ldk = 0.0;
+  for (int64_t i = threadIdx.x; i < (int64_t)Mp * Mp; i += blockDim.x) {
+    const double b = Bt_cm[i];
+    tr = fma(b, b, tr);
+  }
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    mm = fma(mt[j], mt[j], mm);
+    ldq += log(Lq[(int64_t)j * Mp + j]);
+    if (centered) ldk += log(Lk[(int64_t)j * Mp + j]);
+  }
+  const double a = block_sum(tr, sred);
+  const double b = block_sum(mm, sred);
+  const double q = block_sum(ldq, sred);
+  const double k = block_sum(ldk, sred);
+  if (threadIdx.x == 0) out[0] = 0.5 * (a + b - (double)M) + k - q;
+}
+
+// dLq (column-major M x M, ld = M) from the row-major Mp x Mp cotangent Xrm (lower part used):
+//   NonCentered: X - Lq + diag(1/Lq_jj);   Centered: X + diag(1/Lq_jj)
+__global__ void finalize_dLq_kernel(const double* Xrm, const double* Lq_cm, int M, int Mp, int centered, double* out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x, cidx = blockIdx.y;
+  if (r >= M) return;
+  double v = 0.0;
+  if (r >= cidx) {
+    v = Xrm[(int64_t)r * Mp + cidx];
+    const double l = Lq_cm[(int64_t)cidx * Mp + r];
+    if (!centered) v -= l;
+    if (r == cidx) v += 1.0 / l;
+  }
+  out[(int64_t)cidx * M + r] = v;
+}
+
+// Lbar (row-major) = -tril(V) [- tril(X2) - diag(1/Lk_jj)]
+__global__ void build_Lbar_kernel(const double* V, const double* X2, const double* Lk_cm, int Mp, int M, int centered, double* out) {
+  const int cidx = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (cidx >= Mp) return;
+  double v = 0.0;
+  if (r >= cidx) {
+    v = -V[(int64_t)r * Mp + cidx];
+    if (centered) {
+      v -= X2[(int64_t)r * Mp + cidx];
+      if (r == cidx && r < M) v -= 1.0 / Lk_cm[(int64_t)r * Mp + r];
+    }
+  }
+  out[(int64_t)r * Mp + cidx] = v;
+}
+
+__global__ void axpby_kernel(double a, const double* x, double b, const double* y, double* out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = a * x[i] + (y ? b * y[i] : 0.0);
+}
+// column 0 of a [Mp][64] row-major block <- v ; other columns zero
+__global__ void vec_to_rhs_kernel(const double* v, double shift, int M, int Mp, double* rhs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Mp * 64) return;
+  const int r = i / 64, cidx = i % 64;
+  rhs[i] = (cidx == 0 && r < M) ? v[r] - shift : 0.0;
+}
+__global__ void rhs_to_vec_kernel(const double* rhs, int Mp, double* v) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < Mp) v[r] = rhs[(int64_t)r * 64];
+}
+__global__ void __launch_bounds__(256) vec_sum_kernel(const double* v, int n, double* out) {
+  __shared__ double sred[8];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+  const double r = block_sum(s, sred);
+  if (threadIdx.x == 0) out[0] = r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SVGP: per-step preparation
+// ---------------------------------------------------------------------------------------------------
+static int32_t resolve_params(const agp_svgp_params* p, SvgpState& st) {
+  if (!p) return fail(AGP_ERR_INVALID, "params is NULL");
+  if (p->M < 1 || p->D < 1 || !p->Z || !p->m || !p->Lq) return fail(AGP_ERR_INVALID, "params: M, D, Z, m, Lq are required");
+  if (p->D > MAXD) return fail(AGP_ERR_UNSUPPORTED, "input dimension %d > %d is not supported on device", p->D, MAXD);
+  if (p->kernel.kind < AGP_KERNEL_SE || p->kernel.kind > AGP_KERNEL_LINEAR) return fail(AGP_ERR_UNSUPPORTED, "unsupported kernel kind %d", p->kernel.kind);
+  if (p->kernel.n_scale != 1 && p->kernel.n_scale != p->D) return fail(AGP_ERR_INVALID, "kernel.n_scale must be 1 or D");
+  if (!p->kernel.inv_lengthscale) return fail(AGP_ERR_INVALID, "kernel.inv_lengthscale is NULL");
+  if (p->lik.kind < AGP_LIK_GAUSSIAN || p->lik.kind > AGP_LIK_POISSON_EXP) return fail(AGP_ERR_UNSUPPORTED, "unsupported likelihood kind %d", p->lik.kind);
+  if (p->parametrization != AGP_NONCENTERED && p->parametrization != AGP_CENTERED) return fail(AGP_ERR_INVALID, "unknown parametrization");
+  st.M = p->M;
+  st.D = p->D;
+  st.Mp = (int)round_up(p->M, BM);
+  st.nb = st.Mp / BM;
+  st.n_scale = p->kernel.n_scale;
+  st.centered = p->parametrization == AGP_CENTERED;
+  st.mean_const = p->mean_const;
+  st.jitter = p->jitter;
+  memset(&st.kp, 0, sizeof st.kp);
+  st.kp.kind = p->kernel.kind;
+  st.kp.D = p->D;
+  st.kp.M = p->M;
+  st.kp.ard = p->kernel.n_scale != 1;
+  st.kp.variance = p->kernel.variance;
+  st.kp.c = p->kernel.linear_c;
+  for (int d = 0; d < p->D; d++) st.kp.s[d] = p->kernel.inv_lengthscale[p->kernel.n_scale == 1 ? 0 : d];
+  st.lp.kind = p->lik.kind;
+  st.lp.sigma2 = p->lik.sigma2;
+  int method = p->expect.method;
+  if (method == AGP_EXPECT_DEFAULT) {
+    // GPLikelihoods.DefaultExpectationMethod: analytic for Gaussian and Poisson-exp, else Gauss-Hermite(20)
+    method = (p->lik.kind == AGP_LIK_GAUSSIAN || p->lik.kind == AGP_LIK_POISSON_EXP) ? AGP_EXPECT_ANALYTIC : AGP_EXPECT_GAUSS_HERMITE;
+  }
+  if (method == AGP_EXPECT_ANALYTIC && p->lik.kind == AGP_LIK_BERNOULLI_LOGIT)
+    return fail(AGP_ERR_UNSUPPORTED, "no analytic expectation for the Bernoulli likelihood");
+  st.lp.method = method;
+  st.lp.ngh = 0;
+  if (method == AGP_EXPECT_GAUSS_HERMITE) {
+    if (p->expect.n_points < 1 || p->expect.n_points > AGP_MAX_GH_POINTS || !p->expect.nodes || !p->expect.weights)
+      return fail(AGP_ERR_INVALID, "Gauss-Hermite needs 1..%d nodes and weights from the caller", AGP_MAX_GH_POINTS);
+    st.lp.ngh = p->expect.n_points;
+  } else if (method != AGP_EXPECT_ANALYTIC) {
+    return fail(AGP_ERR_UNSUPPORTED, "unsupported expectation method %d", method);
+  }
+  if (p->lik.kind == AGP_LIK_GAUSSIAN && !(p->lik.sigma2 > 0)) return fail(AGP_ERR_INVALID, "GaussianLikelihood needs sigma2 > 0");
+  return AGP_OK;
+}
+
+// Uploads the parameters and builds every once-per-step operand: zs, zn, Kuu, Lk, Lt, Ut, mt, Bt.
+static int32_t prepare_step(agp_ctx* c, const agp_svgp_params* p) {
+  SvgpState& st = c->st;
+  st.valid = false;
+  OK(resolve_params(p, st));
+  CU(cudaSetDevice(c->device));
+  const int M = st.M, Mp = st.Mp, D = st.D, nb = st.nb;
+  const int64_t MM = (int64_t)Mp * Mp;
+  OK(c->z.ensure((int64_t)Mp * D));
+  OK(c->zs.ensure((int64_t)Mp * D));
+  OK(c->zn.ensure(Mp));
+  OK(c->mvec.ensure(Mp));
+  OK(c->mt.ensure(Mp));
+  OK(c->vec64.ensure((int64_t)Mp * 64));
+  OK(c->vec64b.ensure((int64_t)Mp * 64));
+  DevBuf* mats[] = {&c->Lq, &c->Kw, &c->Lk, &c->Lt, &c->Ut, &c->Bt_cm, &c->Bt_rm};
+  for (DevBuf* b : mats) OK(b->ensure(MM));
+  OK(c->small.ensure(64 + 2 * MAXD));
+  // host staging: padded m and Lq (lower triangle only)
+  st.h_m.assign(Mp, 0.0);
+  for (int i = 0; i < M; i++) st.h_m[i] = p->m[i];
+  st.h_Lq.assign(MM, 0.0);
+  const int ldq = p->ldLq > 0 ? p->ldLq : M;
+  for (int j = 0; j < M; j++)
+    for (int i = j; i < M; i++) st.h_Lq[(int64_t)j * Mp + i] = p->Lq[(int64_t)j * ldq + i];
+  for (int j = 0; j < M; j++)
+    if (!(st.h_Lq[(int64_t)j * Mp + j] > 0.0))
+      return fail(AGP_ERR_DOMAIN, "q.Sigma Cholesky factor has a non-positive diagonal entry at %d (logdet would throw)", j + 1);
+  CU(cudaMemsetAsync(c->z.p, 0, sizeof(double) * Mp * D, c->stream));
+  CU(cudaMemcpyAsync(c->z.p, p->Z, sizeof(double) * M * D, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->mvec.p, st.h_m.data(), sizeof(double) * Mp, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->Lq.p, st.h_Lq.data(), sizeof(double) * MM, cudaMemcpyHostToDevice, c->stream));
+  if (st.lp.ngh > 0) {
+    CU(cudaMemcpyToSymbolAsync(c_gh_x, p->expect.nodes, sizeof(double) * st.lp.ngh, 0, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyToSymbolAsync(c_gh_w, p->expect.weights, sizeof(double) * st.lp.ngh, 0, cudaMemcpyHostToDevice, c->stream));
+  }
+  CU(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int), c->stream));
+  prep_z_kernel<<<(Mp + 127) / 128, 128, 0, c->stream>>>(c->z.p, c->zs.p, c->zn.p, Mp, st.kp);
+  LAUNCHED(c);
+  KCHECK();
+  build_kuu_kernel<<<dim3((Mp + 127) / 128, Mp), 128, 0, c->stream>>>(c->Kw.p, Mp, c->zs.p, c->zn.p, st.jitter, st.kp);
+  LAUNCHED(c);
+  KCHECK();
+  OK(fill(c, c->Lk.p, MM, 0.0));
+  OK(fill(c, c->Lt.p, MM, 0.0));
+  OK(fill(c, c->Ut.p, MM, 0.0));
+  OK(blocked_cholesky(c, c->Kw.p, c->Lk.p, c->Lt.p, c->Ut.p, nb, Mp, c->d_flags));
+  OK(build_block_scaled(c, c->Lk.p, c->Lt.p, c->Ut.p, nb, Mp));
+  int h_flags[4];
+  CU(cudaMemcpyAsync(h_flags, c->d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (h_flags[0] != 0)
+    return fail(AGP_ERR_NOT_PD, "PosDefException: cov(fz) is not positive definite; Cholesky failed at column %d", h_flags[0]);
+  if (!st.centered) {
+    CU(cudaMemcpyAsync(c->mt.p, c->mvec.p, sizeof(double) * Mp, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->Bt_cm.p, c->Lq.p, sizeof(double) * MM, cudaMemcpyDeviceToDevice, c->stream));
+    OK(transpose(c, c->Bt_cm.p, c->Bt_rm.p, Mp, Mp));
+  } else {
+    // mt = Lk^-1 (m - mean(fz));  Bt = Lk^-1 Lq   (SVA.jl:132-133 rewritten in whitened variables)
+    vec_to_rhs_kernel<<<(Mp * 64 + 255) / 256, 256, 0, c->stream>>>(c->mvec.p, st.mean_const, M, Mp, c->vec64.p);
+    LAUNCHED(c);
+    KCHECK();
+    TrsmArgs a{};
+    a.T = c->Lt.p;
+    a.ldt = Mp;
+    a.nb = nb;
+    a.X = c->vec64.p;
+    a.ldx = 64;
+    a.kp = st.kp;
+    OK(launch_trsm<TR_RHS_FWD>(c, a, 1));
+    rhs_to_vec_kernel<<<(Mp + 255) / 256, 256, 0, c->stream>>>(c->vec64.p, Mp, c->mt.p);
+    LAUNCHED(c);
+    KCHECK();
+    OK(transpose(c, c->Lq.p, c->Bt_rm.p, Mp, Mp));  // row-major Lq as the right-hand side
+    a.X = c->Bt_rm.p;
+    a.ldx = Mp;
+    OK(launch_trsm<TR_RHS_FWD>(c, a, Mp / BN));
+    OK(transpose(c, c->Bt_rm.p, c->Bt_cm.p, Mp, Mp));
+  }
+  st.valid = true;
+  return AGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SVGP: the data sweep
+// ---------------------------------------------------------------------------------------------------
+static int64_t pick_chunk_cols(agp_ctx* c, int64_t count) {
+  int64_t wave = (int64_t)c->sms * 2 * BN;  // one full wave of column tiles at 2 CTAs / SM
+  int64_t cap = 2 * wave;
+  if (const char* e = getenv("AGP_CHUNK_COLS")) cap = std::max<int64_t>(BN, round_up(atoll(e), BN));
+  return std::min<int64_t>(cap, round_up(std::max<int64_t>(count, 1), BN));
+}
+
+static int32_t ensure_sweep_workspace(agp_ctx* c, int64_t cols, bool grad) {
+  const SvgpState& st = c->st;
+  const int Mp = st.Mp, D = st.D, nb = st.nb;
+  const int64_t MM = (int64_t)Mp * Mp;
+  if (cols > c->chunk_cols) c->chunk_cols = cols;
+  const int64_t cc = c->chunk_cols;
+  OK(c->A.ensure((int64_t)Mp * cc));
+  OK(c->C.ensure((int64_t)Mp * cc));
+  OK(c->saa.ensure(cc));
+  OK(c->sam.ensure(cc));
+  OK(c->scc_part.ensure((int64_t)nb * cc));
+  OK(c->dmu.ensure(cc));
+  OK(c->dv.ensure(cc));
+  OK(c->sc_part.ensure((cc / 256 + 2) * NSC));
+  OK(c->red.ensure(NSC + Mp + MM + (int64_t)Mp * D + 2 + D));
+  if (grad) {
+    OK(c->Ab.ensure((int64_t)Mp * cc));
+    OK(c->As.ensure((int64_t)Mp * cc));
+    OK(c->gpart.ensure((cc / BN) * Mp));
+    const int ntiles = nb * (nb + 1);
+    c->nsplit = std::max(1, (2 * c->sms) / ntiles);
+    OK(c->Gpart.ensure((int64_t)c->nsplit * MM));
+    c->nslab = (int)std::max<int64_t>((cc + 2047) / 2048, (Mp + 2047) / 2048);
+    OK(c->kpart.ensure((int64_t)c->nslab * Mp * (2 * D + 3)));
+    DevBuf* w[] = {&c->W1, &c->W2, &c->W3, &c->W4};
+    for (DevBuf* b : w) OK(b->ensure(MM));
+  }
+  return AGP_OK;
+}
+
+static int32_t run_kgrad(agp_ctx* c, const double* Kb, int64_t ld, const double* pts, int npts, int nslab) {
+  const SvgpState& st = c->st;
+  KgradArgs a{};
+  a.Kb = Kb;
+  a.ld = ld;
+  a.pts = pts;
+  a.npts = npts;
+  a.zs = c->zs.p;
+  a.zn = c->zn.p;
+  a.slab = 2048;
+  a.part = c->kpart.p;
+  a.stride = 2 * st.D + 3;
+  a.Mp = st.Mp;
+  a.kp = st.kp;
+  dim3 grid((st.M + 7) / 8, nslab);
+  if (st.D <= 4)
+    kgrad_kernel<4><<<grid, 256, 0, c->stream>>>(a);
+  else if (st.D <= 8)
+    kgrad_kernel<8><<<grid, 256, 0, c->stream>>>(a);
+  else if (st.D <= 16)
+    kgrad_kernel<16><<<grid, 256, 0, c->stream>>>(a);
+  else
+    kgrad_kernel<32><<<grid, 256, 0, c->stream>>>(a);
+  LAUNCHED(c);
+  KCHECK();
+  return AGP_OK;
+}
+
+static int32_t finish_kgrad(agp_ctx* c, int nslab, double zfac, double* dZ, double* theta) {
+  const SvgpState& st = c->st;
+  KgradFinishArgs a{};
+  a.part = c->kpart.p;
+  a.nslab = nslab;
+  a.Mp = st.Mp;
+  a.stride = 2 * st.D + 3;
+  a.zs = c->zs.p;
+  a.zfac = zfac;
+  a.dZ = dZ;
+  a.theta = theta;
+  a.kp = st.kp;
+  kgrad_finish_kernel<<<1, 256, 0, c->stream>>>(a);
+  LAUNCHED(c);
+  KCHECK();
+  return AGP_OK;
+}
+
+// layout of the packed reduce buffer
+struct RedLayout {
+  int64_t scal, g, G, dZ, theta, total;
+  RedLayout(int Mp, int D) {
+    scal = 0;
+    g = NSC;
+    G = g + Mp;
+    dZ = G + (int64_t)Mp * Mp;
+    theta = dZ + (int64_t)Mp * D;
+    total = theta + 2 + D;
+  }
+};
+
+// forward (+ backward) sweep over points [offset, offset+count) of ds.  predict != 0: only S1-S3 writing mu/var.
+static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_t count, bool grad, bool predict, double* mu_out,
+                            double* var_out) {
+  SvgpState& st = c->st;
+  const int Mp = st.Mp, D = st.D, nb = st.nb;
+  const int64_t MM = (int64_t)Mp * Mp;
+  const int64_t cols = pick_chunk_cols(c, count);
+  OK(ensure_sweep_workspace(c, cols, grad));
+  const int64_t ldc = c->chunk_cols;
+  RedLayout rl(Mp, D);
+  if (!predict) {
+    OK(fill(c, c->red.p, rl.total, 0.0));
+    if (grad) {
+      OK(fill(c, c->gpart.p, (ldc / BN) * Mp, 0.0));
+      OK(fill(c, c->Gpart.p, (int64_t)c->nsplit * MM, 0.0));
+      OK(fill(c, c->kpart.p, (int64_t)c->nslab * Mp * (2 * D + 3), 0.0));
+    }
+  }
+  for (int64_t lo = 0; lo < count; lo += cols) {
+    const int npts = (int)std::min<int64_t>(cols, count - lo);
+    const int ncols = (int)round_up(npts, BN);
+    const int tiles_n = ncols / BN;
+    const double* pts = X + lo * D;
+    // S1: A = Lk^-1 Kuf
+    TrsmArgs t1{};
+    t1.T = c->Lt.p;
+    t1.ldt = Mp;
+    t1.nb = nb;
+    t1.X = c->A.p;
+    t1.ldx = ldc;
+    t1.pts = pts;
+    t1.npts = npts;
+    t1.zs = c->zs.p;
+    t1.zn = c->zn.p;
+    t1.mt = c->mt.p;
+    t1.saa = c->saa.p;
+    t1.sam = c->sam.p;
+    t1.kp = st.kp;
+    OK(launch_trsm<TR_KUF_FWD>(c, t1, tiles_n));
+    // S2: C = Bt^T A  (A operand (m=j, k=l) = Bt[l][j] = Bt_rm[l*Mp + j]; nonzero for l >= j)
+    EpiS2 e2{c->C.p, ldc, c->scc_part.p, ldc};
+    OK((run_gemm<A_KM, B_KN>(c, nb, tiles_n, c->Bt_rm.p, Mp, c->A.p, ldc, Mp, KR_UPPER, TS_ALL, e2)));
+    // S3: per-point stage
+    PerPointArgs pp{};
+    pp.saa = c->saa.p;
+    pp.sam = c->sam.p;
+    pp.scc_part = c->scc_part.p;
+    pp.ldp = ldc;
+    pp.nb = nb;
+    pp.pts = pts;
+    pp.y = y ? y + lo : nullptr;
+    pp.npts = npts;
+    pp.ncols = ncols;
+    pp.scale = st.scale;
+    pp.mean_const = st.mean_const;
+    pp.kp = st.kp;
+    pp.lp = st.lp;
+    pp.dmu = c->dmu.p;
+    pp.dv = c->dv.p;
+    pp.mu_out = mu_out ? mu_out + lo : nullptr;
+    pp.var_out = var_out ? var_out + lo : nullptr;
+    pp.sc_part = c->sc_part.p;
+    pp.flag = c->d_flags + 1;
+    pp.predict_only = predict ? 1 : 0;
+    const int pblocks = (ncols + 255) / 256;
+    perpoint_kernel<<<pblocks, 256, 0, c->stream>>>(pp);
+    LAUNCHED(c);
+    KCHECK();
+    if (predict) continue;
+    const int nsc_used = st.kp.kind == AGP_KERNEL_LINEAR ? SC_DS + D : SC_DS;
+    scal_reduce_kernel<<<1, 256, 0, c->stream>>>(c->sc_part.p, pblocks, nsc_used, c->red.p + rl.scal);
+    LAUNCHED(c);
+    KCHECK();
+    if (!grad) continue;
+    // S4: Ab = dmu (x) mt + 2 dv (Bt C - A), As = dv A, g partial   (A operand (m=j,k=l) = Bt[j][l], l <= j)
+    EpiS4 e4{c->A.p, c->Ab.p, c->As.p, ldc, c->dmu.p, c->dv.p, c->mt.p, c->gpart.p, Mp};
+    OK((run_gemm<A_KM, B_KN>(c, nb, tiles_n, c->Bt_cm.p, Mp, c->C.p, ldc, Mp, KR_LOWER, TS_ALL, e4)));
+    // S5: Kb = Lk^-T Ab (in place)
+    TrsmArgs t5{};
+    t5.T = c->Ut.p;
+    t5.ldt = Mp;
+    t5.nb = nb;
+    t5.X = c->Ab.p;
+    t5.ldx = ldc;
+    t5.kp = st.kp;
+    OK(launch_trsm<TR_RHS_BWD>(c, t5, tiles_n));
+    // S6: G += As A^T
+    {
+      SyrkArgs s{};
+      s.As = c->As.p;
+      s.A = c->A.p;
+      s.ld = ldc;
+      s.ncols = ncols;
+      s.kchunk = (int)round_up((ncols + c->nsplit - 1) / c->nsplit, BK);
+      s.G = c->Gpart.p;
+      s.Mp = Mp;
+      using Cfg = StageCfg<A_MK, B_NK>;
+      CU(cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes));
+      dim3 grid(nb * (nb + 1), c->nsplit);
+      syrk_kernel<<<grid, NTHREADS, Cfg::smem_bytes, c->stream>>>(s);
+      LAUNCHED(c);
+      KCHECK();
+    }
+    // S7: contraction of Kb with the kernel derivatives
+    OK(run_kgrad(c, c->Ab.p, ldc, pts, npts, (npts + 2047) / 2048));
+  }
+  if (predict || !grad) return AGP_OK;
+  // local reductions into the packed buffer
+  sum_slices_kernel<<<(Mp + 255) / 256, 256, 0, c->stream>>>(c->gpart.p, (int)(ldc / BN), Mp, Mp, c->red.p + rl.g);
+  LAUNCHED(c);
+  KCHECK();
+  sum_slices_kernel<<<1024, 256, 0, c->stream>>>(c->Gpart.p, c->nsplit, MM, MM, c->red.p + rl.G);
+  LAUNCHED(c);
+  KCHECK();
+  OK(finish_kgrad(c, c->nslab, 1.0, c->red.p + rl.dZ, c->red.p + rl.theta));
+  return AGP_OK;
+}
+
+static int32_t check_dataset(agp_ctx* c, agp_dataset* ds, int64_t offset, int64_t count, int D) {
+  if (!c || !ds) return fail(AGP_ERR_INVALID, "NULL context or dataset");
+  if (ds->ctx != c) return fail(AGP_ERR_INVALID, "dataset belongs to another context");
+  if (ds->D != D) return fail(AGP_ERR_INVALID, "dataset dimension %d != params.D %d", ds->D, D);
+  if (offset < 0 || count < 1 || offset + count > ds->N)
+    return fail(AGP_ERR_INVALID, "points [%lld, %lld) outside the dataset (N=%lld)", (long long)offset, (long long)(offset + count), (long long)ds->N);
+  return AGP_OK;
+}
+
+extern "C" int32_t agp_svgp_sweep(agp_ctx* c, agp_dataset* ds, int64_t offset, int64_t count, const agp_svgp_params* p,
+                                  double num_data, int64_t global_batch, int32_t want_grad) {
+  if (!c || !p) return fail(AGP_ERR_INVALID, "agp_svgp_sweep: NULL argument");
+  OK(check_dataset(c, ds, offset, count, p->D));
+  OK(prepare_step(c, p));
+  SvgpState& st = c->st;
+  const int64_t gb = global_batch > 0 ? global_batch : count;
+  st.scale = (num_data > 0 ? num_data : (double)gb) / (double)gb;  // SVA.jl:357-358
+  st.want_grad = want_grad;
+  OK(sweep_points(c, ds->X + offset * ds->D, ds->y + offset, count, want_grad != 0, false, nullptr, nullptr));
+  return AGP_OK;
+}
+
+extern "C" int32_t agp_svgp_reduce_buffer(agp_ctx* c, void** dptr, int64_t* n) {
+  if (!c || !c->st.valid) return fail(AGP_ERR_INVALID, "agp_svgp_reduce_buffer: no sweep pending");
+  RedLayout rl(c->st.Mp, c->st.D);
+  if (dptr) *dptr = c->red.p;
+  if (n) *n = c->st.want_grad ? rl.total : NSC;
+  CU(cudaStreamSynchronize(c->stream));  // the caller's collective runs on its own stream
+  return AGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SVGP: replicated epilogue (KL, Cholesky pullback, Kuu part of dZ / dtheta)
+// ---------------------------------------------------------------------------------------------------
+extern "C" int32_t agp_svgp_finish(agp_ctx* c, double* elbo_out, agp_svgp_grads* go) {
+  if (!c || !c->st.valid) return fail(AGP_ERR_INVALID, "agp_svgp_finish: no sweep pending");
+  CU(cudaSetDevice(c->device));
+  SvgpState& st = c->st;
+  const int M = st.M, Mp = st.Mp, D = st.D, nb = st.nb;
+  const int64_t MM = (int64_t)Mp * Mp;
+  RedLayout rl(Mp, D);
+  double* red = c->red.p;
+  double* small = c->small.p;  // [0] KL, [1] sum(mbar) (centered)
+  kl_kernel<<<1, 256, 0, c->stream>>>(c->mt.p, c->Bt_cm.p, c->Lk.p, c->Lq.p, M, Mp, st.centered ? 1 : 0, small);
+  LAUNCHED(c);
+  KCHECK();
+  std::vector<double> h_scal(NSC), h_small(4, 0.0);
+  if (!st.want_grad || !go) {
+    CU(cudaMemcpyAsync(h_scal.data(), red + rl.scal, sizeof(double) * NSC, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(h_small.data(), small, sizeof(double) * 1, cudaMemcpyDeviceToHost, c->stream));
+    int h_flags[4];
+    CU(cudaMemcpyAsync(h_flags, c->d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (h_flags[1] != 0) return fail(AGP_ERR_DOMAIN, "DomainError: a marginal variance is not positive");
+    if (elbo_out) *elbo_out = h_scal[SC_E] * st.scale - h_small[0];
+    return AGP_OK;
+  }
+  double* g = red + rl.g;
+  double* G = red + rl.G;
+  double* dZ = red + rl.dZ;
+  double* theta = red + rl.theta;
+  double *W1 = c->W1.p, *W2 = c->W2.p, *W3 = c->W3.p, *W4 = c->W4.p;
+  // G: lower tiles -> full symmetric
+  symmetrize_from_lower_kernel<<<dim3((Mp + 127) / 128, Mp), 128, 0, c->stream>>>(G, Mp, Mp);
+  LAUNCHED(c);
+  KCHECK();
+  // W1 = P1 = Bt Bt^T - I
+  OK((run_gemm<A_KM, B_KN>(c, nb, Mp / BN, c->Bt_cm.p, Mp, c->Bt_cm.p, Mp, Mp, KR_FULL, TS_ALL,
+                           epi_store(W1, Mp, false, 1.0, 0.0, MASK_NONE, -1.0))));
+  // W2 (row-major) = Asum = mt g^T + 2 P1 G
+  OK((run_gemm<A_KM, B_KN>(c, nb, Mp / BN, W1, Mp, G, Mp, Mp, KR_FULL, TS_ALL,
+                           epi_store(W2, Mp, true, 2.0, 0.0, MASK_NONE, 0.0, c->mt.p, g, 1.0))));
+  // W2 <- V = Lk^-T Asum
+  TrsmArgs tb{};
+  tb.T = c->Ut.p;
+  tb.ldt = Mp;
+  tb.nb = nb;
+  tb.ldx = Mp;
+  tb.kp = st.kp;
+  tb.X = W2;
+  OK(launch_trsm<TR_RHS_BWD>(c, tb, Mp / BN));
+  // W3 (row-major) = Bt-bar = tril(2 G Bt) [- Bt if centered]
+  //   B operand (k, n) = Bt[k][n] = Bt_rm[k*Mp + n]
+  OK((run_gemm<A_KM, B_KN>(c, nb, Mp / BN, G, Mp, c->Bt_rm.p, Mp, Mp, KR_FULL, TS_ALL, epi_store(W3, Mp, true, 2.0, 0.0, MASK_LOWER))));
+  double* dLq_src = W3;
+  if (st.centered) {
+    // Bt-bar -= Bt ;  mt-bar = g - mt
+    axpby_kernel<<<1024, 256, 0, c->stream>>>(1.0, W3, -1.0, c->Bt_rm.p, W3, MM);
+    LAUNCHED(c);
+    KCHECK();
+    axpby_kernel<<<(Mp + 255) / 256, 256, 0, c->stream>>>(1.0, g, -1.0, c->mt.p, c->vec64b.p, Mp);  // mt-bar in vec64b[0..Mp)
+    LAUNCHED(c);
+    KCHECK();
+    // m-bar = Lk^-T mt-bar
+    vec_to_rhs_kernel<<<(Mp * 64 + 255) / 256, 256, 0, c->stream>>>(c->vec64b.p, 0.0, Mp, Mp, c->vec64.p);
+    LAUNCHED(c);
+    KCHECK();
+    tb.X = c->vec64.p;
+    tb.ldx = 64;
+    OK(launch_trsm<TR_RHS_BWD>(c, tb, 1));
+    rhs_to_vec_kernel<<<(Mp + 255) / 256, 256, 0, c->stream>>>(c->vec64.p, Mp, c->vec64b.p + Mp);  // m-bar in vec64b[Mp..2Mp)
+    LAUNCHED(c);
+    KCHECK();
+    vec_sum_kernel<<<1, 256, 0, c->stream>>>(c->vec64b.p + Mp, M, small + 1);
+    LAUNCHED(c);
+    KCHECK();
+    // W3 <- Y = Lk^-T Bt-bar (row-major, in place)
+    tb.X = W3;
+    tb.ldx = Mp;
+    OK(launch_trsm<TR_RHS_BWD>(c, tb, Mp / BN));
+    // W4 (row-major) = X2 = Y Bt^T + m-bar mt^T ;  A operand (m,k) = Y[m][k] row-major (MK); B (k,n) = Bt[n][k] = Bt_cm[n + k*Mp]
+    OK((run_gemm<A_MK, B_KN>(c, nb, Mp / BN, W3, Mp, c->Bt_cm.p, Mp, Mp, KR_FULL, TS_ALL,
+                             epi_store(W4, Mp, true, 1.0, 0.0, MASK_NONE, 0.0, c->vec64b.p + Mp, c->mt.p, 1.0))));
+  }
+  // W1 (row-major) = Lk-bar
+  build_Lbar_kernel<<<dim3((Mp + 127) / 128, Mp), 128, 0, c->stream>>>(W2, W4, c->Lk.p, Mp, M, st.centered ? 1 : 0, W1);
+  LAUNCHED(c);
+  KCHECK();
+  // W2 (row-major) = Phi(Lk^T Lk-bar);  A operand (m,k) = Lk[k][m] = Lk_cm[k + m*Mp] (MK), nonzero for k >= m
+  OK((run_gemm<A_MK, B_KN>(c, nb, Mp / BN, c->Lk.p, Mp, W1, Mp, Mp, KR_UPPER, TS_ALL, epi_store(W2, Mp, true, 1.0, 0.0, MASK_PHI))));
+  // Y1 = Lk^-T W2 ; Y2 = Lk^-T Y1^T ; Kuu-bar = (Y2 + Y2^T)/2
+  tb.X = W2;
+  tb.ldx = Mp;
+  OK(launch_trsm<TR_RHS_BWD>(c, tb, Mp / BN));
+  OK(transpose(c, W2, W1, Mp, Mp));
+  tb.X = W1;
+  OK(launch_trsm<TR_RHS_BWD>(c, tb, Mp / BN));
+  OK(transpose(c, W1, W2, Mp, Mp));
+  sym_average_kernel<<<1024, 256, 0, c->stream>>>(W1, W2, W4, MM);  // W4 = Kuu-bar (symmetric)
+  LAUNCHED(c);
+  KCHECK();
+  // Kuu part of dZ / dtheta: contraction with k(Z, Z); both arguments move -> zfac = 2
+  const int nslab_z = (M + 2047) / 2048;
+  OK(fill(c, c->kpart.p, (int64_t)nslab_z * Mp * (2 * D + 3), 0.0));
+  OK(run_kgrad(c, W4, Mp, c->z.p, M, nslab_z));
+  OK(finish_kgrad(c, nslab_z, 2.0, dZ, theta));
+  // outputs
+  std::vector<double> h_theta(2 + D), h_dZ((int64_t)Mp * D), h_vec(2 * (int64_t)Mp), h_g(Mp);
+  std::vector<double> h_dLq;
+  CU(cudaMemcpyAsync(h_scal.data(), red + rl.scal, sizeof(double) * NSC, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(h_small.data(), small, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(h_theta.data(), theta, sizeof(double) * (2 + D), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(h_dZ.data(), dZ, sizeof(double) * Mp * D, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(h_g.data(), g, sizeof(double) * Mp, cudaMemcpyDeviceToHost, c->stream));
+  if (st.centered) CU(cudaMemcpyAsync(h_vec.data(), c->vec64b.p, sizeof(double) * 2 * Mp, cudaMemcpyDeviceToHost, c->stream));
+  if (go->dLq) {
+    OK(c->A.ensure((int64_t)M * M));  // reuse chunk scratch as the staging area
+    finalize_dLq_kernel<<<dim3((M + 127) / 128, M), 128, 0, c->stream>>>(dLq_src, c->Lq.p, M, Mp, st.centered ? 1 : 0, c->A.p);
+    LAUNCHED(c);
+    KCHECK();
+    CU(cudaMemcpyAsync(go->dLq, c->A.p, sizeof(double) * M * M, cudaMemcpyDeviceToHost, c->stream));
+  }
+  int h_flags[4];
+  CU(cudaMemcpyAsync(h_flags, c->d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (h_flags[1] != 0) return fail(AGP_ERR_DOMAIN, "DomainError: a marginal variance is not positive");
+  if (elbo_out) *elbo_out = h_scal[SC_E] * st.scale - h_small[0];
+  if (go->dm) {
+    for (int i = 0; i < M; i++) go->dm[i] = st.centered ? h_vec[Mp + i] : h_g[i] - st.h_m[i];
+  }
+  if (go->dZ) memcpy(go->dZ, h_dZ.data(), sizeof(double) * M * D);
+  if (go->dvariance) *go->dvariance = h_theta[0] + h_scal[SC_DKXX];
+  if (go->dlinear_c) *go->dlinear_c = h_theta[1] + h_scal[SC_DC];
+  if (go->dinv_lengthscale) {
+    const bool linear = st.kp.kind == AGP_KERNEL_LINEAR;
+    if (st.n_scale == 1) {
+      double s = 0.0;
+      for (int d = 0; d < D; d++) s += h_theta[2 + d] + (linear ? h_scal[SC_DS + d] : 0.0);
+      go->dinv_lengthscale[0] = s;
+    } else {
+      for (int d = 0; d < D; d++) go->dinv_lengthscale[d] = h_theta[2 + d] + (linear ? h_scal[SC_DS + d] : 0.0);
+    }
+  }
+  if (go->dmean_const) *go->dmean_const = h_scal[SC_DMU] - (st.centered ? h_small[1] : 0.0);
+  if (go->dlik_sigma2) *go->dlik_sigma2 = h_scal[SC_DS2];
+  return AGP_OK;
+}
+
+static int32_t allreduce_if_needed(agp_ctx* c) {
+  if (!c->comm || c->nranks == 1) return AGP_OK;
+  RedLayout rl(c->st.Mp, c->st.D);
+  const size_t n = c->st.want_grad ? (size_t)rl.total : (size_t)NSC;
+  ncclResult_t r = g_nccl.AllReduce(c->red.p, c->red.p, n, ncclDouble, ncclSum, c->comm, c->stream);
+  if (r != ncclSuccess) return fail(AGP_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  return AGP_OK;
+}
+
+extern "C" int32_t agp_svgp_elbo_grad(agp_ctx* c, agp_dataset* ds, int64_t offset, int64_t count, const agp_svgp_params* p,
+                                      double num_data, int64_t global_batch, double* elbo_out, agp_svgp_grads* go) {
+  OK(agp_svgp_sweep(c, ds, offset, count, p, num_data, global_batch, go ? 1 : 0));
+  OK(allreduce_if_needed(c));
+  return agp_svgp_finish(c, elbo_out, go);
+}
+
+extern "C" int32_t agp_svgp_elbo(agp_ctx* c, agp_dataset* ds, int64_t offset, int64_t count, const agp_svgp_params* p,
+                                 double num_data, int64_t global_batch, double* elbo_out) {
+  OK(agp_svgp_sweep(c, ds, offset, count, p, num_data, global_batch, 0));
+  OK(allreduce_if_needed(c));
+  return agp_svgp_finish(c, elbo_out, nullptr);
+}
+
+extern "C" int32_t agp_svgp_prior_kl(agp_ctx* c, const agp_svgp_params* p, double* kl_out) {
+  if (!c || !p || !kl_out) return fail(AGP_ERR_INVALID, "agp_svgp_prior_kl: NULL argument");
+  OK(prepare_step(c, p));
+  SvgpState& st = c->st;
+  kl_kernel<<<1, 256, 0, c->stream>>>(c->mt.p, c->Bt_cm.p, c->Lk.p, c->Lq.p, st.M, st.Mp, st.centered ? 1 : 0, c->small.p);
+  LAUNCHED(c);
+  KCHECK();
+  CU(cudaMemcpyAsync(kl_out, c->small.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return AGP_OK;
+}
+
+extern "C" int32_t agp_svgp_posterior(agp_ctx* c, const agp_svgp_params* p, double* Lk_out, double* B_out, double* alpha_out) {
+  if (!c || !p) return fail(AGP_ERR_INVALID, "agp_svgp_posterior: NULL argument");
+  OK(prepare_step(c, p));
+  SvgpState& st = c->st;
+  const int M = st.M, Mp = st.Mp;
+  if (alpha_out) {
+    // alpha = Lk^-T mt   (NonCentered: Lk' \ m, SVA.jl:182; Centered: Kuu \ (m - mean(fz)), SVA.jl:133)
+    vec_to_rhs_kernel<<<(Mp * 64 + 255) / 256, 256, 0, c->stream>>>(c->mt.p, 0.0, Mp, Mp, c->vec64.p);
+    LAUNCHED(c);
+    KCHECK();
+    TrsmArgs tb{};
+    tb.T = c->Ut.p;
+    tb.ldt = Mp;
+    tb.nb = st.nb;
+    tb.X = c->vec64.p;
+    tb.ldx = 64;
+    tb.kp = st.kp;
+    OK(launch_trsm<TR_RHS_BWD>(c, tb, 1));
+    rhs_to_vec_kernel<<<(Mp + 255) / 256, 256, 0, c->stream>>>(c->vec64.p, Mp, c->vec64b.p);
+    LAUNCHED(c);
+    KCHECK();
+    CU(cudaMemcpyAsync(alpha_out, c->vec64b.p, sizeof(double) * M, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (Lk_out) CU(cudaMemcpy2DAsync(Lk_out, sizeof(double) * M, c->Lk.p, sizeof(double) * Mp, sizeof(double) * M, M, cudaMemcpyDeviceToHost, c->stream));
+  if (B_out) CU(cudaMemcpy2DAsync(B_out, sizeof(double) * M, c->Bt_cm.p, sizeof(double) * Mp, sizeof(double) * M, M, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return AGP_OK;
+}
+
+extern "C" int32_t agp_svgp_mean_and_var(agp_ctx* c, const agp_svgp_params* p, const double* Xnew, int64_t n, double* mu_out,
+                                         double* var_out) {
+  if (!c || !p || !Xnew || n < 1) return fail(AGP_ERR_INVALID, "agp_svgp_mean_and_var: bad arguments");
+  OK(prepare_step(c, p));
+  SvgpState& st = c->st;
+  st.scale = 1.0;
+  const int D = st.D;
+  OK(c->mu_out.ensure(n + BN));
+  OK(c->var_out.ensure(n + BN));
+  DevBuf xbuf;
+  OK(xbuf.ensure((n + BN) * D));
+  CU(cudaMemcpyAsync(xbuf.p, Xnew, sizeof(double) * n * D, cudaMemcpyHostToDevice, c->stream));
+  int32_t s = sweep_points(c, xbuf.p, nullptr, n, false, true, c->mu_out.p, c->var_out.p);
+  if (s == AGP_OK) {
+    if (mu_out) cudaMemcpyAsync(mu_out, c->mu_out.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream);
+    if (var_out) cudaMemcpyAsync(var_out, c->var_out.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream);
+  }
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  xbuf.release();
+  if (s != AGP_OK) return s;
+  if (e != cudaSuccess) return fail(AGP_ERR_CUDA, "mean_and_var: %s", cudaGetErrorString(e));
+  return AGP_OK;
+}
+
+#include "laplace_host.inc"

@@ -1,0 +1,146 @@
+// gemm.cuh -- the generic tile GEMM kernel (C tile 128 x 64 per CTA) on the DMMA mainloop of
+// common.cuh, with structured k-ranges (triangular operands) and pluggable epilogues.
+#pragma once
+#include "common.cuh"
+
+namespace agp {
+
+// k-range of a row tile (tile_m = blockIdx.x), in elements
+constexpr int KR_FULL = 0;   // [0, K)
+constexpr int KR_LOWER = 1;  // [0, (tile_m+1)*BM)        A lower triangular (block rows)
+constexpr int KR_UPPER = 2;  // [tile_m*BM, K)            A upper triangular
+constexpr int KR_DIAG = 3;   // [tile_m*BM, (tile_m+1)*BM)
+// which output tiles are computed (others are left untouched)
+constexpr int TS_ALL = 0;
+constexpr int TS_NBLK_LT = 1;  // column block (of BM) <  tile_m
+constexpr int TS_NBLK_GT = 2;  // column block (of BM) >  tile_m
+constexpr int TS_NBLK_LE = 3;  // column block (of BM) <= tile_m   (lower triangle incl. diagonal block)
+
+struct GemmArgs {
+  const double* A;
+  int64_t lda;
+  const double* B;
+  int64_t ldb;
+  int K;
+  int kmode;
+  int tmode;
+};
+
+template <int LA, int LB>
+__device__ __forceinline__ void gemm_mainloop(Acc& acc, double* smem, const double* __restrict__ gA, int64_t lda,
+                                              const double* __restrict__ gB, int64_t ldb, int nsteps,
+                                              const ThreadMap& tm) {
+  using Cfg = StageCfg<LA, LB>;
+  constexpr int S = Cfg::stages;
+  const int tid = threadIdx.x;
+  const int64_t a_step = (LA == A_KM) ? (int64_t)BK * lda : (int64_t)BK;
+  const int64_t b_step = (LB == B_KN) ? (int64_t)BK * ldb : (int64_t)BK;
+#pragma unroll
+  for (int s = 0; s < S - 1; s++) {
+    if (s < nsteps) {
+      double* st = smem + s * Cfg::elems;
+      load_a_tile<LA>(st, gA + s * a_step, lda, tid);
+      load_b_tile<LB>(st + Cfg::a_elems, gB + s * b_step, ldb, tid);
+    }
+    cp_async_commit();
+  }
+  for (int step = 0; step < nsteps; step++) {
+    cp_async_wait<S - 2>();
+    __syncthreads();
+    int nxt = step + S - 1;
+    if (nxt < nsteps) {
+      double* st = smem + (nxt % S) * Cfg::elems;
+      load_a_tile<LA>(st, gA + nxt * a_step, lda, tid);
+      load_b_tile<LB>(st + Cfg::a_elems, gB + nxt * b_step, ldb, tid);
+    }
+    cp_async_commit();
+    const double* st = smem + (step % S) * Cfg::elems;
+    mma_stage<LA, LB>(acc, st, st + Cfg::a_elems, tm);
+  }
+  cp_async_wait<0>();
+  __syncthreads();  // smem is free for the epilogue
+}
+
+template <int LA, int LB, class Epi>
+__global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(GemmArgs g, Epi epi) {
+  extern __shared__ __align__(128) double smem[];
+  ThreadMap tm;
+  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+  const int m0 = tile_m * BM, n0 = tile_n * BN;
+  const int nblk = n0 / BM;
+  if (g.tmode == TS_NBLK_LT && !(nblk < tile_m)) return;
+  if (g.tmode == TS_NBLK_GT && !(nblk > tile_m)) return;
+  if (g.tmode == TS_NBLK_LE && !(nblk <= tile_m)) return;
+  int kb = 0, ke = g.K;
+  if (g.kmode == KR_LOWER) ke = min(g.K, (tile_m + 1) * BM);
+  if (g.kmode == KR_UPPER) kb = tile_m * BM;
+  if (g.kmode == KR_DIAG) {
+    kb = tile_m * BM;
+    ke = kb + BM;
+  }
+  const double* gA = (LA == A_KM) ? g.A + (int64_t)kb * g.lda + m0 : g.A + (int64_t)m0 * g.lda + kb;
+  const double* gB = (LB == B_KN) ? g.B + (int64_t)kb * g.ldb + n0 : g.B + (int64_t)n0 * g.ldb + kb;
+  Acc acc;
+  acc_zero(acc);
+  gemm_mainloop<LA, LB>(acc, smem, gA, g.lda, gB, g.ldb, (ke - kb) / BK, tm);
+  epi(acc, tm, m0, n0, smem);
+}
+
+// ---- generic store epilogue for the once-per-step M x M algebra -----------------------------------
+constexpr int MASK_NONE = 0;
+constexpr int MASK_LOWER = 1;  // zero where col > row
+constexpr int MASK_PHI = 2;    // lower triangle, diagonal halved (Cholesky pullback)
+
+struct EpiStore {
+  double* C;
+  int64_t ldc;
+  int rowmajor;  // 1: C[row*ldc + col], 0: C[col*ldc + row]
+  double alpha;
+  double beta;  // adds beta * C_old (same location)
+  int mask;
+  double diag_add;
+  const double* r1u;  // optional rank-1 term r1 * u[row] * v[col]
+  const double* r1v;
+  double r1;
+  __device__ __forceinline__ void operator()(Acc& acc, const ThreadMap& tm, int m0, int n0, double*) const {
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) {
+      const int row = m0 + tm.row(mi);
+      const double ur = r1u ? r1 * r1u[row] : 0.0;
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int col = n0 + tm.col(ni, e);
+          double* p = rowmajor ? C + (int64_t)row * ldc + col : C + (int64_t)col * ldc + row;
+          double v = alpha * acc[mi][ni][e];
+          if (beta != 0.0) v += beta * (*p);
+          if (r1u) v += ur * r1v[col];
+          if (row == col) v += diag_add;
+          if (mask != MASK_NONE) {
+            if (col > row) v = 0.0;
+            if (mask == MASK_PHI && col == row) v *= 0.5;
+          }
+          *p = v;
+        }
+      }
+    }
+  }
+};
+
+template <int LA, int LB, class Epi>
+inline cudaError_t launch_gemm(cudaStream_t st, int tiles_m, int tiles_n, const GemmArgs& g, const Epi& epi) {
+  using Cfg = StageCfg<LA, LB>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<LA, LB, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::smem_bytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid(tiles_m, tiles_n);
+  gemm_kernel<LA, LB, Epi><<<grid, NTHREADS, Cfg::smem_bytes, st>>>(g, epi);
+  return cudaGetLastError();
+}
+
+}  // namespace agp

@@ -1,0 +1,150 @@
+// kfun.cuh -- covariance functions and likelihood expectations evaluated on the device.
+//
+// Semantics follow what the reference reaches through KernelFunctions / Distances
+// (cov(f.prior, z, x), SVA.jl:216) and GPLikelihoods.expected_loglikelihood (SVA.jl:355); see
+// oracle/kernels.py and oracle/likelihoods.py for the CPU restatement these are tested against.
+#pragma once
+#include <math.h>
+#include "../../include/agp.h"
+#include "common.cuh"
+
+namespace agp {
+
+constexpr int MAXD = 32;  // compile-time bound on the input dimension handled on device
+
+struct KernelParams {
+  int kind;
+  int D;
+  int M;  // valid inducing points (rows >= M of every padded operand are zero)
+  int ard;
+  double variance;
+  double c;
+  double s[MAXD];  // per-dimension input scale (ScaleTransform replicated, or ARDTransform)
+};
+
+// kappa(u): u = squared distance of the scaled inputs (stationary) or their dot product (linear)
+__device__ __forceinline__ double kappa(int kind, double u, double c) {
+  if (kind == AGP_KERNEL_SE) return exp(-0.5 * u);
+  if (kind == AGP_KERNEL_LINEAR) return u + c;
+  const double d = sqrt(u);
+  if (kind == AGP_KERNEL_MATERN32) {
+    const double r = 1.7320508075688772 * d;
+    return (1.0 + r) * exp(-r);
+  }
+  const double r = 2.23606797749979 * d;
+  return (1.0 + r + (5.0 / 3.0) * u) * exp(-r);
+}
+// kappa and d kappa / d u in one go (finite at u == 0)
+__device__ __forceinline__ void kappa_and_du(int kind, double u, double c, double& k, double& dk) {
+  if (kind == AGP_KERNEL_SE) {
+    k = exp(-0.5 * u);
+    dk = -0.5 * k;
+    return;
+  }
+  if (kind == AGP_KERNEL_LINEAR) {
+    k = u + c;
+    dk = 1.0;
+    return;
+  }
+  const double d = sqrt(u);
+  if (kind == AGP_KERNEL_MATERN32) {
+    const double r = 1.7320508075688772 * d;
+    const double e = exp(-r);
+    k = (1.0 + r) * e;
+    dk = -1.5 * e;
+    return;
+  }
+  const double r = 2.23606797749979 * d;
+  const double e = exp(-r);
+  k = (1.0 + r + (5.0 / 3.0) * u) * e;
+  dk = -(5.0 / 6.0) * (1.0 + r) * e;
+}
+// combine |xs|^2, |zs|^2 and xs.zs into u (Distances.jl: GEMM form with max(., 0) for D > 1)
+__device__ __forceinline__ double u_from_dot(int kind, double xn, double zn, double dot) {
+  if (kind == AGP_KERNEL_LINEAR) return dot;
+  return fmax(xn + zn - 2.0 * dot, 0.0);
+}
+
+// ---- likelihood expectations ------------------------------------------------------------------
+struct LikParams {
+  int kind;
+  int method;  // resolved: AGP_EXPECT_ANALYTIC or AGP_EXPECT_GAUSS_HERMITE
+  int ngh;
+  double sigma2;
+};
+
+__constant__ double c_gh_x[AGP_MAX_GH_POINTS];
+__constant__ double c_gh_w[AGP_MAX_GH_POINTS];
+
+__device__ __forceinline__ double softplus(double x) { return fmax(x, 0.0) + log1p(exp(-fabs(x))); }
+__device__ __forceinline__ double logistic(double x) {
+  if (x >= 0.0) return 1.0 / (1.0 + exp(-x));
+  const double e = exp(x);
+  return e / (1.0 + e);
+}
+
+// log p(y | f) and d/df (closed forms of Distributions.logpdf for the three likelihoods; the
+// Bernoulli form is the overflow-free -softplus(-+f), an intentional divergence from the
+// reference's log(logistic(f)) which returns -Inf for |f| > 36.7)
+__device__ __forceinline__ void loglik_d1(const LikParams& lp, double f, double y, double lg_y1, double& ll, double& dll) {
+  if (lp.kind == AGP_LIK_BERNOULLI_LOGIT) {
+    const bool one = y > 0.5;
+    ll = -softplus(one ? -f : f);
+    dll = (one ? 1.0 : 0.0) - logistic(f);
+  } else if (lp.kind == AGP_LIK_POISSON_EXP) {
+    const double lam = exp(f);
+    ll = y * f - lam - lg_y1;
+    dll = y - lam;
+  } else {
+    const double r = y - f;
+    ll = -0.5 * (1.8378770664093453 + log(lp.sigma2)) - 0.5 * r * r / lp.sigma2;
+    dll = r / lp.sigma2;
+  }
+}
+
+// E = E_{N(mu, var)}[log p(y|f)], dE/dmu, dE/dvar, dE/dsigma2 (derivatives of the finite
+// quadrature sum, which is what Zygote differentiates in the reference).
+__device__ __forceinline__ void expected_loglik(const LikParams& lp, double mu, double var, double y, double& E,
+                                                double& dmu, double& dvar, double& ds2) {
+  const double sd = sqrt(var);
+  ds2 = 0.0;
+  if (lp.method == AGP_EXPECT_ANALYTIC) {
+    const double v = sd * sd;  // Normal(mu, sqrt(var)) re-squared, as in the reference
+    if (lp.kind == AGP_LIK_GAUSSIAN) {
+      const double r = y - mu, s2 = lp.sigma2;
+      E = -0.5 * (1.8378770664093453 + log(s2) + (r * r + v) / s2);
+      dmu = r / s2;
+      dvar = -0.5 / s2;
+      ds2 = -0.5 / s2 + 0.5 * (r * r + v) / (s2 * s2);
+    } else {  // Poisson, exp link
+      const double e = exp(mu + 0.5 * v);
+      E = y * mu - e - lgamma(y + 1.0);
+      dmu = y - e;
+      dvar = -0.5 * e;
+    }
+    return;
+  }
+  const double lg_y1 = (lp.kind == AGP_LIK_POISSON_EXP) ? lgamma(y + 1.0) : 0.0;
+  const double sq2sd = 1.4142135623730951 * sd;
+  double sE = 0.0, sM = 0.0, sS = 0.0, sG = 0.0;
+  for (int k = 0; k < lp.ngh; k++) {
+    const double x = c_gh_x[k], w = c_gh_w[k];
+    const double f = mu + sq2sd * x;
+    double ll, dll;
+    loglik_d1(lp, f, y, lg_y1, ll, dll);
+    sE += w * ll;
+    sM += w * dll;
+    sS += w * dll * (1.4142135623730951 * x);
+    if (lp.kind == AGP_LIK_GAUSSIAN) {
+      const double r = y - f;
+      sG += w * (-0.5 / lp.sigma2 + 0.5 * r * r / (lp.sigma2 * lp.sigma2));
+    }
+  }
+  const double isp = 0.5641895835477563;  // 1/sqrt(pi)
+  E = isp * sE;
+  dmu = isp * sM;
+  dvar = isp * sS / (2.0 * sd);
+  ds2 = isp * sG;
+}
+
+}  // namespace agp

@@ -1,0 +1,607 @@
+// sweep.cuh -- the data-parallel SVGP sweep kernels (per chunk of points).
+//
+//   S1  trsm_kernel<TR_KUF_FWD>   A  = Lk^-1 Kuf   blocked left-looking TRSM; Kuf tiles are generated
+//                                 straight into the B-operand stage of the DMMA pipeline (never in HBM)
+//   S2  gemm + EpiS2              C  = Bt^T A       (upper-triangular operand)        + column |c|^2
+//   S3  perpoint_kernel           mu, var, E[log p], dE/dmu, dE/dvar                  (HBM-bound)
+//   S4  gemm + EpiS4              Ab = dmu (x) mt + 2 dv (Bt C - A),  As = dv A,  g += A dmu
+//   S5  trsm_kernel<TR_RHS_BWD>   Kb = Lk^-T Ab     (in place)
+//   S6  syrk_kernel               G += As A^T       (lower tiles, split over point slabs)
+//   S7  kgrad_kernel              contraction of Kb with dk/dz, dk/dtheta
+//
+// Reference counterparts: S1 = cov(f.prior, z, x) + `_chol_lower(Kuu) \ Kuf` (SVA.jl:215-219);
+// S2 = `f.data.B' * A` and diag_At_A (SVA.jl:251); S3 = marginals + expected_loglikelihood
+// (SVA.jl:354-355); S4-S7 = the Zygote pullbacks of those.
+#pragma once
+#include "gemm.cuh"
+#include "kfun.cuh"
+
+namespace agp {
+
+constexpr int TR_KUF_FWD = 0, TR_RHS_FWD = 1, TR_RHS_BWD = 2;
+
+struct TrsmArgs {
+  const double* T;  // Lt (forward) or Ut (backward): column-major Mp x Mp.  Diagonal blocks hold the
+                    // inverse of the factor's diagonal block, off-diagonal blocks the negated product.
+  int64_t ldt;
+  int nb;     // Mp / BM
+  double* X;  // [Mp][ldx] row-major: solution (and, in RHS modes, the right-hand side; in place)
+  int64_t ldx;
+  // TR_KUF_FWD only
+  const double* pts;  // chunk's points, point-major [npts][D]
+  int npts;
+  const double* zs;  // [Mp][D] scaled inducing inputs
+  const double* zn;  // [Mp] their squared norms
+  const double* mt;  // [Mp] whitened variational mean
+  double* saa;       // [ldx] sum_m a^2 per point
+  double* sam;       // [ldx] sum_m a*mt per point
+  KernelParams kp;
+};
+
+struct StepIter {
+  int J, q, kk, cnt, nb;
+  bool fwd;
+  __device__ __forceinline__ void init(bool f, int nb_) {
+    fwd = f;
+    nb = nb_;
+    J = f ? 0 : nb_ - 1;
+    q = 0;
+    kk = 0;
+    cnt = 1 + (f ? J : nb - 1 - J);
+  }
+  __device__ __forceinline__ int src() const { return q == 0 ? J : (fwd ? q - 1 : nb - q); }
+  __device__ __forceinline__ bool last_in_row() const { return q == cnt - 1 && kk == BM / BK - 1; }
+  __device__ __forceinline__ void next() {
+    if (++kk == BM / BK) {
+      kk = 0;
+      if (++q == cnt) {
+        q = 0;
+        J += fwd ? 1 : -1;
+        cnt = 1 + (fwd ? J : nb - 1 - J);
+      }
+    }
+  }
+};
+
+// Kuf rows [row0, row0+16) x the CTA's 64 points, written as a B-operand stage tile.
+__device__ __forceinline__ void gen_kuf_tile(double* sB, int row0, const TrsmArgs& a, const double* xsT,
+                                             const double* xn, int tid) {
+  const int n = tid & 63, lr = tid >> 6;
+  const int D = a.kp.D, kind = a.kp.kind;
+  const double xnn = xn[n];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int l = lr + 4 * i;
+    const int row = row0 + l;
+    double v = 0.0;
+    if (row < a.kp.M) {
+      const double* z = a.zs + (int64_t)row * D;
+      double u;
+      if (D == 1 && kind != AGP_KERNEL_LINEAR) {
+        const double df = xsT[n] - z[0];
+        u = df * df;
+      } else {
+        double dot = 0.0;
+        for (int d = 0; d < D; d++) dot = fma(xsT[d * 64 + n], z[d], dot);
+        u = u_from_dot(kind, xnn, a.zn[row], dot);
+      }
+      v = a.kp.variance * kappa(kind, u, a.kp.c);
+    }
+    sB[l * BTile<B_KN>::ld + n] = v;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
+  extern __shared__ __align__(128) double smem[];
+  using Cfg = StageCfg<A_KM, B_KN>;
+  constexpr int S = Cfg::stages;
+  ThreadMap tm;
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * BN;
+  double* xsT = smem + S * Cfg::elems;  // [D][64]
+  double* xn = xsT + ((MODE == TR_KUF_FWD) ? a.kp.D * 64 : 0);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(xn + 64);
+
+  if (MODE == TR_KUF_FWD) {
+    // ---- stage the X tile: TMA bulk copy into the (still unused) first pipeline stage, then scale and
+    //      transpose into xsT so that the Kuf generator reads it conflict-free.
+    const int D = a.kp.D;
+    const int nvalid = max(0, min(BN, a.npts - n0));
+    double* raw = smem;  // 64 * D doubles <= one stage
+    const double* src = a.pts + (int64_t)n0 * D;
+    const unsigned bytes = (unsigned)(nvalid * D * 8);
+    const bool use_tma = nvalid > 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15) == 0);
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+    if (use_tma) {
+      if (tid == 0) {
+        mbar_expect_tx(bar, bytes);
+        tma_bulk_g2s(raw, src, bytes, bar);
+      }
+      mbar_wait(bar, 0);
+    } else {
+      for (int i = tid; i < nvalid * D; i += NTHREADS) raw[i] = src[i];
+      __syncthreads();
+    }
+    for (int i = tid; i < BN * D; i += NTHREADS) {
+      const int n = i / D, d = i % D;
+      xsT[d * 64 + n] = (n < nvalid) ? raw[i] * a.kp.s[d] : 0.0;
+    }
+    __syncthreads();
+    if (tid < BN) {
+      double s = 0.0;
+      for (int d = 0; d < D; d++) s = fma(xsT[d * 64 + tid], xsT[d * 64 + tid], s);
+      xn[tid] = s;
+    }
+    __syncthreads();
+  }
+
+  StepIter it_issue, it_cons;
+  it_issue.init(MODE != TR_RHS_BWD, a.nb);
+  it_cons.init(MODE != TR_RHS_BWD, a.nb);
+  const int total = (BM / BK) * a.nb * (a.nb + 1) / 2;
+
+  auto issue = [&](int slot) {
+    double* st = smem + slot * Cfg::elems;
+    const int J = it_issue.J, L = it_issue.src(), kk = it_issue.kk;
+    load_a_tile<A_KM>(st, a.T + (int64_t)(L * BM + kk * BK) * a.ldt + J * BM, a.ldt, tid);
+    if (MODE == TR_KUF_FWD && it_issue.q == 0)
+      gen_kuf_tile(st + Cfg::a_elems, J * BM + kk * BK, a, xsT, xn, tid);
+    else
+      load_b_tile<B_KN>(st + Cfg::a_elems, a.X + (int64_t)(L * BM + kk * BK) * a.ldx + n0, a.ldx, tid);
+    it_issue.next();
+  };
+
+  Acc acc;
+  acc_zero(acc);
+  double paa[4][2], pam[4][2];
+#pragma unroll
+  for (int ni = 0; ni < 4; ni++) paa[ni][0] = paa[ni][1] = pam[ni][0] = pam[ni][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < S - 1; s++) {
+    if (s < total) issue(s);
+    cp_async_commit();
+  }
+  for (int step = 0; step < total; step++) {
+    cp_async_wait<S - 2>();
+    __syncthreads();
+    if (step + S - 1 < total) issue((step + S - 1) % S);
+    cp_async_commit();
+    const double* st = smem + (step % S) * Cfg::elems;
+    mma_stage<A_KM, B_KN>(acc, st, st + Cfg::a_elems, tm);
+    if (it_cons.last_in_row()) {
+      const int J = it_cons.J;
+#pragma unroll
+      for (int mi = 0; mi < 4; mi++) {
+        const int row = J * BM + tm.row(mi);
+        const double mtr = (MODE == TR_KUF_FWD) ? a.mt[row] : 0.0;
+        double* xr = a.X + (int64_t)row * a.ldx + n0;
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+          const double v0 = acc[mi][ni][0], v1 = acc[mi][ni][1];
+          *reinterpret_cast<double2*>(xr + tm.col(ni, 0)) = make_double2(v0, v1);
+          if (MODE == TR_KUF_FWD) {
+            paa[ni][0] = fma(v0, v0, paa[ni][0]);
+            paa[ni][1] = fma(v1, v1, paa[ni][1]);
+            pam[ni][0] = fma(v0, mtr, pam[ni][0]);
+            pam[ni][1] = fma(v1, mtr, pam[ni][1]);
+          }
+        }
+      }
+      acc_zero(acc);
+      __threadfence();  // the block just written is re-read through L2 (cp.async.cg) by later block rows
+    }
+    it_cons.next();
+  }
+  cp_async_wait<0>();
+  if (MODE == TR_KUF_FWD) {
+    __syncthreads();
+    double* sred = smem;  // [2][4 m-warps][64]
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        double v = paa[ni][e], w = pam[ni][e];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          v += __shfl_xor_sync(0xffffffffu, v, o);
+          w += __shfl_xor_sync(0xffffffffu, w, o);
+        }
+        if (tm.g == 0) {
+          sred[(tm.warp & 3) * 64 + tm.col(ni, e)] = v;
+          sred[256 + (tm.warp & 3) * 64 + tm.col(ni, e)] = w;
+        }
+      }
+    __syncthreads();
+    if (tid < BN) {
+      a.saa[n0 + tid] = ((sred[tid] + sred[64 + tid]) + sred[128 + tid]) + sred[192 + tid];
+      a.sam[n0 + tid] = ((sred[256 + tid] + sred[320 + tid]) + sred[384 + tid]) + sred[448 + tid];
+    }
+  }
+}
+
+// ---- S2 epilogue: store C and the per-point partial |c|^2 of this row block ---------------------------
+struct EpiS2 {
+  double* C;
+  int64_t ldc;
+  double* scc_part;  // [nb][ldp]
+  int64_t ldp;
+  __device__ __forceinline__ void operator()(Acc& acc, const ThreadMap& tm, int m0, int n0, double* sred) const {
+    double pcc[4][2];
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) pcc[ni][0] = pcc[ni][1] = 0.0;
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) {
+      double* cr = C + (int64_t)(m0 + tm.row(mi)) * ldc + n0;
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) {
+        const double v0 = acc[mi][ni][0], v1 = acc[mi][ni][1];
+        *reinterpret_cast<double2*>(cr + tm.col(ni, 0)) = make_double2(v0, v1);
+        pcc[ni][0] = fma(v0, v0, pcc[ni][0]);
+        pcc[ni][1] = fma(v1, v1, pcc[ni][1]);
+      }
+    }
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        double v = pcc[ni][e];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (tm.g == 0) sred[(tm.warp & 3) * 64 + tm.col(ni, e)] = v;
+      }
+    __syncthreads();
+    if (threadIdx.x < BN) {
+      const int t = threadIdx.x;
+      scc_part[(int64_t)(m0 / BM) * ldp + n0 + t] = ((sred[t] + sred[64 + t]) + sred[128 + t]) + sred[192 + t];
+    }
+  }
+};
+
+// ---- S4 epilogue: acc = (Bt C) tile.  Ab = dmu (x) mt + 2 dv (acc - A);  As = dv A;  g partial ---------
+struct EpiS4 {
+  const double* A;
+  double* Ab;
+  double* As;
+  int64_t ld;
+  const double* dmu;
+  const double* dv;
+  const double* mt;
+  double* gpart;  // [tiles_n][ldg]
+  int64_t ldg;
+  __device__ __forceinline__ void operator()(Acc& acc, const ThreadMap& tm, int m0, int n0, double* sred) const {
+    double dm[4][2], dvv[4][2];
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) {
+      const double2 a = *reinterpret_cast<const double2*>(dmu + n0 + tm.col(ni, 0));
+      const double2 b = *reinterpret_cast<const double2*>(dv + n0 + tm.col(ni, 0));
+      dm[ni][0] = a.x;
+      dm[ni][1] = a.y;
+      dvv[ni][0] = b.x;
+      dvv[ni][1] = b.y;
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) {
+      const int row = m0 + tm.row(mi);
+      const double mtr = mt[row];
+      const int64_t off = (int64_t)row * ld + n0;
+      double gp = 0.0;
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) {
+        const int c = tm.col(ni, 0);
+        const double2 a = *reinterpret_cast<const double2*>(A + off + c);
+        double2 ab, as;
+        ab.x = fma(dm[ni][0], mtr, 2.0 * dvv[ni][0] * (acc[mi][ni][0] - a.x));
+        ab.y = fma(dm[ni][1], mtr, 2.0 * dvv[ni][1] * (acc[mi][ni][1] - a.y));
+        as.x = dvv[ni][0] * a.x;
+        as.y = dvv[ni][1] * a.y;
+        *reinterpret_cast<double2*>(Ab + off + c) = ab;
+        *reinterpret_cast<double2*>(As + off + c) = as;
+        gp = fma(dm[ni][0], a.x, gp);
+        gp = fma(dm[ni][1], a.y, gp);
+      }
+      gp += __shfl_xor_sync(0xffffffffu, gp, 1);
+      gp += __shfl_xor_sync(0xffffffffu, gp, 2);
+      if (tm.t == 0) sred[(tm.warp >> 2) * BM + tm.row(mi)] = gp;
+    }
+    __syncthreads();
+    if (threadIdx.x < BM) gpart[(int64_t)(n0 / BN) * ldg + m0 + threadIdx.x] += sred[threadIdx.x] + sred[BM + threadIdx.x];
+  }
+};
+
+// ---- S3: per-point stage -------------------------------------------------------------------------------
+constexpr int SC_E = 0, SC_DMU = 1, SC_DKXX = 2, SC_DS2 = 3, SC_DC = 4, SC_DS = 5;  // SC_DS .. SC_DS+D-1
+constexpr int NSC = SC_DS + MAXD;
+
+struct PerPointArgs {
+  const double* saa;
+  const double* sam;
+  const double* scc_part;
+  int64_t ldp;
+  int nb;
+  const double* pts;  // [npts][D]
+  const double* y;
+  int npts;  // valid points
+  int ncols; // padded columns (multiple of BN) to fill with zeros beyond npts
+  double scale;
+  double mean_const;
+  KernelParams kp;
+  LikParams lp;
+  double* dmu;
+  double* dv;
+  double* mu_out;   // optional (prediction)
+  double* var_out;  // optional (prediction): variance WITHOUT the 1e-18 jitter
+  double* sc_part;  // [gridDim.x][NSC] block partial sums
+  int* flag;        // set to AGP_ERR_DOMAIN when a marginal variance is not positive
+  int predict_only;
+};
+
+__global__ void __launch_bounds__(256) perpoint_kernel(PerPointArgs p) {
+  __shared__ double sred[8];
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  double E = 0.0, dmu = 0.0, dvar = 0.0, ds2 = 0.0, kxxfac = 0.0, dc = 0.0;
+  const bool linear = p.kp.kind == AGP_KERNEL_LINEAR;
+  if (n < p.npts) {
+    double scc = 0.0;
+    for (int j = 0; j < p.nb; j++) scc += p.scc_part[(int64_t)j * p.ldp + n];
+    double kxx;
+    if (linear) {
+      double s = 0.0;
+      for (int d = 0; d < p.kp.D; d++) {
+        const double xs = p.pts[(int64_t)n * p.kp.D + d] * p.kp.s[d];
+        s = fma(xs, xs, s);
+      }
+      kxxfac = s + p.kp.c;
+      kxx = p.kp.variance * kxxfac;
+    } else {
+      kxxfac = 1.0;
+      kxx = p.kp.variance;
+    }
+    const double mu = p.mean_const + p.sam[n];
+    const double var0 = kxx - p.saa[n] + scc;
+    if (p.mu_out) p.mu_out[n] = mu;
+    if (p.var_out) p.var_out[n] = var0;
+    if (!p.predict_only) {
+      const double var = var0 + 1e-18;  // AbstractGPs default jitter of f_post(x), SVA.jl:354
+      if (!(var > 0.0)) atomicExch(p.flag, AGP_ERR_DOMAIN);
+      expected_loglik(p.lp, mu, var, p.y[n], E, dmu, dvar, ds2);
+      dmu *= p.scale;
+      dvar *= p.scale;
+      ds2 *= p.scale;
+      dc = dvar * p.kp.variance;
+    }
+  }
+  if (p.predict_only) return;
+  if (n < p.ncols) {
+    p.dmu[n] = dmu;
+    p.dv[n] = dvar;
+  }
+  double* out = p.sc_part + (int64_t)blockIdx.x * NSC;
+  double r;
+  r = block_sum(E, sred);
+  if (threadIdx.x == 0) out[SC_E] = r;
+  r = block_sum(dmu, sred);
+  if (threadIdx.x == 0) out[SC_DMU] = r;
+  r = block_sum(dvar * kxxfac, sred);
+  if (threadIdx.x == 0) out[SC_DKXX] = r;
+  r = block_sum(ds2, sred);
+  if (threadIdx.x == 0) out[SC_DS2] = r;
+  r = block_sum(linear ? dc : 0.0, sred);
+  if (threadIdx.x == 0) out[SC_DC] = r;
+  if (linear) {
+    for (int d = 0; d < p.kp.D; d++) {
+      double v = 0.0;
+      if (n < p.npts) {
+        const double x = p.pts[(int64_t)n * p.kp.D + d];
+        v = dvar * 2.0 * p.kp.variance * p.kp.s[d] * x * x;
+      }
+      r = block_sum(v, sred);
+      if (threadIdx.x == 0) out[SC_DS + d] = r;
+    }
+  }
+}
+
+// Deterministic reduction of the per-block scalars: acc[j] += sum_b part[b][j]
+__global__ void __launch_bounds__(256) scal_reduce_kernel(const double* part, int nblocks, int nsc_used, double* acc) {
+  __shared__ double sred[8];
+  for (int j = 0; j < nsc_used; j++) {
+    double v = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) v += part[(int64_t)b * NSC + j];
+    const double r = block_sum(v, sred);
+    if (threadIdx.x == 0) acc[j] += r;
+  }
+}
+
+// ---- S6: G_part[split] += As A^T on the lower-triangular tiles -------------------------------------------
+struct SyrkArgs {
+  const double* As;
+  const double* A;
+  int64_t ld;
+  int ncols;   // padded point count of this chunk (multiple of BN)
+  int kchunk;  // points per split (multiple of BK)
+  double* G;   // [nsplit][Mp*Mp] column-major
+  int Mp;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 2) syrk_kernel(SyrkArgs a) {
+  extern __shared__ __align__(128) double smem[];
+  ThreadMap tm;
+  // decode the tile index: row block ti (BM rows), column block tj (BN cols), tj <= 2*ti + 1
+  int t = blockIdx.x, ti = 0;
+  while (t >= 2 * ti + 2) {
+    t -= 2 * ti + 2;
+    ti++;
+  }
+  const int tj = t;
+  const int split = blockIdx.y;
+  const int kb = split * a.kchunk;
+  const int ke = min(a.ncols, kb + a.kchunk);
+  if (kb >= ke) return;
+  const int m0 = ti * BM, n0 = tj * BN;
+  Acc acc;
+  acc_zero(acc);
+  gemm_mainloop<A_MK, B_NK>(acc, smem, a.As + (int64_t)m0 * a.ld + kb, a.ld, a.A + (int64_t)n0 * a.ld + kb, a.ld,
+                            (ke - kb) / BK, tm);
+  double* G = a.G + (int64_t)split * a.Mp * a.Mp;
+#pragma unroll
+  for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) G[(int64_t)(n0 + tm.col(ni, e)) * a.Mp + m0 + tm.row(mi)] += acc[mi][ni][e];
+}
+
+// ---- S7: contraction of a cotangent Kb (row-major [Mp][ld], rows = inducing points, columns = points)
+//          with the derivatives of k(z_l, x_n).  One warp per row, lanes stride over a slab of points.
+// Per (slab, row) it accumulates  rs = sum_n W,  wx[d] = sum_n W xs_nd,  dsd[d],  dvar  with
+// W = Kb * variance * kappa'(u).  kgrad_finish_kernel turns these into dZ, ds, dvariance, dc.
+struct KgradArgs {
+  const double* Kb;
+  int64_t ld;
+  const double* pts;  // [npts][D] raw points
+  int npts;
+  const double* zs;
+  const double* zn;
+  int slab;      // points per slab
+  double* part;  // [nslab][Mp][stride]
+  int stride;    // 2*D + 3
+  int Mp;
+  KernelParams kp;
+};
+
+template <int DMAX>
+__global__ void __launch_bounds__(256) kgrad_kernel(KgradArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  const int slab = blockIdx.y;
+  const int D = a.kp.D, kind = a.kp.kind;
+  if (row >= a.kp.M) return;
+  const int nb = slab * a.slab, ne = min(a.npts, nb + a.slab);
+  double z[DMAX];
+#pragma unroll
+  for (int d = 0; d < DMAX; d++) z[d] = (d < D) ? a.zs[(int64_t)row * D + d] : 0.0;
+  const double znr = a.zn[row];
+  double rs = 0.0, dvar = 0.0, dcc = 0.0, wx[DMAX], dsd[DMAX];
+#pragma unroll
+  for (int d = 0; d < DMAX; d++) wx[d] = dsd[d] = 0.0;
+  const double* kr = a.Kb + (int64_t)row * a.ld;
+  for (int n = nb + lane; n < ne; n += 32) {
+    const double kb = kr[n];
+    double xs[DMAX];
+    double xnn = 0.0, dot = 0.0;
+#pragma unroll
+    for (int d = 0; d < DMAX; d++) {
+      xs[d] = (d < D) ? a.pts[(int64_t)n * D + d] * a.kp.s[d] : 0.0;
+      xnn = fma(xs[d], xs[d], xnn);
+      dot = fma(xs[d], z[d], dot);
+    }
+    double u;
+    if (D == 1 && kind != AGP_KERNEL_LINEAR) {
+      const double df = xs[0] - z[0];
+      u = df * df;
+    } else {
+      u = u_from_dot(kind, xnn, znr, dot);
+    }
+    double k, dk;
+    kappa_and_du(kind, u, a.kp.c, k, dk);
+    dvar = fma(kb, k, dvar);
+    dcc += kb;
+    const double W = kb * a.kp.variance * dk;
+    rs += W;
+#pragma unroll
+    for (int d = 0; d < DMAX; d++) {
+      wx[d] = fma(W, xs[d], wx[d]);
+      const double df = xs[d] - z[d];
+      dsd[d] = fma(W, (kind == AGP_KERNEL_LINEAR) ? xs[d] * z[d] : df * df, dsd[d]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    dvar += __shfl_xor_sync(0xffffffffu, dvar, o);
+    dcc += __shfl_xor_sync(0xffffffffu, dcc, o);
+#pragma unroll
+    for (int d = 0; d < DMAX; d++) {
+      wx[d] += __shfl_xor_sync(0xffffffffu, wx[d], o);
+      dsd[d] += __shfl_xor_sync(0xffffffffu, dsd[d], o);
+    }
+  }
+  if (lane == 0) {
+    double* out = a.part + ((int64_t)slab * a.Mp + row) * a.stride;
+    out[0] += rs;
+    out[1] += dvar;
+    out[2] += dcc;
+#pragma unroll
+    for (int d = 0; d < DMAX; d++)
+      if (d < D) {
+        out[3 + d] += wx[d];
+        out[3 + D + d] += dsd[d];
+      }
+  }
+}
+
+// dZ[l][d] += zfac * (stationary: 2 s_d (zs_ld rs - wx_d) | linear: s_d wx_d);  row-wise theta partials
+// are reduced over rows by thread 0 of each block into tpart, then summed by the host-side epilogue.
+struct KgradFinishArgs {
+  const double* part;
+  int nslab;
+  int Mp;
+  int stride;
+  const double* zs;
+  double zfac;
+  double* dZ;     // [Mp][D] accumulated
+  double* theta;  // [2 + D]: dvariance, dc, ds[d]  (accumulated; single block)
+  KernelParams kp;
+};
+
+__global__ void __launch_bounds__(256) kgrad_finish_kernel(KgradFinishArgs a) {
+  __shared__ double sred[8];
+  const int D = a.kp.D;
+  const bool linear = a.kp.kind == AGP_KERNEL_LINEAR;
+  double tv = 0.0, tc = 0.0;
+  // one block; threads stride over rows
+  for (int j = 0; j < 2 + D; j++) {
+    double v = 0.0;
+    for (int row = threadIdx.x; row < a.kp.M; row += blockDim.x) {
+      double s = 0.0;
+      for (int sl = 0; sl < a.nslab; sl++) {
+        const double* in = a.part + ((int64_t)sl * a.Mp + row) * a.stride;
+        s += (j == 0) ? in[1] : (j == 1) ? in[2] : in[3 + D + (j - 2)];
+      }
+      v += s;
+    }
+    const double r = block_sum(v, sred);
+    if (threadIdx.x == 0) {
+      if (j == 0) tv = r;
+      else if (j == 1) tc = r;
+      else {
+        const int d = j - 2;
+        // stationary: ds_d = (2/s_d) sum W (xs-zs)^2 ; linear: (2/s_d) sum W xs zs
+        a.theta[2 + d] += (a.kp.s[d] != 0.0) ? 2.0 / a.kp.s[d] * r : 0.0;
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    a.theta[0] += tv;
+    a.theta[1] += linear ? a.kp.variance * tc : 0.0;
+  }
+  for (int i = threadIdx.x; i < a.kp.M * D; i += blockDim.x) {
+    const int row = i / D, d = i % D;
+    double rs = 0.0, wx = 0.0;
+    for (int sl = 0; sl < a.nslab; sl++) {
+      const double* in = a.part + ((int64_t)sl * a.Mp + row) * a.stride;
+      rs += in[0];
+      wx += in[3 + d];
+    }
+    const double sd = a.kp.s[d];
+    const double g = linear ? sd * wx : 2.0 * sd * (a.zs[(int64_t)row * D + d] * rs - wx);
+    a.dZ[i] += a.zfac * g;
+  }
+}
+
+}  // namespace agp

