@@ -402,7 +402,7 @@ static int32_t transpose(agp_ctx* c, const double* in, double* out, int n, int64
 // Blocked right-looking Cholesky of the n x n (n = nb*128) matrix Kw (column-major, lower triangle read,
 // destroyed) into L; also produces the inverse diagonal blocks in the diagonal blocks of Lt (inv) and Ut (inv^T).
 static int32_t blocked_cholesky(agp_ctx* c, double* Kw, double* L, double* Lt, double* Ut, int nb, int64_t ld, int* info) {
-  const int smem_potrf = 128 * 129 * 8, smem_trinv = 2 * 128 * 129 * 8;
+  const int smem_potrf = 128 * 129 * 8, smem_trinv = 128 * 129 * 8;
   CU(cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_potrf));
   CU(cudaFuncSetAttribute(trinv128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_trinv));
   for (int J = 0; J < nb; J++) {
@@ -649,6 +649,20 @@ static int32_t prepare_step(agp_ctx* c, const agp_svgp_params* p) {
 // ---------------------------------------------------------------------------------------------------
 // SVGP: the data sweep
 // ---------------------------------------------------------------------------------------------------
+// layout of the packed reduce buffer
+struct RedLayout {
+  int64_t scal, g, G, dZ, theta, total;
+  RedLayout(int Mp, int D) {
+    // every segment starts on a 128-byte boundary (G is a cp.async.16 GEMM operand)
+    scal = 0;
+    g = round_up(NSC, 16);
+    G = g + Mp;
+    dZ = G + (int64_t)Mp * Mp;
+    theta = round_up(dZ + (int64_t)Mp * D, 16);
+    total = theta + 2 + D;
+  }
+};
+
 static int64_t pick_chunk_cols(agp_ctx* c, int64_t count) {
   int64_t wave = (int64_t)c->sms * 2 * BN;  // one full wave of column tiles at 2 CTAs / SM
   int64_t cap = 2 * wave;
@@ -670,7 +684,7 @@ static int32_t ensure_sweep_workspace(agp_ctx* c, int64_t cols, bool grad) {
   OK(c->dmu.ensure(cc));
   OK(c->dv.ensure(cc));
   OK(c->sc_part.ensure((cc / 256 + 2) * NSC));
-  OK(c->red.ensure(NSC + Mp + MM + (int64_t)Mp * D + 2 + D));
+  OK(c->red.ensure(RedLayout(Mp, D).total));
   if (grad) {
     OK(c->Ab.ensure((int64_t)Mp * cc));
     OK(c->As.ensure((int64_t)Mp * cc));
@@ -731,19 +745,6 @@ static int32_t finish_kgrad(agp_ctx* c, int nslab, double zfac, double* dZ, doub
   KCHECK();
   return AGP_OK;
 }
-
-// layout of the packed reduce buffer
-struct RedLayout {
-  int64_t scal, g, G, dZ, theta, total;
-  RedLayout(int Mp, int D) {
-    scal = 0;
-    g = NSC;
-    G = g + Mp;
-    dZ = G + (int64_t)Mp * Mp;
-    theta = dZ + (int64_t)Mp * D;
-    total = theta + 2 + D;
-  }
-};
 
 // forward (+ backward) sweep over points [offset, offset+count) of ds.  predict != 0: only S1-S3 writing mu/var.
 static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_t count, bool grad, bool predict, double* mu_out,

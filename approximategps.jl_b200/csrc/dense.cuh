@@ -85,28 +85,29 @@ __global__ void __launch_bounds__(256) potrf128_kernel(const double* src, double
 }
 
 // Inverse of the 128 x 128 lower-triangular block L (column-major, ld): inv -> dstL (column-major),
-// inv^T -> dstU (column-major).  One thread per column of the inverse.
+// inv^T -> dstU (column-major).  One thread per column of the inverse, in place in shared memory: row i of
+// L is last read at step i, so X(i, :) can overwrite it (one barrier between the reads and the write).
 __global__ void __launch_bounds__(128) trinv128_kernel(const double* L, int64_t ld, double* dstL, double* dstU, int64_t ldd) {
-  extern __shared__ double s[];  // L [128][129] then X [128][129]
+  extern __shared__ double s[];  // [128][129]
   constexpr int N = 128, LD = 129;
-  double* sl = s;
-  double* sx = s + N * LD;
   const int j = threadIdx.x;
   for (int i = j; i < N * N; i += 128) {
     const int r = i % N, c = i / N;
-    sl[r * LD + c] = L[(int64_t)c * ld + r];
+    s[r * LD + c] = (r >= c) ? L[(int64_t)c * ld + r] : 0.0;
   }
   __syncthreads();
   for (int i = 0; i < N; i++) {
     double acc = (i == j) ? 1.0 : 0.0;
-    for (int k = 0; k < i; k++) acc = fma(-sl[i * LD + k], sx[k * LD + j], acc);
-    sx[i * LD + j] = (i >= j) ? acc / sl[i * LD + i] : 0.0;
+    for (int k = 0; k < i; k++) acc = fma(-s[i * LD + k], s[k * LD + j], acc);
+    const double v = (i >= j) ? acc / s[i * LD + i] : 0.0;
+    __syncthreads();
+    s[i * LD + j] = v;
   }
   __syncthreads();
   for (int i = j; i < N * N; i += 128) {
     const int r = i % N, c = i / N;
-    dstL[(int64_t)c * ldd + r] = sx[r * LD + c];
-    dstU[(int64_t)c * ldd + r] = sx[c * LD + r];
+    dstL[(int64_t)c * ldd + r] = s[r * LD + c];
+    dstU[(int64_t)c * ldd + r] = s[c * LD + r];
   }
 }
 
