@@ -85,6 +85,9 @@ SYMBOLS = {
     "agp_build_arch": (C.c_int32, []),
     "agp_ctx_stream": (C.c_int32, [_vp, C.POINTER(_vp)]),
     "agp_ctx_launch_count": (C.c_int32, [_vp, C.POINTER(C.c_int64)]),
+    "agp_ctx_profile": (C.c_int32, [_vp, C.c_int32]),
+    "agp_ctx_profile_read": (C.c_int32, [_vp, C.c_int32, c_double_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "agp_profile_class_name": (C.c_char_p, [C.c_int32]),
     "agp_comm_unique_id": (C.c_int32, [_vp]),
     "agp_comm_init": (C.c_int32, [_vp, C.c_int32, C.c_int32, _vp]),
     "agp_comm_destroy": (C.c_int32, [_vp]),

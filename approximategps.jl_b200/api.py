@@ -292,6 +292,18 @@ class Context:
         L.check(self.lib.agp_ctx_launch_count(self.h, C.byref(n)))
         return n.value
 
+    def profile(self, enable: bool = True):
+        """Switch the per-kernel-class CUDA-event timers on / off."""
+        L.check(self.lib.agp_ctx_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self) -> dict:
+        """{class name: (milliseconds, launch groups)} accumulated since the last read."""
+        n = C.c_int32()
+        ms = (C.c_double * 64)()
+        cnt = (C.c_int64 * 64)()
+        L.check(self.lib.agp_ctx_profile_read(self.h, 64, ms, cnt, C.byref(n)))
+        return {self.lib.agp_profile_class_name(i).decode(): (ms[i], cnt[i]) for i in range(n.value)}
+
     def stream(self) -> int:
         s = C.c_void_p()
         L.check(self.lib.agp_ctx_stream(self.h, C.byref(s)))

@@ -115,7 +115,34 @@ struct SvgpState {
   std::vector<double> h_m, h_Lq;  // padded host copies (Lq column-major Mp x Mp)
 };
 
+// Optional per-kernel-class timing with CUDA events on the context's stream (agp_ctx_profile*):
+// this is how bench.py measures the launch durations behind its roofline figures.
+enum { PC_TRSM_FWD = 0, PC_GEMM_BTA, PC_PERPOINT, PC_GEMM_BC, PC_TRSM_BWD, PC_SYRK, PC_KGRAD, PC_PREPARE, PC_FINISH, PC_ALLREDUCE, PC_LAPLACE, PC_COUNT };
+static const char* const kProfNames[PC_COUNT] = {"trsm_kuf_fwd", "gemm_BtA", "perpoint", "gemm_BC", "trsm_bwd", "syrk_G", "kgrad",
+                                                 "prepare_step", "finish_epilogue", "allreduce", "laplace"};
+struct ProfRec {
+  int cls;
+  cudaEvent_t a, b;
+};
+struct Prof {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  std::vector<ProfRec> recs;
+  double ms[PC_COUNT] = {0};
+  int64_t cnt[PC_COUNT] = {0};
+  cudaEvent_t get() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+};
+
 struct agp_ctx {
+  Prof prof;
   int device = 0;
   cudaStream_t stream = nullptr;
   int sms = 148;
@@ -146,6 +173,19 @@ struct agp_dataset {
 };
 
 #define LAUNCHED(ctx) ((ctx)->launches++)
+struct ProfScope {
+  agp_ctx* c;
+  bool on;
+  ProfScope(agp_ctx* c_, int cls) : c(c_), on(c_->prof.on) {
+    if (!on) return;
+    ProfRec r{cls, c->prof.get(), c->prof.get()};
+    cudaEventRecord(r.a, c->stream);
+    c->prof.recs.push_back(r);
+  }
+  ~ProfScope() {
+    if (on) cudaEventRecord(c->prof.recs.back().b, c->stream);
+  }
+};
 #define KCHECK()                                                                                   \
   do {                                                                                             \
     cudaError_t e_ = cudaGetLastError();                                                           \
@@ -185,6 +225,7 @@ extern "C" int32_t agp_ctx_destroy(agp_ctx* c) {
                     &c->mu_out, &c->var_out};
   for (DevBuf* b : bufs) b->release();
   if (c->d_flags) cudaFree(c->d_flags);
+  for (cudaEvent_t e : c->prof.pool) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
   return AGP_OK;
@@ -193,6 +234,37 @@ extern "C" int32_t agp_ctx_destroy(agp_ctx* c) {
 extern "C" int32_t agp_ctx_stream(agp_ctx* c, void** s) {
   if (!c || !s) return fail(AGP_ERR_INVALID, "agp_ctx_stream: NULL argument");
   *s = (void*)c->stream;
+  return AGP_OK;
+}
+extern "C" int32_t agp_ctx_profile(agp_ctx* c, int32_t enable) {
+  if (!c) return fail(AGP_ERR_INVALID, "agp_ctx_profile: NULL");
+  c->prof.on = enable != 0;
+  return AGP_OK;
+}
+extern "C" const char* agp_profile_class_name(int32_t cls) { return (cls >= 0 && cls < PC_COUNT) ? kProfNames[cls] : nullptr; }
+extern "C" int32_t agp_ctx_profile_read(agp_ctx* c, int32_t max_classes, double* ms_out, int64_t* count_out, int32_t* n_classes) {
+  if (!c) return fail(AGP_ERR_INVALID, "agp_ctx_profile_read: NULL");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  Prof& p = c->prof;
+  for (const ProfRec& r : p.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      p.ms[r.cls] += ms;
+      p.cnt[r.cls]++;
+    }
+  }
+  p.recs.clear();
+  p.used = 0;
+  for (int i = 0; i < PC_COUNT && i < max_classes; i++) {
+    if (ms_out) ms_out[i] = p.ms[i];
+    if (count_out) count_out[i] = p.cnt[i];
+  }
+  if (n_classes) *n_classes = PC_COUNT;
+  for (int i = 0; i < PC_COUNT; i++) {
+    p.ms[i] = 0;
+    p.cnt[i] = 0;
+  }
   return AGP_OK;
 }
 extern "C" int32_t agp_ctx_launch_count(agp_ctx* c, int64_t* out) {
@@ -784,10 +856,16 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
     t1.saa = c->saa.p;
     t1.sam = c->sam.p;
     t1.kp = st.kp;
-    OK(launch_trsm<TR_KUF_FWD>(c, t1, tiles_n));
+    {
+      ProfScope ps(c, PC_TRSM_FWD);
+      OK(launch_trsm<TR_KUF_FWD>(c, t1, tiles_n));
+    }
     // S2: C = Bt^T A  (A operand (m=j, k=l) = Bt[l][j] = Bt_rm[l*Mp + j]; nonzero for l >= j)
     EpiS2 e2{c->C.p, ldc, c->scc_part.p, ldc};
-    OK((run_gemm<A_KM, B_KN>(c, nb, tiles_n, c->Bt_rm.p, Mp, c->A.p, ldc, Mp, KR_UPPER, TS_ALL, e2)));
+    {
+      ProfScope ps(c, PC_GEMM_BTA);
+      OK((run_gemm<A_KM, B_KN>(c, nb, tiles_n, c->Bt_rm.p, Mp, c->A.p, ldc, Mp, KR_UPPER, TS_ALL, e2)));
+    }
     // S3: per-point stage
     PerPointArgs pp{};
     pp.saa = c->saa.p;
@@ -811,18 +889,24 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
     pp.flag = c->d_flags + 1;
     pp.predict_only = predict ? 1 : 0;
     const int pblocks = (ncols + 255) / 256;
-    perpoint_kernel<<<pblocks, 256, 0, c->stream>>>(pp);
-    LAUNCHED(c);
-    KCHECK();
-    if (predict) continue;
-    const int nsc_used = st.kp.kind == AGP_KERNEL_LINEAR ? SC_DS + D : SC_DS;
-    scal_reduce_kernel<<<1, 256, 0, c->stream>>>(c->sc_part.p, pblocks, nsc_used, c->red.p + rl.scal);
-    LAUNCHED(c);
-    KCHECK();
+    {
+      ProfScope ps(c, PC_PERPOINT);
+      perpoint_kernel<<<pblocks, 256, 0, c->stream>>>(pp);
+      LAUNCHED(c);
+      KCHECK();
+      if (predict) continue;
+      const int nsc_used = st.kp.kind == AGP_KERNEL_LINEAR ? SC_DS + D : SC_DS;
+      scal_reduce_kernel<<<1, 256, 0, c->stream>>>(c->sc_part.p, pblocks, nsc_used, c->red.p + rl.scal);
+      LAUNCHED(c);
+      KCHECK();
+    }
     if (!grad) continue;
     // S4: Ab = dmu (x) mt + 2 dv (Bt C - A), As = dv A, g partial   (A operand (m=j,k=l) = Bt[j][l], l <= j)
     EpiS4 e4{c->A.p, c->Ab.p, c->As.p, ldc, c->dmu.p, c->dv.p, c->mt.p, c->gpart.p, Mp};
-    OK((run_gemm<A_KM, B_KN>(c, nb, tiles_n, c->Bt_cm.p, Mp, c->C.p, ldc, Mp, KR_LOWER, TS_ALL, e4)));
+    {
+      ProfScope ps(c, PC_GEMM_BC);
+      OK((run_gemm<A_KM, B_KN>(c, nb, tiles_n, c->Bt_cm.p, Mp, c->C.p, ldc, Mp, KR_LOWER, TS_ALL, e4)));
+    }
     // S5: Kb = Lk^-T Ab (in place)
     TrsmArgs t5{};
     t5.T = c->Ut.p;
@@ -831,9 +915,13 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
     t5.X = c->Ab.p;
     t5.ldx = ldc;
     t5.kp = st.kp;
-    OK(launch_trsm<TR_RHS_BWD>(c, t5, tiles_n));
+    {
+      ProfScope ps(c, PC_TRSM_BWD);
+      OK(launch_trsm<TR_RHS_BWD>(c, t5, tiles_n));
+    }
     // S6: G += As A^T
     {
+      ProfScope ps(c, PC_SYRK);
       SyrkArgs s{};
       s.As = c->As.p;
       s.A = c->A.p;
@@ -850,7 +938,10 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
       KCHECK();
     }
     // S7: contraction of Kb with the kernel derivatives
-    OK(run_kgrad(c, c->Ab.p, ldc, pts, npts, (npts + 2047) / 2048));
+    {
+      ProfScope ps(c, PC_KGRAD);
+      OK(run_kgrad(c, c->Ab.p, ldc, pts, npts, (npts + 2047) / 2048));
+    }
   }
   if (predict || !grad) return AGP_OK;
   // local reductions into the packed buffer
@@ -877,7 +968,10 @@ extern "C" int32_t agp_svgp_sweep(agp_ctx* c, agp_dataset* ds, int64_t offset, i
                                   double num_data, int64_t global_batch, int32_t want_grad) {
   if (!c || !p) return fail(AGP_ERR_INVALID, "agp_svgp_sweep: NULL argument");
   OK(check_dataset(c, ds, offset, count, p->D));
-  OK(prepare_step(c, p));
+  {
+    ProfScope ps(c, PC_PREPARE);
+    OK(prepare_step(c, p));
+  }
   SvgpState& st = c->st;
   const int64_t gb = global_batch > 0 ? global_batch : count;
   st.scale = (num_data > 0 ? num_data : (double)gb) / (double)gb;  // SVA.jl:357-358
@@ -901,6 +995,7 @@ extern "C" int32_t agp_svgp_reduce_buffer(agp_ctx* c, void** dptr, int64_t* n) {
 extern "C" int32_t agp_svgp_finish(agp_ctx* c, double* elbo_out, agp_svgp_grads* go) {
   if (!c || !c->st.valid) return fail(AGP_ERR_INVALID, "agp_svgp_finish: no sweep pending");
   CU(cudaSetDevice(c->device));
+  ProfScope ps_finish(c, PC_FINISH);
   SvgpState& st = c->st;
   const int M = st.M, Mp = st.Mp, D = st.D, nb = st.nb;
   const int64_t MM = (int64_t)Mp * Mp;
@@ -1046,6 +1141,7 @@ static int32_t allreduce_if_needed(agp_ctx* c) {
   if (!c->comm || c->nranks == 1) return AGP_OK;
   RedLayout rl(c->st.Mp, c->st.D);
   const size_t n = c->st.want_grad ? (size_t)rl.total : (size_t)NSC;
+  ProfScope ps(c, PC_ALLREDUCE);
   ncclResult_t r = g_nccl.AllReduce(c->red.p, c->red.p, n, ncclDouble, ncclSum, c->comm, c->stream);
   if (r != ncclSuccess) return fail(AGP_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   return AGP_OK;

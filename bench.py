@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- SVGP ELBO+gradient throughput (points/s) of the B200 path, FP64.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c4|c2|c1]
+
+A "step" is one full `elbo` + all-gradients evaluation (agp_svgp_elbo_grad through the C ABI) over
+the whole synthetic data set of BASELINE.json config 4 (SVGP PoissonLikelihood, SqExponential,
+N = 1e7, D = 8, M = 1024, Float64).  With N > 1 ranks (torchrun, one process per GPU) the N points
+are sharded contiguously over the ranks ("strong" scaling: the total work is fixed, as config 4
+states) and the partial sums are combined by one ncclAllReduce per step inside the library.
+
+One JSON line is printed by rank 0 (see DESIGN.md "Measurement" for every key):
+  value     points/s with the (x, y) shard already resident in HBM when the timed region starts
+  e2e       points/s through the same C-ABI calls with HOST (pinned) x, y: every step uploads the
+            shard (agp_dataset_upload), evaluates, and reads ELBO + gradients back
+  roofline  dominant kernel class: algorithmic FP64 flop / CUDA-event launch time vs the measured
+            FP64 peak (profiles/r01_fp64_peak.jsonl; MEASURED_PEAKS.json has no FP64 entry)
+  cpu_baseline  the NumPy/OpenBLAS restatement of the reference's op sequence (oracle/), timed on
+            this box's host cores on a bounded sample (rank 0, N = 1 only)
+
+`--impl reference` times that CPU restatement alone (Julia is not installed, so the reference
+itself cannot run) and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "SVGP ELBO+grad points/sec (FP64)"
+UNIT = "points/s"
+
+# measured on this pool's B200 (tools/fp64_peak.cu, tools/dgemm_peak.py -> profiles/r01_*): FP64 DMMA
+# issue peak and cuBLAS DGEMM 8192^3.  MEASURED_PEAKS.json carries no FP64 figure.
+FP64_PEAK_TFLOPS_DMMA = 37.1
+FP64_PEAK_TFLOPS_DGEMM = 35.5
+
+WORKLOADS = {
+    # BASELINE.json configs[3] (the configuration `metric` is quoted on)
+    "c4": dict(label="C4 SVGP Poisson(exp) analytic, SqExponential, N=1e7, D=8, M=1024, FP64", N=10_000_000, D=8, M=1024, kind="se",
+               lik="poisson_exp", method="default", seed=4, lengthscale=math.sqrt(8.0), variance=1.0, jitter=1e-6),
+    # BASELINE.json configs[1]
+    "c2": dict(label="C2 SVGP Bernoulli GH-20, Matern52, N=1e6, D=8, M=512, FP64", N=1_000_000, D=8, M=512, kind="matern52",
+               lik="bernoulli_logit", method="default", seed=2, lengthscale=math.sqrt(8.0), variance=1.0, jitter=1e-6),
+    # BASELINE.json configs[4], one rank-step of the minibatch (2^20 points per rank), num_data = 1e8
+    "c5mb": dict(label="C5 minibatch SVGP Gaussian, SqExponential, B=2^20/rank, num_data=1e8, D=16, M=2048, FP64", N=1 << 20, D=16,
+                 M=2048, kind="se", lik="gaussian", method="default", seed=5, lengthscale=4.0, variance=1.0, jitter=1e-6,
+                 num_data=1e8, weak=True),
+}
+
+BLOCK = 1 << 20  # rows per generation block: the global data set is independent of the rank count
+
+
+def flops_per_point(M: int, D: int) -> float:
+    """algorithmic flop per point for ELBO + gradient."""
+    return 6.0 * M * M + 6.0 * M * D
+
+
+# algorithmic flop per point of each kernel class (they add up to flops_per_point; DESIGN.md "Kernels")
+def class_flops_per_point(M: int, D: int) -> dict:
+    return {"trsm_kuf_fwd": M * M + 2.0 * M * D, "gemm_BtA": 1.0 * M * M, "gemm_BC": 1.0 * M * M, "trsm_bwd": 1.0 * M * M,
+            "syrk_G": 2.0 * M * M, "kgrad": 4.0 * M * D, "fused_sweep": 6.0 * M * M + 6.0 * M * D}
+
+
+def gen_rows(w: dict, lo: int, hi: int, wvec: np.ndarray):
+    """Rows [lo, hi) of the synthetic data set (SURVEY.md section 8(d) recipe), block-seeded."""
+    D = w["D"]
+    X = np.empty((hi - lo, D))
+    y = np.empty(hi - lo)
+    b0, b1 = lo // BLOCK, (hi - 1) // BLOCK
+    for b in range(b0, b1 + 1):
+        rng = np.random.default_rng([w["seed"], b])
+        Xb = rng.standard_normal((BLOCK, D))
+        g = np.sin(Xb @ wvec)
+        if w["lik"] == "poisson_exp":
+            yb = rng.poisson(np.exp(0.5 * g)).astype(np.float64)
+        elif w["lik"] == "bernoulli_logit":
+            yb = (rng.random(BLOCK) < 1.0 / (1.0 + np.exp(-2.0 * g))).astype(np.float64)
+        else:
+            yb = g + 0.1 * rng.standard_normal(BLOCK)
+        s, e = max(lo, b * BLOCK), min(hi, (b + 1) * BLOCK)
+        X[s - lo:e - lo] = Xb[s - b * BLOCK:e - b * BLOCK]
+        y[s - lo:e - lo] = yb[s - b * BLOCK:e - b * BLOCK]
+    return X, y
+
+
+def make_params(w: dict):
+    """Replicated (tiny) inputs: Z, m, Lq, kernel."""
+    rng = np.random.default_rng([w["seed"], 10_000_019])
+    D, M = w["D"], w["M"]
+    wvec = rng.standard_normal(D)
+    X0, _ = gen_rows(w, 0, M, wvec)
+    Z = X0 + 1e-3 * rng.standard_normal((M, D))
+    m = 0.1 * rng.standard_normal(M)
+    A = 0.5 * np.eye(M) + 0.01 * np.tril(rng.standard_normal((M, M)))
+    A[np.diag_indices(M)] = np.abs(np.diag(A))
+    return wvec, Z, m, A
+
+
+def shard_range(N: int, rank: int, world: int):
+    """Contiguous block partition of [0, N)."""
+    base, rem = divmod(N, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def oracle_objects(w, Z, m, A):
+    from oracle import kernels as ok, likelihoods as ol, svgp as osv
+
+    k = ok.Kernel(w["kind"], w["variance"], np.array([1.0 / w["lengthscale"]]), 0.0)
+    s = osv.SVGP(k, Z, m, A, jitter=w["jitter"])
+    return s, ol.Likelihood(w["lik"], 0.01), ol.Expectation(w["method"], 20)
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:  # pragma: no cover
+        return os.cpu_count() or 1
+
+
+def time_oracle(w, Z, m, A, wvec, n_sample: int, reps: int, chunk: int = 65536):
+    """points/s of the CPU restatement on rows [0, n_sample) (OpenBLAS threads = host cores)."""
+    from threadpoolctl import threadpool_limits
+
+    from oracle import svgp as osv
+
+    s, lik, ex = oracle_objects(w, Z, m, A)
+    X, y = gen_rows(w, 0, n_sample, wvec)
+    times = []
+    with threadpool_limits(limits=host_threads()):
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            osv.elbo_and_grad(s, X, y, lik, ex, num_data=w.get("num_data", w["N"]), chunk=chunk)
+            times.append(time.perf_counter() - t0)
+    return n_sample / statistics.median(times), times
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(gpu_index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in self.f.read().splitlines():
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            load = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+            out = {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+        return out
+
+
+def run_reference(args, w):
+    """--impl reference: the CPU restatement of the reference's op sequence on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wvec, Z, m, A = make_params(w)
+    cores = host_threads()
+    pps, _ = time_oracle(w, Z, m, A, wvec, 8192, 1, chunk=8192)  # pilot
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    n_sample = int(min(262144, max(8192, 2 ** int(math.log2(max(1.0, pps * min(budget, 20.0)))))))
+    from threadpoolctl import threadpool_limits
+
+    from oracle import svgp as osv
+
+    s, lik, ex = oracle_objects(w, Z, m, A)
+    X, y = gen_rows(w, 0, n_sample, wvec)
+    with threadpool_limits(limits=cores):
+        for _ in range(args.warmup):
+            osv.elbo_and_grad(s, X, y, lik, ex, num_data=w["N"], chunk=65536)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            osv.elbo_and_grad(s, X, y, lik, ex, num_data=w["N"], chunk=65536)
+        dt = time.perf_counter() - t0
+    value = n_sample * args.steps / dt
+    sample = f"rows [0,{n_sample}) of the workload per step, chunked 65536, NumPy/SciPy OpenBLAS threads={cores}"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak" if w.get("weak") else "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": w["label"], "N": w["N"], "M": w["M"], "D": w["D"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference-algorithm CPU restatement (oracle/, NumPy + OpenBLAS); Julia is not installed so ApproximateGPs.jl itself cannot run"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="override the number of points (debugging only; the line says so)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.n:
+        w["N"] = args.n
+        w["label"] += f" [N overridden to {args.n}]"
+    if args.impl == "reference":
+        return run_reference(args, w)
+
+    import torch
+    import torch.distributed as dist
+
+    import agp_b200 as agp
+    from agp_b200 import _lib as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    weak = bool(w.get("weak"))
+    N_total = w["N"] * world if weak else w["N"]
+    lo, hi = shard_range(N_total, rank, world)
+    n_local = hi - lo
+    D, M = w["D"], w["M"]
+    wvec, Z, m, A = make_params(w)
+
+    # host (pinned) copy of this rank's shard -- the e2e leg uploads it every step
+    Xh = torch.empty((n_local, D), dtype=torch.float64).pin_memory()
+    yh = torch.empty((n_local,), dtype=torch.float64).pin_memory()
+    for s in range(0, n_local, BLOCK):
+        e = min(n_local, s + BLOCK)
+        Xb, yb = gen_rows(w, lo + s, lo + e, wvec)
+        Xh[s:e] = torch.from_numpy(Xb)
+        yh[s:e] = torch.from_numpy(yb)
+
+    ctx = agp.Context(local)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(ctx.unique_id()), dtype=torch.uint8).clone()
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        ctx.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+
+    ds = agp.DeviceData(capacity=n_local, D=D, ctx=ctx)
+    lib = ctx.lib
+
+    def upload():
+        L.check(lib.agp_dataset_upload(ds.h, C.c_void_p(Xh.data_ptr()), n_local, D, L.POINT_MAJOR, C.c_void_p(yh.data_ptr()), L.Y_F64, L.HOST))
+        ds.N = n_local
+
+    base = {"se": agp.SqExponentialKernel, "matern32": agp.Matern32Kernel, "matern52": agp.Matern52Kernel}[w["kind"]]()
+    f = agp.GP(w["variance"] * agp.with_lengthscale(base, w["lengthscale"]))
+    sva = agp.SparseVariationalApproximation(f(Z, w["jitter"]), agp.MvNormal(m, chol_lower=A))
+    lik = {"gaussian": agp.GaussianLikelihood(0.01), "bernoulli_logit": agp.BernoulliLikelihood(), "poisson_exp": agp.PoissonLikelihood()}[w["lik"]]
+    from agp_b200.api import _Packed
+
+    pk = _Packed(sva, lik, None)
+    g_m, g_Lq, g_Z = np.zeros(M), np.zeros((M, M), order="F"), np.zeros((M, D))
+    sc = np.zeros(4)
+    g_ils = np.zeros(1)
+    G = L.AgpSvgpGrads(L.dptr(g_m), L.dptr(g_Lq), L.dptr(g_Z), sc[0:1].ctypes.data_as(L.c_double_p), L.dptr(g_ils),
+                       sc[1:2].ctypes.data_as(L.c_double_p), sc[2:3].ctypes.data_as(L.c_double_p), sc[3:4].ctypes.data_as(L.c_double_p))
+    out = C.c_double()
+    num_data = float(w.get("num_data", N_total))
+
+    def step():
+        L.check(lib.agp_svgp_elbo_grad(ctx.h, ds.h, 0, n_local, C.byref(pk.p), num_data, N_total, C.byref(out), C.byref(G)))
+        return out.value
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        """K calls of fn bracketed by barrier + synchronize; device time (ms) on the library stream, max over ranks."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(k):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident leg ---------------------------------------------------------------------------
+    upload()
+    for _ in range(max(3, args.warmup)):
+        val = step()
+    ctx.profile_read()
+    ctx.profile(True)
+    l0 = ctx.launch_count()
+    clocks = ClockSampler(local) if rank == 0 else None
+    ms = timed(step, args.steps)
+    clk = clocks.stop() if clocks else {}
+    launches = ctx.launch_count() - l0
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    value = N_total * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end leg: host buffers, upload + evaluate + read back every step ------------------------
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            upload()
+            step()
+
+        e2e_step()
+        ms_e = timed(e2e_step, args.steps)
+        p_bytes = 8 * (M * D + M + M * M + 4)
+        g_bytes = 8 * (M + M * M + M * D + 6)
+        e2e = {"value": N_total * args.steps / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e / args.steps,
+               "h2d_bytes_per_step": 8 * N_total * (D + 1) + world * p_bytes, "d2h_bytes_per_step": world * g_bytes}
+
+    if world > 1:
+        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+
+    if rank == 0:
+        cf = class_flops_per_point(M, D)
+        sweep = {k: v for k, v in prof.items() if v[1] > 0}
+        tot_ms = sum(v[0] for v in sweep.values())
+        kernels = {}
+        for k, (kms, cnt) in sweep.items():
+            ent = {"ms_per_step": kms / args.steps, "share": kms / tot_ms if tot_ms else None, "launch_groups_per_step": cnt / args.steps}
+            if k in cf:
+                ent["alg_tflops"] = cf[k] * n_local * args.steps / (kms * 1e-3) / 1e12
+            kernels[k] = ent
+        dom = max((k for k in sweep if k in cf), key=lambda k: sweep[k][0])
+        dms, dcnt = sweep[dom]
+        achieved = cf[dom] * n_local * args.steps / (dms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": FP64_PEAK_TFLOPS_DMMA, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS_DMMA,
+                "traffic": None, "avg_launch_ms": dms / dcnt, "alg_flop_per_launch": cf[dom] * n_local * args.steps / dcnt,
+                "peak_source": "measured FP64 DMMA issue peak on this pool's B200 (profiles/r01_fp64_peak.jsonl; cuBLAS DGEMM 8192^3 = 35.5); MEASURED_PEAKS.json has no FP64 entry",
+                "whole_step": {"alg_tflops": flops_per_point(M, D) * N_total / (ms / args.steps * 1e-3) / 1e12 / world,
+                               "frac_of_fp64_peak_per_gpu": flops_per_point(M, D) * N_total / (ms / args.steps * 1e-3) / 1e12 / world / FP64_PEAK_TFLOPS_DMMA}}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": w["label"], "N": N_total, "M": M, "D": D, "points_per_rank": n_local, "parallelism": f"dp{world} (N-sharded, 1 ncclAllReduce/step)",
+                           "l2": "no flush needed: every step streams the X shard plus >1 GB of per-chunk scratch, far beyond the 126 MB L2"},
+                "elbo": val, "gpu_launches": launches, "clocks": clk, "roofline": roof, "kernels": kernels}
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            cores = host_threads()
+            n_s = 65536
+            pps, times = time_oracle(w, Z, m, A, wvec, n_s, 3)
+            line["cpu_baseline"] = {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"rows [0,{n_s}) of the same workload, median of 3 runs ({sum(times):.1f} s total), NumPy/SciPy OpenBLAS threads={cores}",
+                                    "gflops": pps * flops_per_point(M, D) / 1e9}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -132,6 +132,15 @@ int32_t agp_ctx_stream(agp_ctx* ctx, void** stream_out);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int32_t agp_ctx_launch_count(agp_ctx* ctx, int64_t* out);
 
+/* Per-kernel-class device timing (CUDA events on the context's stream), used by bench.py for its
+ * roofline figures.  agp_ctx_profile_read synchronises, returns the accumulated milliseconds and
+ * launch-group counts per class since the last read and resets them; class names come from
+ * agp_profile_class_name (NULL past the last class).                                            */
+int32_t agp_ctx_profile(agp_ctx* ctx, int32_t enable);
+int32_t agp_ctx_profile_read(agp_ctx* ctx, int32_t max_classes, double* ms_out, int64_t* count_out,
+                             int32_t* n_classes);
+const char* agp_profile_class_name(int32_t cls);
+
 /* ---- data-parallel communicator (NCCL over NVLink; one process per GPU) --------------------- */
 /* unique_id: the 128 bytes of an ncclUniqueId created by rank 0 (agp_comm_unique_id).          */
 int32_t agp_comm_unique_id(void* unique_id_128);
