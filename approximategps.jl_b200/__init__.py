@@ -14,8 +14,15 @@ from ._lib import AgpError, DomainError, PosDefException, load_library, LIB_PATH
 from .api import *  # noqa: F401,F403
 from .api import _prior_kl  # noqa: F401
 from .laplace_api import (  # noqa: F401
+    LaplaceCacheView,
+    LaplaceGradient,
+    LaplaceObjectiveCache,
     LaplacePosterior,
+    LaplaceResult,
     build_laplace_objective,
+    build_laplace_objective_,
+    laplace_approx_lml_and_gradient,
     laplace_f_and_lml,
-    laplace_lml_and_grad,
+    laplace_lml,
+    laplace_lml_and_grad_K,
 )

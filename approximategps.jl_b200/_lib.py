@@ -76,6 +76,40 @@ class AgpSvgpGrads(C.Structure):
     ]
 
 
+NEWTON_CALLBACK = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.c_void_p)
+
+
+class AgpLaplaceProblem(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32),
+        ("K", c_double_p),
+        ("kernel", C.POINTER(AgpKernel)),
+        ("X", c_double_p),
+        ("D", C.c_int32),
+        ("jitter", C.c_double),
+        ("y", c_double_p),
+        ("lik", AgpLikelihood),
+        ("f_init", c_double_p),
+        ("maxiter", C.c_int32),
+        ("callback", NEWTON_CALLBACK),
+        ("user", C.c_void_p),
+    ]
+
+
+class AgpLaplaceResult(C.Structure):
+    _fields_ = [
+        ("f_opt", c_double_p),
+        ("lml", C.c_double),
+        ("steps", C.c_int32),
+        ("converged", C.c_int32),
+        ("dK", c_double_p),
+        ("dvariance", c_double_p),
+        ("dinv_lengthscale", c_double_p),
+        ("dlinear_c", c_double_p),
+        ("dX", c_double_p),
+    ]
+
+
 # every symbol include/agp.h declares: name -> (restype, argtypes)
 _vp = C.c_void_p
 SYMBOLS = {
@@ -106,11 +140,7 @@ SYMBOLS = {
     "agp_svgp_prior_kl": (C.c_int32, [_vp, C.POINTER(AgpSvgpParams), c_double_p]),
     "agp_svgp_posterior": (C.c_int32, [_vp, C.POINTER(AgpSvgpParams), c_double_p, c_double_p, c_double_p]),
     "agp_svgp_mean_and_var": (C.c_int32, [_vp, C.POINTER(AgpSvgpParams), c_double_p, C.c_int64, c_double_p, c_double_p]),
-    "agp_laplace_f_and_lml": (
-        C.c_int32,
-        [_vp, c_double_p, C.c_int32, c_double_p, C.POINTER(AgpLikelihood), c_double_p, C.c_int32, c_double_p, c_double_p,
-         C.POINTER(C.c_int32), c_double_p, C.POINTER(_vp)],
-    ),
+    "agp_laplace_f_and_lml": (C.c_int32, [_vp, C.POINTER(AgpLaplaceProblem), C.POINTER(AgpLaplaceResult), C.POINTER(_vp)]),
     "agp_laplace_cache_fetch": (C.c_int32, [_vp, C.c_int32, c_double_p]),
     "agp_laplace_cache_destroy": (C.c_int32, [_vp]),
 }

@@ -560,7 +560,7 @@ def mean_and_var(post: ApproxPosteriorGP, x):
     from .laplace_api import LaplacePosterior
 
     if isinstance(post, LaplacePosterior):
-        return post.mean_and_var(x)
+        raise NotImplementedError("prediction from the Laplace posterior (Laplace.jl:425-463) is outside the built path (DESIGN.md, 'next')")
     x = _points(x)
     mu, var = np.zeros(len(x)), np.zeros(len(x))
     L.check(post.ctx.lib.agp_svgp_mean_and_var(post.ctx.h, C.byref(post._pk.p), L.dptr(x), len(x), L.dptr(mu), L.dptr(var)))

@@ -141,8 +141,10 @@ struct Prof {
   }
 };
 
+static void lap_release(agp_ctx* c);
 struct agp_ctx {
   Prof prof;
+  void* lap = nullptr;  // LapWork (laplace_host.inc)
   int device = 0;
   cudaStream_t stream = nullptr;
   int sms = 148;
@@ -224,6 +226,7 @@ extern "C" int32_t agp_ctx_destroy(agp_ctx* c) {
                     &c->scc_part, &c->dmu, &c->dv, &c->sc_part, &c->gpart, &c->Gpart, &c->kpart, &c->red, &c->small,
                     &c->mu_out, &c->var_out};
   for (DevBuf* b : bufs) b->release();
+  lap_release(c);
   if (c->d_flags) cudaFree(c->d_flags);
   for (cudaEvent_t e : c->prof.pool) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);

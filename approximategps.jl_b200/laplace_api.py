@@ -1,61 +1,237 @@
-"""Host-side mirror of src/LaplaceApproximationModule.jl's entry points (Laplace.jl:39-165, :77-132)."""
+"""Host-side mirror of src/LaplaceApproximationModule.jl's entry points (paths relative to
+/root/reference): ``approx_lml`` :58-60, ``posterior`` :39-48, ``build_laplace_objective(!)`` :77-132,
+``laplace_f_and_lml`` :140-145, ``laplace_lml`` :152-165, ``_check_laplace_inputs`` :167-179.
+
+Only argument checking and packing happens here; the Newton loop, ``_laplace_lml`` and their reverse
+pass run in libagp_b200.so (agp_laplace_f_and_lml).  There is no CPU fallback.
+"""
 from __future__ import annotations
 
 import ctypes as C
+from dataclasses import dataclass
 
 import numpy as np
 
 from . import _lib as L
 
-
-def _kernel_matrix_host(kernel, x, jitter):
-    raise NotImplementedError
+_FIELDS = {"W": 0, "Wsqrt": 1, "d_loglik": 2, "a": 3, "f": 4, "B_ch_L": 5, "fnew": 6, "loglik": 7}
 
 
-class LaplacePosterior:
-    """``ApproxPosteriorGP(la, lfx.fx, cache)`` -- Laplace.jl:39-48; prediction :425-463."""
+class LaplaceCacheView:
+    """``LaplaceCache`` (Laplace.jl:181-199) living on the device; fields are fetched on first access."""
 
-    def __init__(self, approx, fx, cache_fields, ctx):
-        self.approx, self.prior, self.data, self.ctx = approx, fx, cache_fields, ctx
+    def __init__(self, lib, handle, n, owning):
+        self._lib, self._h, self.n, self._owning, self._memo = lib, handle, n, owning, {}
+
+    def __getattr__(self, name):
+        if name.startswith("_") or name not in _FIELDS:
+            raise AttributeError(name)
+        if name not in self._memo:
+            fld = _FIELDS[name]
+            out = np.zeros((self.n, self.n), order="F") if fld == 5 else np.zeros(1 if fld == 7 else self.n)
+            L.check(self._lib.agp_laplace_cache_fetch(self._h, fld, L.dptr(out)))
+            self._memo[name] = float(out[0]) if fld == 7 else out
+        return self._memo[name]
+
+    def close(self):
+        if self._owning and self._h:
+            self._lib.agp_laplace_cache_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
-def laplace_f_and_lml(K, y, lik, f_init=None, maxiter=100, want_grad=False, ctx=None):
-    """``laplace_f_and_lml`` (Laplace.jl:140-145) on a dense ``K = cov(fx)``; returns
-    (f_opt, lml, n_newton_steps[, dlml/dK])."""
+@dataclass
+class LaplaceGradient:
+    """Structural tangent of ``approx_lml`` w.r.t. the kernel of ``lfx.fx.f`` (and the inputs)."""
+
+    variance: float
+    inv_lengthscale: np.ndarray
+    linear_c: float
+    X: np.ndarray
+
+
+@dataclass
+class LaplaceResult:
+    f: np.ndarray
+    lml: float
+    steps: int
+    converged: bool
+    dK: np.ndarray | None = None
+    grad: LaplaceGradient | None = None
+    cache: LaplaceCacheView | None = None
+
+
+def _run(ctx, *, K=None, kernel=None, X=None, jitter=0.0, y, lik, f_init=None, maxiter=100, callback=None, want_dK=False, want_grad=False,
+         want_cache=False) -> LaplaceResult:
     from .api import default_context
 
     ctx = ctx or default_context()
-    K = np.asfortranarray(K, dtype=np.float64)
-    n = K.shape[0]
-    assert K.shape == (n, n)
+    lib = ctx.lib
     y = np.ascontiguousarray(y, dtype=np.float64)
-    assert len(y) == n  # Laplace.jl:172
-    assert maxiter >= 1  # Laplace.jl:257
-    f0 = None if f_init is None else np.ascontiguousarray(f_init, dtype=np.float64)
+    n = len(y)
+    pr, rs = L.AgpLaplaceProblem(), L.AgpLaplaceResult()
+    keep = [y]
+    pr.n = n
+    if K is not None:
+        K = np.asfortranarray(K, dtype=np.float64)
+        if K.shape != (n, n):
+            raise AssertionError("length(ys) == length(lfx.fx)")  # Laplace.jl:172
+        pr.K = L.dptr(K)
+        keep.append(K)
+    else:
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim == 1:
+            X = X[:, None]
+        if X.shape[0] != n:
+            raise AssertionError("length(ys) == length(lfx.fx)")  # Laplace.jl:172
+        ils = np.ascontiguousarray(kernel.inv_lengthscale, dtype=np.float64)
+        kk = L.AgpKernel(kernel.kind, ils.size, kernel.variance, L.dptr(ils), kernel.c)
+        pr.kernel, pr.X, pr.D, pr.jitter = C.pointer(kk), L.dptr(X), X.shape[1], float(jitter)
+        keep += [X, ils, kk]
+    pr.y = L.dptr(y)
+    pr.lik = L.AgpLikelihood(lik.kind, float(lik.sigma2))
+    if f_init is not None:
+        f0 = np.ascontiguousarray(f_init, dtype=np.float64)
+        assert f0.shape == (n,)
+        pr.f_init = L.dptr(f0)
+        keep.append(f0)
+    if maxiter < 1:
+        raise AssertionError("maxiter >= 1")  # Laplace.jl:257
+    pr.maxiter = int(maxiter)
+    if callback is not None:
+        def _cb(user, it, handle):
+            view = LaplaceCacheView(lib, C.c_void_p(handle), n, owning=False)
+            callback(view.fnew, view)
+            return 0
+
+        cb = L.NEWTON_CALLBACK(_cb)
+        pr.callback = cb
+        keep.append(cb)
     f_opt = np.zeros(n)
-    lml = C.c_double()
-    steps = C.c_int32()
-    dK = np.zeros((n, n), order="F") if want_grad else None
-    lk = L.AgpLikelihood(lik.kind, float(lik.sigma2))
-    L.check(ctx.lib.agp_laplace_f_and_lml(ctx.h, L.dptr(K), n, L.dptr(y), C.byref(lk), L.dptr(f0), int(maxiter), L.dptr(f_opt),
-                                          C.byref(lml), C.byref(steps), L.dptr(dK), None))
+    rs.f_opt = L.dptr(f_opt)
+    dK = np.zeros((n, n), order="F") if want_dK else None
+    rs.dK = L.dptr(dK)
+    grad = None
     if want_grad:
-        return f_opt, lml.value, steps.value, dK
-    return f_opt, lml.value, steps.value
+        if K is not None:
+            raise ValueError("kernel-parameter gradients need the (kernel, X) form")
+        sc = np.zeros(2)
+        dils, dX = np.zeros(ils.size), np.zeros_like(X)
+        rs.dvariance, rs.dlinear_c = sc[0:1].ctypes.data_as(L.c_double_p), sc[1:2].ctypes.data_as(L.c_double_p)
+        rs.dinv_lengthscale, rs.dX = L.dptr(dils), L.dptr(dX)
+    h = C.c_void_p()
+    L.check(lib.agp_laplace_f_and_lml(ctx.h, C.byref(pr), C.byref(rs), C.byref(h) if want_cache else None))
+    if want_grad:
+        grad = LaplaceGradient(float(sc[0]), dils, float(sc[1]), dX)
+    cache = LaplaceCacheView(lib, h, n, owning=True) if want_cache else None
+    return LaplaceResult(f_opt, rs.lml, rs.steps, bool(rs.converged), dK, grad, cache)
 
 
-def laplace_lml_and_grad(K, y, lik, f_init=None, maxiter=100, ctx=None):
-    f_opt, lml, steps, dK = laplace_f_and_lml(K, y, lik, f_init, maxiter, True, ctx)
-    return lml, dK, f_opt, steps
+def _check_laplace_inputs(lfx, ys, f_init=None, maxiter=100, callback=None):
+    """``_check_laplace_inputs`` (Laplace.jl:167-179): zero prior mean, matching lengths."""
+    fx = lfx.fx
+    if fx.f.mean_const != 0.0:
+        raise AssertionError("mean(lfx.fx) == zero(mean(lfx.fx))")  # Laplace.jl:171
+    if len(ys) != len(fx):
+        raise AssertionError("length(ys) == length(lfx.fx)")  # Laplace.jl:172
+    if not hasattr(lfx.lik, "kind"):
+        raise ValueError(f"unsupported likelihood {lfx.lik!r}")
+    if np.ndim(fx.Sigma_y) != 0:
+        raise ValueError("lfx.fx.Sigma_y must be an isotropic jitter for the device path")
+    return dict(kernel=fx.f.kernel, X=fx.x, jitter=float(fx.Sigma_y), y=ys, lik=lfx.lik, f_init=f_init, maxiter=maxiter, callback=callback)
 
 
-def laplace_approx_lml(la, lfx, ys, **kwargs):
-    raise NotImplementedError("Laplace host API is completed together with the device path")
+def laplace_f_and_lml(lfx, ys, *, ctx=None, **newton_kwargs):
+    """``laplace_f_and_lml(lfx, ys; newton_kwargs...)`` (Laplace.jl:140-145) -> (f_opt, lml)."""
+    r = _run(ctx, **_check_laplace_inputs(lfx, ys, **newton_kwargs))
+    return r.f, r.lml
 
 
-def laplace_posterior(la, lfx, ys, ctx):
-    raise NotImplementedError("Laplace host API is completed together with the device path")
+def laplace_lml(*args, ctx=None, f_init=None, maxiter=100, callback=None):
+    """``laplace_lml(lfx, ys; ...)`` (Laplace.jl:152-155) or ``laplace_lml(lik, ys, K; f_init, maxiter)`` (:157-160)."""
+    if len(args) == 2:
+        return _run(ctx, **_check_laplace_inputs(args[0], args[1], f_init, maxiter, callback)).lml
+    lik, ys, K = args
+    return _run(ctx, K=K, y=ys, lik=lik, f_init=f_init, maxiter=maxiter, callback=callback).lml
 
 
-def build_laplace_objective(build_latent_gp, xs, ys, **kwargs):
-    raise NotImplementedError("Laplace host API is completed together with the device path")
+def laplace_lml_and_grad_K(lik, ys, K, *, f_init=None, maxiter=100, ctx=None):
+    """Value and d/dK of ``laplace_lml(lik, ys, K)``: what ``Zygote.gradient`` returns through
+    ``rrule(newton_inner_loop)`` (Laplace.jl:330-369).  Returns a LaplaceResult."""
+    return _run(ctx, K=K, y=ys, lik=lik, f_init=f_init, maxiter=maxiter, want_dK=True)
+
+
+def laplace_approx_lml(la, lfx, ys, ctx=None):
+    """``approx_lml(la::LaplaceApproximation, lfx, ys)`` (Laplace.jl:58-60)."""
+    return _run(ctx, **_check_laplace_inputs(lfx, ys, **la.newton_kwargs)).lml
+
+
+def laplace_approx_lml_and_gradient(la, lfx, ys, ctx=None) -> LaplaceResult:
+    """``approx_lml`` and its gradient w.r.t. the kernel parameters of ``lfx.fx.f`` (the tangent Zygote
+    would return for ``lfx.fx.f.kernel``) and the inputs."""
+    return _run(ctx, want_grad=True, **_check_laplace_inputs(lfx, ys, **la.newton_kwargs))
+
+
+class LaplacePosterior:
+    """``ApproxPosteriorGP(la, lfx.fx, cache)`` (Laplace.jl:39-48); ``data`` is the LaplaceCache at f_opt."""
+
+    def __init__(self, approx, fx, result: LaplaceResult, ctx):
+        self.approx, self.prior, self.data, self.ctx = approx, fx, result.cache, ctx
+        self.f, self.lml, self.steps = result.f, result.lml, result.steps
+
+
+def laplace_posterior(la, lfx, ys, ctx=None):
+    """``posterior(la, lfx, ys)`` (Laplace.jl:39-48)."""
+    r = _run(ctx, want_cache=True, **_check_laplace_inputs(lfx, ys, **la.newton_kwargs))
+    return LaplacePosterior(la, lfx.fx, r, ctx)
+
+
+class LaplaceObjectiveCache:  # Laplace.jl:91-93
+    def __init__(self, f=None):
+        self.f = f
+
+
+class _LaplaceObjective:
+    """The closure returned by ``build_laplace_objective`` (Laplace.jl:95-132): ``objective(args...)``
+    returns ``-approx_lml``; ``objective.cache.f`` is the warm-start vector."""
+
+    def __init__(self, cache, build_latent_gp, xs, ys, newton_warmstart, newton_callback, newton_maxiter, ctx):
+        self.cache, self._build, self._xs, self._ys = cache, build_latent_gp, xs, ys
+        self._warm, self._cb, self._maxiter, self._ctx = newton_warmstart, newton_callback, newton_maxiter, ctx
+        self.newton_steps = 0
+
+    def _eval(self, args, want_grad):
+        lfx = self._build(*args)(self._xs)  # Laplace.jl:107-108
+        f_init = self.cache.f if (self._warm and self.cache.f is not None) else None  # :109-118 (zeros otherwise)
+        r = _run(self._ctx, want_grad=want_grad, **_check_laplace_inputs(lfx, self._ys, f_init, self._maxiter, self._cb))
+        self.newton_steps += r.steps
+        if self._warm:
+            self.cache.f = r.f  # :122-127
+        return r
+
+    def __call__(self, *args):
+        return -self._eval(args, False).lml
+
+    def value_and_gradient(self, *args):
+        """(-lml, LaplaceGradient of -lml w.r.t. the kernel built by ``build_latent_gp(args...)``)."""
+        r = self._eval(args, True)
+        g = r.grad
+        return -r.lml, LaplaceGradient(-g.variance, -g.inv_lengthscale, -g.linear_c, -g.X)
+
+
+def build_laplace_objective(build_latent_gp, xs, ys, *, newton_warmstart=True, newton_callback=None, newton_maxiter=100, ctx=None):
+    """``build_laplace_objective(build_latent_gp, xs, ys; kwargs...)`` (Laplace.jl:77-89)."""
+    return build_laplace_objective_(LaplaceObjectiveCache(None), build_latent_gp, xs, ys, newton_warmstart=newton_warmstart,
+                                    newton_callback=newton_callback, newton_maxiter=newton_maxiter, ctx=ctx)
+
+
+def build_laplace_objective_(cache, build_latent_gp, xs, ys, *, newton_warmstart=True, newton_callback=None, newton_maxiter=100, ctx=None):
+    """``build_laplace_objective!(f_init | cache, ...)`` (Laplace.jl:95-132)."""
+    if not isinstance(cache, LaplaceObjectiveCache):
+        cache = LaplaceObjectiveCache(np.array(cache, dtype=np.float64))
+    return _LaplaceObjective(cache, build_latent_gp, xs, ys, newton_warmstart, newton_callback, newton_maxiter, ctx)

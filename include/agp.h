@@ -193,18 +193,51 @@ int32_t agp_svgp_mean_and_var(agp_ctx* ctx, const agp_svgp_params* p, const doub
                               double* mu_out, double* var_out);
 
 /* ---- Laplace --------------------------------------------------------------------------------- */
-/* Replaces newton_inner_loop / _newton_inner_loop (Laplace.jl:256-276, :304-307) followed by the
- * recomputation of _laplace_train_intermediates at f_opt (:201-222) and _laplace_lml (:250-254),
- * i.e. laplace_f_and_lml (:140-145).  K: host column-major n x n (cov(fx), Laplace.jl:174);
- * y: host float64; f_init may be NULL (zeros).  Outputs: f_opt (n), lml, number of Newton steps.
- * If dK_out != NULL it receives d lml / d K (n x n column-major): the explicit part plus the
- * rrule(newton_inner_loop) part (Laplace.jl:330-369).  cache_out (optional) keeps W, Wsqrt,
- * d_loglik, a and the Cholesky factor of B on the device for prediction (Laplace.jl:425-463).  */
-int32_t agp_laplace_f_and_lml(agp_ctx* ctx, const double* K, int32_t n, const double* y,
-                              const agp_likelihood* lik, const double* f_init, int32_t maxiter,
-                              double* f_opt_out, double* lml_out, int32_t* steps_out,
-                              double* dK_out, agp_laplace_cache** cache_out);
-/* field: 0 = W, 1 = Wsqrt, 2 = d_loglik, 3 = a, 4 = f (n doubles each); 5 = B_ch.L (n x n col-major) */
+/* Newton callback(fnew, cache) of _newton_inner_loop (Laplace.jl:263-265): called after every Newton
+ * step with a view of the device-resident LaplaceCache (fields fetched lazily with
+ * agp_laplace_cache_fetch; the view is only valid during the call).  Return 0 to continue.      */
+typedef int32_t (*agp_newton_callback)(void* user, int32_t iteration, agp_laplace_cache* cache);
+
+/* `laplace_f_and_lml(lfx, ys; f_init, maxiter, callback)` (Laplace.jl:140-145) after
+ * _check_laplace_inputs (:167-179).  cov(fx) is either given (K, host column-major n x n) or built on
+ * the device from `kernel` at the inputs X (host point-major n x D) plus `jitter` (fx.Sigma_y[1]).  */
+typedef struct {
+  int32_t n;
+  const double* K;          /* cov(fx), Laplace.jl:174; NULL -> use (kernel, X, D, jitter)        */
+  const agp_kernel* kernel;
+  const double* X;
+  int32_t D;
+  double jitter;
+  const double* y;          /* n observations as float64                                          */
+  agp_likelihood lik;       /* lfx.lik                                                            */
+  const double* f_init;     /* NULL -> zeros (mean(fx) of the zero-mean prior, Laplace.jl:175)    */
+  int32_t maxiter;          /* >= 1 (AssertionError otherwise, Laplace.jl:257); reference default 100 */
+  agp_newton_callback callback; /* may be NULL */
+  void* user;
+} agp_laplace_problem;
+
+/* Outputs.  Pointers are caller-allocated host buffers or NULL (= not wanted).  The gradient is the
+ * total derivative the reference obtains from Zygote: the pullback of _laplace_train_intermediates /
+ * _laplace_lml at f_opt plus rrule(newton_inner_loop) (Laplace.jl:330-369).                     */
+typedef struct {
+  double* f_opt;            /* n                                                                   */
+  double lml;               /* _laplace_lml(f_opt, cache), Laplace.jl:250-254                     */
+  int32_t steps;            /* Newton steps taken                                                  */
+  int32_t converged;        /* 1 if isapprox(f, fnew) stopped the loop, 0 if maxiter did           */
+  double* dK;               /* d lml / d K, column-major n x n                                     */
+  double* dvariance;        /* (kernel, X) form only: d lml / d kernel parameters and inputs       */
+  double* dinv_lengthscale; /* n_scale                                                             */
+  double* dlinear_c;
+  double* dX;               /* point-major n x D                                                   */
+} agp_laplace_result;
+
+/* Replaces newton_inner_loop / _newton_inner_loop (Laplace.jl:256-276, :304-307), the intermediates at
+ * f_opt (:201-222), _laplace_lml (:250-254) and their reverse pass.  cache_out (optional) receives the
+ * LaplaceCache at f_opt, kept on the device for posterior(la, lfx, ys) / prediction (:39-48, :425-463). */
+int32_t agp_laplace_f_and_lml(agp_ctx* ctx, const agp_laplace_problem* problem, agp_laplace_result* result,
+                              agp_laplace_cache** cache_out);
+/* field: 0 = W, 1 = Wsqrt, 2 = d_loglik, 3 = a, 4 = f, 6 = fnew (callback view only) (n doubles each);
+ *        5 = B_ch.L (n x n column-major); 7 = loglik (1 double, owned caches only)              */
 int32_t agp_laplace_cache_fetch(agp_laplace_cache* cache, int32_t field, double* host_out);
 int32_t agp_laplace_cache_destroy(agp_laplace_cache* cache);
 

@@ -1,0 +1,182 @@
+"""GPU parity of the Laplace path (through the C ABI) against the NumPy oracle and the reference's goldens.
+
+Tolerances (Float64): lml and f_opt 1e-10 relative; gradients 1e-8 relative to the max-abs entry (the
+pullback goes through an explicit B^-1, cond(B) up to ~1e3 here).  Known answers of the reference:
+test/LaplaceApproximationModule.jl:168 (L-BFGS optimum on the fixed 48-point data set).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _cases import rel_err  # noqa: E402
+
+from oracle import kernels as ok, laplace as olap, likelihoods as ol  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_LBFGS = np.array([7.709076337653239, 1.51820292019697])  # test/LaplaceApproximationModule.jl:168
+
+
+@pytest.fixture(scope="module")
+def agp():
+    import agp_b200
+
+    return agp_b200
+
+
+def _softplus(x):
+    return np.logaddexp(0.0, x)
+
+
+def _build_latent_gp(agp, theta):
+    """src/TestUtils.jl:32-37"""
+    variance, lengthscale = _softplus(theta[0]), _softplus(theta[1])
+    kernel = variance * agp.with_lengthscale(agp.SqExponentialKernel(), lengthscale)
+    return agp.LatentGP(agp.GP(kernel), agp.BernoulliLikelihood(), 1e-8)
+
+
+def _lik(agp, name):
+    return {"gaussian": agp.GaussianLikelihood(0.01), "bernoulli_logit": agp.BernoulliLikelihood(), "poisson_exp": agp.PoissonLikelihood()}[name]
+
+
+def _problem(seed, n, D, lik):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(0, 4, size=(n, D))
+    k = ok.Kernel(ok.SE, 1.3, np.array([1.0 / 0.8]))
+    K = ok.kernelmatrix(k, X) + 1e-6 * np.eye(n)
+    g = np.sin(X @ rng.normal(size=D))
+    if lik == "bernoulli_logit":
+        y = (rng.random(n) < 1 / (1 + np.exp(-3 * g))).astype(np.float64)
+    elif lik == "poisson_exp":
+        y = rng.poisson(np.exp(g)).astype(np.float64)
+    else:
+        y = g + 0.1 * rng.normal(size=n)
+    return X, k, K, y
+
+
+@pytest.mark.parametrize("lik", ["bernoulli_logit", "poisson_exp", "gaussian"])
+@pytest.mark.parametrize("n,D", [(48, 1), (300, 2), (1000, 3)])
+def test_matrix_form_value_and_dK(agp, lik, n, D):
+    X, k, K, y = _problem(11 + n, n, D, lik)
+    olik = ol.Likelihood(lik, 0.01)
+    lml, Kbar, f_opt, steps = olap.lml_and_grad_K(olik, y, K)
+    r = agp.laplace_lml_and_grad_K(_lik(agp, lik), y, K)
+    print(f"\n[laplace {lik} n={n}] lml={r.lml:.10f} rel={abs(r.lml - lml) / abs(lml):.1e} steps={r.steps}/{steps} f={rel_err(r.f, f_opt):.1e} dK={rel_err(r.dK, Kbar):.1e}")
+    assert r.steps == steps and r.converged
+    assert abs(r.lml - lml) < 1e-10 * abs(lml)
+    assert rel_err(r.f, f_opt) < 1e-10
+    assert rel_err(r.dK, Kbar) < 1e-8
+    assert abs(agp.laplace_lml(_lik(agp, lik), y, K) - lml) < 1e-10 * abs(lml)
+
+
+def test_not_converged_uses_newton_cache(agp):
+    # maxiter = 1 and 2: the loop stops before isapprox holds; f_opt = K a of the last step, the lml is evaluated at
+    # a new point and the rrule uses the cache of the previous iterate (Laplace.jl:256-276, :330-369)
+    X, k, K, y = _problem(5, 200, 2, "bernoulli_logit")
+    olik = ol.Likelihood("bernoulli_logit")
+    for maxiter in (1, 2):
+        lml, Kbar, f_opt, steps = olap.lml_and_grad_K(olik, y, K, maxiter=maxiter)
+        r = agp.laplace_lml_and_grad_K(agp.BernoulliLikelihood(), y, K, maxiter=maxiter)
+        assert r.steps == steps == maxiter and not r.converged
+        assert abs(r.lml - lml) < 1e-10 * abs(lml) and rel_err(r.f, f_opt) < 1e-10 and rel_err(r.dK, Kbar) < 1e-8
+
+
+def test_kernel_form_objective_and_gradient(agp):
+    # -approx_lml(LaplaceApproximation(), build_latent_gp(theta)(X), y) and d/dtheta on the reference's fixture
+    X, y = olap.generate_data()
+    for theta in ([5.0, 1.0], [1.0, 2.0], list(GOLDEN_LBFGS)):
+        theta = np.array(theta)
+        ref, rgrad, f_opt, steps = olap.objective_and_grad(theta, X, y)
+        lfx = _build_latent_gp(agp, theta)(X)
+        r = agp.laplace_approx_lml_and_gradient(agp.LaplaceApproximation(), lfx, y)
+        sig = 1.0 / (1.0 + np.exp(-theta))
+        ls = _softplus(theta[1])
+        grad = -np.array([r.grad.variance * sig[0], r.grad.inv_lengthscale[0] * (-1.0 / ls**2) * sig[1]])
+        print(f"\n[laplace objective theta={theta}] obj={-r.lml:.12f} ref={ref:.12f} grad={grad} ref={rgrad}")
+        assert abs(-r.lml - ref) < 1e-10 * abs(ref)
+        assert r.steps == steps
+        assert np.max(np.abs(grad - rgrad)) < 1e-8 * max(1.0, np.max(np.abs(rgrad)))
+        assert abs(agp.approx_lml(agp.LaplaceApproximation(), lfx, y) + ref) < 1e-10 * abs(ref)
+    # the reference's L-BFGS optimum is a stationary point of the device objective
+    assert np.max(np.abs(grad)) < 1e-6
+
+
+def test_golden_lbfgs_optimum(agp):
+    """test/LaplaceApproximationModule.jl:167-177: optimise from [5.0, 1.0] with L-BFGS."""
+    from scipy.optimize import minimize
+
+    X, y = olap.generate_data()
+    objective = agp.build_laplace_objective(lambda *th: _build_latent_gp(agp, np.array(th)), X, y)
+
+    def fg(theta):
+        val, g = objective.value_and_gradient(*theta)
+        sig = 1.0 / (1.0 + np.exp(-theta))
+        ls = _softplus(theta[1])
+        return val, np.array([g.variance * sig[0], g.inv_lengthscale[0] * (-1.0 / ls**2) * sig[1]])
+
+    res = minimize(fg, np.array([5.0, 1.0]), jac=True, method="L-BFGS-B", options=dict(gtol=1e-10, ftol=1e-15, maxiter=500))
+    print("\n[laplace golden] theta_hat =", res.x, "objective =", res.fun, "newton steps =", objective.newton_steps)
+    assert np.allclose(res.x, GOLDEN_LBFGS, rtol=1e-6)
+    # (warm-started Newton solves stop at isapprox rtol 1.5e-8, so the objective carries ~1e-8 of solver noise)
+    assert abs(res.fun - 25.661864672178) < 1e-6
+
+
+def test_warmstart_and_callback(agp):
+    """test/LaplaceApproximationModule.jl:180-204: warm start saves Newton steps, same values."""
+    X, y = olap.generate_data()
+    thetas = [np.array([5.0, 1.0]) + 0.05 * i for i in range(6)]
+    counts = {}
+    vals = {}
+    for warm in (False, True):
+        n_cb = [0]
+
+        def cb(fnew, cache):
+            n_cb[0] += 1
+            assert fnew.shape == (48,) and cache.W.shape == (48,)
+
+        obj = agp.build_laplace_objective(lambda *th: _build_latent_gp(agp, np.array(th)), X, y, newton_warmstart=warm, newton_callback=cb)
+        vals[warm] = [obj(*th) for th in thetas]
+        counts[warm] = obj.newton_steps
+        assert n_cb[0] == obj.newton_steps
+        assert (obj.cache.f is not None) == warm
+    print("\n[laplace warm start] newton steps cold/warm:", counts[False], counts[True])
+    assert counts[True] < counts[False]
+    assert np.allclose(vals[True], vals[False], rtol=1e-9)
+
+
+def test_gaussian_laplace_equals_exact_gpr(agp):
+    """src/TestUtils.jl:99-108: with a Gaussian 'likelihood' Laplace is exact; two Newton steps suffice."""
+    rng = np.random.default_rng(3)
+    n = 60
+    X = np.sort(rng.uniform(0, 5, n))
+    k = ok.Kernel(ok.SE, 1.0, np.array([1.0]))
+    y = np.sin(X) + 0.1 * rng.normal(size=n)
+    f = agp.GP(agp.SqExponentialKernel())
+    lfx = agp.LatentGP(f, agp.GaussianLikelihood(0.01), 1e-8)(X)
+    post = agp.posterior(agp.LaplaceApproximation(maxiter=2), lfx, y)
+    K = ok.kernelmatrix(k, X[:, None]) + 1e-8 * np.eye(n)
+    f_exact = K @ np.linalg.solve(K + 0.01 * np.eye(n), y)
+    assert rel_err(post.f, f_exact) < 1e-9
+    # LaplaceCache fields at f_opt (Laplace.jl:181-199)
+    c = olap.train_intermediates(ol.Likelihood("gaussian", 0.01), y, K, post.f)
+    assert rel_err(post.data.W, c.W) < 1e-12 and rel_err(post.data.Wsqrt, c.Wsqrt) < 1e-12
+    assert rel_err(post.data.d_loglik, c.d_loglik) < 1e-7  # (y - f)/sigma2 amplifies the 1e-9 of f by 1/sigma2
+    assert rel_err(np.tril(post.data.B_ch_L), c.B_L) < 1e-10
+    # exact log marginal likelihood of the GPR model
+    exact = float(-0.5 * y @ np.linalg.solve(K + 0.01 * np.eye(n), y) - 0.5 * np.linalg.slogdet(K + 0.01 * np.eye(n))[1] - 0.5 * n * np.log(2 * np.pi))
+    assert abs(post.lml - exact) < 1e-8 * abs(exact)
+
+
+def test_laplace_errors(agp):
+    X, y = olap.generate_data()
+    f = agp.GP(0.5, agp.SqExponentialKernel())
+    with pytest.raises(AssertionError):  # non-zero prior mean, Laplace.jl:171
+        agp.approx_lml(agp.LaplaceApproximation(), agp.LatentGP(f, agp.BernoulliLikelihood(), 1e-8)(X), y)
+    g = agp.GP(agp.SqExponentialKernel())
+    with pytest.raises(AssertionError):  # length mismatch, Laplace.jl:172
+        agp.approx_lml(agp.LaplaceApproximation(), agp.LatentGP(g, agp.BernoulliLikelihood(), 1e-8)(X), y[:-1])
+    with pytest.raises(AssertionError):  # maxiter >= 1, Laplace.jl:257
+        agp.approx_lml(agp.LaplaceApproximation(maxiter=0), agp.LatentGP(g, agp.BernoulliLikelihood(), 1e-8)(X), y)

@@ -66,8 +66,8 @@ def test_multi_block_M(agp, centered):
     # lengthscale 1.0 in D = 4 keeps cond(Kuu) ~ 1e4 so that the 1e-9 gradient budget measures the kernels,
     # not the conditioning of the problem (with lengthscale 2 the oracle's own log(logistic) overflows to -inf)
     # (Centered with an un-whitened random q has huge marginal variances; the oracle's faithful log(logistic(f)) then overflows to
-    #  -inf where the device's softplus form stays finite -- an intentional divergence -- so that case uses the Poisson likelihood.)
-    lik = "poisson_exp" if centered else "bernoulli_logit"
+    #  -inf where the device's softplus form stays finite -- an intentional divergence -- so that case uses the Gaussian likelihood.)
+    lik = "gaussian" if centered else "bernoulli_logit"
     _run_case(agp, make_problem(seed=3, kind="se", N=1500, M=300, D=4, centered=centered, lik=lik, zdist="random", lengthscale=1.0), num_data=1e5)
 
 
