@@ -13,6 +13,7 @@ reference's Julia interface for this path).
 from ._lib import AgpError, DomainError, PosDefException, load_library, LIB_PATH, SYMBOLS  # noqa: F401
 from .api import *  # noqa: F401,F403
 from .api import _prior_kl  # noqa: F401
+from .sharding import attach_communicator, shard_range  # noqa: F401
 from .laplace_api import (  # noqa: F401
     LaplaceCacheView,
     LaplaceGradient,

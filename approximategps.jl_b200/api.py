@@ -467,9 +467,9 @@ def _dataset_for(fx: FiniteGP, y, ctx: Context):
 
 def elbo(sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx: Context | None = None, offset=0, count=None) -> float:
     """``AbstractGPs.elbo(sva, fx | lfx, y; num_data, quadrature)`` -- SVA.jl:307-360."""
-    ctx = ctx or default_context()
-    fx, lik = _resolve_lik(sva, l_fx)
+    fx, lik = _resolve_lik(sva, l_fx)  # argument errors first: they never cross the ABI
     pk = _Packed(sva, lik, quadrature)
+    ctx = ctx or default_context()
     ds, own = _dataset_for(fx, y, ctx)
     try:
         count = len(ds) - offset if count is None else count
@@ -483,9 +483,9 @@ def elbo(sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx: Context | No
 
 def elbo_and_gradient(sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx: Context | None = None, offset=0, count=None):
     """Value and gradient of ``elbo``: the forward + pullback of the new ``ChainRulesCore.rrule``."""
-    ctx = ctx or default_context()
     fx, lik = _resolve_lik(sva, l_fx)
     pk = _Packed(sva, lik, quadrature)
+    ctx = ctx or default_context()
     ds, own = _dataset_for(fx, y, ctx)
     try:
         count = len(ds) - offset if count is None else count

@@ -110,13 +110,6 @@ def make_params(w: dict):
     return wvec, Z, m, A
 
 
-def shard_range(N: int, rank: int, world: int):
-    """Contiguous block partition of [0, N)."""
-    base, rem = divmod(N, world)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
-
-
 def oracle_objects(w, Z, m, A):
     from oracle import kernels as ok, likelihoods as ol, svgp as osv
 
@@ -251,6 +244,7 @@ def main():
 
     import agp_b200 as agp
     from agp_b200 import _lib as L
+    from agp_b200 import shard_range
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -281,12 +275,7 @@ def main():
 
     ctx = agp.Context(local)
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            uid = torch.frombuffer(bytearray(ctx.unique_id()), dtype=torch.uint8).clone()
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
-        ctx.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+        agp.attach_communicator(ctx, dist)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
 
     ds = agp.DeviceData(capacity=n_local, D=D, ctx=ctx)

@@ -1,0 +1,74 @@
+"""CPU: host-side logic of the data-parallel path.  The N > 1 protocol (contiguous shards, partial sums
+scaled with the GLOBAL batch size, one sum-all-reduce of the packed buffer, replicated KL epilogue) is run
+with world_size = 2 over gloo, the oracle standing in for the device sweep, and must equal the
+single-process evaluation."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+
+def test_shard_range_partitions():
+    import agp_b200 as agp
+
+    for n in (0, 1, 7, 10_000_000, 10_000_003):
+        for world in (1, 2, 3, 4, 8):
+            edges = [agp.shard_range(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in edges]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        agp.shard_range(10, 2, 2)
+
+
+def _pack(val, g):
+    return np.concatenate([[val], g.m, g.Lq.ravel(), g.Z.ravel(), [g.kernel.variance], g.kernel.inv_lengthscale, [g.mean_const, g.lik_sigma2]])
+
+
+def _worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+
+    from _cases import make_problem, oracle_objects
+
+    import agp_b200 as agp
+    from oracle import svgp as osv
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    p = make_problem(seed=77, kind="matern52", N=301, M=9, D=3, lik="poisson_exp")
+    s, lik, ex = oracle_objects(p)
+    N, num_data = len(p["y"]), 5000.0
+    lo, hi = agp.shard_range(N, rank, world)
+    # "sweep": this rank's share of the data term, scaled with the global batch (num_data / N, SVA.jl:357-358)
+    nd_local = num_data * (hi - lo) / N
+    v1, g1 = osv.elbo_and_grad(s, p["X"][lo:hi], p["y"][lo:hi], lik, ex, num_data=nd_local)
+    v0, g0 = osv.elbo_and_grad(s, p["X"][lo:hi], p["y"][lo:hi], lik, ex, num_data=0.0)  # = -KL and its gradient
+    buf = torch.from_numpy(_pack(v1, g1) - _pack(v0, g0))
+    dist.all_reduce(buf)  # the one collective of the step
+    total = buf.numpy() + _pack(v0, g0)  # replicated epilogue: subtract KL once
+    if rank == 0:
+        vf, gf = osv.elbo_and_grad(s, p["X"], p["y"], lik, ex, num_data=num_data)
+        np.save(out, np.stack([total, _pack(vf, gf)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_allreduce_equals_single_process(tmp_path):
+    import torch.multiprocessing as mp
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    out = str(tmp_path / "res.npy")
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got, ref = np.load(out)
+    assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6)) < 1e-9

@@ -1,0 +1,171 @@
+"""CPU: pins the SVGP oracle (oracle/svgp.py) with the property tests of the reference's own suite
+(test/SparseVariationalApproximationModule.jl) and cross-checks its hand-derived reverse pass against
+torch.float64 autograd of the same forward pass (the role Zygote plays in the reference), finite
+differences and mpmath.  No GPU, no product code."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _cases import make_problem, oracle_objects, rel_err  # noqa: E402
+from _torch_ref import torch_elbo_and_grad  # noqa: E402
+
+from oracle import kernels as ok, likelihoods as ol, svgp as osv  # noqa: E402
+
+
+def _small(seed=123456, N=5, M=4, kind="matern32"):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-1, 1, N)
+    z = x[:M].copy()
+    k = ok.Kernel(kind, 1.0, np.array([1.0]))
+    return rng, x, z, k
+
+
+def test_centered_equals_noncentered():
+    """test/SVA...:45-69: whitening round trip; KL rtol 1e-5; mean / cov / elbo agree."""
+    rng, x, z, k = _small()
+    M = len(z)
+    jitter = 1e-12
+    Kuu = ok.kernelmatrix(k, z[:, None]) + jitter * np.eye(M)
+    Lk = np.linalg.cholesky(Kuu)
+    m_w = rng.normal(size=M)
+    A = np.tril(rng.normal(size=(M, M)))
+    A[np.diag_indices(M)] = np.abs(np.diag(A)) + 0.5
+    nc = osv.SVGP(k, z, m_w, A, jitter=jitter, centered=False)
+    ce = osv.SVGP(k, z, Lk @ m_w, Lk @ A, jitter=jitter, centered=True)  # q_ex = (Lk m, Lk S Lk')
+    assert abs(osv.prior_kl(nc) - osv.prior_kl(ce)) <= 1e-5 * abs(osv.prior_kl(ce))
+    mu1, c1 = osv.mean_and_cov(nc, x)
+    mu2, c2 = osv.mean_and_cov(ce, x)
+    assert np.allclose(mu1, mu2) and np.allclose(c1, c2)
+    y = rng.normal(size=len(x))
+    lik = ol.Likelihood("gaussian", 0.1)
+    assert np.isclose(osv.elbo(nc, x, y, lik), osv.elbo(ce, x, y, lik))
+
+
+def test_elbo_below_logpdf_and_gpr_equivalence():
+    """test/SVA...:99-134 with the reference's recipe (x = 10 rand(20), z = x, fz = f(z) i.e. jitter 1e-18,
+    kernel = softplus(0.2) * SE o ScaleTransform(softplus(0.6)), noise 0.1):
+    SVGP(Centered, q*, Z = X) == exact GPR at atol 1e-10 (:126-127); elbo <= logpdf + 1e-5 (:132-133)."""
+    sp = lambda v: np.logaddexp(0.0, v)
+    k = ok.Kernel("se", sp(0.2), np.array([sp(0.6)]))
+    worst, used = 0.0, 0
+    for seed in range(8):
+        rng = np.random.default_rng(654321 + seed)
+        N = 20
+        x = rng.random(N) * 10
+        if np.min(np.diff(np.sort(x))) < 0.05:
+            continue  # near-duplicate inputs: cholesky(Kuu + 1e-18 I) throws PosDefException in the reference too
+        used += 1
+        y = np.sin(x) + 0.9 * np.cos(x * 1.6) + 0.4 * rng.random(N)
+        s2, jitter = 0.1, 1e-18
+        m, S = osv.optimal_variational_posterior(k, x[:, None], jitter, x[:, None], y, s2)
+        s = osv.SVGP(k, x, m, np.linalg.cholesky(S), jitter=jitter, centered=True)
+        mu, cov = osv.mean_and_cov(s, x)
+        mu_e, cov_e = osv.exact_gpr_posterior(k, x[:, None], y, s2, x[:, None])
+        worst = max(worst, np.max(np.abs(mu - mu_e)), np.max(np.abs(cov - cov_e)))
+        lik = ol.Likelihood("gaussian", s2)
+        lp = osv.exact_gpr_logpdf(k, x[:, None], y, s2)
+        e = osv.elbo(s, x, y, lik)
+        assert e <= lp + 1e-5
+        assert lp - e < 1e-3  # and the bound is tight at the optimum (not asserted by the reference)
+    assert used >= 3 and worst < 1e-10, (used, worst)
+
+
+def test_mean_and_var_is_diag_of_cov():
+    """AbstractGPs internal-interface consistency (test/SVA...:30-34, :54-58)."""
+    for centered in (False, True):
+        p = make_problem(seed=3, kind="matern32", N=40, M=7, D=2, centered=centered)
+        s, _, _ = oracle_objects(p)
+        mu, var = osv.mean_and_var(s, p["X"])
+        mu2, cov = osv.mean_and_cov(s, p["X"])
+        assert np.allclose(mu, mu2) and np.allclose(var, np.diag(cov), atol=1e-12)
+
+
+CASES = [
+    dict(kind="se", D=2, centered=False, lik="gaussian", method="default"),
+    dict(kind="matern52", D=3, centered=False, lik="bernoulli_logit", method="default"),
+    dict(kind="matern32", D=1, centered=True, lik="poisson_exp", method="default"),
+    dict(kind="se", D=4, centered=True, lik="poisson_exp", method="gauss_hermite", ard=True, mean_const=0.3),
+    dict(kind="linear", D=3, centered=False, lik="gaussian", method="gauss_hermite", jitter=1e-3, zdist="random", lengthscale=1.5, M=3),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_reverse_pass_matches_autograd(case):
+    """The oracle's gradient == torch autograd through the reference's forward op sequence (rtol 1e-9)."""
+    kw = dict(seed=21, N=60, M=8)
+    kw.update(case)
+    p = make_problem(**kw)
+    s, lik, ex = oracle_objects(p)
+    val, g = osv.elbo_and_grad(s, p["X"], p["y"], lik, ex, num_data=777.0)
+    tval, tg = torch_elbo_and_grad(s, p["X"], p["y"], lik, ex, num_data=777.0)
+    assert abs(val - tval) <= 1e-12 * abs(tval)
+    assert rel_err(g.m, tg["m"]) < 1e-9 and rel_err(g.Lq, np.tril(tg["Lq"])) < 1e-9 and rel_err(g.Z, tg["Z"]) < 1e-8
+    assert rel_err(g.kernel.variance, tg["variance"]) < 1e-9 and rel_err(g.kernel.inv_lengthscale, tg["inv_lengthscale"]) < 1e-8
+    if p["kind"] == "linear":
+        assert rel_err(g.kernel.c, tg["c"]) < 1e-9
+    if p["mean_const"] != 0.0:
+        assert rel_err(g.mean_const, tg["mean_const"]) < 1e-9
+    if p["lik"] == "gaussian":
+        assert rel_err(g.lik_sigma2, tg["lik_sigma2"]) < 1e-9
+
+
+def test_gradient_vs_finite_differences():
+    """central_fdm(5, 1)-style check (rtol 1e-6 as in test/Laplace...:51-53) of d elbo / d m, d variance."""
+    p = make_problem(seed=5, kind="matern52", N=50, M=6, D=2, lik="bernoulli_logit")
+    s, lik, ex = oracle_objects(p)
+    _, g = osv.elbo_and_grad(s, p["X"], p["y"], lik, ex)
+    h = 1e-3
+    c = np.array([1.0, -8.0, 8.0, -1.0]) / (12.0 * h)
+    for i in range(3):
+        vals = []
+        for d in (-2, -1, 1, 2):
+            m2 = p["m"].copy()
+            m2[i] += d * h
+            s2 = osv.SVGP(s.kernel, s.Z, m2, s.Lq, jitter=s.jitter)
+            vals.append(osv.elbo(s2, p["X"], p["y"], lik, ex))
+        assert abs(np.dot(c, vals) - g.m[i]) < 1e-6 * max(1.0, abs(g.m[i]))
+    vals = []
+    for d in (-2, -1, 1, 2):
+        k2 = ok.Kernel(s.kernel.kind, s.kernel.variance + d * h, s.kernel.inv_lengthscale, s.kernel.c)
+        vals.append(osv.elbo(osv.SVGP(k2, s.Z, s.m, s.Lq, jitter=s.jitter), p["X"], p["y"], lik, ex))
+    assert abs(np.dot(c, vals) - g.kernel.variance) < 1e-6 * max(1.0, abs(g.kernel.variance))
+
+
+def test_gauss_hermite_against_mpmath():
+    """GH-20 expected log-likelihood (Appendix A) vs 40-digit quadrature of the same integral."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    mu, var = 0.3, 0.49
+    for kind, y in (("bernoulli_logit", 1.0), ("poisson_exp", 3.0)):
+        lik = ol.Likelihood(kind)
+        E, _, _, _ = ol.expected_loglik_terms(ol.Expectation("gauss_hermite", 20), lik, np.array([mu]), np.array([var]), np.array([y]))
+
+        def integrand(f):
+            if kind == "bernoulli_logit":
+                ll = -mp.log(1 + mp.exp(-f))
+            else:
+                ll = y * f - mp.exp(f) - mp.loggamma(y + 1)
+            return ll * mp.npdf(f, mu, mp.sqrt(var))
+
+        exact = mp.quad(integrand, [-mp.inf, mu, mp.inf])
+        assert abs(E[0] - float(exact)) < 1e-7 * abs(float(exact))  # truncation error of 20 nodes, not rounding
+    # analytic Poisson expectation is exact
+    E, _, _, _ = ol.expected_loglik_terms(ol.Expectation("analytic"), ol.Likelihood("poisson_exp"), np.array([mu]), np.array([var]), np.array([3.0]))
+    exact = mp.quad(lambda f: (3.0 * f - mp.exp(f) - mp.loggamma(4.0)) * mp.npdf(f, mu, mp.sqrt(var)), [-mp.inf, mu, mp.inf])
+    assert abs(E[0] - float(exact)) < 1e-12 * abs(float(exact))
+
+
+def test_num_data_rescaling_and_chunking():
+    """SVA.jl:357-359: sum * num_data / length(y); chunked evaluation (bench CPU baseline) is identical."""
+    p = make_problem(seed=9, kind="se", N=300, M=10, D=2, lik="poisson_exp")
+    s, lik, ex = oracle_objects(p)
+    e1 = osv.elbo(s, p["X"], p["y"], lik, ex)
+    e2 = osv.elbo(s, p["X"], p["y"], lik, ex, num_data=3000)
+    kl = osv.prior_kl(s)
+    assert np.isclose(e2 + kl, 10.0 * (e1 + kl), rtol=1e-12)
+    v1, g1 = osv.elbo_and_grad(s, p["X"], p["y"], lik, ex, num_data=3000)
+    v2, g2 = osv.elbo_and_grad(s, p["X"], p["y"], lik, ex, num_data=3000, chunk=64)
+    assert np.isclose(v1, v2, rtol=1e-13) and rel_err(g1.Z, g2.Z) < 1e-11 and rel_err(g1.Lq, g2.Lq) < 1e-11
