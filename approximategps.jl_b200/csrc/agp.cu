@@ -152,7 +152,7 @@ struct agp_ctx {
   int64_t chunk_cols = 0;  // capacity of the per-chunk scratch (columns)
   int nslab = 0, nsplit = 0;
   // once-per-step M x M operands (column-major, ld = Mp unless noted)
-  DevBuf z, zs, zn, mvec, mt, Lq, Kw, Lk, Lt, Ut, Bt_cm, Bt_rm, W1, W2, W3, W4, vec64, vec64b;
+  DevBuf z, zs, zn, zsp, mvec, mt, Lq, Kw, Lk, Lt, Ut, Bt_cm, Bt_rm, W1, W2, W3, W4, vec64, vec64b;
   // per-chunk scratch [Mp][chunk_cols]
   DevBuf A, C, Ab, As, saa, sam, scc_part, dmu, dv, sc_part;
   // accumulators
@@ -221,7 +221,7 @@ extern "C" int32_t agp_ctx_destroy(agp_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-  DevBuf* bufs[] = {&c->z, &c->zs, &c->zn, &c->mvec, &c->mt, &c->Lq, &c->Kw, &c->Lk, &c->Lt, &c->Ut, &c->Bt_cm, &c->Bt_rm,
+  DevBuf* bufs[] = {&c->z, &c->zs, &c->zn, &c->zsp, &c->mvec, &c->mt, &c->Lq, &c->Kw, &c->Lk, &c->Lt, &c->Ut, &c->Bt_cm, &c->Bt_rm,
                     &c->W1, &c->W2, &c->W3, &c->W4, &c->vec64, &c->vec64b, &c->A, &c->C, &c->Ab, &c->As, &c->saa, &c->sam,
                     &c->scc_part, &c->dmu, &c->dv, &c->sc_part, &c->gpart, &c->Gpart, &c->kpart, &c->red, &c->small,
                     &c->mu_out, &c->var_out};
@@ -414,15 +414,22 @@ extern "C" int32_t agp_dataset_destroy(agp_dataset* ds) {
 // ---------------------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------------------
-template <int MODE>
-static int32_t launch_trsm(agp_ctx* c, const TrsmArgs& a, int tiles_n) {
+template <int MODE, int S>
+static int32_t launch_trsm_s(agp_ctx* c, const TrsmArgs& a, int tiles_n) {
   using Cfg = StageCfg<A_KM, B_KN>;
-  const int smem = Cfg::smem_bytes + ((MODE == TR_KUF_FWD) ? a.kp.D * 64 * 8 : 0) + 64 * 8 + 16;
-  CU(cudaFuncSetAttribute(trsm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  trsm_kernel<MODE><<<tiles_n, NTHREADS, smem, c->stream>>>(a);
+  const int Sx = (MODE == TR_KUF_FWD) ? kuf_dp(a.kp.D) + 2 : 0;
+  const int smem = (S * (Cfg::elems + BK * Sx) + 64 * Sx) * 8 + 16;
+  CU(cudaFuncSetAttribute(trsm_kernel<MODE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  trsm_kernel<MODE, S><<<tiles_n, NTHREADS, smem, c->stream>>>(a);
   LAUNCHED(c);
   KCHECK();
   return AGP_OK;
+}
+// 4 pipeline stages; the Kuf generator drops to 3 when the z slabs of a wide input (D > 8) would cost the second CTA per SM
+template <int MODE>
+static int32_t launch_trsm(agp_ctx* c, const TrsmArgs& a, int tiles_n) {
+  if (MODE == TR_KUF_FWD && a.kp.D > 8) return launch_trsm_s<MODE, 3>(c, a, tiles_n);
+  return launch_trsm_s<MODE, 4>(c, a, tiles_n);
 }
 
 template <int LA, int LB, class Epi>
@@ -649,6 +656,7 @@ static int32_t prepare_step(agp_ctx* c, const agp_svgp_params* p) {
   OK(c->z.ensure((int64_t)Mp * D));
   OK(c->zs.ensure((int64_t)Mp * D));
   OK(c->zn.ensure(Mp));
+  OK(c->zsp.ensure((int64_t)Mp * (kuf_dp(D) + 2)));
   OK(c->mvec.ensure(Mp));
   OK(c->mt.ensure(Mp));
   OK(c->vec64.ensure((int64_t)Mp * 64));
@@ -675,7 +683,7 @@ static int32_t prepare_step(agp_ctx* c, const agp_svgp_params* p) {
     CU(cudaMemcpyToSymbolAsync(c_gh_w, p->expect.weights, sizeof(double) * st.lp.ngh, 0, cudaMemcpyHostToDevice, c->stream));
   }
   CU(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int), c->stream));
-  prep_z_kernel<<<(Mp + 127) / 128, 128, 0, c->stream>>>(c->z.p, c->zs.p, c->zn.p, Mp, st.kp);
+  prep_z_kernel<<<(Mp + 127) / 128, 128, 0, c->stream>>>(c->z.p, c->zs.p, c->zn.p, c->zsp.p, Mp, st.kp);
   LAUNCHED(c);
   KCHECK();
   build_kuu_kernel<<<dim3((Mp + 127) / 128, Mp), 128, 0, c->stream>>>(c->Kw.p, Mp, c->zs.p, c->zn.p, st.jitter, st.kp);
@@ -853,8 +861,7 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
     t1.ldx = ldc;
     t1.pts = pts;
     t1.npts = npts;
-    t1.zs = c->zs.p;
-    t1.zn = c->zn.p;
+    t1.zsp = c->zsp.p;
     t1.mt = c->mt.p;
     t1.saa = c->saa.p;
     t1.sam = c->sam.p;

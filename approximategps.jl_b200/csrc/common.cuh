@@ -156,9 +156,15 @@ struct ThreadMap {
     lane = tid & 31;
     g = lane >> 2;
     t = lane & 3;
-    wm = (warp & 3) * 32;
+    // Row quarter of the warp: warps w and w+4 live on the same SM sub-partition (w mod 4); giving them the quarters
+    // q and 3-q balances the sub-partitions when triangular operands let a warp skip the zero part of a diagonal block.
+    wm = ((warp < 4) ? warp : 3 - (warp & 3)) * 32;
     wn = (warp >> 2) * 32;
   }
+  // Triangular A operand, diagonal 128 x 128 block, k-step starting at column krel of that block: does this warp's
+  // 32-row slice hold any non-zero?  lower: k <= m, upper: k >= m.
+  __device__ __forceinline__ bool tri_active_lower(int krel) const { return krel < wm + 32; }
+  __device__ __forceinline__ bool tri_active_upper(int krel) const { return krel + BK > wm; }
   // accumulator element acc[mi][ni][e] is C(row(mi), col(ni, e)) of the CTA tile
   __device__ __forceinline__ int row(int mi) const { return wm + mi * 8 + g; }
   __device__ __forceinline__ int col(int ni, int e) const { return wn + ni * 8 + 2 * t + e; }

@@ -26,10 +26,17 @@ struct GemmArgs {
   int tmode;
 };
 
+// tri / diag_step: when the A operand is triangular (TRI_LOWER: k <= m, TRI_UPPER: k >= m) the k-steps
+// [diag_step, diag_step + BM/BK) cover its diagonal 128 x 128 block and a warp skips the steps in which its
+// 32-row slice of A is identically zero (12.5 % of a triangular sweep at M = 1024).  whole_active == false
+// skips every MMA of this warp (SYRK tiles above the diagonal).
+constexpr int TRI_NONE = 0, TRI_LOWER = 1, TRI_UPPER = 2;
+
 template <int LA, int LB>
 __device__ __forceinline__ void gemm_mainloop(Acc& acc, double* smem, const double* __restrict__ gA, int64_t lda,
                                               const double* __restrict__ gB, int64_t ldb, int nsteps,
-                                              const ThreadMap& tm) {
+                                              const ThreadMap& tm, int tri = TRI_NONE, int diag_step = 0,
+                                              bool whole_active = true) {
   using Cfg = StageCfg<LA, LB>;
   constexpr int S = Cfg::stages;
   const int tid = threadIdx.x;
@@ -55,7 +62,12 @@ __device__ __forceinline__ void gemm_mainloop(Acc& acc, double* smem, const doub
     }
     cp_async_commit();
     const double* st = smem + (step % S) * Cfg::elems;
-    mma_stage<LA, LB>(acc, st, st + Cfg::a_elems, tm);
+    bool active = whole_active;
+    if (tri != TRI_NONE) {
+      const int d = step - diag_step;
+      if (d >= 0 && d < BM / BK) active = (tri == TRI_LOWER) ? tm.tri_active_lower(d * BK) : tm.tri_active_upper(d * BK);
+    }
+    if (active) mma_stage<LA, LB>(acc, st, st + Cfg::a_elems, tm);
   }
   cp_async_wait<0>();
   __syncthreads();  // smem is free for the epilogue
@@ -82,7 +94,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(GemmArgs g, Epi epi) 
   const double* gB = (LB == B_KN) ? g.B + (int64_t)kb * g.ldb + n0 : g.B + (int64_t)n0 * g.ldb + kb;
   Acc acc;
   acc_zero(acc);
-  gemm_mainloop<LA, LB>(acc, smem, gA, g.lda, gB, g.ldb, (ke - kb) / BK, tm);
+  const int nsteps = (ke - kb) / BK;
+  int tri = TRI_NONE, diag_step = 0;
+  if (g.kmode == KR_LOWER && ke == (tile_m + 1) * BM) {
+    tri = TRI_LOWER;
+    diag_step = nsteps - BM / BK;
+  } else if (g.kmode == KR_UPPER) {
+    tri = TRI_UPPER;
+  }
+  gemm_mainloop<LA, LB>(acc, smem, gA, g.lda, gB, g.ldb, nsteps, tm, tri, diag_step);
   epi(acc, tm, m0, n0, smem);
 }
 

@@ -30,8 +30,7 @@ struct TrsmArgs {
   // TR_KUF_FWD only
   const double* pts;  // chunk's points, point-major [npts][D]
   int npts;
-  const double* zs;  // [Mp][D] scaled inducing inputs
-  const double* zn;  // [Mp] their squared norms
+  const double* zsp;  // [Mp][Dp + 2] padded scaled inducing inputs with their squared norm at column Dp (prep_z_kernel)
   const double* mt;  // [Mp] whitened variational mean
   double* saa;       // [ldx] sum_m a^2 per point
   double* sam;       // [ldx] sum_m a*mt per point
@@ -63,50 +62,64 @@ struct StepIter {
   }
 };
 
-// Kuf rows [row0, row0+16) x the CTA's 64 points, written as a B-operand stage tile.
-__device__ __forceinline__ void gen_kuf_tile(double* sB, int row0, const TrsmArgs& a, const double* xsT,
-                                             const double* xn, int tid) {
-  const int n = tid & 63, lr = tid >> 6;
-  const int D = a.kp.D, kind = a.kp.kind;
-  const double xnn = xn[n];
+// Padded widths used by the Kuf generator: Dp = D rounded up to 2 (16-byte vector loads); a z row of the padded
+// copy `zsp` is [zs_0 .. zs_{D-1}, 0.., |zs|^2, 0] (Dz = Dp + 2 doubles), an x row in shared memory is
+// [xs_0 .. xs_{D-1}, 0.., |xs|^2, 0] (Sx = Dp + 2 doubles: 16-byte aligned and conflict-free for LDS.128).
+__host__ __device__ __forceinline__ int kuf_dp(int D) { return (D + 1) & ~1; }
+
+// Kuf rows [row0, row0+16) x the CTA's 64 points, written as a B-operand stage tile.  Thread (l, c) = (tid / 16,
+// tid % 16) produces row l, columns c + 16 j: the z row is read once (broadcast LDS.128) for its 4 elements.
+__device__ __forceinline__ void gen_kuf_tile(double* __restrict__ sB, const double* __restrict__ sZ, const double* __restrict__ xs, int row0,
+                                             const KernelParams& kp, int tid) {
+  const int l = tid >> 4, c = tid & 15;
+  const int D = kp.D, kind = kp.kind, Dp = kuf_dp(D), Sx = Dp + 2;
+  const double* z = sZ + l * Sx;
+  const double* x0 = xs + c * Sx;
+  double u[4];
+  if (D == 1 && kind != AGP_KERNEL_LINEAR) {
+    const double z0 = z[0];
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int l = lr + 4 * i;
-    const int row = row0 + l;
-    double v = 0.0;
-    if (row < a.kp.M) {
-      const double* z = a.zs + (int64_t)row * D;
-      double u;
-      if (D == 1 && kind != AGP_KERNEL_LINEAR) {
-        const double df = xsT[n] - z[0];
-        u = df * df;
-      } else {
-        double dot = 0.0;
-        for (int d = 0; d < D; d++) dot = fma(xsT[d * 64 + n], z[d], dot);
-        u = u_from_dot(kind, xnn, a.zn[row], dot);
-      }
-      v = a.kp.variance * kappa(kind, u, a.kp.c);
+    for (int j = 0; j < 4; j++) {
+      const double df = x0[j * 16 * Sx] - z0;
+      u[j] = df * df;
     }
-    sB[l * BTile<B_KN>::ld + n] = v;
+  } else {
+    double dot[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int d = 0; d < Dp; d += 2) {
+      const double2 zz = *reinterpret_cast<const double2*>(z + d);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double2 xx = *reinterpret_cast<const double2*>(x0 + j * 16 * Sx + d);
+        dot[j] = fma(xx.y, zz.y, fma(xx.x, zz.x, dot[j]));
+      }
+    }
+    const double zn = z[Dp];
+#pragma unroll
+    for (int j = 0; j < 4; j++) u[j] = u_from_dot(kind, x0[j * 16 * Sx + Dp], zn, dot[j]);
   }
+  const bool valid = row0 + l < kp.M;
+#pragma unroll
+  for (int j = 0; j < 4; j++) sB[l * BTile<B_KN>::ld + c + 16 * j] = valid ? kp.variance * kappa(kind, u[j], kp.c) : 0.0;
 }
 
-template <int MODE>
+// Blocked left-looking triangular solve on one 64-column tile per CTA.  MODE TR_KUF_FWD generates its right-hand
+// side (the Kuf tile) on the fly; S = pipeline depth (4, or 3 when the z slabs of a wide input would not fit).
+template <int MODE, int S>
 __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
   extern __shared__ __align__(128) double smem[];
   using Cfg = StageCfg<A_KM, B_KN>;
-  constexpr int S = Cfg::stages;
+  constexpr bool FWD = MODE == TR_KUF_FWD;
   ThreadMap tm;
   const int tid = threadIdx.x;
   const int n0 = blockIdx.x * BN;
-  double* xsT = smem + S * Cfg::elems;  // [D][64]
-  double* xn = xsT + ((MODE == TR_KUF_FWD) ? a.kp.D * 64 : 0);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(xn + 64);
+  const int Sx = FWD ? kuf_dp(a.kp.D) + 2 : 0;       // row length of the padded z / x rows
+  const int stage_elems = Cfg::elems + BK * Sx;      // A tile | B tile | z slab
+  double* xs = smem + S * stage_elems;               // [64][Sx]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(xs + 64 * Sx);
 
-  if (MODE == TR_KUF_FWD) {
-    // ---- stage the X tile: TMA bulk copy into the (still unused) first pipeline stage, then scale and
-    //      transpose into xsT so that the Kuf generator reads it conflict-free.
-    const int D = a.kp.D;
+  if (FWD) {
+    // ---- stage the X tile: TMA bulk copy into the (still unused) first pipeline stage, then scale into xs rows
+    const int D = a.kp.D, Dp = kuf_dp(D);
     const int nvalid = max(0, min(BN, a.npts - n0));
     double* raw = smem;  // 64 * D doubles <= one stage
     const double* src = a.pts + (int64_t)n0 * D;
@@ -127,33 +140,41 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
       for (int i = tid; i < nvalid * D; i += NTHREADS) raw[i] = src[i];
       __syncthreads();
     }
-    for (int i = tid; i < BN * D; i += NTHREADS) {
-      const int n = i / D, d = i % D;
-      xsT[d * 64 + n] = (n < nvalid) ? raw[i] * a.kp.s[d] : 0.0;
-    }
-    __syncthreads();
     if (tid < BN) {
-      double s = 0.0;
-      for (int d = 0; d < D; d++) s = fma(xsT[d * 64 + tid], xsT[d * 64 + tid], s);
-      xn[tid] = s;
+      double nrm = 0.0;
+      for (int d = 0; d < D; d++) {
+        const double v = (tid < nvalid) ? raw[tid * D + d] * a.kp.s[d] : 0.0;
+        xs[tid * Sx + d] = v;
+        nrm = fma(v, v, nrm);
+      }
+      for (int d = D; d < Sx; d++) xs[tid * Sx + d] = 0.0;
+      xs[tid * Sx + Dp] = nrm;
     }
-    __syncthreads();
+    __syncthreads();  // raw (stage 0) may be overwritten from here on
   }
 
-  StepIter it_issue, it_cons;
+  StepIter it_issue, it_cons, it_gen;
   it_issue.init(MODE != TR_RHS_BWD, a.nb);
   it_cons.init(MODE != TR_RHS_BWD, a.nb);
+  it_gen.init(true, a.nb);
   const int total = (BM / BK) * a.nb * (a.nb + 1) / 2;
 
   auto issue = [&](int slot) {
-    double* st = smem + slot * Cfg::elems;
+    double* st = smem + slot * stage_elems;
     const int J = it_issue.J, L = it_issue.src(), kk = it_issue.kk;
     load_a_tile<A_KM>(st, a.T + (int64_t)(L * BM + kk * BK) * a.ldt + J * BM, a.ldt, tid);
-    if (MODE == TR_KUF_FWD && it_issue.q == 0)
-      gen_kuf_tile(st + Cfg::a_elems, J * BM + kk * BK, a, xsT, xn, tid);
-    else
+    if (FWD && it_issue.q == 0) {
+      // z slab of the 16 inducing rows this stage turns into Kuf rows (contiguous in the padded copy)
+      const double* zsrc = a.zsp + (int64_t)(J * BM + kk * BK) * Sx;
+      for (int ch = tid; ch < BK * Sx / 2; ch += NTHREADS) cp_async16(st + Cfg::elems + ch * 2, zsrc + ch * 2);
+    } else {
       load_b_tile<B_KN>(st + Cfg::a_elems, a.X + (int64_t)(L * BM + kk * BK) * a.ldx + n0, a.ldx, tid);
+    }
     it_issue.next();
+  };
+  auto gen = [&](int slot) {  // it_gen describes the stage living in `slot`
+    double* st = smem + slot * stage_elems;
+    gen_kuf_tile(st + Cfg::a_elems, st + Cfg::elems, xs, it_gen.J * BM + it_gen.kk * BK, a.kp, tid);
   };
 
   Acc acc;
@@ -167,25 +188,41 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
     if (s < total) issue(s);
     cp_async_commit();
   }
-  for (int step = 0; step < total; step++) {
+  if (FWD) {
+    // the very first stage is a generator stage: build its Kuf rows before entering the loop
     cp_async_wait<S - 2>();
+    __syncthreads();
+    gen(0);
+    it_gen.next();
+  }
+  for (int step = 0; step < total; step++) {
+    // FWD keeps one stage less in flight: the z slab of stage step+1 must have landed so that its Kuf rows can be
+    // generated behind this stage's MMAs (the FP64 work of the generator overlaps the DMMA drain of the warp).
+    if (FWD) cp_async_wait<(S >= 3 ? S - 3 : 0)>();
+    else cp_async_wait<S - 2>();
     __syncthreads();
     if (step + S - 1 < total) issue((step + S - 1) % S);
     cp_async_commit();
-    const double* st = smem + (step % S) * Cfg::elems;
-    mma_stage<A_KM, B_KN>(acc, st, st + Cfg::a_elems, tm);
+    const double* st = smem + (step % S) * stage_elems;
+    // q == 0 is the (triangular) inverse diagonal block: skip the k-steps in which this warp's rows are all zero
+    const bool active = it_cons.q != 0 || ((MODE == TR_RHS_BWD) ? tm.tri_active_upper(it_cons.kk * BK) : tm.tri_active_lower(it_cons.kk * BK));
+    if (active) mma_stage<A_KM, B_KN>(acc, st, st + Cfg::a_elems, tm);
+    if (FWD) {
+      if (step + 1 < total && it_gen.q == 0) gen((step + 1) % S);
+      it_gen.next();
+    }
     if (it_cons.last_in_row()) {
       const int J = it_cons.J;
 #pragma unroll
       for (int mi = 0; mi < 4; mi++) {
         const int row = J * BM + tm.row(mi);
-        const double mtr = (MODE == TR_KUF_FWD) ? a.mt[row] : 0.0;
+        const double mtr = FWD ? a.mt[row] : 0.0;
         double* xr = a.X + (int64_t)row * a.ldx + n0;
 #pragma unroll
         for (int ni = 0; ni < 4; ni++) {
           const double v0 = acc[mi][ni][0], v1 = acc[mi][ni][1];
           *reinterpret_cast<double2*>(xr + tm.col(ni, 0)) = make_double2(v0, v1);
-          if (MODE == TR_KUF_FWD) {
+          if (FWD) {
             paa[ni][0] = fma(v0, v0, paa[ni][0]);
             paa[ni][1] = fma(v1, v1, paa[ni][1]);
             pam[ni][0] = fma(v0, mtr, pam[ni][0]);
@@ -199,7 +236,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
     it_cons.next();
   }
   cp_async_wait<0>();
-  if (MODE == TR_KUF_FWD) {
+  if (FWD) {
     __syncthreads();
     double* sred = smem;  // [2][4 m-warps][64]
 #pragma unroll
@@ -445,8 +482,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) syrk_kernel(SyrkArgs a) {
   const int m0 = ti * BM, n0 = tj * BN;
   Acc acc;
   acc_zero(acc);
+  // only the lower triangle of G is used: a warp whose 32 x 32 sub-tile lies strictly above the diagonal does no MMA
+  const bool needed = m0 + tm.wm + 31 >= n0 + tm.wn;
   gemm_mainloop<A_MK, B_NK>(acc, smem, a.As + (int64_t)m0 * a.ld + kb, a.ld, a.A + (int64_t)n0 * a.ld + kb, a.ld,
-                            (ke - kb) / BK, tm);
+                            (ke - kb) / BK, tm, TRI_NONE, 0, needed);
   double* G = a.G + (int64_t)split * a.Mp * a.Mp;
 #pragma unroll
   for (int mi = 0; mi < 4; mi++)
