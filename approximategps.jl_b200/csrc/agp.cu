@@ -484,15 +484,10 @@ static int32_t transpose(agp_ctx* c, const double* in, double* out, int n, int64
 // Blocked right-looking Cholesky of the n x n (n = nb*128) matrix Kw (column-major, lower triangle read,
 // destroyed) into L; also produces the inverse diagonal blocks in the diagonal blocks of Lt (inv) and Ut (inv^T).
 static int32_t blocked_cholesky(agp_ctx* c, double* Kw, double* L, double* Lt, double* Ut, int nb, int64_t ld, int* info) {
-  const int smem_potrf = 128 * 129 * 8, smem_trinv = 128 * 129 * 8;
-  CU(cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_potrf));
-  CU(cudaFuncSetAttribute(trinv128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_trinv));
+  CU(cudaFuncSetAttribute(potrf_trinv128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES));
   for (int J = 0; J < nb; J++) {
     const int64_t djj = (int64_t)J * BM * ld + (int64_t)J * BM;
-    potrf128_kernel<<<1, 256, smem_potrf, c->stream>>>(Kw + djj, L + djj, ld, J * BM, info);
-    LAUNCHED(c);
-    KCHECK();
-    trinv128_kernel<<<1, 128, smem_trinv, c->stream>>>(L + djj, ld, Lt + djj, Ut + djj, ld);
+    potrf_trinv128_kernel<<<1, 256, PT_SMEM_BYTES, c->stream>>>(Kw + djj, L + djj, Lt + djj, Ut + djj, ld, J * BM, info);
     LAUNCHED(c);
     KCHECK();
     const int rem = nb - 1 - J;

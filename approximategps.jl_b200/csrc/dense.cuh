@@ -55,67 +55,237 @@ __global__ void build_kuu_kernel(double* K, int Mp, const double* zs, const doub
   K[(int64_t)b * Mp + a] = v;
 }
 
-// In-place Cholesky of one 128 x 128 diagonal block (column-major, leading dimension ld): reads the lower
-// triangle of src, writes L (strict upper zeroed) to dst.  info[0] = first failing global column + 1.
-__global__ void __launch_bounds__(256) potrf128_kernel(const double* src, double* dst, int64_t ld, int col0, int* info) {
-  extern __shared__ double s[];  // [128][129]
-  constexpr int N = 128, LD = 129;
-  const int tid = threadIdx.x;
+// ---- diagonal-block kernel of the blocked Cholesky -----------------------------------------------------------
+// One CTA factorises a 128 x 128 diagonal block (lower triangle of src) and inverts the factor:
+//   dstL  <- L (strict upper zeroed),  dstLt <- inv(L),  dstUt <- inv(L)^T        (all column-major, leading dim ld)
+// info[0] = first failing global column + 1 (PosDefException).  Everything runs out of shared memory with 32-wide
+// blocking so that only a dozen block-wide barriers are needed: per 32-block a warp-level factorisation of the
+// diagonal, a register-resident row solve of the panel and a rank-32 trailing update; then the inverse by the
+// recursive rule  inv([L11 0; L21 L22]) = [X11 0; -X22 L21 X11  X22].
+constexpr int PT_LD = 129;
+constexpr int PT_SMEM_BYTES = (128 * PT_LD + 64 * 65 + 128) * 8;
+
+// Compile-time recursion over the 32 columns keeps every register-array index a constant (a plain doubly nested
+// `#pragma unroll` of the triangular loops is not fully unrolled by nvcc and the arrays fall into local memory).
+template <int J>
+struct PtPotrfCol {  // right-looking Cholesky step J of a 32 x 32 block: lane i holds row i in a[]
+  static __device__ __forceinline__ void run(double (&a)[32], int lane, double* rdiag, int col0, int* info) {
+    const double d = __shfl_sync(0xffffffffu, a[J], J);
+    if (lane == 0 && !(d > 0.0)) atomicCAS(info, 0, col0 + J + 1);
+    // sqrt(d), 1/sqrt(d) and a/sqrt(d) from one rsqrt plus FMA corrections (the results agree with sqrt() and the
+    // true quotients to the last bit or one ulp; a dependent sqrt + two divisions cost 4x the latency per column)
+    const double y = rsqrt(d);
+    const double s0 = d * y;
+    const double sq = fma(fma(-s0, s0, d), 0.5 * y, s0);
+    const double inv = fma(fma(-sq, y, 1.0), y, y);
+    const double l0 = a[J] * inv;
+    const double lij = (lane == J) ? sq : fma(fma(-l0, sq, a[J]), inv, l0);
+    a[J] = (lane >= J) ? lij : 0.0;
+    if (lane == J) rdiag[J] = inv;
+#pragma unroll
+    for (int k = J + 1; k < 32; k++) {
+      const double lkj = __shfl_sync(0xffffffffu, lij, k);
+      if (lane >= k) a[k] = fma(-lij, lkj, a[k]);
+    }
+    PtPotrfCol<J + 1>::run(a, lane, rdiag, col0, info);
+  }
+};
+template <>
+struct PtPotrfCol<32> {
+  static __device__ __forceinline__ void run(double (&)[32], int, double*, int, int*) {}
+};
+template <int J>
+struct PtSolveRow {  // x L_d^T = a for one row held in x[] (right-looking: x[J] is final, then x[k > J] -= x[J] L[k][J])
+  static __device__ __forceinline__ void run(double (&x)[32], const double* Ld, const double* rdiag) {
+    x[J] *= rdiag[J];
+#pragma unroll
+    for (int k = J + 1; k < 32; k++) x[k] = fma(-x[J], Ld[k * PT_LD + J], x[k]);
+    PtSolveRow<J + 1>::run(x, Ld, rdiag);
+  }
+};
+template <>
+struct PtSolveRow<32> {
+  static __device__ __forceinline__ void run(double (&)[32], const double*, const double*) {}
+};
+template <int I>
+struct PtInvCol {  // column `lane` of inv(L_d) in x[] (right-looking forward substitution of the unit vector e_lane)
+  static __device__ __forceinline__ void run(double (&x)[32], const double* Ld, const double* rdiag, int lane) {
+    x[I] = (I >= lane) ? x[I] * rdiag[I] : 0.0;
+#pragma unroll
+    for (int k = I + 1; k < 32; k++) x[k] = fma(-x[I], Ld[k * PT_LD + I], x[k]);
+    PtInvCol<I + 1>::run(x, Ld, rdiag, lane);
+  }
+};
+template <>
+struct PtInvCol<32> {
+  static __device__ __forceinline__ void run(double (&)[32], const double*, const double*, int) {}
+};
+
+// X[r0.., c0..] (sz x sz) <- -X22 * L21 * X11 with X22 = s[r0.., r0..], L21 = s[r0.., c0..], X11 = s[c0.., c0..]
+// (both already inverted, upper parts zero); tb is a [sz][sz+1] scratch.  All 256 threads must call this.
+__device__ __forceinline__ void pt_offdiag(double* s, double* tb, int r0, int c0, int sz) {
+  constexpr int LD = PT_LD;
+  const int q = sz / 4, ldt = sz + 1;
+  const int t = threadIdx.x;
+  const bool on = t < q * q;
+  const int ti = t / q, tj = t % q;  // the thread owns elements (ti + a q, tj + b q): neighbouring lanes, neighbouring columns
+  double acc[4][4];
+  if (on) {
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < sz; k++) {  // T = L21 * X11
+      double av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) av[a] = s[(r0 + ti + a * q) * LD + c0 + k];
+#pragma unroll
+      for (int b = 0; b < 4; b++) bv[b] = s[(c0 + k) * LD + c0 + tj + b * q];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) tb[(ti + a * q) * ldt + tj + b * q] = acc[a][b];
+  }
+  __syncthreads();
+  if (on) {
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < sz; k++) {  // X22 * T  (X22[i][k] = 0 for k > i)
+      double av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) av[a] = s[(r0 + ti + a * q) * LD + r0 + k];
+#pragma unroll
+      for (int b = 0; b < 4; b++) bv[b] = tb[k * ldt + tj + b * q];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) s[(r0 + ti + a * q) * LD + c0 + tj + b * q] = -acc[a][b];  // L21 was consumed before the barrier
+  }
+  __syncthreads();
+}
+
+#ifdef AGP_PT_TIMING
+#define PT_TICK(k) if (threadIdx.x == 0) pt_ticks[k] = clock64();
+__device__ long long pt_ticks[16];
+#else
+#define PT_TICK(k)
+#endif
+__global__ void __launch_bounds__(256) potrf_trinv128_kernel(const double* src, double* dstL, double* dstLt, double* dstUt, int64_t ld, int col0,
+                                                             int* info) {
+  extern __shared__ double s[];  // [128][129] + scratch [64][65]
+  constexpr int N = 128, LD = PT_LD;
+  double* tb = s + N * LD;
+  double* rdiag = tb + 64 * 65;  // 1 / L_jj
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < N * N; i += 256) {
     const int r = i % N, c = i / N;
     s[r * LD + c] = (r >= c) ? src[(int64_t)c * ld + r] : 0.0;
   }
   __syncthreads();
-  for (int j = 0; j < N; j++) {
-    if (tid == 0) {
-      const double d = s[j * LD + j];
-      if (!(d > 0.0)) atomicCAS(info, 0, col0 + j + 1);
-      s[j * LD + j] = sqrt(d);
+  PT_TICK(0)
+  // ---- Cholesky, 32-wide blocks -------------------------------------------------------------------------------
+  for (int o = 0; o < N; o += 32) {
+    if (warp == 0) {  // diagonal 32 x 32 block: lane i holds row o + i in registers, columns exchanged by shuffles
+      double* row = s + (o + lane) * LD + o;
+      double a[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) a[j] = row[j];
+      PtPotrfCol<0>::run(a, lane, rdiag + o, col0 + o, info);
+#pragma unroll
+      for (int j = 0; j < 32; j++) row[j] = a[j];
     }
     __syncthreads();
-    const double dj = s[j * LD + j];
-    if (tid > j && tid < N) s[tid * LD + j] /= dj;
-    __syncthreads();
-    // trailing update of the lower triangle: rows i > j, columns j < k <= i
-    const int i = j + 1 + (tid & 127);
-    if (i < N) {
-      const double lij = s[i * LD + j];
-      const int half = tid >> 7;  // two threads per row split the columns
-      for (int k = j + 1 + half; k <= i; k += 2) s[i * LD + k] = fma(-lij, s[k * LD + j], s[i * LD + k]);
+    if (o == 0) { PT_TICK(1) }
+    const int T = N - o - 32;  // rows below the diagonal block
+    if (tid < T) {             // panel: X L_d^T = A, one row per thread, held in registers
+      double* row = s + (o + 32 + tid) * LD + o;
+      double x[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) x[j] = row[j];
+      PtSolveRow<0>::run(x, s + o * LD + o, rdiag + o);
+#pragma unroll
+      for (int j = 0; j < 32; j++) row[j] = x[j];
     }
     __syncthreads();
+    if (o == 0) { PT_TICK(2) }
+    // trailing update of the lower triangle: A[i][c] -= sum_k P[i][k] P[c][k]; a thread owns the 4 x 4 elements
+    // (ti + a q, tc + b q) so that neighbouring lanes read neighbouring rows (conflict-free with ld = 129)
+    const int q = T / 4;
+    for (int mt = tid; mt < q * q; mt += 256) {
+      const int ti = mt / q, tc = mt % q;
+      double acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+      const double* pi = s + (o + 32 + ti) * LD + o;
+      const double* pc = s + (o + 32 + tc) * LD + o;
+#pragma unroll 4
+      for (int k = 0; k < 32; k++) {
+        double av[4], bv[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) av[a] = pi[a * q * LD + k];
+#pragma unroll
+        for (int b = 0; b < 4; b++) bv[b] = pc[b * q * LD + k];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int b = 0; b < 4; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+          if (tc + b * q <= ti + a * q) s[(o + 32 + ti + a * q) * LD + o + 32 + tc + b * q] -= acc[a][b];
+    }
+    __syncthreads();
+    if (o == 0) { PT_TICK(3) }
   }
+  PT_TICK(4)
   for (int i = tid; i < N * N; i += 256) {
     const int r = i % N, c = i / N;
-    dst[(int64_t)c * ld + r] = s[r * LD + c];
-  }
-}
-
-// Inverse of the 128 x 128 lower-triangular block L (column-major, ld): inv -> dstL (column-major),
-// inv^T -> dstU (column-major).  One thread per column of the inverse, in place in shared memory: row i of
-// L is last read at step i, so X(i, :) can overwrite it (one barrier between the reads and the write).
-__global__ void __launch_bounds__(128) trinv128_kernel(const double* L, int64_t ld, double* dstL, double* dstU, int64_t ldd) {
-  extern __shared__ double s[];  // [128][129]
-  constexpr int N = 128, LD = 129;
-  const int j = threadIdx.x;
-  for (int i = j; i < N * N; i += 128) {
-    const int r = i % N, c = i / N;
-    s[r * LD + c] = (r >= c) ? L[(int64_t)c * ld + r] : 0.0;
+    dstL[(int64_t)c * ld + r] = s[r * LD + c];
   }
   __syncthreads();
-  for (int i = 0; i < N; i++) {
-    double acc = (i == j) ? 1.0 : 0.0;
-    for (int k = 0; k < i; k++) acc = fma(-s[i * LD + k], s[k * LD + j], acc);
-    const double v = (i >= j) ? acc / s[i * LD + i] : 0.0;
-    __syncthreads();
-    s[i * LD + j] = v;
+  PT_TICK(5)
+  // ---- inverse: the four 32 x 32 diagonal blocks (one warp each; lane j builds column j in registers) ------------
+  if (warp < 4) {
+    const int o = warp * 32;
+    double x[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) x[i] = (i == lane) ? 1.0 : 0.0;
+    PtInvCol<0>::run(x, s + o * LD + o, rdiag + o, lane);
+    __syncwarp();  // every lane has finished reading the L rows of this block
+#pragma unroll
+    for (int i = 0; i < 32; i++) s[(o + i) * LD + o + lane] = x[i];
   }
   __syncthreads();
-  for (int i = j; i < N * N; i += 128) {
+  PT_TICK(6)
+  pt_offdiag(s, tb, 32, 0, 32);
+  pt_offdiag(s, tb, 96, 64, 32);
+  PT_TICK(7)
+  pt_offdiag(s, tb, 64, 0, 64);
+  PT_TICK(8)
+  for (int i = tid; i < N * N; i += 256) {
     const int r = i % N, c = i / N;
-    dstL[(int64_t)c * ldd + r] = s[r * LD + c];
-    dstU[(int64_t)c * ldd + r] = s[c * LD + r];
+    dstLt[(int64_t)c * ld + r] = s[r * LD + c];
+    dstUt[(int64_t)c * ld + r] = s[c * LD + r];
   }
+  PT_TICK(9)
 }
 
 // out = in^T for square n x n matrices with leading dimension ld (out != in)
