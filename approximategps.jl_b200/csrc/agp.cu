@@ -481,24 +481,39 @@ static int32_t transpose(agp_ctx* c, const double* in, double* out, int n, int64
   return AGP_OK;
 }
 
-// Blocked right-looking Cholesky of the n x n (n = nb*128) matrix Kw (column-major, lower triangle read,
+// Two-level blocked right-looking Cholesky of the n x n (n = nb*128) matrix Kw (column-major, lower triangle read,
 // destroyed) into L; also produces the inverse diagonal blocks in the diagonal blocks of Lt (inv) and Ut (inv^T).
+// Inner level: 128-blocks (diagonal kernel + panel GEMM + an update confined to the current 512-wide super-panel);
+// outer level: one trailing update per super-panel with K = 512, which quadruples the flop per byte of the
+// dominant GEMM compared with a rank-128 update.
 static int32_t blocked_cholesky(agp_ctx* c, double* Kw, double* L, double* Lt, double* Ut, int nb, int64_t ld, int* info) {
   CU(cudaFuncSetAttribute(potrf_trinv128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES));
-  for (int J = 0; J < nb; J++) {
-    const int64_t djj = (int64_t)J * BM * ld + (int64_t)J * BM;
-    potrf_trinv128_kernel<<<1, 256, PT_SMEM_BYTES, c->stream>>>(Kw + djj, L + djj, Lt + djj, Ut + djj, ld, J * BM, info);
-    LAUNCHED(c);
-    KCHECK();
-    const int rem = nb - 1 - J;
-    if (rem == 0) break;
-    const int64_t pnl = (int64_t)J * BM * ld + (int64_t)(J + 1) * BM;  // block column J, rows below the diagonal block
-    // panel: L[>J, J] = Kw[>J, J] * inv(L_JJ)^T ;  B(k, n) = inv[n][k] = Lt[djj + n + k*ld]
-    OK((run_gemm<A_KM, B_KN>(c, rem, 2, Kw + pnl, ld, Lt + djj, ld, BM, KR_FULL, TS_ALL, epi_store(L + pnl, ld, false))));
-    // trailing update (lower tiles): Kw[>J, >J] -= P P^T
-    const int64_t trl = (int64_t)(J + 1) * BM * ld + (int64_t)(J + 1) * BM;
-    OK((run_gemm<A_KM, B_KN>(c, rem, 2 * rem, L + pnl, ld, L + pnl, ld, BM, KR_FULL, TS_NBLK_LE,
-                             epi_store(Kw + trl, ld, false, -1.0, 1.0))));
+  constexpr int OB = 4;  // inner blocks per super-panel
+  for (int J0 = 0; J0 < nb; J0 += OB) {
+    const int J1 = std::min(nb, J0 + OB);  // super-panel = block columns [J0, J1)
+    for (int J = J0; J < J1; J++) {
+      const int64_t djj = (int64_t)J * BM * ld + (int64_t)J * BM;
+      potrf_trinv128_kernel<<<1, 256, PT_SMEM_BYTES, c->stream>>>(Kw + djj, L + djj, Lt + djj, Ut + djj, ld, J * BM, info);
+      LAUNCHED(c);
+      KCHECK();
+      const int rem = nb - 1 - J;
+      if (rem == 0) break;
+      const int64_t pnl = (int64_t)J * BM * ld + (int64_t)(J + 1) * BM;  // block column J, rows below the diagonal block
+      // panel: L[>J, J] = Kw[>J, J] * inv(L_JJ)^T ;  B(k, n) = inv[n][k] = Lt[djj + n + k*ld]
+      OK((run_gemm<A_KM, B_KN>(c, rem, 2, Kw + pnl, ld, Lt + djj, ld, BM, KR_FULL, TS_ALL, epi_store(L + pnl, ld, false))));
+      // update of the remaining block columns (J, J1) of this super-panel (lower tiles): Kw[>J, J+1..J1) -= P P^T
+      const int wcols = J1 - 1 - J;
+      if (wcols > 0) {
+        const int64_t trl = (int64_t)(J + 1) * BM * ld + (int64_t)(J + 1) * BM;
+        OK((run_gemm<A_KM, B_KN>(c, rem, 2 * wcols, L + pnl, ld, L + pnl, ld, BM, KR_FULL, TS_NBLK_LE, epi_store(Kw + trl, ld, false, -1.0, 1.0))));
+      }
+    }
+    const int rem = nb - J1;
+    if (rem <= 0) break;
+    // trailing update with the whole super-panel: Kw[>=J1, >=J1] -= L[>=J1, J0..J1) L[>=J1, J0..J1)^T
+    const int64_t pnl = (int64_t)J0 * BM * ld + (int64_t)J1 * BM;
+    const int64_t trl = (int64_t)J1 * BM * ld + (int64_t)J1 * BM;
+    OK((run_gemm<A_KM, B_KN>(c, rem, 2 * rem, L + pnl, ld, L + pnl, ld, (J1 - J0) * BM, KR_FULL, TS_NBLK_LE, epi_store(Kw + trl, ld, false, -1.0, 1.0))));
   }
   return AGP_OK;
 }
