@@ -807,15 +807,17 @@ static int32_t run_kgrad(agp_ctx* c, const double* Kb, int64_t ld, const double*
   a.stride = 2 * st.D + 3;
   a.Mp = st.Mp;
   a.kp = st.kp;
-  dim3 grid((st.M + 7) / 8, nslab);
-  if (st.D <= 4)
-    kgrad_kernel<4><<<grid, 256, 0, c->stream>>>(a);
-  else if (st.D <= 8)
-    kgrad_kernel<8><<<grid, 256, 0, c->stream>>>(a);
-  else if (st.D <= 16)
-    kgrad_kernel<16><<<grid, 256, 0, c->stream>>>(a);
-  else
-    kgrad_kernel<32><<<grid, 256, 0, c->stream>>>(a);
+  const int smem = 256 * (kuf_dp(st.D) + 2) * 8;
+  if (st.D <= 4) {
+    kgrad_kernel<4, 1><<<dim3((st.M + 7) / 8, nslab), 256, smem, c->stream>>>(a);
+  } else if (st.D <= 8) {
+    kgrad_kernel<8, 1><<<dim3((st.M + 7) / 8, nslab), 256, smem, c->stream>>>(a);
+  } else if (st.D <= 16) {
+    kgrad_kernel<16, 1><<<dim3((st.M + 7) / 8, nslab), 256, smem, c->stream>>>(a);
+  } else {
+    CU(cudaFuncSetAttribute(kgrad_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kgrad_kernel<32, 1><<<dim3((st.M + 7) / 8, nslab), 256, smem, c->stream>>>(a);
+  }
   LAUNCHED(c);
   KCHECK();
   return AGP_OK;

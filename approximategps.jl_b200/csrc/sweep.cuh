@@ -513,74 +513,130 @@ struct KgradArgs {
   KernelParams kp;
 };
 
-template <int DMAX>
-__global__ void __launch_bounds__(256) kgrad_kernel(KgradArgs a) {
+// RW rows per warp (16 or 8 rows per CTA): the points of a slab are staged through shared memory in tiles of 256
+// (scaled, with their squared norm) and shared by all rows of the CTA; each lane handles 8 points of a tile for its
+// RW rows, the Kb values of a tile are fetched up front so that the HBM latency overlaps the exp / FMA work.
+template <int DMAX, int RW>
+__global__ void __launch_bounds__(256, (DMAX <= 8 && RW == 1) ? 2 : 1) kgrad_kernel(KgradArgs a) {
+  extern __shared__ __align__(16) double kg_smem[];  // [256][Sx]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
+  const int row0 = (blockIdx.x * 8 + warp) * RW;
   const int slab = blockIdx.y;
-  const int D = a.kp.D, kind = a.kp.kind;
-  if (row >= a.kp.M) return;
+  const int D = a.kp.D, kind = a.kp.kind, Dp = (D + 1) & ~1, Sx = Dp + 2;
+  const bool direct = D == 1 && kind != AGP_KERNEL_LINEAR;
   const int nb = slab * a.slab, ne = min(a.npts, nb + a.slab);
-  double z[DMAX];
+  double z[RW][DMAX], znr[RW];
+  bool rvalid[RW];
 #pragma unroll
-  for (int d = 0; d < DMAX; d++) z[d] = (d < D) ? a.zs[(int64_t)row * D + d] : 0.0;
-  const double znr = a.zn[row];
-  double rs = 0.0, dvar = 0.0, dcc = 0.0, wx[DMAX], dsd[DMAX];
+  for (int r = 0; r < RW; r++) {
+    rvalid[r] = row0 + r < a.kp.M;
 #pragma unroll
-  for (int d = 0; d < DMAX; d++) wx[d] = dsd[d] = 0.0;
-  const double* kr = a.Kb + (int64_t)row * a.ld;
-  for (int n = nb + lane; n < ne; n += 32) {
-    const double kb = kr[n];
-    double xs[DMAX];
-    double xnn = 0.0, dot = 0.0;
-#pragma unroll
-    for (int d = 0; d < DMAX; d++) {
-      xs[d] = (d < D) ? a.pts[(int64_t)n * D + d] * a.kp.s[d] : 0.0;
-      xnn = fma(xs[d], xs[d], xnn);
-      dot = fma(xs[d], z[d], dot);
-    }
-    double u;
-    if (D == 1 && kind != AGP_KERNEL_LINEAR) {
-      const double df = xs[0] - z[0];
-      u = df * df;
-    } else {
-      u = u_from_dot(kind, xnn, znr, dot);
-    }
-    double k, dk;
-    kappa_and_du(kind, u, a.kp.c, k, dk);
-    dvar = fma(kb, k, dvar);
-    dcc += kb;
-    const double W = kb * a.kp.variance * dk;
-    rs += W;
-#pragma unroll
-    for (int d = 0; d < DMAX; d++) {
-      wx[d] = fma(W, xs[d], wx[d]);
-      const double df = xs[d] - z[d];
-      dsd[d] = fma(W, (kind == AGP_KERNEL_LINEAR) ? xs[d] * z[d] : df * df, dsd[d]);
-    }
+    for (int d = 0; d < DMAX; d++) z[r][d] = (d < D && rvalid[r]) ? a.zs[(int64_t)(row0 + r) * D + d] : 0.0;
+    znr[r] = rvalid[r] ? a.zn[row0 + r] : 0.0;
   }
+  double rs[RW], dvar[RW], dcc[RW], wx[RW][DMAX], wxx[RW][DMAX];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    rs += __shfl_xor_sync(0xffffffffu, rs, o);
-    dvar += __shfl_xor_sync(0xffffffffu, dvar, o);
-    dcc += __shfl_xor_sync(0xffffffffu, dcc, o);
+  for (int r = 0; r < RW; r++) {
+    rs[r] = dvar[r] = dcc[r] = 0.0;
 #pragma unroll
-    for (int d = 0; d < DMAX; d++) {
-      wx[d] += __shfl_xor_sync(0xffffffffu, wx[d], o);
-      dsd[d] += __shfl_xor_sync(0xffffffffu, dsd[d], o);
-    }
+    for (int d = 0; d < DMAX; d++) wx[r][d] = wxx[r][d] = 0.0;
   }
-  if (lane == 0) {
-    double* out = a.part + ((int64_t)slab * a.Mp + row) * a.stride;
-    out[0] += rs;
-    out[1] += dvar;
-    out[2] += dcc;
-#pragma unroll
-    for (int d = 0; d < DMAX; d++)
-      if (d < D) {
-        out[3 + d] += wx[d];
-        out[3 + D + d] += dsd[d];
+  for (int t0 = nb; t0 < ne; t0 += 256) {
+    __syncthreads();  // the previous tile is no longer read
+    {
+      const int n = t0 + threadIdx.x;
+      double* xr = kg_smem + threadIdx.x * Sx;
+      double nrm = 0.0;
+      for (int d = 0; d < D; d++) {
+        const double v = (n < ne) ? a.pts[(int64_t)n * D + d] * a.kp.s[d] : 0.0;
+        xr[d] = v;
+        nrm = fma(v, v, nrm);
       }
+      for (int d = D; d < Sx; d++) xr[d] = 0.0;
+      xr[Dp] = nrm;
+    }
+    __syncthreads();
+    const int cnt = min(256, ne - t0);
+    double kb[RW][8];
+#pragma unroll
+    for (int r = 0; r < RW; r++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int p = lane + 32 * i;
+        kb[r][i] = (p < cnt && rvalid[r]) ? a.Kb[(int64_t)(row0 + r) * a.ld + t0 + p] : 0.0;
+      }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int p = lane + 32 * i;
+      if (p >= cnt) continue;
+      const double* xr = kg_smem + p * Sx;
+      double xs[DMAX];
+#pragma unroll
+      for (int d = 0; d < DMAX; d += 2) {
+        if (d < Dp) {
+          const double2 v = *reinterpret_cast<const double2*>(xr + d);
+          xs[d] = v.x;
+          if (d + 1 < DMAX) xs[d + 1] = v.y;
+        } else {
+          xs[d] = 0.0;
+          if (d + 1 < DMAX) xs[d + 1] = 0.0;
+        }
+      }
+      const double xnn = xr[Dp];
+#pragma unroll
+      for (int r = 0; r < RW; r++) {
+        double u;
+        if (direct) {
+          const double df = xs[0] - z[r][0];
+          u = df * df;
+        } else {
+          double dot = 0.0;
+#pragma unroll
+          for (int d = 0; d < DMAX; d++) dot = fma(xs[d], z[r][d], dot);
+          u = u_from_dot(kind, xnn, znr[r], dot);
+        }
+        double k, dk;
+        kappa_and_du(kind, u, a.kp.c, k, dk);
+        const double kbv = kb[r][i];
+        dvar[r] = fma(kbv, k, dvar[r]);
+        dcc[r] += kbv;
+        const double W = kbv * a.kp.variance * dk;
+        rs[r] += W;
+#pragma unroll
+        for (int d = 0; d < DMAX; d++) {
+          const double wxd = W * xs[d];
+          wx[r][d] += wxd;
+          wxx[r][d] = fma(wxd, xs[d], wxx[r][d]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RW; r++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], o);
+      dvar[r] += __shfl_xor_sync(0xffffffffu, dvar[r], o);
+      dcc[r] += __shfl_xor_sync(0xffffffffu, dcc[r], o);
+#pragma unroll
+      for (int d = 0; d < DMAX; d++) {
+        wx[r][d] += __shfl_xor_sync(0xffffffffu, wx[r][d], o);
+        wxx[r][d] += __shfl_xor_sync(0xffffffffu, wxx[r][d], o);
+      }
+    }
+    if (lane == 0 && rvalid[r]) {
+      double* out = a.part + ((int64_t)slab * a.Mp + row0 + r) * a.stride;
+      out[0] += rs[r];
+      out[1] += dvar[r];
+      out[2] += dcc[r];
+#pragma unroll
+      for (int d = 0; d < DMAX; d++)
+        if (d < D) {
+          out[3 + d] += wx[r][d];
+          // sum W (xs - zs)^2 = sum W xs^2 - 2 zs sum W xs + zs^2 sum W   (linear: sum W xs zs = zs sum W xs)
+          out[3 + D + d] += (kind == AGP_KERNEL_LINEAR) ? z[r][d] * wx[r][d] : fma(z[r][d], fma(z[r][d], rs[r], -2.0 * wx[r][d]), wxx[r][d]);
+        }
+    }
   }
 }
 
