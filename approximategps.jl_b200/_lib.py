@@ -140,6 +140,11 @@ SYMBOLS = {
     "agp_svgp_prior_kl": (C.c_int32, [_vp, C.POINTER(AgpSvgpParams), c_double_p]),
     "agp_svgp_posterior": (C.c_int32, [_vp, C.POINTER(AgpSvgpParams), c_double_p, c_double_p, c_double_p]),
     "agp_svgp_mean_and_var": (C.c_int32, [_vp, C.POINTER(AgpSvgpParams), c_double_p, C.c_int64, c_double_p, c_double_p]),
+    "agp_svgp_mean_and_cov": (C.c_int32, [_vp, C.POINTER(AgpSvgpParams), c_double_p, C.c_int64, c_double_p, C.c_int64, c_double_p, c_double_p]),
+    "agp_laplace_predict": (
+        C.c_int32,
+        [_vp, C.POINTER(AgpKernel), c_double_p, C.c_int32, c_double_p, C.c_int64, c_double_p, C.c_int64, c_double_p, c_double_p, c_double_p],
+    ),
     "agp_laplace_f_and_lml": (C.c_int32, [_vp, C.POINTER(AgpLaplaceProblem), C.POINTER(AgpLaplaceResult), C.POINTER(_vp)]),
     "agp_laplace_cache_fetch": (C.c_int32, [_vp, C.c_int32, c_double_p]),
     "agp_laplace_cache_destroy": (C.c_int32, [_vp]),

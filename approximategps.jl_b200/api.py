@@ -555,16 +555,43 @@ def posterior(approx, l_fx=None, ys=None, ctx: Context | None = None):
     return ApproxPosteriorGP(approx, approx.fz.f, ctx)
 
 
-def mean_and_var(post: ApproxPosteriorGP, x):
-    """``StatsBase.mean_and_var(f_post, x)`` -- SVA.jl:246-253."""
+def mean_and_var(post, x):
+    """``StatsBase.mean_and_var(f_post, x)`` -- SVA.jl:246-253 / Laplace.jl:433-437."""
     from .laplace_api import LaplacePosterior
 
     if isinstance(post, LaplacePosterior):
-        raise NotImplementedError("prediction from the Laplace posterior (Laplace.jl:425-463) is outside the built path (DESIGN.md, 'next')")
+        return post.mean_and_var(x)
     x = _points(x)
     mu, var = np.zeros(len(x)), np.zeros(len(x))
     L.check(post.ctx.lib.agp_svgp_mean_and_var(post.ctx.h, C.byref(post._pk.p), L.dptr(x), len(x), L.dptr(mu), L.dptr(var)))
     return mu, var
+
+
+def mean_and_cov(post, x):
+    """``StatsBase.mean_and_cov(f_post, x)`` -- SVA.jl:237-244 / Laplace.jl:439-443."""
+    from .laplace_api import LaplacePosterior
+
+    if isinstance(post, LaplacePosterior):
+        return post.mean_and_cov(x)
+    x = _points(x)
+    mu, cov_ = np.zeros(len(x)), np.zeros((len(x), len(x)), order="F")
+    L.check(post.ctx.lib.agp_svgp_mean_and_cov(post.ctx.h, C.byref(post._pk.p), L.dptr(x), len(x), None, 0, L.dptr(mu), L.dptr(cov_)))
+    return mu, cov_
+
+
+def cov(post, x, y=None):
+    """``Statistics.cov(f_post, x)`` -- SVA.jl:223-228 -- and the cross-covariance ``cov(f_post, x, y)`` -- :255-264
+    (Laplace.jl:453-463 for the Laplace posterior)."""
+    from .laplace_api import LaplacePosterior
+
+    if isinstance(post, LaplacePosterior):
+        return post.cov(x, y)
+    if y is None:
+        return mean_and_cov(post, x)[1]
+    x, y = _points(x), _points(y)
+    out = np.zeros((len(x), len(y)), order="F")
+    L.check(post.ctx.lib.agp_svgp_mean_and_cov(post.ctx.h, C.byref(post._pk.p), L.dptr(x), len(x), L.dptr(y), len(y), None, L.dptr(out)))
+    return out
 
 
 def mean(post, x):

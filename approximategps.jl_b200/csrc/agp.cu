@@ -161,8 +161,8 @@ struct agp_ctx {
   SvgpState st;
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
-  // prediction outputs
-  DevBuf mu_out, var_out;
+  // prediction outputs / scratch
+  DevBuf mu_out, var_out, px1, px2, pxs1, pxn1, pxs2, pxn2, pcov;
 };
 
 struct agp_dataset {
@@ -224,7 +224,7 @@ extern "C" int32_t agp_ctx_destroy(agp_ctx* c) {
   DevBuf* bufs[] = {&c->z, &c->zs, &c->zn, &c->zsp, &c->mvec, &c->mt, &c->Lq, &c->Kw, &c->Lk, &c->Lt, &c->Ut, &c->Bt_cm, &c->Bt_rm,
                     &c->W1, &c->W2, &c->W3, &c->W4, &c->vec64, &c->vec64b, &c->A, &c->C, &c->Ab, &c->As, &c->saa, &c->sam,
                     &c->scc_part, &c->dmu, &c->dv, &c->sc_part, &c->gpart, &c->Gpart, &c->kpart, &c->red, &c->small,
-                    &c->mu_out, &c->var_out};
+                    &c->mu_out, &c->var_out, &c->px1, &c->px2, &c->pxs1, &c->pxn1, &c->pxs2, &c->pxn2, &c->pcov};
   for (DevBuf* b : bufs) b->release();
   lap_release(c);
   if (c->d_flags) cudaFree(c->d_flags);
@@ -417,7 +417,7 @@ extern "C" int32_t agp_dataset_destroy(agp_dataset* ds) {
 template <int MODE, int S>
 static int32_t launch_trsm_s(agp_ctx* c, const TrsmArgs& a, int tiles_n) {
   using Cfg = StageCfg<A_KM, B_KN>;
-  const int Sx = (MODE == TR_KUF_FWD) ? kuf_dp(a.kp.D) + 2 : 0;
+  const int Sx = (MODE == TR_KUF_FWD || MODE == TR_KUF_FWD_SCALED) ? kuf_dp(a.kp.D) + 2 : 0;
   const int smem = (S * (Cfg::elems + BK * Sx) + 64 * Sx) * 8 + 16;
   CU(cudaFuncSetAttribute(trsm_kernel<MODE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   trsm_kernel<MODE, S><<<tiles_n, NTHREADS, smem, c->stream>>>(a);
@@ -428,7 +428,7 @@ static int32_t launch_trsm_s(agp_ctx* c, const TrsmArgs& a, int tiles_n) {
 // 4 pipeline stages; the Kuf generator drops to 3 when the z slabs of a wide input (D > 8) would cost the second CTA per SM
 template <int MODE>
 static int32_t launch_trsm(agp_ctx* c, const TrsmArgs& a, int tiles_n) {
-  if (MODE == TR_KUF_FWD && a.kp.D > 8) return launch_trsm_s<MODE, 3>(c, a, tiles_n);
+  if ((MODE == TR_KUF_FWD || MODE == TR_KUF_FWD_SCALED) && a.kp.D > 8) return launch_trsm_s<MODE, 3>(c, a, tiles_n);
   return launch_trsm_s<MODE, 4>(c, a, tiles_n);
 }
 
@@ -1245,6 +1245,115 @@ extern "C" int32_t agp_svgp_mean_and_var(agp_ctx* c, const agp_svgp_params* p, c
   xbuf.release();
   if (s != AGP_OK) return s;
   if (e != cudaSuccess) return fail(AGP_ERR_CUDA, "mean_and_var: %s", cudaGetErrorString(e));
+  return AGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SVGP: full (cross-)covariance of the approximate posterior
+// ---------------------------------------------------------------------------------------------------
+// A = Lk^-1 Kuf and C = Bt^T A for one set of points (single chunk), into the given scratch matrices.
+static int32_t project_points(agp_ctx* c, const double* X_dev, int n, int ncols, double* Abuf, double* Cbuf, int64_t ldc) {
+  SvgpState& st = c->st;
+  TrsmArgs t1{};
+  t1.T = c->Lt.p;
+  t1.ldt = st.Mp;
+  t1.nb = st.nb;
+  t1.X = Abuf;
+  t1.ldx = ldc;
+  t1.pts = X_dev;
+  t1.npts = n;
+  t1.zsp = c->zsp.p;
+  t1.mt = c->mt.p;
+  t1.saa = c->saa.p;
+  t1.sam = c->sam.p;
+  t1.kp = st.kp;
+  OK(launch_trsm<TR_KUF_FWD>(c, t1, ncols / BN));
+  EpiS2 e2{Cbuf, ldc, c->scc_part.p, ldc};
+  OK((run_gemm<A_KM, B_KN>(c, st.nb, ncols / BN, c->Bt_rm.p, st.Mp, Abuf, ldc, st.Mp, KR_UPPER, TS_ALL, e2)));
+  return AGP_OK;
+}
+
+constexpr int64_t AGP_MAX_COV_POINTS = 16384;
+
+extern "C" int32_t agp_svgp_mean_and_cov(agp_ctx* c, const agp_svgp_params* p, const double* X1, int64_t n1, const double* X2, int64_t n2,
+                                         double* mu1_out, double* cov_out) {
+  if (!c || !p || !X1 || n1 < 1 || !cov_out) return fail(AGP_ERR_INVALID, "agp_svgp_mean_and_cov: bad arguments");
+  const bool cross = X2 != nullptr;
+  if (!cross) n2 = n1;
+  if (n2 < 1) return fail(AGP_ERR_INVALID, "agp_svgp_mean_and_cov: bad arguments");
+  if (n1 > AGP_MAX_COV_POINTS || n2 > AGP_MAX_COV_POINTS)
+    return fail(AGP_ERR_UNSUPPORTED, "full covariances are limited to %lld points per argument (the matrix is dense)", (long long)AGP_MAX_COV_POINTS);
+  OK(prepare_step(c, p));
+  SvgpState& st = c->st;
+  st.scale = 1.0;
+  const int D = st.D, Mp = st.Mp;
+  const int n1p = (int)round_up(n1, BM), n2p = (int)round_up(n2, BM);
+  OK(ensure_sweep_workspace(c, std::max(n1p, n2p), true));
+  const int64_t ldc = c->chunk_cols;
+  OK(c->px1.ensure((int64_t)n1p * D));
+  OK(c->pxs1.ensure((int64_t)n1p * D));
+  OK(c->pxn1.ensure(n1p));
+  OK(c->pcov.ensure((int64_t)n1p * n2p));
+  OK(c->mu_out.ensure(n1p));
+  OK(c->var_out.ensure(n1p));
+  CU(cudaMemsetAsync(c->px1.p, 0, sizeof(double) * n1p * D, c->stream));
+  CU(cudaMemcpyAsync(c->px1.p, X1, sizeof(double) * n1 * D, cudaMemcpyHostToDevice, c->stream));
+  KernelParams kx = st.kp;
+  kx.M = (int)n1;
+  prep_z_kernel<<<(n1p + 127) / 128, 128, 0, c->stream>>>(c->px1.p, c->pxs1.p, c->pxn1.p, nullptr, n1p, kx);
+  LAUNCHED(c);
+  KCHECK();
+  OK(project_points(c, c->px1.p, (int)n1, n1p, c->A.p, c->C.p, ldc));
+  if (mu1_out) {
+    PerPointArgs pp{};
+    pp.saa = c->saa.p;
+    pp.sam = c->sam.p;
+    pp.scc_part = c->scc_part.p;
+    pp.ldp = ldc;
+    pp.nb = st.nb;
+    pp.pts = c->px1.p;
+    pp.npts = (int)n1;
+    pp.ncols = n1p;
+    pp.scale = 1.0;
+    pp.mean_const = st.mean_const;
+    pp.kp = st.kp;
+    pp.lp = st.lp;
+    pp.mu_out = c->mu_out.p;
+    pp.var_out = c->var_out.p;
+    pp.flag = c->d_flags + 1;
+    pp.predict_only = 1;
+    perpoint_kernel<<<(n1p + 255) / 256, 256, 0, c->stream>>>(pp);
+    LAUNCHED(c);
+    KCHECK();
+    CU(cudaMemcpyAsync(mu1_out, c->mu_out.p, sizeof(double) * n1, cudaMemcpyDeviceToHost, c->stream));
+  }
+  const double *A2 = c->A.p, *C2 = c->C.p;
+  if (cross) {
+    OK(c->px2.ensure((int64_t)n2p * D));
+    OK(c->pxs2.ensure((int64_t)n2p * D));
+    OK(c->pxn2.ensure(n2p));
+    CU(cudaMemsetAsync(c->px2.p, 0, sizeof(double) * n2p * D, c->stream));
+    CU(cudaMemcpyAsync(c->px2.p, X2, sizeof(double) * n2 * D, cudaMemcpyHostToDevice, c->stream));
+    KernelParams ky = st.kp;
+    ky.M = (int)n2;
+    prep_z_kernel<<<(n2p + 127) / 128, 128, 0, c->stream>>>(c->px2.p, c->pxs2.p, c->pxn2.p, nullptr, n2p, ky);
+    LAUNCHED(c);
+    KCHECK();
+    OK(project_points(c, c->px2.p, (int)n2, n2p, c->Ab.p, c->As.p, ldc));
+    A2 = c->Ab.p;
+    C2 = c->As.p;
+    cross_k_kernel<<<dim3((n1p + 127) / 128, n2p), 128, 0, c->stream>>>(c->pcov.p, n1p, c->pxs1.p, c->pxn1.p, (int)n1, c->pxs2.p, c->pxn2.p, (int)n2, n1p, st.kp);
+  } else {
+    // cov(f.prior, x): the one-argument kernelmatrix (exactly zero distances on the diagonal)
+    build_kuu_kernel<<<dim3((n1p + 127) / 128, n1p), 128, 0, c->stream>>>(c->pcov.p, n1p, c->pxs1.p, c->pxn1.p, 0.0, kx);
+  }
+  LAUNCHED(c);
+  KCHECK();
+  // cov = K - A1^T A2 + C1^T C2   (SVA.jl:227 / :263)
+  OK((run_gemm<A_KM, B_KN>(c, n1p / BM, n2p / BN, c->A.p, ldc, A2, ldc, Mp, KR_FULL, TS_ALL, epi_store(c->pcov.p, n1p, false, -1.0, 1.0))));
+  OK((run_gemm<A_KM, B_KN>(c, n1p / BM, n2p / BN, c->C.p, ldc, C2, ldc, Mp, KR_FULL, TS_ALL, epi_store(c->pcov.p, n1p, false, 1.0, 1.0))));
+  CU(cudaMemcpy2DAsync(cov_out, sizeof(double) * n1, c->pcov.p, sizeof(double) * n1p, sizeof(double) * n1, n2, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return AGP_OK;
 }
 

@@ -55,6 +55,29 @@ __global__ void build_kuu_kernel(double* K, int Mp, const double* zs, const doub
   K[(int64_t)b * Mp + a] = v;
 }
 
+// K[a + b*ld] = k(x_a, y_b) for two point sets given as scaled points / squared norms (cov(f.prior, x, y));
+// entries with a >= nx or b >= ny are zero.
+__global__ void cross_k_kernel(double* K, int64_t ld, const double* xs, const double* xn, int nx, const double* ys, const double* yn, int ny,
+                               int rows, KernelParams kp) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (a >= rows) return;
+  double v = 0.0;
+  if (a < nx && b < ny) {
+    double u;
+    if (kp.D == 1 && kp.kind != AGP_KERNEL_LINEAR) {
+      const double df = xs[a] - ys[b];
+      u = df * df;
+    } else {
+      double dot = 0.0;
+      for (int d = 0; d < kp.D; d++) dot = fma(xs[(int64_t)a * kp.D + d], ys[(int64_t)b * kp.D + d], dot);
+      u = u_from_dot(kp.kind, xn[a], yn[b], dot);
+    }
+    v = kp.variance * kappa(kp.kind, u, kp.c);
+  }
+  K[(int64_t)b * ld + a] = v;
+}
+
 // ---- diagonal-block kernel of the blocked Cholesky -----------------------------------------------------------
 // One CTA factorises a 128 x 128 diagonal block (lower triangle of src) and inverts the factor:
 //   dstL  <- L (strict upper zeroed),  dstLt <- inv(L),  dstUt <- inv(L)^T        (all column-major, leading dim ld)

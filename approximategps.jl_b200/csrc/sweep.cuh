@@ -18,7 +18,9 @@
 
 namespace agp {
 
-constexpr int TR_KUF_FWD = 0, TR_RHS_FWD = 1, TR_RHS_BWD = 2;
+constexpr int TR_KUF_FWD = 0, TR_RHS_FWD = 1, TR_RHS_BWD = 2, TR_KUF_FWD_SCALED = 3;
+// TR_KUF_FWD_SCALED (Laplace prediction, Laplace.jl:427-431): the generated rows are k(x_l, x*) scaled by rowscale[l]
+// (Wsqrt) before the solve, and skd[n] = sum_l k(x_l, x*_n) dvec[l] (k' * d_loglik) is accumulated from the unscaled rows.
 
 struct TrsmArgs {
   const double* T;  // Lt (forward) or Ut (backward): column-major Mp x Mp.  Diagonal blocks hold the
@@ -34,6 +36,9 @@ struct TrsmArgs {
   const double* mt;  // [Mp] whitened variational mean
   double* saa;       // [ldx] sum_m a^2 per point
   double* sam;       // [ldx] sum_m a*mt per point
+  const double* rowscale;  // TR_KUF_FWD_SCALED: [Mp]
+  const double* dvec;      // TR_KUF_FWD_SCALED: [Mp]
+  double* skd;             // TR_KUF_FWD_SCALED: [ldx]
   KernelParams kp;
 };
 
@@ -69,8 +74,9 @@ __host__ __device__ __forceinline__ int kuf_dp(int D) { return (D + 1) & ~1; }
 
 // Kuf rows [row0, row0+16) x the CTA's 64 points, written as a B-operand stage tile.  Thread (l, c) = (tid / 16,
 // tid % 16) produces row l, columns c + 16 j: the z row is read once (broadcast LDS.128) for its 4 elements.
+template <bool SCALED>
 __device__ __forceinline__ void gen_kuf_tile(double* __restrict__ sB, const double* __restrict__ sZ, const double* __restrict__ xs, int row0,
-                                             const KernelParams& kp, int tid) {
+                                             const KernelParams& kp, int tid, const double* rowscale, const double* dvec, double (&pkd)[4]) {
   const int l = tid >> 4, c = tid & 15;
   const int D = kp.D, kind = kp.kind, Dp = kuf_dp(D), Sx = Dp + 2;
   const double* z = sZ + l * Sx;
@@ -98,8 +104,17 @@ __device__ __forceinline__ void gen_kuf_tile(double* __restrict__ sB, const doub
     for (int j = 0; j < 4; j++) u[j] = u_from_dot(kind, x0[j * 16 * Sx + Dp], zn, dot[j]);
   }
   const bool valid = row0 + l < kp.M;
+  double rsc = 1.0, dv = 0.0;
+  if (SCALED) {
+    rsc = rowscale[row0 + l];
+    dv = dvec[row0 + l];
+  }
 #pragma unroll
-  for (int j = 0; j < 4; j++) sB[l * BTile<B_KN>::ld + c + 16 * j] = valid ? kp.variance * kappa(kind, u[j], kp.c) : 0.0;
+  for (int j = 0; j < 4; j++) {
+    const double v = valid ? kp.variance * kappa(kind, u[j], kp.c) : 0.0;
+    if (SCALED) pkd[j] = fma(v, dv, pkd[j]);
+    sB[l * BTile<B_KN>::ld + c + 16 * j] = SCALED ? v * rsc : v;
+  }
 }
 
 // Blocked left-looking triangular solve on one 64-column tile per CTA.  MODE TR_KUF_FWD generates its right-hand
@@ -108,7 +123,8 @@ template <int MODE, int S>
 __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
   extern __shared__ __align__(128) double smem[];
   using Cfg = StageCfg<A_KM, B_KN>;
-  constexpr bool FWD = MODE == TR_KUF_FWD;
+  constexpr bool SCALED = MODE == TR_KUF_FWD_SCALED;
+  constexpr bool FWD = MODE == TR_KUF_FWD || SCALED;
   ThreadMap tm;
   const int tid = threadIdx.x;
   const int n0 = blockIdx.x * BN;
@@ -153,6 +169,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
     __syncthreads();  // raw (stage 0) may be overwritten from here on
   }
 
+  double pkd[4] = {0.0, 0.0, 0.0, 0.0};  // SCALED: partial k' * dvec of this thread's 4 columns
   StepIter it_issue, it_cons, it_gen;
   it_issue.init(MODE != TR_RHS_BWD, a.nb);
   it_cons.init(MODE != TR_RHS_BWD, a.nb);
@@ -174,7 +191,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
   };
   auto gen = [&](int slot) {  // it_gen describes the stage living in `slot`
     double* st = smem + slot * stage_elems;
-    gen_kuf_tile(st + Cfg::a_elems, st + Cfg::elems, xs, it_gen.J * BM + it_gen.kk * BK, a.kp, tid);
+    gen_kuf_tile<SCALED>(st + Cfg::a_elems, st + Cfg::elems, xs, it_gen.J * BM + it_gen.kk * BK, a.kp, tid, a.rowscale, a.dvec, pkd);
   };
 
   Acc acc;
@@ -258,6 +275,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
     if (tid < BN) {
       a.saa[n0 + tid] = ((sred[tid] + sred[64 + tid]) + sred[128 + tid]) + sred[192 + tid];
       a.sam[n0 + tid] = ((sred[256 + tid] + sred[320 + tid]) + sred[384 + tid]) + sred[448 + tid];
+    }
+    if (SCALED) {
+      // thread (l, c) = (tid / 16, tid % 16) holds the partial sums of columns c + 16 j over its rows l, l + 16, ...
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 4; j++) sred[(tid >> 4) * 64 + (tid & 15) + 16 * j] = pkd[j];
+      __syncthreads();
+      if (tid < BN) {
+        double acc = 0.0;
+        for (int l = 0; l < 16; l++) acc += sred[l * 64 + tid];
+        a.skd[n0 + tid] = acc;
+      }
     }
   }
 }

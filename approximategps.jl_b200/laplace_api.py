@@ -178,11 +178,40 @@ def laplace_approx_lml_and_gradient(la, lfx, ys, ctx=None) -> LaplaceResult:
 
 
 class LaplacePosterior:
-    """``ApproxPosteriorGP(la, lfx.fx, cache)`` (Laplace.jl:39-48); ``data`` is the LaplaceCache at f_opt."""
+    """``ApproxPosteriorGP(la, lfx.fx, cache)`` (Laplace.jl:39-48); ``data`` is the LaplaceCache at f_opt, which stays
+    on the device; the prediction methods (Laplace.jl:425-463) run there (agp_laplace_predict)."""
 
     def __init__(self, approx, fx, result: LaplaceResult, ctx):
         self.approx, self.prior, self.data, self.ctx = approx, fx, result.cache, ctx
         self.f, self.lml, self.steps = result.f, result.lml, result.steps
+
+    def _predict(self, x, y=None, want_mean=False, want_var=False, want_cov=False):
+        from .api import _points
+
+        k = self.prior.f.kernel
+        ils = np.ascontiguousarray(k.inv_lengthscale, dtype=np.float64)
+        kk = L.AgpKernel(k.kind, ils.size, k.variance, L.dptr(ils), k.c)
+        Xt = _points(self.prior.x)
+        x = _points(x)
+        yy = None if y is None else _points(y)
+        n1, n2 = len(x), (len(x) if yy is None else len(yy))
+        mu = np.zeros(n1) if want_mean else None
+        var = np.zeros(n1) if want_var else None
+        cov = np.zeros((n1, n2), order="F") if want_cov else None
+        L.check(self.data._lib.agp_laplace_predict(self.data._h, C.byref(kk), L.dptr(Xt), Xt.shape[1], L.dptr(x), n1, L.dptr(yy), n2, L.dptr(mu), L.dptr(var),
+                                                   L.dptr(cov)))
+        return mu, var, cov
+
+    def mean_and_var(self, x):  # Laplace.jl:433-437
+        mu, var, _ = self._predict(x, want_mean=True, want_var=True)
+        return mu, var
+
+    def mean_and_cov(self, x):  # Laplace.jl:439-443
+        mu, _, cov = self._predict(x, want_mean=True, want_cov=True)
+        return mu, cov
+
+    def cov(self, x, y=None):  # Laplace.jl:453-463
+        return self._predict(x, y, want_cov=True)[2]
 
 
 def laplace_posterior(la, lfx, ys, ctx=None):

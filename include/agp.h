@@ -192,6 +192,13 @@ int32_t agp_svgp_posterior(agp_ctx* ctx, const agp_svgp_params* p, double* Lk_ou
 int32_t agp_svgp_mean_and_var(agp_ctx* ctx, const agp_svgp_params* p, const double* Xnew, int64_t n,
                               double* mu_out, double* var_out);
 
+/* Replaces StatsBase.mean_and_cov(posterior(sva), x) -- SVA.jl:237-244 -- Statistics.cov(f, x) :223-228 and the
+ * cross-covariance cov(f, x, y) :255-264.  X1 / X2 host point-major; X2 == NULL means y = x (the one-argument
+ * kernel matrix with an exactly zero-distance diagonal).  mu1_out (n1, optional) = mean at X1; cov_out host
+ * column-major n1 x n2.  Dense output: at most 16384 points per argument (AGP_ERR_UNSUPPORTED beyond).        */
+int32_t agp_svgp_mean_and_cov(agp_ctx* ctx, const agp_svgp_params* p, const double* X1, int64_t n1,
+                              const double* X2, int64_t n2, double* mu1_out, double* cov_out);
+
 /* ---- Laplace --------------------------------------------------------------------------------- */
 /* Newton callback(fnew, cache) of _newton_inner_loop (Laplace.jl:263-265): called after every Newton
  * step with a view of the device-resident LaplaceCache (fields fetched lazily with
@@ -240,6 +247,13 @@ int32_t agp_laplace_f_and_lml(agp_ctx* ctx, const agp_laplace_problem* problem, 
  *        5 = B_ch.L (n x n column-major); 7 = loglik (1 double, owned caches only)              */
 int32_t agp_laplace_cache_fetch(agp_laplace_cache* cache, int32_t field, double* host_out);
 int32_t agp_laplace_cache_destroy(agp_laplace_cache* cache);
+/* Replaces the prediction methods of ApproxPosteriorGP{<:LaplaceApproximation} -- Laplace.jl:425-463
+ * (_laplace_predict_intermediates, mean_and_var, mean_and_cov, mean, var, cov(f, x), cov(f, x, y)) on a cache
+ * returned by agp_laplace_f_and_lml: kernel / Xtrain (host, point-major n x D) describe prior_at_x.  Any of
+ * mean1_out (n1), var1_out (n1), cov_out (column-major n1 x n2; X2 == NULL -> y = x) may be NULL.             */
+int32_t agp_laplace_predict(agp_laplace_cache* cache, const agp_kernel* kernel, const double* Xtrain, int32_t D,
+                            const double* X1, int64_t n1, const double* X2, int64_t n2, double* mean1_out,
+                            double* var1_out, double* cov_out);
 
 #ifdef __cplusplus
 }

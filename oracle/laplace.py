@@ -156,6 +156,13 @@ def predict_mean_and_var(kernel: Kernel, X, cache: LaplaceCache, Xnew):
     return f_mean, kernelmatrix_diag(kernel, Xnew) - np.sum(v * v, axis=0)
 
 
+def predict_cov_cross(kernel: Kernel, X, cache: LaplaceCache, Xa, Xb):
+    """``cov(f::LaplacePosteriorGP, x, y)`` (Laplace.jl:457-463)."""
+    vx = solve_triangular(cache.B_L, cache.Wsqrt[:, None] * kernelmatrix(kernel, X, Xa), lower=True)
+    vy = solve_triangular(cache.B_L, cache.Wsqrt[:, None] * kernelmatrix(kernel, X, Xb), lower=True)
+    return kernelmatrix(kernel, Xa, Xb) - vx.T @ vy
+
+
 # --- fixtures of the reference's own tests (src/TestUtils.jl:13-37) ---------------------------
 
 #! format: off

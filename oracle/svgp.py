@@ -110,6 +110,17 @@ def mean_and_cov(s: SVGP, X, data=None):
     return s.mean_const + Kuf.T @ alpha, kernelmatrix(s.kernel, X) - A.T @ A + BtA.T @ BtA
 
 
+def cov_cross(s: SVGP, X, Y, data=None):
+    """``cov(f_post, x, y)`` (SVA.jl:255-264)."""
+    X, Y = np.asarray(X, dtype=np.float64), np.asarray(Y, dtype=np.float64)
+    X = X[:, None] if X.ndim == 1 else X
+    Y = Y[:, None] if Y.ndim == 1 else Y
+    Lk, B, _ = data if data is not None else posterior_data(s)
+    Ax = solve_triangular(Lk, kernelmatrix(s.kernel, s.Z, X), lower=True)
+    Ay = solve_triangular(Lk, kernelmatrix(s.kernel, s.Z, Y), lower=True)
+    return kernelmatrix(s.kernel, X, Y) - Ax.T @ Ay + Ax.T @ B @ B.T @ Ay
+
+
 def prior_kl(s: SVGP) -> float:
     M = s.m.size
     if not s.centered:  # SVA.jl:364-373

@@ -180,3 +180,24 @@ def test_laplace_errors(agp):
         agp.approx_lml(agp.LaplaceApproximation(), agp.LatentGP(g, agp.BernoulliLikelihood(), 1e-8)(X), y[:-1])
     with pytest.raises(AssertionError):  # maxiter >= 1, Laplace.jl:257
         agp.approx_lml(agp.LaplaceApproximation(maxiter=0), agp.LatentGP(g, agp.BernoulliLikelihood(), 1e-8)(X), y)
+
+
+def test_laplace_posterior_prediction(agp):
+    """Laplace.jl:425-463 on the device: mean_and_var, mean_and_cov, cov(f, x), cov(f, x, y) against the oracle."""
+    rng = np.random.default_rng(8)
+    for n, D, lik in ((48, 1, "bernoulli_logit"), (300, 2, "poisson_exp")):
+        X, k, K, y = _problem(21 + n, n, D, lik)
+        kernel = 1.3 * agp.with_lengthscale(agp.SqExponentialKernel(), 0.8)
+        lfx = agp.LatentGP(agp.GP(kernel), _lik(agp, lik), 1e-6)(X)
+        post = agp.posterior(agp.LaplaceApproximation(), lfx, y)
+        f_opt, _, _ = olap.newton_inner_loop(ol.Likelihood(lik, 0.01), y, K)
+        cache = olap.train_intermediates(ol.Likelihood(lik, 0.01), y, K, f_opt)
+        xa, xb = rng.uniform(0, 4, size=(150, D)), rng.uniform(0, 4, size=(33, D))
+        mu, var = agp.mean_and_var(post, xa)
+        rmu, rvar = olap.predict_mean_and_var(k, X, cache, xa)
+        assert rel_err(mu, rmu) < 1e-9 and rel_err(var, rvar) < 1e-9
+        mu2, cov = agp.mean_and_cov(post, xa)
+        _, rcov = olap.predict_mean_and_cov(k, X, cache, xa)
+        assert rel_err(mu2, rmu) < 1e-9 and rel_err(cov, rcov) < 1e-9
+        assert rel_err(agp.cov(post, xa, xb), olap.predict_cov_cross(k, X, cache, xa, xb)) < 1e-9
+        assert rel_err(agp.mean(post, xa), rmu) < 1e-9 and rel_err(agp.var(post, xa), rvar) < 1e-9

@@ -134,3 +134,21 @@ def test_errors(agp):
     bad = agp.SparseVariationalApproximation(f(Z, 0.0), agp.MvNormal(np.zeros(4), chol_lower=np.eye(4)))
     with pytest.raises(agp.PosDefException):
         agp.elbo(bad, f(p["X"], 0.1), p["y"])
+
+
+def test_mean_and_cov_and_cross_cov(agp):
+    """SVA.jl:223-228, :237-244, :255-264 on the device against the oracle (n not a multiple of the tile sizes)."""
+    for centered, kind, D in ((False, "matern52", 3), (True, "se", 1), (False, "linear", 2)):
+        kw = dict(jitter=1e-3, zdist="random", lengthscale=1.5, M=3) if kind == "linear" else dict(M=37)
+        p = make_problem(seed=12, kind=kind, N=100, D=D, centered=centered, mean_const=0.2, **kw)
+        s, _, _ = oracle_objects(p)
+        sva, _, _, _ = agp_objects(agp, p)
+        post = agp.posterior(sva)
+        rng = np.random.default_rng(5)
+        xa, xb = rng.normal(size=(201, D)), rng.normal(size=(77, D))
+        mu, cov = agp.mean_and_cov(post, xa)
+        rmu, rcov = osv.mean_and_cov(s, xa)
+        assert rel_err(mu, rmu) < 1e-10 and rel_err(cov, rcov) < 1e-10
+        assert rel_err(agp.cov(post, xa), rcov) < 1e-10
+        assert rel_err(np.diag(cov), agp.var(post, xa)) < 1e-10  # AbstractGPs interface consistency (test/SVA...:30-34)
+        assert rel_err(agp.cov(post, xa, xb), osv.cov_cross(s, xa, xb)) < 1e-10
