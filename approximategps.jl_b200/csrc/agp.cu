@@ -439,6 +439,12 @@ static int32_t run_gemm(agp_ctx* c, int tiles_m, int tiles_n, const double* A, i
   GemmArgs g{A, lda, B, ldb, K, kmode, tmode};
   CU(cudaFuncSetAttribute(gemm_kernel<LA, LB, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes));
   dim3 grid(tiles_m, tiles_n);
+  if ((kmode == KR_LOWER || kmode == KR_UPPER) && tmode == TS_ALL && tiles_m > 1) {
+    g.swizzle = std::max(1, c->sms);  // half a wave of column tiles per super-group
+    g.tiles_m = tiles_m;
+    g.tiles_n = tiles_n;
+    grid = dim3(tiles_m * tiles_n, 1);
+  }
   gemm_kernel<LA, LB, Epi><<<grid, NTHREADS, Cfg::smem_bytes, c->stream>>>(g, epi);
   LAUNCHED(c);
   KCHECK();

@@ -24,6 +24,8 @@ struct GemmArgs {
   int K;
   int kmode;
   int tmode;
+  int swizzle = 0;  // > 0: 1-D grid of tiles_m * tiles_n blocks, see gemm_kernel
+  int tiles_m = 0, tiles_n = 0;
 };
 
 // tri / diag_step: when the A operand is triangular (TRI_LOWER: k <= m, TRI_UPPER: k >= m) the k-steps
@@ -77,7 +79,20 @@ template <int LA, int LB, class Epi>
 __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(GemmArgs g, Epi epi) {
   extern __shared__ __align__(128) double smem[];
   ThreadMap tm;
-  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+  int tile_m = blockIdx.x, tile_n = blockIdx.y;
+  if (g.swizzle > 0) {
+    // Triangular sweeps: linear block id -> (super-group of `swizzle` column tiles, row tile by decreasing work, column
+    // tile).  Heavy row tiles are scheduled first (no long CTA in the tail of the launch) while the columns of a
+    // super-group (~75 MB of the B operand at M = 1024) stay L2-resident across its row-tile passes.
+    const int tiles_m = g.tiles_m, tiles_n = g.tiles_n, G = g.swizzle;
+    const int id = blockIdx.x;
+    const int sg = id / (G * tiles_m);
+    const int gw = min(G, tiles_n - sg * G);  // width of this (possibly last, narrower) super-group
+    const int r = id - sg * G * tiles_m;
+    const int rank = r / gw;
+    tile_n = sg * G + r % gw;
+    tile_m = (g.kmode == KR_LOWER) ? tiles_m - 1 - rank : rank;
+  }
   const int m0 = tile_m * BM, n0 = tile_n * BN;
   const int nblk = n0 / BM;
   if (g.tmode == TS_NBLK_LT && !(nblk < tile_m)) return;
