@@ -107,45 +107,60 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
 }
 
 // ---- tile loaders (all 256 threads) -----------------------------------------------------------
-// gA points at element (m0, k0) of the operand; gB at element (k0, n0).
+// A thread copies NCH 16-byte chunks per tile; chunk i lives at (global) thread_ptr + i * gstep and (shared)
+// tile + soff + i * SSTEP, so that per stage only the tile base changes (no index arithmetic in the main loop).
 template <int LA>
-__device__ __forceinline__ void load_a_tile(double* sA, const double* __restrict__ gA, int64_t lda, int tid) {
-  if (LA == A_KM) {
-    // BK rows of BM doubles: 16 * 64 chunks of 16 B
-#pragma unroll
-    for (int i = 0; i < (BK * BM / 2) / NTHREADS; i++) {
-      int c = tid + i * NTHREADS;
-      int k = c / (BM / 2), mc = c % (BM / 2);
-      cp_async16(sA + k * ATile<LA>::ld + mc * 2, gA + (int64_t)k * lda + mc * 2);
-    }
-  } else {
-    // BM rows of BK doubles: 128 * 8 chunks
-#pragma unroll
-    for (int i = 0; i < (BM * BK / 2) / NTHREADS; i++) {
-      int c = tid + i * NTHREADS;
-      int m = c / (BK / 2), kc = c % (BK / 2);
-      cp_async16(sA + m * ATile<LA>::ld + kc * 2, gA + (int64_t)m * lda + kc * 2);
+struct ALoad {
+  static constexpr int NCH = (BM * BK / 2) / NTHREADS;  // 4
+  static constexpr int SSTEP = (LA == A_KM) ? (NTHREADS / (BM / 2)) * ATile<LA>::ld : (NTHREADS / (BK / 2)) * ATile<LA>::ld;
+  int64_t goff, gstep;  // element offsets relative to the tile's (m0, k0) element
+  int soff;
+  __device__ __forceinline__ void init(int64_t lda, int tid) {
+    if (LA == A_KM) {
+      const int k = tid / (BM / 2), mc = tid % (BM / 2);
+      goff = (int64_t)k * lda + mc * 2;
+      gstep = (int64_t)(NTHREADS / (BM / 2)) * lda;
+      soff = k * ATile<LA>::ld + mc * 2;
+    } else {
+      const int m = tid / (BK / 2), kc = tid % (BK / 2);
+      goff = (int64_t)m * lda + kc * 2;
+      gstep = (int64_t)(NTHREADS / (BK / 2)) * lda;
+      soff = m * ATile<LA>::ld + kc * 2;
     }
   }
-}
+  __device__ __forceinline__ void load(double* sA, const double* __restrict__ gtile) const {
+    const double* g = gtile + goff;
+    double* s = sA + soff;
+#pragma unroll
+    for (int i = 0; i < NCH; i++) cp_async16(s + i * SSTEP, g + i * gstep);
+  }
+};
 template <int LB>
-__device__ __forceinline__ void load_b_tile(double* sB, const double* __restrict__ gB, int64_t ldb, int tid) {
-  if (LB == B_KN) {
-#pragma unroll
-    for (int i = 0; i < (BK * BN / 2) / NTHREADS; i++) {
-      int c = tid + i * NTHREADS;
-      int k = c / (BN / 2), nc = c % (BN / 2);
-      cp_async16(sB + k * BTile<LB>::ld + nc * 2, gB + (int64_t)k * ldb + nc * 2);
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < (BN * BK / 2) / NTHREADS; i++) {
-      int c = tid + i * NTHREADS;
-      int n = c / (BK / 2), kc = c % (BK / 2);
-      cp_async16(sB + n * BTile<LB>::ld + kc * 2, gB + (int64_t)n * ldb + kc * 2);
+struct BLoad {
+  static constexpr int NCH = (BK * BN / 2) / NTHREADS;  // 2
+  static constexpr int SSTEP = (LB == B_KN) ? (NTHREADS / (BN / 2)) * BTile<LB>::ld : (NTHREADS / (BK / 2)) * BTile<LB>::ld;
+  int64_t goff, gstep;
+  int soff;
+  __device__ __forceinline__ void init(int64_t ldb, int tid) {
+    if (LB == B_KN) {
+      const int k = tid / (BN / 2), nc = tid % (BN / 2);
+      goff = (int64_t)k * ldb + nc * 2;
+      gstep = (int64_t)(NTHREADS / (BN / 2)) * ldb;
+      soff = k * BTile<LB>::ld + nc * 2;
+    } else {
+      const int n = tid / (BK / 2), kc = tid % (BK / 2);
+      goff = (int64_t)n * ldb + kc * 2;
+      gstep = (int64_t)(NTHREADS / (BK / 2)) * ldb;
+      soff = n * BTile<LB>::ld + kc * 2;
     }
   }
-}
+  __device__ __forceinline__ void load(double* sB, const double* __restrict__ gtile) const {
+    const double* g = gtile + goff;
+    double* s = sB + soff;
+#pragma unroll
+    for (int i = 0; i < NCH; i++) cp_async16(s + i * SSTEP, g + i * gstep);
+  }
+};
 
 // Per-thread coordinates inside the CTA tile.
 struct ThreadMap {

@@ -44,26 +44,38 @@ __device__ __forceinline__ void gemm_mainloop(Acc& acc, double* smem, const doub
   const int tid = threadIdx.x;
   const int64_t a_step = (LA == A_KM) ? (int64_t)BK * lda : (int64_t)BK;
   const int64_t b_step = (LB == B_KN) ? (int64_t)BK * ldb : (int64_t)BK;
+  ALoad<LA> la;
+  BLoad<LB> lb;
+  la.init(lda, tid);
+  lb.init(ldb, tid);
+  const double* pa = gA;  // tile bases of the next stage to issue
+  const double* pb = gB;
 #pragma unroll
   for (int s = 0; s < S - 1; s++) {
     if (s < nsteps) {
       double* st = smem + s * Cfg::elems;
-      load_a_tile<LA>(st, gA + s * a_step, lda, tid);
-      load_b_tile<LB>(st + Cfg::a_elems, gB + s * b_step, ldb, tid);
+      la.load(st, pa);
+      lb.load(st + Cfg::a_elems, pb);
+      pa += a_step;
+      pb += b_step;
     }
     cp_async_commit();
   }
+  int slot_issue = S - 1, slot_cons = 0;
   for (int step = 0; step < nsteps; step++) {
     cp_async_wait<S - 2>();
     __syncthreads();
-    int nxt = step + S - 1;
-    if (nxt < nsteps) {
-      double* st = smem + (nxt % S) * Cfg::elems;
-      load_a_tile<LA>(st, gA + nxt * a_step, lda, tid);
-      load_b_tile<LB>(st + Cfg::a_elems, gB + nxt * b_step, ldb, tid);
+    if (step + S - 1 < nsteps) {
+      double* st = smem + slot_issue * Cfg::elems;
+      la.load(st, pa);
+      lb.load(st + Cfg::a_elems, pb);
+      pa += a_step;
+      pb += b_step;
     }
     cp_async_commit();
-    const double* st = smem + (step % S) * Cfg::elems;
+    slot_issue = (slot_issue + 1 == S) ? 0 : slot_issue + 1;
+    const double* st = smem + slot_cons * Cfg::elems;
+    slot_cons = (slot_cons + 1 == S) ? 0 : slot_cons + 1;
     bool active = whole_active;
     if (tri != TRI_NONE) {
       const int d = step - diag_step;

@@ -176,16 +176,20 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
   it_gen.init(true, a.nb);
   const int total = (BM / BK) * a.nb * (a.nb + 1) / 2;
 
+  ALoad<A_KM> la;
+  BLoad<B_KN> lb;
+  la.init(a.ldt, tid);
+  lb.init(a.ldx, tid);
   auto issue = [&](int slot) {
     double* st = smem + slot * stage_elems;
     const int J = it_issue.J, L = it_issue.src(), kk = it_issue.kk;
-    load_a_tile<A_KM>(st, a.T + (int64_t)(L * BM + kk * BK) * a.ldt + J * BM, a.ldt, tid);
+    la.load(st, a.T + (int64_t)(L * BM + kk * BK) * a.ldt + J * BM);
     if (FWD && it_issue.q == 0) {
       // z slab of the 16 inducing rows this stage turns into Kuf rows (contiguous in the padded copy)
       const double* zsrc = a.zsp + (int64_t)(J * BM + kk * BK) * Sx;
       for (int ch = tid; ch < BK * Sx / 2; ch += NTHREADS) cp_async16(st + Cfg::elems + ch * 2, zsrc + ch * 2);
     } else {
-      load_b_tile<B_KN>(st + Cfg::a_elems, a.X + (int64_t)(L * BM + kk * BK) * a.ldx + n0, a.ldx, tid);
+      lb.load(st + Cfg::a_elems, a.X + (int64_t)(L * BM + kk * BK) * a.ldx + n0);
     }
     it_issue.next();
   };
