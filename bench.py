@@ -239,6 +239,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args, w)
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("AGP_NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line only
     import torch
     import torch.distributed as dist
 
