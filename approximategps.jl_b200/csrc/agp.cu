@@ -492,14 +492,14 @@ static int32_t transpose(agp_ctx* c, const double* in, double* out, int n, int64
 // Inner level: 128-blocks (diagonal kernel + panel GEMM + an update confined to the current 512-wide super-panel);
 // outer level: one trailing update per super-panel with K = 512, which quadruples the flop per byte of the
 // dominant GEMM compared with a rank-128 update.
-static int32_t blocked_cholesky(agp_ctx* c, double* Kw, double* L, double* Lt, double* Ut, int nb, int64_t ld, int* info) {
+static int32_t blocked_cholesky(agp_ctx* c, double* Kw, double* L, double* Lt, double* Ut, int nb, int64_t ld, int* info, int nvalid) {
   CU(cudaFuncSetAttribute(potrf_trinv128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES));
   constexpr int OB = 4;  // inner blocks per super-panel
   for (int J0 = 0; J0 < nb; J0 += OB) {
     const int J1 = std::min(nb, J0 + OB);  // super-panel = block columns [J0, J1)
     for (int J = J0; J < J1; J++) {
       const int64_t djj = (int64_t)J * BM * ld + (int64_t)J * BM;
-      potrf_trinv128_kernel<<<1, 256, PT_SMEM_BYTES, c->stream>>>(Kw + djj, L + djj, Lt + djj, Ut + djj, ld, J * BM, info);
+      potrf_trinv128_kernel<<<1, 256, PT_SMEM_BYTES, c->stream>>>(Kw + djj, L + djj, Lt + djj, Ut + djj, ld, J * BM, info, std::max(0, std::min(BM, nvalid - J * BM)));
       LAUNCHED(c);
       KCHECK();
       const int rem = nb - 1 - J;
@@ -708,13 +708,9 @@ static int32_t prepare_step(agp_ctx* c, const agp_svgp_params* p) {
   OK(fill(c, c->Lk.p, MM, 0.0));
   OK(fill(c, c->Lt.p, MM, 0.0));
   OK(fill(c, c->Ut.p, MM, 0.0));
-  OK(blocked_cholesky(c, c->Kw.p, c->Lk.p, c->Lt.p, c->Ut.p, nb, Mp, c->d_flags));
+  OK(blocked_cholesky(c, c->Kw.p, c->Lk.p, c->Lt.p, c->Ut.p, nb, Mp, c->d_flags, M));
   OK(build_block_scaled(c, c->Lk.p, c->Lt.p, c->Ut.p, nb, Mp));
-  int h_flags[4];
-  CU(cudaMemcpyAsync(h_flags, c->d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  if (h_flags[0] != 0)
-    return fail(AGP_ERR_NOT_PD, "PosDefException: cov(fz) is not positive definite; Cholesky failed at column %d", h_flags[0]);
+  // (the Cholesky status word is read together with the results: check_step_flags)
   if (!st.centered) {
     CU(cudaMemcpyAsync(c->mt.p, c->mvec.p, sizeof(double) * Mp, cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaMemcpyAsync(c->Bt_cm.p, c->Lq.p, sizeof(double) * MM, cudaMemcpyDeviceToDevice, c->stream));
@@ -742,6 +738,17 @@ static int32_t prepare_step(agp_ctx* c, const agp_svgp_params* p) {
     OK(transpose(c, c->Bt_rm.p, c->Bt_cm.p, Mp, Mp));
   }
   st.valid = true;
+  return AGP_OK;
+}
+
+// The status words of a step (Cholesky info, domain flag) are read once, together with the results, instead of
+// stalling the stream right after the factorisation.  Synchronises the stream.
+static int32_t check_step_flags(agp_ctx* c, bool domain) {
+  int h_flags[4];
+  CU(cudaMemcpyAsync(h_flags, c->d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (h_flags[0] != 0) return fail(AGP_ERR_NOT_PD, "PosDefException: cov(fz) is not positive definite; Cholesky failed at column %d", h_flags[0]);
+  if (domain && h_flags[1] != 0) return fail(AGP_ERR_DOMAIN, "DomainError: a marginal variance is not positive");
   return AGP_OK;
 }
 
@@ -1040,6 +1047,7 @@ extern "C" int32_t agp_svgp_finish(agp_ctx* c, double* elbo_out, agp_svgp_grads*
     int h_flags[4];
     CU(cudaMemcpyAsync(h_flags, c->d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if (h_flags[0] != 0) return fail(AGP_ERR_NOT_PD, "PosDefException: cov(fz) is not positive definite; Cholesky failed at column %d", h_flags[0]);
     if (h_flags[1] != 0) return fail(AGP_ERR_DOMAIN, "DomainError: a marginal variance is not positive");
     if (elbo_out) *elbo_out = h_scal[SC_E] * st.scale - h_small[0];
     return AGP_OK;
@@ -1142,6 +1150,7 @@ extern "C" int32_t agp_svgp_finish(agp_ctx* c, double* elbo_out, agp_svgp_grads*
   int h_flags[4];
   CU(cudaMemcpyAsync(h_flags, c->d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  if (h_flags[0] != 0) return fail(AGP_ERR_NOT_PD, "PosDefException: cov(fz) is not positive definite; Cholesky failed at column %d", h_flags[0]);
   if (h_flags[1] != 0) return fail(AGP_ERR_DOMAIN, "DomainError: a marginal variance is not positive");
   if (elbo_out) *elbo_out = h_scal[SC_E] * st.scale - h_small[0];
   if (go->dm) {
@@ -1197,8 +1206,7 @@ extern "C" int32_t agp_svgp_prior_kl(agp_ctx* c, const agp_svgp_params* p, doubl
   LAUNCHED(c);
   KCHECK();
   CU(cudaMemcpyAsync(kl_out, c->small.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  return AGP_OK;
+  return check_step_flags(c, false);
 }
 
 extern "C" int32_t agp_svgp_posterior(agp_ctx* c, const agp_svgp_params* p, double* Lk_out, double* B_out, double* alpha_out) {
@@ -1226,8 +1234,7 @@ extern "C" int32_t agp_svgp_posterior(agp_ctx* c, const agp_svgp_params* p, doub
   }
   if (Lk_out) CU(cudaMemcpy2DAsync(Lk_out, sizeof(double) * M, c->Lk.p, sizeof(double) * Mp, sizeof(double) * M, M, cudaMemcpyDeviceToHost, c->stream));
   if (B_out) CU(cudaMemcpy2DAsync(B_out, sizeof(double) * M, c->Bt_cm.p, sizeof(double) * Mp, sizeof(double) * M, M, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  return AGP_OK;
+  return check_step_flags(c, false);
 }
 
 extern "C" int32_t agp_svgp_mean_and_var(agp_ctx* c, const agp_svgp_params* p, const double* Xnew, int64_t n, double* mu_out,
@@ -1251,7 +1258,7 @@ extern "C" int32_t agp_svgp_mean_and_var(agp_ctx* c, const agp_svgp_params* p, c
   xbuf.release();
   if (s != AGP_OK) return s;
   if (e != cudaSuccess) return fail(AGP_ERR_CUDA, "mean_and_var: %s", cudaGetErrorString(e));
-  return AGP_OK;
+  return check_step_flags(c, false);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1359,8 +1366,7 @@ extern "C" int32_t agp_svgp_mean_and_cov(agp_ctx* c, const agp_svgp_params* p, c
   OK((run_gemm<A_KM, B_KN>(c, n1p / BM, n2p / BN, c->A.p, ldc, A2, ldc, Mp, KR_FULL, TS_ALL, epi_store(c->pcov.p, n1p, false, -1.0, 1.0))));
   OK((run_gemm<A_KM, B_KN>(c, n1p / BM, n2p / BN, c->C.p, ldc, C2, ldc, Mp, KR_FULL, TS_ALL, epi_store(c->pcov.p, n1p, false, 1.0, 1.0))));
   CU(cudaMemcpy2DAsync(cov_out, sizeof(double) * n1, c->pcov.p, sizeof(double) * n1p, sizeof(double) * n1, n2, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  return AGP_OK;
+  return check_step_flags(c, false);
 }
 
 #include "laplace_host.inc"

@@ -207,8 +207,10 @@ __device__ long long pt_ticks[16];
 #else
 #define PT_TICK(k)
 #endif
+// nvalid: leading rows / columns of the block that hold data; the rest must be identity padding, for which the 32-blocks
+// of the factorisation and of the inverse are skipped (a 20 x 20 problem costs one 32-block instead of four).
 __global__ void __launch_bounds__(256) potrf_trinv128_kernel(const double* src, double* dstL, double* dstLt, double* dstUt, int64_t ld, int col0,
-                                                             int* info) {
+                                                             int* info, int nvalid) {
   extern __shared__ double s[];  // [128][129] + scratch [64][65]
   constexpr int N = 128, LD = PT_LD;
   double* tb = s + N * LD;
@@ -221,7 +223,10 @@ __global__ void __launch_bounds__(256) potrf_trinv128_kernel(const double* src, 
   __syncthreads();
   PT_TICK(0)
   // ---- Cholesky, 32-wide blocks -------------------------------------------------------------------------------
-  for (int o = 0; o < N; o += 32) {
+  const int nact = min(N, (nvalid + 31) & ~31);  // active leading part (multiple of 32)
+  if (tid < N) rdiag[tid] = 1.0;
+  __syncthreads();
+  for (int o = 0; o < nact; o += 32) {
     if (warp == 0) {  // diagonal 32 x 32 block: lane i holds row o + i in registers, columns exchanged by shuffles
       double* row = s + (o + lane) * LD + o;
       double a[32];
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(256) potrf_trinv128_kernel(const double* src, 
     }
     __syncthreads();
     if (o == 0) { PT_TICK(1) }
-    const int T = N - o - 32;  // rows below the diagonal block
+    const int T = nact - o - 32;  // rows below the diagonal block (rows >= nact are identity padding: zero below the diagonal)
     if (tid < T) {             // panel: X L_d^T = A, one row per thread, held in registers
       double* row = s + (o + 32 + tid) * LD + o;
       double x[32];
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(256) potrf_trinv128_kernel(const double* src, 
   __syncthreads();
   PT_TICK(5)
   // ---- inverse: the four 32 x 32 diagonal blocks (one warp each; lane j builds column j in registers) ------------
-  if (warp < 4) {
+  if (warp < 4 && warp * 32 < nact) {
     const int o = warp * 32;
     double x[32];
 #pragma unroll
@@ -298,10 +303,10 @@ __global__ void __launch_bounds__(256) potrf_trinv128_kernel(const double* src, 
   }
   __syncthreads();
   PT_TICK(6)
-  pt_offdiag(s, tb, 32, 0, 32);
-  pt_offdiag(s, tb, 96, 64, 32);
+  if (nact > 32) pt_offdiag(s, tb, 32, 0, 32);
+  if (nact > 96) pt_offdiag(s, tb, 96, 64, 32);
   PT_TICK(7)
-  pt_offdiag(s, tb, 64, 0, 64);
+  if (nact > 64) pt_offdiag(s, tb, 64, 0, 64);
   PT_TICK(8)
   for (int i = tid; i < N * N; i += 256) {
     const int r = i % N, c = i / N;

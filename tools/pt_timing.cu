@@ -14,10 +14,10 @@ int main() {
   cudaMalloc(&info, 16); cudaMemset(info, 0, 16);
   cudaMemcpy(dA, A.data(), sizeof(double) * ld * n, cudaMemcpyHostToDevice);
   cudaFuncSetAttribute(potrf_trinv128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES);
-  for (int it = 0; it < 3; it++) potrf_trinv128_kernel<<<1, 256, PT_SMEM_BYTES>>>(dA, dL, dLt, dUt, ld, 0, info);
+  for (int it = 0; it < 3; it++) potrf_trinv128_kernel<<<1, 256, PT_SMEM_BYTES>>>(dA, dL, dLt, dUt, ld, 0, info, 128);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
-  for (int it = 0; it < 10; it++) potrf_trinv128_kernel<<<1, 256, PT_SMEM_BYTES>>>(dA, dL, dLt, dUt, ld, 0, info);
+  for (int it = 0; it < 10; it++) potrf_trinv128_kernel<<<1, 256, PT_SMEM_BYTES>>>(dA, dL, dLt, dUt, ld, 0, info, 128);
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   long long t[16]; cudaMemcpyFromSymbol(t, pt_ticks, sizeof t);
