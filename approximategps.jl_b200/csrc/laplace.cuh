@@ -113,9 +113,15 @@ __global__ void __launch_bounds__(256) trsv_fwd_step_kernel(const double* L, con
   {
     const double* inv = Linv + (int64_t)J * 128 * ld + (int64_t)J * 128;
     const double* bj = b + (int64_t)J * 128;
-    double acc = 0.0;
-    for (int k = h * 64; k < h * 64 + 64; k++) acc = fma(inv[i + (int64_t)k * ld], bj[k], acc);
-    part[tid] = acc;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;  // independent chains: 16 loads in flight per thread
+#pragma unroll 4
+    for (int k = h * 64; k < h * 64 + 64; k += 4) {
+      acc0 = fma(inv[i + (int64_t)k * ld], bj[k], acc0);
+      acc1 = fma(inv[i + (int64_t)(k + 1) * ld], bj[k + 1], acc1);
+      acc2 = fma(inv[i + (int64_t)(k + 2) * ld], bj[k + 2], acc2);
+      acc3 = fma(inv[i + (int64_t)(k + 3) * ld], bj[k + 3], acc3);
+    }
+    part[tid] = (acc0 + acc1) + (acc2 + acc3);
     __syncthreads();
     if (tid < 128) xj[tid] = part[tid] + part[tid + 128];
     __syncthreads();
@@ -126,9 +132,15 @@ __global__ void __launch_bounds__(256) trsv_fwd_step_kernel(const double* L, con
   }
   const int64_t r = (int64_t)(J + blockIdx.x) * 128 + i;
   const double* Lp = L + (int64_t)J * 128 * ld + r;
-  double acc = 0.0;
-  for (int k = h * 64; k < h * 64 + 64; k++) acc = fma(Lp[(int64_t)k * ld], xj[k], acc);
-  part[tid] = acc;
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll 4
+  for (int k = h * 64; k < h * 64 + 64; k += 4) {
+    acc0 = fma(Lp[(int64_t)k * ld], xj[k], acc0);
+    acc1 = fma(Lp[(int64_t)(k + 1) * ld], xj[k + 1], acc1);
+    acc2 = fma(Lp[(int64_t)(k + 2) * ld], xj[k + 2], acc2);
+    acc3 = fma(Lp[(int64_t)(k + 3) * ld], xj[k + 3], acc3);
+  }
+  part[tid] = (acc0 + acc1) + (acc2 + acc3);
   __syncthreads();
   if (tid < 128) b[r] -= part[tid] + part[tid + 128];
 }
@@ -142,9 +154,15 @@ __global__ void __launch_bounds__(256) trsv_bwd_step_kernel(const double* L, con
   {
     const double* inv = LinvT + (int64_t)J * 128 * ld + (int64_t)J * 128;
     const double* bj = b + (int64_t)J * 128;
-    double acc = 0.0;
-    for (int k = h * 64; k < h * 64 + 64; k++) acc = fma(inv[i + (int64_t)k * ld], bj[k], acc);
-    part[tid] = acc;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;  // independent chains: 16 loads in flight per thread
+#pragma unroll 4
+    for (int k = h * 64; k < h * 64 + 64; k += 4) {
+      acc0 = fma(inv[i + (int64_t)k * ld], bj[k], acc0);
+      acc1 = fma(inv[i + (int64_t)(k + 1) * ld], bj[k + 1], acc1);
+      acc2 = fma(inv[i + (int64_t)(k + 2) * ld], bj[k + 2], acc2);
+      acc3 = fma(inv[i + (int64_t)(k + 3) * ld], bj[k + 3], acc3);
+    }
+    part[tid] = (acc0 + acc1) + (acc2 + acc3);
     __syncthreads();
     if (tid < 128) xj[tid] = part[tid] + part[tid + 128];
     __syncthreads();
@@ -156,6 +174,7 @@ __global__ void __launch_bounds__(256) trsv_bwd_step_kernel(const double* L, con
   const int warp = tid >> 5, lane = tid & 31;
   const int c0 = (blockIdx.x - 1) * 128 + warp * 16;
   const double x0 = xj[lane], x1 = xj[lane + 32], x2 = xj[lane + 64], x3 = xj[lane + 96];
+#pragma unroll 8
   for (int cc = 0; cc < 16; cc++) {
     const int c = c0 + cc;
     const double* Lp = L + (int64_t)c * ld + (int64_t)J * 128;
