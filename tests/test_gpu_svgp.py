@@ -152,3 +152,78 @@ def test_mean_and_cov_and_cross_cov(agp):
         assert rel_err(agp.cov(post, xa), rcov) < 1e-10
         assert rel_err(np.diag(cov), agp.var(post, xa)) < 1e-10  # AbstractGPs interface consistency (test/SVA...:30-34)
         assert rel_err(agp.cov(post, xa, xb), osv.cov_cross(s, xa, xb)) < 1e-10
+
+
+def test_dataset_layouts_types_and_minibatch_views(agp):
+    """agp_dataset_upload: RowVecs (feature-major) input, Bool / Int / Float32 observations; [offset, offset+count) views with
+    num_data rescaling (examples/a-regression/script.jl:176-194) equal the oracle on the same slice."""
+    import ctypes as C
+
+    from agp_b200 import _lib as L
+
+    p = make_problem(seed=31, kind="matern32", N=777, M=19, D=3, lik="bernoulli_logit")
+    s, lik, ex = oracle_objects(p)
+    sva, lfx, quad, f = agp_objects(agp, p)
+    ctx = agp.default_context()
+    ref, rg = osv.elbo_and_grad(s, p["X"], p["y"], lik, ex, num_data=9000.0)
+    for ydt in (np.bool_, np.int64, np.float32, np.uint8):
+        ds = agp.DeviceData(p["X"], p["y"].astype(ydt), ctx=ctx)
+        val, g = agp.elbo_and_gradient(sva, agp.LatentGP(f, agp.BernoulliLikelihood(), 1e-18)(ds), None, num_data=9000.0, quadrature=quad)
+        assert abs(val - ref) < 1e-10 * abs(ref) and rel_err(g.Z, rg.Z) < 1e-9
+        ds.close()
+    # RowVecs(N x D): feature-major memory, transposed once on upload
+    ds = agp.DeviceData(capacity=777, D=3, ctx=ctx)
+    Xf = np.asfortranarray(p["X"])  # column-major N x D == d-major
+    L.check(ctx.lib.agp_dataset_upload(ds.h, Xf.ctypes.data_as(C.c_void_p), 777, 777, L.FEATURE_MAJOR, p["y"].ctypes.data_as(C.c_void_p), L.Y_F64, L.HOST))
+    ds.N = 777
+    lds = agp.LatentGP(f, agp.BernoulliLikelihood(), 1e-18)(ds)
+    val, _ = agp.elbo_and_gradient(sva, lds, None, num_data=9000.0, quadrature=quad)
+    assert abs(val - ref) < 1e-10 * abs(ref)
+    # minibatch view
+    lo, cnt = 130, 257
+    rv, rgm = osv.elbo_and_grad(s, p["X"][lo:lo + cnt], p["y"][lo:lo + cnt], lik, ex, num_data=9000.0)
+    val, g = agp.elbo_and_gradient(sva, lds, None, num_data=9000.0, quadrature=quad, offset=lo, count=cnt)
+    assert abs(val - rv) < 1e-10 * abs(rv) and rel_err(g.m, rgm.m) < 1e-9 and rel_err(g.Lq, rgm.Lq) < 1e-9
+    with pytest.raises(ValueError):
+        agp.elbo(sva, lds, None, offset=700, count=100)  # outside the data set
+    ds.close()
+
+
+def test_split_phase_api_equals_fused_call(agp):
+    """agp_svgp_sweep -> (caller-owned all-reduce of the packed buffer) -> agp_svgp_finish: two half-shards swept separately and
+    summed on the host reproduce the single-call result (this is the N > 1 protocol with the collective done by the caller)."""
+    import ctypes as C
+
+    import torch
+
+    from agp_b200 import _lib as L
+    from agp_b200.api import _Packed
+
+    p = make_problem(seed=41, kind="se", N=600, M=150, D=2, lik="poisson_exp")
+    sva, lfx, quad, f = agp_objects(agp, p)
+    ctx = agp.default_context()
+    lib = ctx.lib
+    ds = agp.DeviceData(p["X"], p["y"], ctx=ctx)
+    lds = agp.LatentGP(f, agp.PoissonLikelihood(), 1e-18)(ds)
+    ref, rg = agp.elbo_and_gradient(sva, lds, None, num_data=6000.0)
+    pk = _Packed(sva, agp.PoissonLikelihood(), None)
+    bufs = []
+    for lo, cnt in ((0, 256), (256, 344)):
+        L.check(lib.agp_svgp_sweep(ctx.h, ds.h, lo, cnt, C.byref(pk.p), 6000.0, 600, 1))
+        ptr, n = C.c_void_p(), C.c_int64()
+        L.check(lib.agp_svgp_reduce_buffer(ctx.h, C.byref(ptr), C.byref(n)))
+        t = torch.empty(n.value, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        C.cdll.LoadLibrary("libcudart.so.12").cudaMemcpy(C.c_void_p(t.data_ptr()), ptr, C.c_size_t(8 * n.value), 3)
+        bufs.append(t.clone())
+    total = bufs[0] + bufs[1]  # the caller's all-reduce
+    C.cdll.LoadLibrary("libcudart.so.12").cudaMemcpy(ptr, C.c_void_p(total.data_ptr()), C.c_size_t(8 * n.value), 3)
+    M, D = 150, 2
+    g_m, g_Lq, g_Z, sc, g_ils = np.zeros(M), np.zeros((M, M), order="F"), np.zeros((M, D)), np.zeros(4), np.zeros(1)
+    G = L.AgpSvgpGrads(L.dptr(g_m), L.dptr(g_Lq), L.dptr(g_Z), sc[0:1].ctypes.data_as(L.c_double_p), L.dptr(g_ils), sc[1:2].ctypes.data_as(L.c_double_p),
+                       sc[2:3].ctypes.data_as(L.c_double_p), sc[3:4].ctypes.data_as(L.c_double_p))
+    out = C.c_double()
+    L.check(lib.agp_svgp_finish(ctx.h, C.byref(out), C.byref(G)))
+    assert abs(out.value - ref) < 1e-12 * abs(ref)
+    assert rel_err(g_m, rg.m) < 1e-11 and rel_err(g_Lq, rg.Lq) < 1e-11 and rel_err(g_Z, rg.Z) < 1e-10 and rel_err(sc[0], rg.variance) < 1e-10
+    ds.close()
