@@ -821,16 +821,30 @@ static int32_t run_kgrad(agp_ctx* c, const double* Kb, int64_t ld, const double*
   a.Mp = st.Mp;
   a.kp = st.kp;
   const int smem = 256 * (kuf_dp(st.D) + 2) * 8;
-  if (st.D <= 4) {
-    kgrad_kernel<4, 1><<<dim3((st.M + 7) / 8, nslab), 256, smem, c->stream>>>(a);
-  } else if (st.D <= 8) {
-    kgrad_kernel<8, 1><<<dim3((st.M + 7) / 8, nslab), 256, smem, c->stream>>>(a);
-  } else if (st.D <= 16) {
-    kgrad_kernel<16, 1><<<dim3((st.M + 7) / 8, nslab), 256, smem, c->stream>>>(a);
-  } else {
-    CU(cudaFuncSetAttribute(kgrad_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kgrad_kernel<32, 1><<<dim3((st.M + 7) / 8, nslab), 256, smem, c->stream>>>(a);
+  const dim3 grid((st.M + 7) / 8, nslab);
+#define AGP_KGRAD_ONE(DM, KD)                                                                                        \
+  {                                                                                                                \
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kgrad_kernel<DM, 1, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    kgrad_kernel<DM, 1, KD><<<grid, 256, smem, c->stream>>>(a);                                                   \
   }
+#define AGP_KGRAD_LAUNCH(DM)                                          \
+  switch (st.kp.kind) {                                               \
+    case AGP_KERNEL_SE: AGP_KGRAD_ONE(DM, AGP_KERNEL_SE) break;       \
+    case AGP_KERNEL_MATERN32: AGP_KGRAD_ONE(DM, AGP_KERNEL_MATERN32) break; \
+    case AGP_KERNEL_MATERN52: AGP_KGRAD_ONE(DM, AGP_KERNEL_MATERN52) break; \
+    default: AGP_KGRAD_ONE(DM, AGP_KERNEL_LINEAR) break;              \
+  }
+  if (st.D <= 4) {
+    AGP_KGRAD_LAUNCH(4)
+  } else if (st.D <= 8) {
+    AGP_KGRAD_LAUNCH(8)
+  } else if (st.D <= 16) {
+    AGP_KGRAD_LAUNCH(16)
+  } else {
+    AGP_KGRAD_LAUNCH(32)
+  }
+#undef AGP_KGRAD_LAUNCH
+#undef AGP_KGRAD_ONE
   LAUNCHED(c);
   KCHECK();
   return AGP_OK;

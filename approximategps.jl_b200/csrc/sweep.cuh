@@ -549,13 +549,14 @@ struct KgradArgs {
 // RW rows per warp (16 or 8 rows per CTA): the points of a slab are staged through shared memory in tiles of 256
 // (scaled, with their squared norm) and shared by all rows of the CTA; each lane handles 8 points of a tile for its
 // RW rows, the Kb values of a tile are fetched up front so that the HBM latency overlaps the exp / FMA work.
-template <int DMAX, int RW>
+template <int DMAX, int RW, int KIND>
 __global__ void __launch_bounds__(256, (DMAX <= 8 && RW == 1) ? 2 : 1) kgrad_kernel(KgradArgs a) {
   extern __shared__ __align__(16) double kg_smem[];  // [256][Sx]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = (blockIdx.x * 8 + warp) * RW;
   const int slab = blockIdx.y;
-  const int D = a.kp.D, kind = a.kp.kind, Dp = (D + 1) & ~1, Sx = Dp + 2;
+  constexpr int kind = KIND;  // compile-time covariance function: no per-element dispatch
+  const int D = a.kp.D, Dp = (D + 1) & ~1, Sx = Dp + 2;
   const bool direct = D == 1 && kind != AGP_KERNEL_LINEAR;
   const int nb = slab * a.slab, ne = min(a.npts, nb + a.slab);
   double z[RW][DMAX], znr[RW];
