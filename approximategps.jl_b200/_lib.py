@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libagp_b200.so")
+LIB_PATH = os.environ.get("AGP_B200_LIB") or os.path.join(HERE, "libagp_b200.so")  # same override the Julia shim reads
 
 # status codes (include/agp.h)
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_NOT_PD, ERR_DOMAIN, ERR_CUDA, ERR_NCCL, ERR_ALLOC = range(8)

@@ -77,6 +77,9 @@ __host__ __device__ __forceinline__ int kuf_dp(int D) { return (D + 1) & ~1; }
 template <bool SCALED>
 __device__ __forceinline__ void gen_kuf_tile(double* __restrict__ sB, const double* __restrict__ sZ, const double* __restrict__ xs, int row0,
                                              const KernelParams& kp, int tid, const double* rowscale, const double* dvec, double (&pkd)[4]) {
+#ifdef AGP_EXP_NOGEN
+  return;  // timing experiment only (tools/s1_experiments.sh): results are garbage
+#endif
   const int l = tid >> 4, c = tid & 15;
   const int D = kp.D, kind = kp.kind, Dp = kuf_dp(D), Sx = Dp + 2;
   const double* z = sZ + l * Sx;
@@ -111,7 +114,11 @@ __device__ __forceinline__ void gen_kuf_tile(double* __restrict__ sB, const doub
   }
 #pragma unroll
   for (int j = 0; j < 4; j++) {
+#ifdef AGP_EXP_NOEXP
+    const double v = valid ? kp.variance * u[j] : 0.0;  // timing experiment only
+#else
     const double v = valid ? kp.variance * kappa(kind, u[j], kp.c) : 0.0;
+#endif
     if (SCALED) pkd[j] = fma(v, dv, pkd[j]);
     sB[l * BTile<B_KN>::ld + c + 16 * j] = SCALED ? v * rsc : v;
   }
@@ -219,8 +226,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
   for (int step = 0; step < total; step++) {
     // FWD keeps one stage less in flight: the z slab of stage step+1 must have landed so that its Kuf rows can be
     // generated behind this stage's MMAs (the FP64 work of the generator overlaps the DMMA drain of the warp).
+#ifdef AGP_EXP_WAIT2
+    cp_async_wait<S - 2>();  // timing experiment only: the z slab of the next stage may not have landed
+#else
     if (FWD) cp_async_wait<(S >= 3 ? S - 3 : 0)>();
     else cp_async_wait<S - 2>();
+#endif
     __syncthreads();
     if (step + S - 1 < total) issue((step + S - 1) % S);
     cp_async_commit();
