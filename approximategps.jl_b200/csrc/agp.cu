@@ -414,12 +414,24 @@ extern "C" int32_t agp_dataset_destroy(agp_dataset* ds) {
 // ---------------------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------------------
+// Opt-in dynamic shared memory, set once per kernel instantiation and device (not on every launch: the call costs
+// a few microseconds, which matters for the latency-bound small-M path).
+template <auto Kernel>
+static int32_t ensure_smem(agp_ctx* c, int bytes) {
+  static int granted[64] = {0};
+  int& g = granted[c->device & 63];
+  if (g >= bytes) return AGP_OK;
+  CU(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  g = bytes;
+  return AGP_OK;
+}
+
 template <int MODE, int S>
 static int32_t launch_trsm_s(agp_ctx* c, const TrsmArgs& a, int tiles_n) {
   using Cfg = StageCfg<A_KM, B_KN>;
   const int Sx = (MODE == TR_KUF_FWD || MODE == TR_KUF_FWD_SCALED) ? kuf_dp(a.kp.D) + 2 : 0;
   const int smem = (S * (Cfg::elems + BK * Sx) + 64 * Sx) * 8 + 16;
-  CU(cudaFuncSetAttribute(trsm_kernel<MODE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  OK((ensure_smem<trsm_kernel<MODE, S>>(c, smem)));
   trsm_kernel<MODE, S><<<tiles_n, NTHREADS, smem, c->stream>>>(a);
   LAUNCHED(c);
   KCHECK();
@@ -437,7 +449,7 @@ static int32_t run_gemm(agp_ctx* c, int tiles_m, int tiles_n, const double* A, i
                         int kmode, int tmode, const Epi& epi) {
   using Cfg = StageCfg<LA, LB>;
   GemmArgs g{A, lda, B, ldb, K, kmode, tmode};
-  CU(cudaFuncSetAttribute(gemm_kernel<LA, LB, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes));
+  OK((ensure_smem<gemm_kernel<LA, LB, Epi>>(c, Cfg::smem_bytes)));
   dim3 grid(tiles_m, tiles_n);
   if ((kmode == KR_LOWER || kmode == KR_UPPER) && tmode == TS_ALL && tiles_m > 1) {
     g.swizzle = std::max(1, c->sms);  // half a wave of column tiles per super-group
@@ -493,7 +505,7 @@ static int32_t transpose(agp_ctx* c, const double* in, double* out, int n, int64
 // outer level: one trailing update per super-panel with K = 512, which quadruples the flop per byte of the
 // dominant GEMM compared with a rank-128 update.
 static int32_t blocked_cholesky(agp_ctx* c, double* Kw, double* L, double* Lt, double* Ut, int nb, int64_t ld, int* info, int nvalid) {
-  CU(cudaFuncSetAttribute(potrf_trinv128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES));
+  OK((ensure_smem<potrf_trinv128_kernel>(c, PT_SMEM_BYTES)));
   constexpr int OB = 4;  // inner blocks per super-panel
   for (int J0 = 0; J0 < nb; J0 += OB) {
     const int J1 = std::min(nb, J0 + OB);  // super-panel = block columns [J0, J1)
@@ -824,7 +836,7 @@ static int32_t run_kgrad(agp_ctx* c, const double* Kb, int64_t ld, const double*
   const dim3 grid((st.M + 7) / 8, nslab);
 #define AGP_KGRAD_ONE(DM, KD)                                                                                        \
   {                                                                                                                \
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kgrad_kernel<DM, 1, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    if (smem > 48 * 1024) OK((ensure_smem<kgrad_kernel<DM, 1, KD>>(c, smem)));                                      \
     kgrad_kernel<DM, 1, KD><<<grid, 256, smem, c->stream>>>(a);                                                   \
   }
 #define AGP_KGRAD_LAUNCH(DM)                                          \
@@ -980,7 +992,7 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
       s.G = c->Gpart.p;
       s.Mp = Mp;
       using Cfg = StageCfg<A_MK, B_NK>;
-      CU(cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes));
+      OK((ensure_smem<syrk_kernel>(c, Cfg::smem_bytes)));
       dim3 grid(nb * (nb + 1), c->nsplit);
       syrk_kernel<<<grid, NTHREADS, Cfg::smem_bytes, c->stream>>>(s);
       LAUNCHED(c);

@@ -175,19 +175,4 @@ struct EpiStore {
   }
 };
 
-template <int LA, int LB, class Epi>
-inline cudaError_t launch_gemm(cudaStream_t st, int tiles_m, int tiles_n, const GemmArgs& g, const Epi& epi) {
-  using Cfg = StageCfg<LA, LB>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<LA, LB, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::smem_bytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  dim3 grid(tiles_m, tiles_n);
-  gemm_kernel<LA, LB, Epi><<<grid, NTHREADS, Cfg::smem_bytes, st>>>(g, epi);
-  return cudaGetLastError();
-}
-
 }  // namespace agp
