@@ -227,3 +227,18 @@ def test_split_phase_api_equals_fused_call(agp):
     assert abs(out.value - ref) < 1e-12 * abs(ref)
     assert rel_err(g_m, rg.m) < 1e-11 and rel_err(g_Lq, rg.Lq) < 1e-11 and rel_err(g_Z, rg.Z) < 1e-10 and rel_err(sc[0], rg.variance) < 1e-10
     ds.close()
+
+
+@pytest.mark.parametrize("N", [37888, 37889, 75841])
+def test_real_chunk_boundaries(agp, N):
+    """The sweep processes 37 888 points (two waves of 64-point tiles) per launch group: N equal to one chunk, one point more,
+    and two chunks plus a ragged tail must accumulate exactly like the oracle's single pass."""
+    p = make_problem(seed=51, kind="matern52", N=N, M=24, D=2, lik="poisson_exp")
+    _run_case(agp, p, num_data=1e6)
+
+
+def test_wide_inputs_and_large_m(agp):
+    """D = 16 / 32 take the 3-stage generator pipeline; M = 2048 is the C5 shape (16 diagonal blocks, two Cholesky super-panels x 2)."""
+    _run_case(agp, make_problem(seed=52, kind="se", N=1000, M=70, D=16, lik="gaussian", lengthscale=4.0, ard=True))
+    _run_case(agp, make_problem(seed=53, kind="matern32", N=600, M=40, D=32, lik="bernoulli_logit", lengthscale=6.0))
+    _run_case(agp, make_problem(seed=54, kind="se", N=2500, M=2048, D=16, lik="gaussian", lengthscale=4.0, variance=1.0, zdist="random"), num_data=1e8)
