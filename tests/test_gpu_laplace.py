@@ -201,3 +201,18 @@ def test_laplace_posterior_prediction(agp):
         assert rel_err(mu2, rmu) < 1e-9 and rel_err(cov, rcov) < 1e-9
         assert rel_err(agp.cov(post, xa, xb), olap.predict_cov_cross(k, X, cache, xa, xb)) < 1e-9
         assert rel_err(agp.mean(post, xa), rmu) < 1e-9 and rel_err(agp.var(post, xa), rvar) < 1e-9
+
+
+def test_issue_109_smoke(agp):
+    """test/LaplaceApproximationModule.jl:219-227: 2-D inputs (ColVecs(randn(2, 5))) with BernoulliLikelihood just have to work."""
+    rng = np.random.default_rng(109)
+    X = rng.normal(size=(5, 2))
+    y = np.array([1, 0, 1, 1, 0], dtype=np.float64)
+    lfx = agp.LatentGP(agp.GP(agp.SqExponentialKernel()), agp.BernoulliLikelihood(), 1e-8)(X)
+    lml = agp.approx_lml(agp.LaplaceApproximation(), lfx, y)
+    K = ok.kernelmatrix(ok.Kernel(ok.SE, 1.0, np.array([1.0])), X) + 1e-8 * np.eye(5)
+    _, ref, _ = olap.laplace_f_and_lml(ol.Likelihood("bernoulli_logit"), y, K)
+    assert np.isfinite(lml) and abs(lml - ref) < 1e-10 * abs(ref)
+    post = agp.posterior(agp.LaplaceApproximation(), lfx, y)
+    mu, var = agp.mean_and_var(post, X)
+    assert np.all(np.isfinite(mu)) and np.all(var > 0)

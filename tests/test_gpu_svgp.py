@@ -242,3 +242,24 @@ def test_wide_inputs_and_large_m(agp):
     _run_case(agp, make_problem(seed=52, kind="se", N=1000, M=70, D=16, lik="gaussian", lengthscale=4.0, ard=True))
     _run_case(agp, make_problem(seed=53, kind="matern32", N=600, M=40, D=32, lik="bernoulli_logit", lengthscale=6.0))
     _run_case(agp, make_problem(seed=54, kind="se", N=2500, M=2048, D=16, lik="gaussian", lengthscale=4.0, variance=1.0, zdist="random"), num_data=1e8)
+
+
+def test_optimised_posterior_matches_gpr(agp):
+    """The reference's end-to-end optimisation test (test/SVA...:136-186) driven through the C ABI: 20 000 Adam steps on (m, A)."""
+    from _train import adam_train, exact_gpr, problem
+
+    x, y, variance, inv_ls, noise, jitter = problem()
+    f = agp.GP(variance * agp.ScaleTransform(agp.SqExponentialKernel(), inv_ls))
+    ds = agp.DeviceData(x, y)
+    fx = agp.FiniteGP(f, ds, noise)
+
+    def loss(m, A):
+        sva = agp.SparseVariationalApproximation(f(x, jitter), agp.MvNormal(m, chol_lower=A))
+        v, g = agp.elbo_and_gradient(sva, fx, None)
+        return -v, -g.m, -g.Lq
+
+    m, A = adam_train(loss, len(x))
+    post = agp.posterior(agp.SparseVariationalApproximation(f(x, jitter), agp.MvNormal(m, chol_lower=A)))
+    mu, cov = agp.mean_and_cov(post, x)
+    mu_e, cov_e = exact_gpr(x, y, variance, inv_ls, noise)
+    assert np.max(np.abs(mu - mu_e)) < 1e-4 and np.max(np.abs(cov - cov_e)) < 1e-4

@@ -169,3 +169,24 @@ def test_num_data_rescaling_and_chunking():
     v1, g1 = osv.elbo_and_grad(s, p["X"], p["y"], lik, ex, num_data=3000)
     v2, g2 = osv.elbo_and_grad(s, p["X"], p["y"], lik, ex, num_data=3000, chunk=64)
     assert np.isclose(v1, v2, rtol=1e-13) and rel_err(g1.Z, g2.Z) < 1e-11 and rel_err(g1.Lq, g2.Lq) < 1e-11
+
+
+def test_optimised_posterior_matches_gpr():
+    """test/SVA...:136-186 with the oracle's ELBO and gradient driving Flux.Adam(1e-3) for 20 000 steps: atol 1e-4 (:184-185)."""
+    from _train import adam_train, exact_gpr, problem
+
+    x, y, variance, inv_ls, noise, jitter = problem()
+    k = ok.Kernel("se", variance, np.array([inv_ls]))
+    lik = ol.Likelihood("gaussian", noise)
+
+    def f(m, A):
+        v, g = osv.elbo_and_grad(osv.SVGP(k, x, m, A, jitter=jitter), x, y, lik)
+        return -v, -g.m, -g.Lq
+
+    from threadpoolctl import threadpool_limits
+
+    with threadpool_limits(limits=1):  # 20 x 20 matrices: BLAS threading only adds overhead
+        m, A = adam_train(f, len(x))
+    mu, cov = osv.mean_and_cov(osv.SVGP(k, x, m, A, jitter=jitter), x)
+    mu_e, cov_e = exact_gpr(x, y, variance, inv_ls, noise)
+    assert np.max(np.abs(mu - mu_e)) < 1e-4 and np.max(np.abs(cov - cov_e)) < 1e-4
