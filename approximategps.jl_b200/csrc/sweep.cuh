@@ -612,8 +612,8 @@ __global__ void __launch_bounds__(256, (DMAX <= 8 && RW == 1) ? 2 : 1) kgrad_ker
       }
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      const int p = lane + 32 * i;
-      if (p >= cnt) continue;
+      const int p = lane + 32 * i;  // rows >= cnt of the tile are zero and their Kb was loaded as 0: no branch needed, so that
+                                    // the eight points of a lane form one basic block and their exp / FMA chains interleave
       const double* xr = kg_smem + p * Sx;
       double xs[DMAX];
 #pragma unroll
