@@ -229,10 +229,10 @@ def test_split_phase_api_equals_fused_call(agp):
     ds.close()
 
 
-@pytest.mark.parametrize("N", [37888, 37889, 75841])
+@pytest.mark.parametrize("N", [37888, 151552, 151553, 303169])
 def test_real_chunk_boundaries(agp, N):
-    """The sweep processes 37 888 points (two waves of 64-point tiles) per launch group: N equal to one chunk, one point more,
-    and two chunks plus a ragged tail must accumulate exactly like the oracle's single pass."""
+    """The sweep processes up to 151 552 points (eight waves of 64-point tiles) per launch group: N equal to one chunk, one point
+    more, and two chunks plus a ragged tail must accumulate exactly like the oracle's single pass."""
     p = make_problem(seed=51, kind="matern52", N=N, M=24, D=2, lik="poisson_exp")
     _run_case(agp, p, num_data=1e6)
 
