@@ -9,11 +9,11 @@
 namespace agp {
 
 // zs = s (.) z, zn = |zs|^2 ; rows >= M are zero.  z is point-major [M][D].  zsp (optional) is the padded copy the
-// Kuf generator streams: row = [zs_0 .. zs_{D-1}, 0.., zn, 0] with Dp + 2 doubles, Dp = D rounded up to 2.
+// Kuf generator streams: row = [zs_0 .. zs_{D-1}, 0.., zn, 0] with kuf_dp(D) + 2 doubles.
 __global__ void prep_z_kernel(const double* z, double* zs, double* zn, double* zsp, int Mp, KernelParams kp) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= Mp) return;
-  const int Dp = (kp.D + 1) & ~1, Sx = Dp + 2;
+  const int Dp = kuf_dp(kp.D), Sx = Dp + 2;
   double s = 0.0;
   for (int d = 0; d < kp.D; d++) {
     const double v = (row < kp.M) ? z[(int64_t)row * kp.D + d] * kp.s[d] : 0.0;

@@ -22,6 +22,10 @@ struct KernelParams {
   double s[MAXD];  // per-dimension input scale (ScaleTransform replicated, or ARDTransform)
 };
 
+// Padded row width of the operands of the Kuf generator: Dq = D rounded up to 4 (one DMMA k-step); a padded row is
+// [v_0 .. v_{D-1}, 0.., |v|^2, 0] with Dq + 2 doubles (16-byte aligned rows).
+__host__ __device__ __forceinline__ int kuf_dp(int D) { return (D + 3) & ~3; }
+
 // kappa(u): u = squared distance of the scaled inputs (stationary) or their dot product (linear)
 __device__ __forceinline__ double kappa(int kind, double u, double c) {
   if (kind == AGP_KERNEL_SE) return exp(-0.5 * u);

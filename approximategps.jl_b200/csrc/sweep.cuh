@@ -67,60 +67,65 @@ struct StepIter {
   }
 };
 
-// Padded widths used by the Kuf generator: Dp = D rounded up to 2 (16-byte vector loads); a z row of the padded
-// copy `zsp` is [zs_0 .. zs_{D-1}, 0.., |zs|^2, 0] (Dz = Dp + 2 doubles), an x row in shared memory is
-// [xs_0 .. xs_{D-1}, 0.., |xs|^2, 0] (Sx = Dp + 2 doubles: 16-byte aligned and conflict-free for LDS.128).
-__host__ __device__ __forceinline__ int kuf_dp(int D) { return (D + 1) & ~1; }
-
-// Kuf rows [row0, row0+16) x the CTA's 64 points, written as a B-operand stage tile.  Thread (l, c) = (tid / 16,
-// tid % 16) produces row l, columns c + 16 j: the z row is read once (broadcast LDS.128) for its 4 elements.
+// Kuf rows [row0, row0+16) x the CTA's 64 points, written as a B-operand stage tile.  The 16 x 64 scaled dot products
+// z_l . x_n run on the tensor pipe: warp w owns the 8 columns 8w..8w+7 and both 8-row halves, i.e. two m8n8k4 DMMA tiles
+// with ceil(D/4) k-steps each, fed straight from the padded z slab (A fragments) and x rows (B fragments); the
+// ||x||^2 + ||z||^2 - 2 x.z combination, the clamp and kappa are applied to the accumulator fragment, which is stored
+// as double2.  (Padded rows: kfun.cuh kuf_dp.)
 template <bool SCALED>
 __device__ __forceinline__ void gen_kuf_tile(double* __restrict__ sB, const double* __restrict__ sZ, const double* __restrict__ xs, int row0,
-                                             const KernelParams& kp, int tid, const double* rowscale, const double* dvec, double (&pkd)[4]) {
+                                             const KernelParams& kp, int warp, int lane, const double* rowscale, const double* dvec, double (&pkd)[2]) {
 #ifdef AGP_EXP_NOGEN
   return;  // timing experiment only (tools/s1_experiments.sh): results are garbage
 #endif
-  const int l = tid >> 4, c = tid & 15;
-  const int D = kp.D, kind = kp.kind, Dp = kuf_dp(D), Sx = Dp + 2;
-  const double* z = sZ + l * Sx;
-  const double* x0 = xs + c * Sx;
-  double u[4];
+  const int g = lane >> 2, t = lane & 3;
+  const int D = kp.D, kind = kp.kind, Dq = kuf_dp(D), Sx = Dq + 2;
+  const int c0 = warp * 8 + 2 * t;  // this thread's two columns
+  const double* z0 = sZ + g * Sx;   // its two rows: g and g + 8
+  const double* z1 = z0 + 8 * Sx;
+  const double* xa = xs + c0 * Sx;
+  const double* xb = xa + Sx;
+  double u[2][2];
   if (D == 1 && kind != AGP_KERNEL_LINEAR) {
-    const double z0 = z[0];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const double df = x0[j * 16 * Sx] - z0;
-      u[j] = df * df;
-    }
+    const double d00 = xa[0] - z0[0], d01 = xb[0] - z0[0], d10 = xa[0] - z1[0], d11 = xb[0] - z1[0];
+    u[0][0] = d00 * d00;
+    u[0][1] = d01 * d01;
+    u[1][0] = d10 * d10;
+    u[1][1] = d11 * d11;
   } else {
-    double dot[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int d = 0; d < Dp; d += 2) {
-      const double2 zz = *reinterpret_cast<const double2*>(z + d);
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const double2 xx = *reinterpret_cast<const double2*>(x0 + j * 16 * Sx + d);
-        dot[j] = fma(xx.y, zz.y, fma(xx.x, zz.x, dot[j]));
-      }
+    double acc0[2] = {0.0, 0.0}, acc1[2] = {0.0, 0.0};
+    const double* xf = xs + (warp * 8 + g) * Sx + t;  // B fragment: column 8w + g, k = t
+    for (int k = 0; k < Dq; k += 4) {
+      const double b = xf[k];
+      dmma884(acc0, z0[k + t], b);
+      dmma884(acc1, z1[k + t], b);
     }
-    const double zn = z[Dp];
-#pragma unroll
-    for (int j = 0; j < 4; j++) u[j] = u_from_dot(kind, x0[j * 16 * Sx + Dp], zn, dot[j]);
-  }
-  const bool valid = row0 + l < kp.M;
-  double rsc = 1.0, dv = 0.0;
-  if (SCALED) {
-    rsc = rowscale[row0 + l];
-    dv = dvec[row0 + l];
+    const double xna = xa[Dq], xnb = xb[Dq], zn0 = z0[Dq], zn1 = z1[Dq];
+    u[0][0] = u_from_dot(kind, xna, zn0, acc0[0]);
+    u[0][1] = u_from_dot(kind, xnb, zn0, acc0[1]);
+    u[1][0] = u_from_dot(kind, xna, zn1, acc1[0]);
+    u[1][1] = u_from_dot(kind, xnb, zn1, acc1[1]);
   }
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
+  for (int h = 0; h < 2; h++) {
+    const int row = row0 + g + 8 * h;
+    const bool valid = row < kp.M;
+    double v0, v1;
 #ifdef AGP_EXP_NOEXP
-    const double v = valid ? kp.variance * u[j] : 0.0;  // timing experiment only
+    v0 = valid ? kp.variance * u[h][0] : 0.0;  // timing experiment only
+    v1 = valid ? kp.variance * u[h][1] : 0.0;
 #else
-    const double v = valid ? kp.variance * kappa(kind, u[j], kp.c) : 0.0;
+    v0 = valid ? kp.variance * kappa(kind, u[h][0], kp.c) : 0.0;
+    v1 = valid ? kp.variance * kappa(kind, u[h][1], kp.c) : 0.0;
 #endif
-    if (SCALED) pkd[j] = fma(v, dv, pkd[j]);
-    sB[l * BTile<B_KN>::ld + c + 16 * j] = SCALED ? v * rsc : v;
+    if (SCALED) {
+      const double dv = dvec[row], rsc = rowscale[row];
+      pkd[0] = fma(v0, dv, pkd[0]);
+      pkd[1] = fma(v1, dv, pkd[1]);
+      v0 *= rsc;
+      v1 *= rsc;
+    }
+    *reinterpret_cast<double2*>(sB + (g + 8 * h) * BTile<B_KN>::ld + c0) = make_double2(v0, v1);
   }
 }
 
@@ -142,7 +147,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
 
   if (FWD) {
     // ---- stage the X tile: TMA bulk copy into the (still unused) first pipeline stage, then scale into xs rows
-    const int D = a.kp.D, Dp = kuf_dp(D);
+    const int D = a.kp.D, Dq = kuf_dp(D);
     const int nvalid = max(0, min(BN, a.npts - n0));
     double* raw = smem;  // 64 * D doubles <= one stage
     const double* src = a.pts + (int64_t)n0 * D;
@@ -171,12 +176,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
         nrm = fma(v, v, nrm);
       }
       for (int d = D; d < Sx; d++) xs[tid * Sx + d] = 0.0;
-      xs[tid * Sx + Dp] = nrm;
+      xs[tid * Sx + Dq] = nrm;
     }
     __syncthreads();  // raw (stage 0) may be overwritten from here on
   }
 
-  double pkd[4] = {0.0, 0.0, 0.0, 0.0};  // SCALED: partial k' * dvec of this thread's 4 columns
+  double pkd[2] = {0.0, 0.0};  // SCALED: partial k' * dvec of this thread's 2 columns
   StepIter it_issue, it_cons, it_gen;
   it_issue.init(MODE != TR_RHS_BWD, a.nb);
   it_cons.init(MODE != TR_RHS_BWD, a.nb);
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
   };
   auto gen = [&](int slot) {  // it_gen describes the stage living in `slot`
     double* st = smem + slot * stage_elems;
-    gen_kuf_tile<SCALED>(st + Cfg::a_elems, st + Cfg::elems, xs, it_gen.J * BM + it_gen.kk * BK, a.kp, tid, a.rowscale, a.dvec, pkd);
+    gen_kuf_tile<SCALED>(st + Cfg::a_elems, st + Cfg::elems, xs, it_gen.J * BM + it_gen.kk * BK, a.kp, tm.warp, tm.lane, a.rowscale, a.dvec, pkd);
   };
 
   Acc acc;
@@ -292,15 +297,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
       a.sam[n0 + tid] = ((sred[256 + tid] + sred[320 + tid]) + sred[384 + tid]) + sred[448 + tid];
     }
     if (SCALED) {
-      // thread (l, c) = (tid / 16, tid % 16) holds the partial sums of columns c + 16 j over its rows l, l + 16, ...
-      __syncthreads();
+      // a thread holds the partial sums of columns 8 warp + 2 t + {0, 1} over its rows: reduce over g; no other warp
+      // touches these columns
 #pragma unroll
-      for (int j = 0; j < 4; j++) sred[(tid >> 4) * 64 + (tid & 15) + 16 * j] = pkd[j];
-      __syncthreads();
-      if (tid < BN) {
-        double acc = 0.0;
-        for (int l = 0; l < 16; l++) acc += sred[l * 64 + tid];
-        a.skd[n0 + tid] = acc;
+      for (int e = 0; e < 2; e++) {
+        double v = pkd[e];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (tm.g == 0) a.skd[n0 + tm.warp * 8 + 2 * tm.t + e] = v;
       }
     }
   }
