@@ -452,7 +452,8 @@ static int32_t run_gemm(agp_ctx* c, int tiles_m, int tiles_n, const double* A, i
   OK((ensure_smem<gemm_kernel<LA, LB, Epi>>(c, Cfg::smem_bytes)));
   dim3 grid(tiles_m, tiles_n);
   if ((kmode == KR_LOWER || kmode == KR_UPPER) && tmode == TS_ALL && tiles_m > 1) {
-    g.swizzle = std::max(1, c->sms);  // half a wave of column tiles per super-group
+    static const int env_g = getenv("AGP_SWIZZLE") ? atoi(getenv("AGP_SWIZZLE")) : 0;  // tuning knob
+    g.swizzle = env_g > 0 ? env_g : std::max(1, c->sms);  // half a wave of column tiles per super-group
     g.tiles_m = tiles_m;
     g.tiles_n = tiles_n;
     grid = dim3(tiles_m * tiles_n, 1);
