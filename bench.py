@@ -48,10 +48,9 @@ UNIT = "points/s"
 FP64_PEAK_TFLOPS_DMMA = 37.1
 FP64_PEAK_TFLOPS_DGEMM = 35.5
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the sweep kernels at the C4 chunk shape (M = 1024, D = 8, 37 888 points per
-# launch), from the `ncu --set full` captures summarised in profiles/r01c_ncu_full_summary.txt and profiles/r01q_ncu_full_trsm_kuf_fwd.txt
-NCU_TRAFFIC_BYTES_C4 = {"trsm_kuf_fwd": 449.2e6 + 330.5e6, "gemm_BtA": 318.6e6 + 281.2e6, "trsm_bwd": 607.4e6 + 267.6e6, "syrk_G": 712.4e6 + 14.7e6,
-                        "kgrad": 316.0e6 + 8.1e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the sweep kernels at the C4 chunk shape (M = 1024, D = 8, 151 552 points per
+# launch), from the `ncu --set full` captures summarised in profiles/r01x_ncu_full_summary.txt
+NCU_TRAFFIC_BYTES_C4 = {"trsm_kuf_fwd": 1.753e9 + 1.336e9, "gemm_BC": 4.599e9 + 2.476e9}
 
 WORKLOADS = {
     # BASELINE.json configs[3] (the configuration `metric` is quoted on)
@@ -378,7 +377,7 @@ def main():
         achieved = cf[dom] * n_local * args.steps / (dms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": FP64_PEAK_TFLOPS_DMMA, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS_DMMA,
                 "traffic": NCU_TRAFFIC_BYTES_C4.get(dom) if (args.workload == "c4" and not args.n) else None,
-                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01q_ncu_full_trsm_kuf_fwd.txt)",
+                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01x_ncu_full_summary.txt)",
                 "alg_bytes_per_launch": (8.0 * (D + 1) + 8.0 * M) * (n_local * args.steps / dcnt) if dom == "trsm_kuf_fwd" else None,
                 "avg_launch_ms": dms / dcnt, "alg_flop_per_launch": cf[dom] * n_local * args.steps / dcnt,
                 "peak_source": "measured FP64 DMMA issue peak on this pool's B200 (profiles/r01_fp64_peak.jsonl; cuBLAS DGEMM 8192^3 = 35.5); MEASURED_PEAKS.json has no FP64 entry",
