@@ -113,15 +113,9 @@ __global__ void __launch_bounds__(256) trsv_fwd_step_kernel(const double* L, con
   {
     const double* inv = Linv + (int64_t)J * 128 * ld + (int64_t)J * 128;
     const double* bj = b + (int64_t)J * 128;
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;  // independent chains: 16 loads in flight per thread
-#pragma unroll 4
-    for (int k = h * 64; k < h * 64 + 64; k += 4) {
-      acc0 = fma(inv[i + (int64_t)k * ld], bj[k], acc0);
-      acc1 = fma(inv[i + (int64_t)(k + 1) * ld], bj[k + 1], acc1);
-      acc2 = fma(inv[i + (int64_t)(k + 2) * ld], bj[k + 2], acc2);
-      acc3 = fma(inv[i + (int64_t)(k + 3) * ld], bj[k + 3], acc3);
-    }
-    part[tid] = (acc0 + acc1) + (acc2 + acc3);
+    double acc = 0.0;
+    for (int k = h * 64; k < h * 64 + 64; k++) acc = fma(inv[i + (int64_t)k * ld], bj[k], acc);
+    part[tid] = acc;
     __syncthreads();
     if (tid < 128) xj[tid] = part[tid] + part[tid + 128];
     __syncthreads();
@@ -132,15 +126,9 @@ __global__ void __launch_bounds__(256) trsv_fwd_step_kernel(const double* L, con
   }
   const int64_t r = (int64_t)(J + blockIdx.x) * 128 + i;
   const double* Lp = L + (int64_t)J * 128 * ld + r;
-  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-#pragma unroll 4
-  for (int k = h * 64; k < h * 64 + 64; k += 4) {
-    acc0 = fma(Lp[(int64_t)k * ld], xj[k], acc0);
-    acc1 = fma(Lp[(int64_t)(k + 1) * ld], xj[k + 1], acc1);
-    acc2 = fma(Lp[(int64_t)(k + 2) * ld], xj[k + 2], acc2);
-    acc3 = fma(Lp[(int64_t)(k + 3) * ld], xj[k + 3], acc3);
-  }
-  part[tid] = (acc0 + acc1) + (acc2 + acc3);
+  double acc = 0.0;
+  for (int k = h * 64; k < h * 64 + 64; k++) acc = fma(Lp[(int64_t)k * ld], xj[k], acc);
+  part[tid] = acc;
   __syncthreads();
   if (tid < 128) b[r] -= part[tid] + part[tid + 128];
 }
@@ -154,15 +142,9 @@ __global__ void __launch_bounds__(256) trsv_bwd_step_kernel(const double* L, con
   {
     const double* inv = LinvT + (int64_t)J * 128 * ld + (int64_t)J * 128;
     const double* bj = b + (int64_t)J * 128;
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;  // independent chains: 16 loads in flight per thread
-#pragma unroll 4
-    for (int k = h * 64; k < h * 64 + 64; k += 4) {
-      acc0 = fma(inv[i + (int64_t)k * ld], bj[k], acc0);
-      acc1 = fma(inv[i + (int64_t)(k + 1) * ld], bj[k + 1], acc1);
-      acc2 = fma(inv[i + (int64_t)(k + 2) * ld], bj[k + 2], acc2);
-      acc3 = fma(inv[i + (int64_t)(k + 3) * ld], bj[k + 3], acc3);
-    }
-    part[tid] = (acc0 + acc1) + (acc2 + acc3);
+    double acc = 0.0;
+    for (int k = h * 64; k < h * 64 + 64; k++) acc = fma(inv[i + (int64_t)k * ld], bj[k], acc);
+    part[tid] = acc;
     __syncthreads();
     if (tid < 128) xj[tid] = part[tid] + part[tid + 128];
     __syncthreads();
@@ -174,7 +156,6 @@ __global__ void __launch_bounds__(256) trsv_bwd_step_kernel(const double* L, con
   const int warp = tid >> 5, lane = tid & 31;
   const int c0 = (blockIdx.x - 1) * 128 + warp * 16;
   const double x0 = xj[lane], x1 = xj[lane + 32], x2 = xj[lane + 64], x3 = xj[lane + 96];
-#pragma unroll 8
   for (int cc = 0; cc < 16; cc++) {
     const int c = c0 + cc;
     const double* Lp = L + (int64_t)c * ld + (int64_t)J * 128;
@@ -183,6 +164,94 @@ __global__ void __launch_bounds__(256) trsv_bwd_step_kernel(const double* L, con
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) b[c] -= acc;
   }
+}
+
+// ---- single-launch blocked triangular solves (one CTA per 128-block, flag-chained) ------------------------------
+// CTA J accumulates  b_J - sum_{L before J} (block J,L) x_L  as the x_L are published, applies the inverse diagonal
+// block and publishes x_J.  A CTA only ever waits for CTAs with a smaller block index, which the hardware schedules
+// first, so the chain cannot deadlock; `epoch` distinguishes successive solves without clearing the flags.
+__device__ __forceinline__ void trsv_wait(volatile int* flag, int epoch) {
+  if (threadIdx.x == 0) {
+    while (*flag != epoch) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void trsv_publish(int* flag, int epoch) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicExch(flag, epoch);
+}
+
+// L x = b.  Linv: inverse diagonal blocks (column-major).  grid = nb, block = 256.
+__global__ void __launch_bounds__(256) trsv_fwd_chain_kernel(const double* L, const double* Linv, int64_t ld, const double* b, double* x, int* flags,
+                                                             int epoch) {
+  __shared__ double xs[128];
+  __shared__ double part[256];
+  const int J = blockIdx.x, tid = threadIdx.x, i = tid & 127, h = tid >> 7;
+  double acc = 0.0;
+  for (int Lb = 0; Lb < J; Lb++) {
+    // the block of L does not depend on x: fetch it before waiting
+    const double* Lp = L + (int64_t)(Lb * 128 + h * 64) * ld + (int64_t)J * 128 + i;
+    double lv[64];
+#pragma unroll
+    for (int k = 0; k < 64; k++) lv[k] = __ldg(Lp + (int64_t)k * ld);
+    trsv_wait(flags + Lb, epoch);
+    if (tid < 128) xs[tid] = __ldcg(x + (int64_t)Lb * 128 + tid);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 64; k++) acc = fma(lv[k], xs[h * 64 + k], acc);
+    __syncthreads();  // xs is rewritten in the next round
+  }
+  part[tid] = acc;
+  __syncthreads();
+  if (tid < 128) xs[tid] = b[(int64_t)J * 128 + tid] - (part[tid] + part[tid + 128]);
+  __syncthreads();
+  const double* inv = Linv + (int64_t)J * 128 * ld + (int64_t)J * 128;
+  double a2 = 0.0;
+  for (int k = h * 64; k < h * 64 + 64; k++) a2 = fma(inv[i + (int64_t)k * ld], xs[k], a2);
+  part[tid] = a2;
+  __syncthreads();
+  if (tid < 128) x[(int64_t)J * 128 + tid] = part[tid] + part[tid + 128];
+  trsv_publish(flags + J, epoch);
+}
+
+// L^T x = b.  LinvT: inverse-transposed diagonal blocks.  Block J = nb-1-blockIdx.x waits for the blocks after it.
+__global__ void __launch_bounds__(256) trsv_bwd_chain_kernel(const double* L, const double* LinvT, int64_t ld, int nb, const double* b, double* x, int* flags,
+                                                             int epoch) {
+  __shared__ double xs[128];
+  __shared__ double part[256];
+  __shared__ double colacc[128];
+  const int J = nb - 1 - blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, i = tid & 127, h = tid >> 7;
+  if (tid < 128) colacc[tid] = 0.0;
+  for (int Lb = nb - 1; Lb > J; Lb--) {
+    trsv_wait(flags + Lb, epoch);
+    if (tid < 128) xs[tid] = __ldcg(x + (int64_t)Lb * 128 + tid);
+    __syncthreads();
+    const double x0 = xs[lane], x1 = xs[lane + 32], x2 = xs[lane + 64], x3 = xs[lane + 96];
+    // (block Lb,J)^T x_Lb: column c of the block is contiguous over the rows; one warp handles 16 columns
+#pragma unroll 4
+    for (int cc = 0; cc < 16; cc++) {
+      const int c = warp * 16 + cc;
+      const double* Lp = L + (int64_t)(J * 128 + c) * ld + (int64_t)Lb * 128;
+      double acc = fma(Lp[lane], x0, fma(Lp[lane + 32], x1, fma(Lp[lane + 64], x2, Lp[lane + 96] * x3)));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) colacc[c] += acc;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (tid < 128) xs[tid] = b[(int64_t)J * 128 + tid] - colacc[tid];
+  __syncthreads();
+  const double* inv = LinvT + (int64_t)J * 128 * ld + (int64_t)J * 128;
+  double a2 = 0.0;
+  for (int k = h * 64; k < h * 64 + 64; k++) a2 = fma(inv[i + (int64_t)k * ld], xs[k], a2);
+  part[tid] = a2;
+  __syncthreads();
+  if (tid < 128) x[(int64_t)J * 128 + tid] = part[tid] + part[tid + 128];
+  trsv_publish(flags + J, epoch);
 }
 
 // ---- small vector kernels ------------------------------------------------------------------------------
