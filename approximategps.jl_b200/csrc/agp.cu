@@ -112,7 +112,7 @@ struct SvgpState {
   int want_grad = 0;
   KernelParams kp;
   LikParams lp;
-  std::vector<double> h_m, h_Lq;  // padded host copies (Lq column-major Mp x Mp)
+  std::vector<double> h_m;  // padded host copy of m
 };
 
 // Optional per-kernel-class timing with CUDA events on the context's stream (agp_ctx_profile*):
@@ -550,15 +550,24 @@ static int32_t build_block_scaled(agp_ctx* c, const double* L, double* Lt, doubl
 // ---------------------------------------------------------------------------------------------------
 // small element-wise kernels of the SVGP epilogue
 // ---------------------------------------------------------------------------------------------------
-// out[0] = KL(q || p) from (mt, Bt row-major, Lk, Lq), cf. SVA.jl:362-373 (see DESIGN.md for the whitened form)
-__global__ void __launch_bounds__(256) kl_kernel(const double* mt, const double* Bt_cm, const double* Lk, const double* Lq, int M,
-                                                 int Mp, int centered, double* out) {
+// KL(q || p) from (mt, Bt, Lk, Lq), cf. SVA.jl:362-373 (DESIGN.md section 2 for the whitened form):
+//   0.5 (|Bt|_F^2 + |mt|^2 - M) + sum log diag Lk [centered] - sum log diag Lq
+// Stage 1: per-block partial sums of |Bt|_F^2 (fixed order); stage 2: one block adds the O(M) terms.
+__global__ void __launch_bounds__(256) kl_partial_kernel(const double* Bt_cm, int64_t n, double* part) {
   __shared__ double sred[8];
-  double tr = 0.0, mm = 0.0, ldq = 0.0, ldk = 0.0;
-  for (int64_t i = threadIdx.x; i < (int64_t)Mp * Mp; i += blockDim.x) {
+  double tr = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double b = Bt_cm[i];
     tr = fma(b, b, tr);
   }
+  const double r = block_sum(tr, sred);
+  if (threadIdx.x == 0) part[blockIdx.x] = r;
+}
+__global__ void __launch_bounds__(256) kl_kernel(const double* mt, const double* part, int nparts, const double* Lk, const double* Lq, int M, int Mp,
+                                                 int centered, double* out) {
+  __shared__ double sred[8];
+  double tr = 0.0, mm = 0.0, ldq = 0.0, ldk = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) tr += part[i];
   for (int j = threadIdx.x; j < M; j += blockDim.x) {
     mm = fma(mt[j], mt[j], mm);
     ldq += log(Lq[(int64_t)j * Mp + j]);
@@ -569,6 +578,12 @@ __global__ void __launch_bounds__(256) kl_kernel(const double* mt, const double*
   const double q = block_sum(ldq, sred);
   const double k = block_sum(ldk, sred);
   if (threadIdx.x == 0) out[0] = 0.5 * (a + b - (double)M) + k - q;
+}
+// zero the strict upper triangle and everything outside the leading M x M block of a column-major Mp x Mp matrix
+__global__ void tril_pad_kernel(double* A, int M, int Mp) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x, cidx = blockIdx.y;
+  if (r >= Mp) return;
+  if (r < cidx || r >= M || cidx >= M) A[(int64_t)cidx * Mp + r] = 0.0;
 }
 
 // dLq (column-major M x M, ld = M) from the row-major Mp x Mp cotangent Xrm (lower part used):
@@ -696,17 +711,19 @@ static int32_t prepare_step(agp_ctx* c, const agp_svgp_params* p) {
   // host staging: padded m and Lq (lower triangle only)
   st.h_m.assign(Mp, 0.0);
   for (int i = 0; i < M; i++) st.h_m[i] = p->m[i];
-  st.h_Lq.assign(MM, 0.0);
   const int ldq = p->ldLq > 0 ? p->ldLq : M;
   for (int j = 0; j < M; j++)
-    for (int i = j; i < M; i++) st.h_Lq[(int64_t)j * Mp + i] = p->Lq[(int64_t)j * ldq + i];
-  for (int j = 0; j < M; j++)
-    if (!(st.h_Lq[(int64_t)j * Mp + j] > 0.0))
+    if (!(p->Lq[(int64_t)j * ldq + j] > 0.0))
       return fail(AGP_ERR_DOMAIN, "q.Sigma Cholesky factor has a non-positive diagonal entry at %d (logdet would throw)", j + 1);
   CU(cudaMemsetAsync(c->z.p, 0, sizeof(double) * Mp * D, c->stream));
   CU(cudaMemcpyAsync(c->z.p, p->Z, sizeof(double) * M * D, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->mvec.p, st.h_m.data(), sizeof(double) * Mp, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->Lq.p, st.h_Lq.data(), sizeof(double) * MM, cudaMemcpyHostToDevice, c->stream));
+  // Lq: straight from the caller's matrix into the leading M x M block (no host staging of M^2 doubles), then the strict
+  // upper triangle and the padding are zeroed on the device (LowerTriangular(A) view, utils.jl:18)
+  CU(cudaMemcpy2DAsync(c->Lq.p, sizeof(double) * Mp, p->Lq, sizeof(double) * ldq, sizeof(double) * M, M, cudaMemcpyHostToDevice, c->stream));
+  tril_pad_kernel<<<dim3((Mp + 127) / 128, Mp), 128, 0, c->stream>>>(c->Lq.p, M, Mp);
+  LAUNCHED(c);
+  KCHECK();
   if (st.lp.ngh > 0) {
     CU(cudaMemcpyToSymbolAsync(c_gh_x, p->expect.nodes, sizeof(double) * st.lp.ngh, 0, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyToSymbolAsync(c_gh_w, p->expect.weights, sizeof(double) * st.lp.ngh, 0, cudaMemcpyHostToDevice, c->stream));
@@ -751,6 +768,19 @@ static int32_t prepare_step(agp_ctx* c, const agp_svgp_params* p) {
     OK(transpose(c, c->Bt_rm.p, c->Bt_cm.p, Mp, Mp));
   }
   st.valid = true;
+  return AGP_OK;
+}
+
+static int32_t run_kl(agp_ctx* c, double* out) {
+  const SvgpState& st = c->st;
+  const int nparts = 128;
+  double* part = c->vec64.p;  // [Mp*64] right-hand-side scratch, free at this point
+  kl_partial_kernel<<<nparts, 256, 0, c->stream>>>(c->Bt_cm.p, (int64_t)st.Mp * st.Mp, part);
+  LAUNCHED(c);
+  KCHECK();
+  kl_kernel<<<1, 256, 0, c->stream>>>(c->mt.p, part, nparts, c->Lk.p, c->Lq.p, st.M, st.Mp, st.centered ? 1 : 0, out);
+  LAUNCHED(c);
+  KCHECK();
   return AGP_OK;
 }
 
@@ -1067,9 +1097,7 @@ extern "C" int32_t agp_svgp_finish(agp_ctx* c, double* elbo_out, agp_svgp_grads*
   RedLayout rl(Mp, D);
   double* red = c->red.p;
   double* small = c->small.p;  // [0] KL, [1] sum(mbar) (centered)
-  kl_kernel<<<1, 256, 0, c->stream>>>(c->mt.p, c->Bt_cm.p, c->Lk.p, c->Lq.p, M, Mp, st.centered ? 1 : 0, small);
-  LAUNCHED(c);
-  KCHECK();
+  OK(run_kl(c, small));
   std::vector<double> h_scal(NSC), h_small(4, 0.0);
   if (!st.want_grad || !go) {
     CU(cudaMemcpyAsync(h_scal.data(), red + rl.scal, sizeof(double) * NSC, cudaMemcpyDeviceToHost, c->stream));
@@ -1234,10 +1262,7 @@ extern "C" int32_t agp_svgp_elbo(agp_ctx* c, agp_dataset* ds, int64_t offset, in
 extern "C" int32_t agp_svgp_prior_kl(agp_ctx* c, const agp_svgp_params* p, double* kl_out) {
   if (!c || !p || !kl_out) return fail(AGP_ERR_INVALID, "agp_svgp_prior_kl: NULL argument");
   OK(prepare_step(c, p));
-  SvgpState& st = c->st;
-  kl_kernel<<<1, 256, 0, c->stream>>>(c->mt.p, c->Bt_cm.p, c->Lk.p, c->Lq.p, st.M, st.Mp, st.centered ? 1 : 0, c->small.p);
-  LAUNCHED(c);
-  KCHECK();
+  OK(run_kl(c, c->small.p));
   CU(cudaMemcpyAsync(kl_out, c->small.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   return check_step_flags(c, false);
 }
