@@ -594,6 +594,17 @@ def cov(post, x, y=None):
     return out
 
 
+def marginals(post, x, jitter: float = 1e-18):
+    """``marginals(f_post(x))`` (AbstractGPs; used at SVA.jl:354): the parameters ``(mu, sigma)`` of
+    ``Normal.(mean, sqrt.(var .+ jitter))`` with AbstractGPs' default ``f_post(x)`` jitter of 1e-18."""
+    mu, v = mean_and_var(post, x)
+    if np.any(v + jitter < 0):
+        from ._lib import DomainError, ERR_DOMAIN
+
+        raise DomainError(ERR_DOMAIN, "DomainError: sqrt of a negative marginal variance")
+    return mu, np.sqrt(v + jitter)
+
+
 def mean(post, x):
     return mean_and_var(post, x)[0]
 
