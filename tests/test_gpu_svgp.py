@@ -263,3 +263,8 @@ def test_optimised_posterior_matches_gpr(agp):
     mu, cov = agp.mean_and_cov(post, x)
     mu_e, cov_e = exact_gpr(x, y, variance, inv_ls, noise)
     assert np.max(np.abs(mu - mu_e)) < 1e-4 and np.max(np.abs(cov - cov_e)) < 1e-4
+
+
+def test_m4096(agp):
+    """32 diagonal blocks: 8 Cholesky super-panels, SYRK without K-split, 1056 lower tiles."""
+    _run_case(agp, make_problem(seed=55, kind="matern52", N=3000, M=4096, D=4, lik="poisson_exp", zdist="random", lengthscale=1.0), num_data=1e6)
