@@ -232,7 +232,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, default=0, help="override the number of points (debugging only; the line says so)")
+    ap.add_argument("--points", "--n", dest="n", type=int, default=0, help="override the number of points (debugging only; the line says so)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -243,7 +243,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args, w)
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("AGP_NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line only
+    # one JSON line only on stdout: NCCL prints its version banner there for any NCCL_DEBUG level >= VERSION (WARN included)
+    if "AGP_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["AGP_NCCL_DEBUG"]
+    else:
+        os.environ.pop("NCCL_DEBUG", None)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
 

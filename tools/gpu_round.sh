@@ -8,5 +8,5 @@ grep -E "passed|failed|EXIT" gpurun_out/${tag}_tests.log | tail -5
 timeout 1200 python bench.py "$@" > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
 tail -c 6000 gpurun_out/${tag}_bench.json; tail -5 gpurun_out/${tag}_bench.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${tag}_launches.csv \
-  python bench.py --n 600000 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1; echo "ncu rc=$?"
+  python bench.py --points 600000 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1; echo "ncu rc=$?"
 wc -l gpurun_out/${tag}_launches.csv

@@ -11,7 +11,7 @@ done
 wait
 if [ "$1" = "run" ]; then
   for v in BASE NOGEN NOEXP WAIT2; do
-    AGP_B200_LIB=$PWD/build/libagp_$v.so python bench.py --n 3000000 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
+    AGP_B200_LIB=$PWD/build/libagp_$v.so python bench.py --points 3000000 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.readline()); k=d['kernels']
 print('$v', 'S1 ms/step', round(k['trsm_kuf_fwd']['ms_per_step'],1), 'S5', round(k['trsm_bwd']['ms_per_step'],1), 'step', round(d['ms_per_step'],1))"
