@@ -388,11 +388,24 @@ def main():
                 "peak_source": "measured FP64 DMMA issue peak on this pool's B200 (profiles/r01_fp64_peak.jsonl; cuBLAS DGEMM 8192^3 = 35.5); MEASURED_PEAKS.json has no FP64 entry",
                 "whole_step": {"alg_tflops": flops_per_point(M, D) * N_total / (ms / args.steps * 1e-3) / 1e12 / world,
                                "frac_of_fp64_peak_per_gpu": flops_per_point(M, D) * N_total / (ms / args.steps * 1e-3) / 1e12 / world / FP64_PEAK_TFLOPS_DMMA}}
+        # the HBM-facing per-point stage (S3): algorithmic bytes 8 (5 + nb) per point against the measured copy bandwidth
+        hbm_peak = None
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                hbm_peak = float(json.load(fh)["hbm_gbs"])
+        except Exception:
+            hbm_peak = 6650.0  # fallback of the profiling recipe
+        pp_ms = sweep.get("perpoint", (0.0, 0))[0] / args.steps
+        nb_blocks = (M + 127) // 128
+        pp_gbs = 8.0 * (5 + nb_blocks) * n_local / (pp_ms * 1e-3) / 1e9 if pp_ms > 0 else None
+        per_point = {"bound": "hbm", "ms_per_step": pp_ms, "alg_bytes_per_point": 8.0 * (5 + nb_blocks), "achieved": pp_gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": pp_gbs / hbm_peak if pp_gbs else None,
+                     "note": "two ~10 us launches per 151 552-point chunk (perpoint + fixed-order scalar reduce): launch-latency-bound, 0.1 % of the step"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": w["label"], "N": N_total, "M": M, "D": D, "points_per_rank": n_local, "parallelism": f"dp{world} (N-sharded, 1 ncclAllReduce/step)",
                            "l2": "no flush needed: every step streams the X shard plus >1 GB of per-chunk scratch, far beyond the 126 MB L2"},
-                "elbo": val, "gpu_launches": launches, "clocks": clk, "roofline": roof, "kernels": kernels}
+                "elbo": val, "gpu_launches": launches, "clocks": clk, "roofline": roof, "per_point_stage": per_point, "kernels": kernels}
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
