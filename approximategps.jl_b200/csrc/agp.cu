@@ -983,7 +983,7 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
     pp.sc_part = c->sc_part.p;
     pp.flag = c->d_flags + 1;
     pp.predict_only = predict ? 1 : 0;
-    const int pblocks = (ncols + 255) / 256;
+    const int pblocks = (ncols + PP_POINTS_PER_BLOCK - 1) / PP_POINTS_PER_BLOCK;
     {
       ProfScope ps(c, PC_PERPOINT);
       perpoint_kernel<<<pblocks, 256, 0, c->stream>>>(pp);
@@ -1393,7 +1393,7 @@ extern "C" int32_t agp_svgp_mean_and_cov(agp_ctx* c, const agp_svgp_params* p, c
     pp.var_out = c->var_out.p;
     pp.flag = c->d_flags + 1;
     pp.predict_only = 1;
-    perpoint_kernel<<<(n1p + 255) / 256, 256, 0, c->stream>>>(pp);
+    perpoint_kernel<<<(n1p + PP_POINTS_PER_BLOCK - 1) / PP_POINTS_PER_BLOCK, 256, 0, c->stream>>>(pp);
     LAUNCHED(c);
     KCHECK();
     CU(cudaMemcpyAsync(mu1_out, c->mu_out.p, sizeof(double) * n1, cudaMemcpyDeviceToHost, c->stream));

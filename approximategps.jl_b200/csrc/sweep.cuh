@@ -400,7 +400,7 @@ struct EpiS4 {
 };
 
 // ---- S3: per-point stage -------------------------------------------------------------------------------
-constexpr int SC_E = 0, SC_DMU = 1, SC_DKXX = 2, SC_DS2 = 3, SC_DC = 4, SC_DS = 5;  // SC_DS .. SC_DS+D-1
+constexpr int SC_E = 0, SC_DMU = 1, SC_DKXX = 2, SC_DS2 = 3, SC_DC = 4, SC_DS = 5;  // SC_DS .. SC_DS+D-1 (the first five are written as a group)
 constexpr int NSC = SC_DS + MAXD;
 
 struct PerPointArgs {
@@ -426,66 +426,95 @@ struct PerPointArgs {
   int predict_only;
 };
 
+// Two consecutive points per thread (16-byte loads of the per-point operands), one fused block reduction of the five
+// scalars.  grid = ceil(ncols / PP_POINTS_PER_BLOCK).
+constexpr int PP_POINTS_PER_BLOCK = 512;
+
+__device__ __forceinline__ void perpoint_one(const PerPointArgs& p, int n, bool linear, double saa, double sam, double scc, double& E, double& dmu,
+                                             double& dvar, double& ds2, double& kxxfac) {
+  E = dmu = dvar = ds2 = 0.0;
+  kxxfac = 0.0;
+  if (n >= p.npts) return;
+  double kxx;
+  if (linear) {
+    double s = 0.0;
+    for (int d = 0; d < p.kp.D; d++) {
+      const double xs = p.pts[(int64_t)n * p.kp.D + d] * p.kp.s[d];
+      s = fma(xs, xs, s);
+    }
+    kxxfac = s + p.kp.c;
+    kxx = p.kp.variance * kxxfac;
+  } else {
+    kxxfac = 1.0;
+    kxx = p.kp.variance;
+  }
+  const double mu = p.mean_const + sam;
+  const double var0 = kxx - saa + scc;
+  if (p.mu_out) p.mu_out[n] = mu;
+  if (p.var_out) p.var_out[n] = var0;
+  if (!p.predict_only) {
+    const double var = var0 + 1e-18;  // AbstractGPs default jitter of f_post(x), SVA.jl:354
+    if (!(var > 0.0)) atomicExch(p.flag, AGP_ERR_DOMAIN);
+    expected_loglik(p.lp, mu, var, p.y[n], E, dmu, dvar, ds2);
+    dmu *= p.scale;
+    dvar *= p.scale;
+    ds2 *= p.scale;
+  }
+}
+
 __global__ void __launch_bounds__(256) perpoint_kernel(PerPointArgs p) {
-  __shared__ double sred[8];
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  double E = 0.0, dmu = 0.0, dvar = 0.0, ds2 = 0.0, kxxfac = 0.0, dc = 0.0;
+  __shared__ double sred[8][5];
+  __shared__ double sred1[8];
+  const int n0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   const bool linear = p.kp.kind == AGP_KERNEL_LINEAR;
-  if (n < p.npts) {
-    double scc = 0.0;
-    for (int j = 0; j < p.nb; j++) scc += p.scc_part[(int64_t)j * p.ldp + n];
-    double kxx;
-    if (linear) {
-      double s = 0.0;
-      for (int d = 0; d < p.kp.D; d++) {
-        const double xs = p.pts[(int64_t)n * p.kp.D + d] * p.kp.s[d];
-        s = fma(xs, xs, s);
+  double E[2], dmu[2], dvar[2], ds2[2], kf[2];
+  {
+    double2 saa = make_double2(0.0, 0.0), sam = saa, scc = saa;
+    if (n0 < p.ncols) {  // ncols is even and the operand rows are 16-byte aligned
+      saa = *reinterpret_cast<const double2*>(p.saa + n0);
+      sam = *reinterpret_cast<const double2*>(p.sam + n0);
+      for (int j = 0; j < p.nb; j++) {
+        const double2 v = *reinterpret_cast<const double2*>(p.scc_part + (int64_t)j * p.ldp + n0);
+        scc.x += v.x;
+        scc.y += v.y;
       }
-      kxxfac = s + p.kp.c;
-      kxx = p.kp.variance * kxxfac;
-    } else {
-      kxxfac = 1.0;
-      kxx = p.kp.variance;
     }
-    const double mu = p.mean_const + p.sam[n];
-    const double var0 = kxx - p.saa[n] + scc;
-    if (p.mu_out) p.mu_out[n] = mu;
-    if (p.var_out) p.var_out[n] = var0;
-    if (!p.predict_only) {
-      const double var = var0 + 1e-18;  // AbstractGPs default jitter of f_post(x), SVA.jl:354
-      if (!(var > 0.0)) atomicExch(p.flag, AGP_ERR_DOMAIN);
-      expected_loglik(p.lp, mu, var, p.y[n], E, dmu, dvar, ds2);
-      dmu *= p.scale;
-      dvar *= p.scale;
-      ds2 *= p.scale;
-      dc = dvar * p.kp.variance;
-    }
+    perpoint_one(p, n0, linear, saa.x, sam.x, scc.x, E[0], dmu[0], dvar[0], ds2[0], kf[0]);
+    perpoint_one(p, n0 + 1, linear, saa.y, sam.y, scc.y, E[1], dmu[1], dvar[1], ds2[1], kf[1]);
   }
   if (p.predict_only) return;
-  if (n < p.ncols) {
-    p.dmu[n] = dmu;
-    p.dv[n] = dvar;
+  if (n0 < p.ncols) {
+    *reinterpret_cast<double2*>(p.dmu + n0) = make_double2(dmu[0], dmu[1]);
+    *reinterpret_cast<double2*>(p.dv + n0) = make_double2(dvar[0], dvar[1]);
   }
+  // fused, fixed-order block reduction of (E, dmu, dvar * kxxfac, ds2, dc)
+  double v[5] = {E[0] + E[1], dmu[0] + dmu[1], dvar[0] * kf[0] + dvar[1] * kf[1], ds2[0] + ds2[1],
+                 linear ? (dvar[0] + dvar[1]) * p.kp.variance : 0.0};
+#pragma unroll
+  for (int q = 0; q < 5; q++)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0)
+#pragma unroll
+    for (int q = 0; q < 5; q++) sred[warp][q] = v[q];
+  __syncthreads();
   double* out = p.sc_part + (int64_t)blockIdx.x * NSC;
-  double r;
-  r = block_sum(E, sred);
-  if (threadIdx.x == 0) out[SC_E] = r;
-  r = block_sum(dmu, sred);
-  if (threadIdx.x == 0) out[SC_DMU] = r;
-  r = block_sum(dvar * kxxfac, sred);
-  if (threadIdx.x == 0) out[SC_DKXX] = r;
-  r = block_sum(ds2, sred);
-  if (threadIdx.x == 0) out[SC_DS2] = r;
-  r = block_sum(linear ? dc : 0.0, sred);
-  if (threadIdx.x == 0) out[SC_DC] = r;
+  if (threadIdx.x < 5) {
+    double r = 0.0;
+    for (int w = 0; w < 8; w++) r += sred[w][threadIdx.x];
+    out[threadIdx.x] = r;  // SC_E, SC_DMU, SC_DKXX, SC_DS2, SC_DC are 0..4
+  }
   if (linear) {
     for (int d = 0; d < p.kp.D; d++) {
-      double v = 0.0;
-      if (n < p.npts) {
-        const double x = p.pts[(int64_t)n * p.kp.D + d];
-        v = dvar * 2.0 * p.kp.variance * p.kp.s[d] * x * x;
-      }
-      r = block_sum(v, sred);
+      double t = 0.0;
+#pragma unroll
+      for (int h = 0; h < 2; h++)
+        if (n0 + h < p.npts) {
+          const double x = p.pts[(int64_t)(n0 + h) * p.kp.D + d];
+          t += dvar[h] * 2.0 * p.kp.variance * p.kp.s[d] * x * x;
+        }
+      const double r = block_sum(t, sred1);
       if (threadIdx.x == 0) out[SC_DS + d] = r;
     }
   }

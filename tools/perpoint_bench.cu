@@ -33,11 +33,11 @@ int main() {
     p.lp.kind = mode == 0 ? AGP_LIK_POISSON_EXP : AGP_LIK_BERNOULLI_LOGIT;
     p.lp.method = mode == 0 ? AGP_EXPECT_ANALYTIC : AGP_EXPECT_GAUSS_HERMITE;
     p.lp.ngh = 20;
-    for (int i = 0; i < 3; i++) perpoint_kernel<<<N / 256, 256>>>(p);
+    for (int i = 0; i < 3; i++) perpoint_kernel<<<(N + PP_POINTS_PER_BLOCK - 1) / PP_POINTS_PER_BLOCK, 256>>>(p);
     CK(cudaDeviceSynchronize());
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    for (int i = 0; i < 10; i++) perpoint_kernel<<<N / 256, 256>>>(p);
+    for (int i = 0; i < 10; i++) perpoint_kernel<<<(N + PP_POINTS_PER_BLOCK - 1) / PP_POINTS_PER_BLOCK, 256>>>(p);
     cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 10;
     printf("{\"kernel\": \"perpoint_kernel\", \"likelihood\": \"%s\", \"points\": %d, \"ms\": %.4f, \"alg_bytes_per_point\": %d, \"GB_per_s\": %.1f, \"frac_of_6550\": %.3f}\n",
