@@ -19,7 +19,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_NOT_PD, ERR_DOMAIN, ERR_CUDA, ERR_NCCL, ER
 
 KERNEL_SE, KERNEL_MATERN32, KERNEL_MATERN52, KERNEL_LINEAR = range(4)
 LIK_GAUSSIAN, LIK_BERNOULLI_LOGIT, LIK_POISSON_EXP = range(3)
-EXPECT_DEFAULT, EXPECT_ANALYTIC, EXPECT_GAUSS_HERMITE = range(3)
+EXPECT_DEFAULT, EXPECT_ANALYTIC, EXPECT_GAUSS_HERMITE, EXPECT_MONTE_CARLO = range(4)
 NONCENTERED, CENTERED = 0, 1
 POINT_MAJOR, FEATURE_MAJOR = 0, 1
 Y_F64, Y_F32, Y_I64, Y_U8 = range(4)
@@ -43,7 +43,7 @@ class AgpLikelihood(C.Structure):
 
 
 class AgpExpectation(C.Structure):
-    _fields_ = [("method", C.c_int32), ("n_points", C.c_int32), ("nodes", c_double_p), ("weights", c_double_p)]
+    _fields_ = [("method", C.c_int32), ("n_points", C.c_int32), ("nodes", c_double_p), ("weights", c_double_p), ("seed", C.c_uint64)]
 
 
 class AgpSvgpParams(C.Structure):

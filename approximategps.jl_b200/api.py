@@ -149,6 +149,16 @@ class GaussHermiteExpectation:
         return np.polynomial.hermite.hermgauss(self.n_points)
 
 
+@dataclass
+class MonteCarloExpectation:
+    """``GPLikelihoods.MonteCarloExpectation(n_samples)``: reparameterised samples ``mu + sigma * randn()``.  The normal
+    variates come from a counter-based Philox stream keyed by ``seed`` (the reference uses Julia's task-local RNG, so only the
+    distribution, not the stream, is shared with it)."""
+
+    n_samples: int = 20
+    seed: int = 0
+
+
 # ---------------------------------------------------------------------------------------------
 # GP containers (AbstractGPs.jl names)
 # ---------------------------------------------------------------------------------------------
@@ -411,13 +421,15 @@ class _Packed:
             gh = q if isinstance(q, GaussHermiteExpectation) else GaussHermiteExpectation(20)
             xs, ws = gh.nodes_weights()
             self.xs, self.ws = np.ascontiguousarray(xs), np.ascontiguousarray(ws)
-            p.expect = L.AgpExpectation(L.EXPECT_GAUSS_HERMITE, len(xs), L.dptr(self.xs), L.dptr(self.ws))
+            p.expect = L.AgpExpectation(L.EXPECT_GAUSS_HERMITE, len(xs), L.dptr(self.xs), L.dptr(self.ws), 0)
         elif isinstance(q, AnalyticExpectation):
-            p.expect = L.AgpExpectation(L.EXPECT_ANALYTIC, 0, None, None)
+            p.expect = L.AgpExpectation(L.EXPECT_ANALYTIC, 0, None, None, 0)
         elif isinstance(q, DefaultExpectationMethod):
-            p.expect = L.AgpExpectation(L.EXPECT_DEFAULT, 0, None, None)
+            p.expect = L.AgpExpectation(L.EXPECT_DEFAULT, 0, None, None, 0)
+        elif isinstance(q, MonteCarloExpectation):
+            p.expect = L.AgpExpectation(L.EXPECT_MONTE_CARLO, int(q.n_samples), None, None, int(q.seed))
         else:
-            raise ValueError(f"unsupported expectation method {q!r} (MonteCarloExpectation is out of scope)")
+            raise ValueError(f"unsupported expectation method {q!r}")
         self.p, self.M, self.D = p, M, D
 
 

@@ -110,6 +110,7 @@ struct SvgpState {
   bool centered = false;
   double mean_const = 0, jitter = 0, scale = 1;
   int want_grad = 0;
+  long long point_base = 0;  // Monte-Carlo counter offset of the batch being swept (dataset offset + rank shard offset)
   KernelParams kp;
   LikParams lp;
   std::vector<double> h_m;  // padded host copy of m
@@ -678,10 +679,15 @@ static int32_t resolve_params(const agp_svgp_params* p, SvgpState& st) {
     return fail(AGP_ERR_UNSUPPORTED, "no analytic expectation for the Bernoulli likelihood");
   st.lp.method = method;
   st.lp.ngh = 0;
+  st.lp.seed = 0;
   if (method == AGP_EXPECT_GAUSS_HERMITE) {
     if (p->expect.n_points < 1 || p->expect.n_points > AGP_MAX_GH_POINTS || !p->expect.nodes || !p->expect.weights)
       return fail(AGP_ERR_INVALID, "Gauss-Hermite needs 1..%d nodes and weights from the caller", AGP_MAX_GH_POINTS);
     st.lp.ngh = p->expect.n_points;
+  } else if (method == AGP_EXPECT_MONTE_CARLO) {
+    if (p->expect.n_points < 1) return fail(AGP_ERR_INVALID, "MonteCarloExpectation needs n_samples >= 1");
+    st.lp.ngh = p->expect.n_points;
+    st.lp.seed = p->expect.seed;
   } else if (method != AGP_EXPECT_ANALYTIC) {
     return fail(AGP_ERR_UNSUPPORTED, "unsupported expectation method %d", method);
   }
@@ -724,7 +730,7 @@ static int32_t prepare_step(agp_ctx* c, const agp_svgp_params* p) {
   tril_pad_kernel<<<dim3((Mp + 127) / 128, Mp), 128, 0, c->stream>>>(c->Lq.p, M, Mp);
   LAUNCHED(c);
   KCHECK();
-  if (st.lp.ngh > 0) {
+  if (st.lp.method == AGP_EXPECT_GAUSS_HERMITE && st.lp.ngh > 0) {
     CU(cudaMemcpyToSymbolAsync(c_gh_x, p->expect.nodes, sizeof(double) * st.lp.ngh, 0, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyToSymbolAsync(c_gh_w, p->expect.weights, sizeof(double) * st.lp.ngh, 0, cudaMemcpyHostToDevice, c->stream));
   }
@@ -983,6 +989,7 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
     pp.sc_part = c->sc_part.p;
     pp.flag = c->d_flags + 1;
     pp.predict_only = predict ? 1 : 0;
+    pp.point0 = c->st.point_base + lo;
     const int pblocks = (ncols + PP_POINTS_PER_BLOCK - 1) / PP_POINTS_PER_BLOCK;
     {
       ProfScope ps(c, PC_PERPOINT);
@@ -1071,6 +1078,7 @@ extern "C" int32_t agp_svgp_sweep(agp_ctx* c, agp_dataset* ds, int64_t offset, i
   const int64_t gb = global_batch > 0 ? global_batch : count;
   st.scale = (num_data > 0 ? num_data : (double)gb) / (double)gb;  // SVA.jl:357-358
   st.want_grad = want_grad;
+  st.point_base = offset + ((long long)c->rank << 40);  // distinct Monte-Carlo streams per rank
   OK(sweep_points(c, ds->X + offset * ds->D, ds->y + offset, count, want_grad != 0, false, nullptr, nullptr));
   return AGP_OK;
 }

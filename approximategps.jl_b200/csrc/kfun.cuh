@@ -72,10 +72,39 @@ __device__ __forceinline__ double u_from_dot(int kind, double xn, double zn, dou
 // ---- likelihood expectations ------------------------------------------------------------------
 struct LikParams {
   int kind;
-  int method;  // resolved: AGP_EXPECT_ANALYTIC or AGP_EXPECT_GAUSS_HERMITE
-  int ngh;
+  int method;  // resolved: AGP_EXPECT_ANALYTIC, AGP_EXPECT_GAUSS_HERMITE or AGP_EXPECT_MONTE_CARLO
+  int ngh;     // Gauss-Hermite nodes / Monte-Carlo samples per point
   double sigma2;
+  unsigned long long seed;  // Monte Carlo
 };
+
+// ---- counter-based normal variates (Philox4x32-10 + Box-Muller) --------------------------------------------------
+// eps(seed, point, sample): counter = (point_lo, point_hi, sample, 0), key = (seed_lo, seed_hi); the first two output words
+// give u1 in (0, 1], the last two u2 in [0, 1); eps = sqrt(-2 ln u1) cos(2 pi u2).  oracle/likelihoods.py restates it.
+__host__ __device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned (&out)[4]) {
+  for (int r = 0; r < 10; r++) {
+    const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+    const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+    c0 = n0;
+    c1 = n1;
+    c2 = n2;
+    c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+__device__ __forceinline__ double philox_normal(unsigned long long seed, long long point, int sample) {
+  unsigned r[4];
+  philox4x32_10((unsigned)point, (unsigned)((unsigned long long)point >> 32), (unsigned)sample, 0u, (unsigned)seed, (unsigned)(seed >> 32), r);
+  const unsigned long long a = ((unsigned long long)r[0] << 32) | r[1], b = ((unsigned long long)r[2] << 32) | r[3];
+  const double u1 = ((double)(a >> 11) + 1.0) * (1.0 / 9007199254740992.0);  // (0, 1]
+  const double u2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);          // [0, 1)
+  return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
 
 __constant__ double c_gh_x[AGP_MAX_GH_POINTS];
 __constant__ double c_gh_w[AGP_MAX_GH_POINTS];
@@ -109,9 +138,34 @@ __device__ __forceinline__ void loglik_d1(const LikParams& lp, double f, double 
 // E = E_{N(mu, var)}[log p(y|f)], dE/dmu, dE/dvar, dE/dsigma2 (derivatives of the finite
 // quadrature sum, which is what Zygote differentiates in the reference).
 __device__ __forceinline__ void expected_loglik(const LikParams& lp, double mu, double var, double y, double& E,
-                                                double& dmu, double& dvar, double& ds2) {
+                                                double& dmu, double& dvar, double& ds2, long long point = 0) {
   const double sd = sqrt(var);
   ds2 = 0.0;
+  if (lp.method == AGP_EXPECT_MONTE_CARLO) {
+    // GPLikelihoods.MonteCarloExpectation(n): mean over n reparameterised samples f = mu + sd * eps of log p(y | f); the
+    // derivatives are those of this finite sum (what Zygote differentiates), eps held fixed.
+    const double lg_y1 = (lp.kind == AGP_LIK_POISSON_EXP) ? lgamma(y + 1.0) : 0.0;
+    double sE = 0.0, sM = 0.0, sS = 0.0, sG = 0.0;
+    for (int k = 0; k < lp.ngh; k++) {
+      const double eps = philox_normal(lp.seed, point, k);
+      const double f = fma(sd, eps, mu);
+      double ll, dll;
+      loglik_d1(lp, f, y, lg_y1, ll, dll);
+      sE += ll;
+      sM += dll;
+      sS = fma(dll, eps, sS);
+      if (lp.kind == AGP_LIK_GAUSSIAN) {
+        const double r = y - f;
+        sG += -0.5 / lp.sigma2 + 0.5 * r * r / (lp.sigma2 * lp.sigma2);
+      }
+    }
+    const double inv = 1.0 / (double)lp.ngh;
+    E = sE * inv;
+    dmu = sM * inv;
+    dvar = sS * inv / (2.0 * sd);
+    ds2 = sG * inv;
+    return;
+  }
   if (lp.method == AGP_EXPECT_ANALYTIC) {
     const double v = sd * sd;  // Normal(mu, sqrt(var)) re-squared, as in the reference
     if (lp.kind == AGP_LIK_GAUSSIAN) {

@@ -424,6 +424,7 @@ struct PerPointArgs {
   double* sc_part;  // [gridDim.x][NSC] block partial sums
   int* flag;        // set to AGP_ERR_DOMAIN when a marginal variance is not positive
   int predict_only;
+  long long point0;  // global index (within the evaluated batch) of this chunk's first point: Monte-Carlo counter
 };
 
 // Two consecutive points per thread (16-byte loads of the per-point operands), one fused block reduction of the five
@@ -455,7 +456,7 @@ __device__ __forceinline__ void perpoint_one(const PerPointArgs& p, int n, bool 
   if (!p.predict_only) {
     const double var = var0 + 1e-18;  // AbstractGPs default jitter of f_post(x), SVA.jl:354
     if (!(var > 0.0)) atomicExch(p.flag, AGP_ERR_DOMAIN);
-    expected_loglik(p.lp, mu, var, p.y[n], E, dmu, dvar, ds2);
+    expected_loglik(p.lp, mu, var, p.y[n], E, dmu, dvar, ds2, p.point0 + n);
     dmu *= p.scale;
     dvar *= p.scale;
     ds2 *= p.scale;

@@ -47,6 +47,7 @@ extern "C" {
 #define AGP_EXPECT_DEFAULT 0       /* GPLikelihoods.DefaultExpectationMethod()                   */
 #define AGP_EXPECT_ANALYTIC 1      /* AnalyticExpectation()                                      */
 #define AGP_EXPECT_GAUSS_HERMITE 2 /* GaussHermiteExpectation(n): caller passes nodes / weights  */
+#define AGP_EXPECT_MONTE_CARLO 3   /* MonteCarloExpectation(n): n reparameterised samples / point */
 
 #define AGP_NONCENTERED 0 /* SparseVariationalApproximation{NonCentered} (the default, SVA.jl:93) */
 #define AGP_CENTERED 1    /* SparseVariationalApproximation{Centered}                             */
@@ -86,9 +87,12 @@ typedef struct {
 
 typedef struct {
   int32_t method;
-  int32_t n_points;      /* Gauss-Hermite only, <= AGP_MAX_GH_POINTS */
+  int32_t n_points;      /* Gauss-Hermite: nodes (<= AGP_MAX_GH_POINTS); Monte Carlo: samples per point */
   const double* nodes;   /* host; FastGaussQuadrature.gausshermite(n)[1] */
   const double* weights; /* host; FastGaussQuadrature.gausshermite(n)[2] */
+  uint64_t seed;         /* Monte Carlo only: f = mu + sigma * eps, eps = N(0,1) from Philox4x32-10 keyed by `seed` with
+                          * counter (global point index, sample index).  GPLikelihoods draws from Julia's task-local RNG, so
+                          * only the distribution (not the stream) can match the reference; the oracle restates this stream. */
 } agp_expectation;
 
 /* One `SparseVariationalApproximation(fz, q)` (SVA.jl:59-95) plus the likelihood / quadrature of

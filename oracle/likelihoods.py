@@ -26,7 +26,7 @@ import numpy as np
 from scipy.special import gammaln, xlogy
 
 GAUSSIAN, BERNOULLI_LOGIT, POISSON_EXP = "gaussian", "bernoulli_logit", "poisson_exp"
-ANALYTIC, GAUSS_HERMITE = "analytic", "gauss_hermite"
+ANALYTIC, GAUSS_HERMITE, MONTE_CARLO = "analytic", "gauss_hermite", "monte_carlo"
 
 _LOG2PI = np.log(2.0 * np.pi)
 _INVSQRTPI = 1.0 / np.sqrt(np.pi)
@@ -45,6 +45,7 @@ class Expectation:
 
     method: str = "default"
     n_points: int = 20
+    seed: int = 0  # MonteCarloExpectation only (include/agp.h agp_expectation.seed)
 
     def resolve(self, lik: Likelihood) -> "Expectation":
         if self.method != "default":
@@ -52,6 +53,36 @@ class Expectation:
         if lik.kind in (GAUSSIAN, POISSON_EXP):
             return Expectation(ANALYTIC, 0)
         return Expectation(GAUSS_HERMITE, 20)
+
+
+def philox_normal(seed: int, points, n_samples: int) -> np.ndarray:
+    """eps[i, k] for global point index points[i] and sample k: the counter-based N(0,1) stream of the device
+    MonteCarloExpectation (Philox4x32-10 keyed by ``seed``, counter (point_lo, point_hi, sample, 0), Box-Muller with
+    u1 from output words 0-1 and u2 from words 2-3) restated with NumPy integer arithmetic.  GPLikelihoods'
+    MonteCarloExpectation draws ``randn`` from Julia's RNG instead: only the distribution is shared with the reference."""
+    pts = np.asarray(points, dtype=np.uint64)
+    M32 = np.uint64(0xFFFFFFFF)
+    c0 = np.repeat((pts & M32)[:, None], n_samples, axis=1)
+    c1 = np.repeat((pts >> np.uint64(32))[:, None], n_samples, axis=1)
+    c2 = np.repeat(np.arange(n_samples, dtype=np.uint64)[None, :], len(pts), axis=0)
+    c3 = np.zeros_like(c0)
+    k0 = np.uint64(seed & 0xFFFFFFFF)
+    k1 = np.uint64((seed >> 32) & 0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c0
+        p1 = np.uint64(0xCD9E8D57) * c2
+        n0 = (p1 >> np.uint64(32)) ^ c1 ^ k0
+        n1 = p1 & M32
+        n2 = (p0 >> np.uint64(32)) ^ c3 ^ k1
+        n3 = p0 & M32
+        c0, c1, c2, c3 = n0, n1, n2, n3
+        k0 = (k0 + np.uint64(0x9E3779B9)) & M32
+        k1 = (k1 + np.uint64(0xBB67AE85)) & M32
+    a = (c0 << np.uint64(32)) | c1
+    b = (c2 << np.uint64(32)) | c3
+    u1 = ((a >> np.uint64(11)).astype(np.float64) + 1.0) / 9007199254740992.0
+    u2 = (b >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
+    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
 
 
 def gausshermite(n: int):
@@ -88,7 +119,7 @@ def loglik_and_derivs(lik: Likelihood, f, y):
     raise ValueError(lik.kind)
 
 
-def expected_loglik_terms(exp_: Expectation, lik: Likelihood, mu, var, y):
+def expected_loglik_terms(exp_: Expectation, lik: Likelihood, mu, var, y, point0: int = 0):
     """Per-point expected log-likelihood under N(mu, var) and its derivatives.
 
     Returns (E, dE/dmu, dE/dvar, dE/dsigma2_lik); arrays of len(y).  ``var`` is the marginal
@@ -111,6 +142,20 @@ def expected_loglik_terms(exp_: Expectation, lik: Likelihood, mu, var, y):
             e = np.exp(mu + v / 2.0)
             return y * mu - e - gammaln(y + 1.0), y - e, -0.5 * e, np.zeros_like(mu)
         raise ValueError(f"no analytic expectation for {lik.kind}")
+    if exp_.method == MONTE_CARLO:
+        # GPLikelihoods.MonteCarloExpectation(n): mean over n reparameterised samples; derivatives of that finite sum
+        eps = philox_normal(exp_.seed, point0 + np.arange(len(mu)), exp_.n_points)
+        f = mu[:, None] + std[:, None] * eps
+        ll, dll, _ = loglik_and_derivs(lik, f, y[:, None])
+        E = ll.mean(axis=1)
+        dmu = dll.mean(axis=1)
+        dvar = (dll * eps).mean(axis=1) / (2.0 * std)
+        if lik.kind == GAUSSIAN:
+            r = y[:, None] - f
+            ds2 = (-0.5 / lik.sigma2 + 0.5 * r * r / lik.sigma2**2).mean(axis=1)
+        else:
+            ds2 = np.zeros_like(mu)
+        return E, dmu, dvar, ds2
     xs, ws = gausshermite(exp_.n_points)
     f = mu[:, None] + (_SQRT2 * std)[:, None] * xs[None, :]
     ll, dll, _ = loglik_and_derivs(lik, f, y[:, None])

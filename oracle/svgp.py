@@ -156,7 +156,7 @@ def elbo(s: SVGP, X, y, lik: Likelihood, exp_: Expectation | None = None, num_da
     total = 0.0
     for lo, hi in _chunks(N, chunk):
         mu, var = mean_and_var(s, X[lo:hi], data)
-        E, _, _, _ = expected_loglik_terms(exp_, lik, mu, var + POSTERIOR_JITTER, y[lo:hi])
+        E, _, _, _ = expected_loglik_terms(exp_, lik, mu, var + POSTERIOR_JITTER, y[lo:hi], point0=lo)
         total += float(np.sum(E))
     scale = (N if num_data is None else num_data) / N  # SVA.jl:357-358
     return total * scale - prior_kl(s)
@@ -200,7 +200,7 @@ def elbo_and_grad(s: SVGP, X, y, lik: Likelihood, exp_: Expectation | None = Non
         mu = s.mean_const + Kuf.T @ alpha
         BtA = B.T @ A
         var = kernelmatrix_diag(k, Xc) - np.sum(A * A, axis=0) + np.sum(BtA * BtA, axis=0)
-        E, dmu, dvar, ds2 = expected_loglik_terms(exp_, lik, mu, var + POSTERIOR_JITTER, yc)
+        E, dmu, dvar, ds2 = expected_loglik_terms(exp_, lik, mu, var + POSTERIOR_JITTER, yc, point0=lo)
         total += float(np.sum(E))
         dmu = dmu * scale
         dvar = dvar * scale

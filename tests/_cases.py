@@ -36,7 +36,7 @@ def oracle_objects(p):
     k = ok.Kernel(p["kind"], p["variance"], p["inv"], p["c"])
     s = osv.SVGP(k, p["Z"], p["m"], p["A"], jitter=p["jitter"], centered=p["centered"], mean_const=p["mean_const"])
     lik = ol.Likelihood(p["lik"], p["sigma2"])
-    ex = ol.Expectation(p["method"], p["n_gh"])
+    ex = ol.Expectation(p["method"], p["n_gh"], p.get("mc_seed", 0))
     return s, lik, ex
 
 
@@ -50,7 +50,8 @@ def agp_objects(agp, p, x=None):
     q = agp.MvNormal(p["m"], chol_lower=p["A"])
     sva = agp.SparseVariationalApproximation(agp.Centered() if p["centered"] else agp.NonCentered(), fz, q)
     lik = {"gaussian": agp.GaussianLikelihood(p["sigma2"]), "bernoulli_logit": agp.BernoulliLikelihood(), "poisson_exp": agp.PoissonLikelihood()}[p["lik"]]
-    quad = {"default": agp.DefaultExpectationMethod(), "analytic": agp.AnalyticExpectation(), "gauss_hermite": agp.GaussHermiteExpectation(p["n_gh"])}[p["method"]]
+    quad = {"default": agp.DefaultExpectationMethod(), "analytic": agp.AnalyticExpectation(), "gauss_hermite": agp.GaussHermiteExpectation(p["n_gh"]),
+            "monte_carlo": agp.MonteCarloExpectation(p["n_gh"], p.get("mc_seed", 0))}[p["method"]]
     lfx = agp.LatentGP(f, lik, 1e-18)(p["X"] if x is None else x)
     return sva, lfx, quad, f
 

@@ -268,3 +268,26 @@ def test_optimised_posterior_matches_gpr(agp):
 def test_m4096(agp):
     """32 diagonal blocks: 8 Cholesky super-panels, SYRK without K-split, 1056 lower tiles."""
     _run_case(agp, make_problem(seed=55, kind="matern52", N=3000, M=4096, D=4, lik="poisson_exp", zdist="random", lengthscale=1.0), num_data=1e6)
+
+
+@pytest.mark.parametrize("lik", ["bernoulli_logit", "poisson_exp", "gaussian"])
+def test_monte_carlo_expectation(agp, lik):
+    """MonteCarloExpectation(n): the device stream (Philox4x32-10, counter = point index x sample) is restated by the oracle, so the
+    value and the gradient of the finite sample mean match to the usual tolerance; minibatch views keep the per-point streams."""
+    p = make_problem(seed=61, kind="matern52", N=700, M=21, D=2, lik=lik, method="monte_carlo", n_gh=24)
+    p["mc_seed"] = 20260101
+    _run_case(agp, p, num_data=7000.0)
+    # a view [offset, offset + count) uses the counters of its own points
+    s, olik, ex = oracle_objects(p)
+    sva, lfx, quad, f = agp_objects(agp, p)
+    ds = agp.DeviceData(p["X"], p["y"])
+    lds = agp.LatentGP(f, lfx.lik, 1e-18)(ds)
+    lo, cnt = 64, 300
+    val = agp.elbo(sva, lds, None, quadrature=quad, offset=lo, count=cnt)
+    mu, var = osv.mean_and_var(s, p["X"][lo:lo + cnt])
+    from oracle import likelihoods as ol2
+
+    E, _, _, _ = ol2.expected_loglik_terms(ex, olik, mu, var + 1e-18, p["y"][lo:lo + cnt], point0=lo)
+    ref = float(np.sum(E)) - osv.prior_kl(s)
+    assert abs(val - ref) < 1e-10 * abs(ref)
+    ds.close()

@@ -190,3 +190,37 @@ def test_optimised_posterior_matches_gpr():
     mu, cov = osv.mean_and_cov(osv.SVGP(k, x, m, A, jitter=jitter), x)
     mu_e, cov_e = exact_gpr(x, y, variance, inv_ls, noise)
     assert np.max(np.abs(mu - mu_e)) < 1e-4 and np.max(np.abs(cov - cov_e)) < 1e-4
+
+
+def test_monte_carlo_stream_and_expectation():
+    """The counter-based normal stream of MonteCarloExpectation: Philox4x32-10 known answers (Random123 kat_vectors), N(0,1)
+    moments, convergence of the Monte-Carlo expectation to Gauss-Hermite, and its gradient against finite differences."""
+    import oracle.likelihoods as L
+
+    # Random123 known-answer vectors for philox4x32-10 (counter, key -> output)
+    def raw(counter, key):
+        c = [np.uint64(v) for v in counter]
+        k = [np.uint64(v) for v in key]
+        M = np.uint64(0xFFFFFFFF)
+        for _ in range(10):
+            p0, p1 = np.uint64(0xD2511F53) * c[0], np.uint64(0xCD9E8D57) * c[2]
+            c = [(p1 >> np.uint64(32)) ^ c[1] ^ k[0], p1 & M, (p0 >> np.uint64(32)) ^ c[3] ^ k[1], p0 & M]
+            k = [(k[0] + np.uint64(0x9E3779B9)) & M, (k[1] + np.uint64(0xBB67AE85)) & M]
+        return [int(v) for v in c]
+
+    assert raw([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert raw([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    eps = L.philox_normal(7, np.arange(50000), 4)
+    assert abs(eps.mean()) < 0.01 and abs(eps.std() - 1.0) < 0.01 and np.all(np.isfinite(eps))
+    assert np.array_equal(L.philox_normal(7, np.array([123]), 4), eps[123:124])  # counter-based: independent of batching
+    mu, var, y = np.full(1, 0.3), np.full(1, 0.49), np.ones(1)
+    lik = L.Likelihood("bernoulli_logit")
+    gh = L.expected_loglik_terms(L.Expectation("gauss_hermite", 20), lik, mu, var, y)
+    mc = L.expected_loglik_terms(L.Expectation("monte_carlo", 200000, 3), lik, mu, var, y)
+    assert abs(mc[0][0] - gh[0][0]) < 5e-3 and abs(mc[1][0] - gh[1][0]) < 5e-3 and abs(mc[2][0] - gh[2][0]) < 5e-3
+    ex = L.Expectation("monte_carlo", 16, 11)
+    E, dmu, dvar, _ = L.expected_loglik_terms(ex, lik, mu, var, y)
+    h = 1e-6
+    fd_mu = (L.expected_loglik_terms(ex, lik, mu + h, var, y)[0] - L.expected_loglik_terms(ex, lik, mu - h, var, y)[0]) / (2 * h)
+    fd_var = (L.expected_loglik_terms(ex, lik, mu, var + h, y)[0] - L.expected_loglik_terms(ex, lik, mu, var - h, y)[0]) / (2 * h)
+    assert abs(fd_mu[0] - dmu[0]) < 1e-8 and abs(fd_var[0] - dvar[0]) < 1e-8
