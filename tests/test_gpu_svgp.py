@@ -291,3 +291,44 @@ def test_monte_carlo_expectation(agp, lik):
     ref = float(np.sum(E)) - osv.prior_kl(s)
     assert abs(val - ref) < 1e-10 * abs(ref)
     ds.close()
+
+
+def test_abi_error_conventions(agp):
+    """Status codes of SURVEY.md section 8b at the C boundary: INVALID -> ValueError (ArgumentError in the Julia shim), UNSUPPORTED ->
+    ValueError, DOMAIN for a non-positive diagonal of the q factor (logdet would throw), nothing silently falls back."""
+    import ctypes as C
+
+    from agp_b200 import _lib as L
+    from agp_b200.api import _Packed
+
+    ctx = agp.default_context()
+    p = make_problem(seed=71, N=80, M=6, D=2)
+    sva, lfx, quad, f = agp_objects(agp, p)
+    ds3 = agp.DeviceData(np.zeros((10, 3)), np.zeros(10), ctx=ctx)
+    with pytest.raises(ValueError, match="dimension"):  # dataset D != params D
+        agp.elbo(sva, agp.LatentGP(f, agp.GaussianLikelihood(0.1), 1e-18)(ds3), None)
+    ds3.close()
+    with pytest.raises(ValueError):  # D > 32 is not supported on device (no CPU fallback)
+        agp.DeviceData(np.zeros((4, 40)), np.zeros(4), ctx=ctx)
+    with pytest.raises(ValueError, match="sigma2"):
+        agp.elbo(sva, agp.LatentGP(f, agp.GaussianLikelihood(-1.0), 1e-18)(p["X"]), p["y"])
+    with pytest.raises(ValueError, match="analytic"):
+        agp.elbo(sva, agp.LatentGP(f, agp.BernoulliLikelihood(), 1e-18)(p["X"]), (p["y"] > 0).astype(float), quadrature=agp.AnalyticExpectation())
+    with pytest.raises(ValueError, match="Gauss-Hermite"):
+        agp.elbo(sva, lfx, p["y"], quadrature=agp.GaussHermiteExpectation(200))
+    with pytest.raises(ValueError, match="n_samples"):
+        agp.elbo(sva, lfx, p["y"], quadrature=agp.MonteCarloExpectation(0))
+    bad = agp.SparseVariationalApproximation(f(p["Z"], 1e-6), agp.MvNormal(p["m"], chol_lower=-np.eye(6)))
+    with pytest.raises(agp.DomainError):  # PDMat(Cholesky(LowerTriangular(A))) with a negative diagonal: logdet throws in the reference
+        agp.elbo(bad, lfx, p["y"])
+    pk = _Packed(sva, agp.GaussianLikelihood(0.3), None)
+    pk.p.kernel.kind = 7
+    out = C.c_double()
+    ds = agp.DeviceData(p["X"], p["y"], ctx=ctx)
+    assert ctx.lib.agp_svgp_elbo(ctx.h, ds.h, 0, 80, C.byref(pk.p), 0.0, 0, C.byref(out)) == L.ERR_UNSUPPORTED
+    assert b"kernel" in ctx.lib.agp_last_error_string()
+    assert ctx.lib.agp_svgp_elbo(ctx.h, ds.h, 0, 80, None, 0.0, 0, C.byref(out)) == L.ERR_INVALID
+    assert ctx.lib.agp_svgp_finish(ctx.h, C.byref(out), None) in (L.OK, L.ERR_INVALID)  # never crashes without a pending sweep
+    ds.close()
+    # the context is still usable after every error
+    assert np.isfinite(agp.elbo(sva, lfx, p["y"]))
