@@ -477,8 +477,12 @@ def _dataset_for(fx: FiniteGP, y, ctx: Context):
     return DeviceData(fx.x, y, ctx=ctx), True
 
 
-def elbo(sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx: Context | None = None, offset=0, count=None) -> float:
-    """``AbstractGPs.elbo(sva, fx | lfx, y; num_data, quadrature)`` -- SVA.jl:307-360."""
+def elbo(sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx: Context | None = None, offset=0, count=None, global_batch=0) -> float:
+    """``AbstractGPs.elbo(sva, fx | lfx, y; num_data, quadrature)`` -- SVA.jl:307-360.
+
+    ``offset`` / ``count`` select a minibatch view of a device-resident data set.  With a communicator attached to ``ctx``
+    (``attach_communicator``) every rank passes its own shard and ``global_batch`` = the number of points over all ranks; the
+    partial sums are all-reduced once inside the library and every rank returns the same value."""
     fx, lik = _resolve_lik(sva, l_fx)  # argument errors first: they never cross the ABI
     pk = _Packed(sva, lik, quadrature)
     ctx = ctx or default_context()
@@ -486,15 +490,15 @@ def elbo(sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx: Context | No
     try:
         count = len(ds) - offset if count is None else count
         out = C.c_double()
-        L.check(ctx.lib.agp_svgp_elbo(ctx.h, ds.h, offset, count, C.byref(pk.p), float(num_data or 0), 0, C.byref(out)))
+        L.check(ctx.lib.agp_svgp_elbo(ctx.h, ds.h, offset, count, C.byref(pk.p), float(num_data or 0), int(global_batch), C.byref(out)))
         return out.value
     finally:
         if own:
             ds.close()
 
 
-def elbo_and_gradient(sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx: Context | None = None, offset=0, count=None):
-    """Value and gradient of ``elbo``: the forward + pullback of the new ``ChainRulesCore.rrule``."""
+def elbo_and_gradient(sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx: Context | None = None, offset=0, count=None, global_batch=0):
+    """Value and gradient of ``elbo``: the forward + pullback of the new ``ChainRulesCore.rrule`` (same keywords as ``elbo``)."""
     fx, lik = _resolve_lik(sva, l_fx)
     pk = _Packed(sva, lik, quadrature)
     ctx = ctx or default_context()
@@ -507,7 +511,7 @@ def elbo_and_gradient(sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx:
         G = L.AgpSvgpGrads(L.dptr(g.m), L.dptr(g.Lq), L.dptr(g.Z), sc[0:1].ctypes.data_as(L.c_double_p), L.dptr(g.inv_lengthscale),
                            sc[1:2].ctypes.data_as(L.c_double_p), sc[2:3].ctypes.data_as(L.c_double_p), sc[3:4].ctypes.data_as(L.c_double_p))
         out = C.c_double()
-        L.check(ctx.lib.agp_svgp_elbo_grad(ctx.h, ds.h, offset, count, C.byref(pk.p), float(num_data or 0), 0, C.byref(out), C.byref(G)))
+        L.check(ctx.lib.agp_svgp_elbo_grad(ctx.h, ds.h, offset, count, C.byref(pk.p), float(num_data or 0), int(global_batch), C.byref(out), C.byref(G)))
         g.variance, g.linear_c, g.mean_const, g.lik_sigma2 = (float(v) for v in sc)
         return out.value, g
     finally:
