@@ -148,6 +148,7 @@ SYMBOLS = {
     "agp_laplace_f_and_lml": (C.c_int32, [_vp, C.POINTER(AgpLaplaceProblem), C.POINTER(AgpLaplaceResult), C.POINTER(_vp)]),
     "agp_laplace_cache_fetch": (C.c_int32, [_vp, C.c_int32, c_double_p]),
     "agp_laplace_cache_destroy": (C.c_int32, [_vp]),
+    "agp_laplace_cache_n": (C.c_int32, [_vp]),
 }
 
 

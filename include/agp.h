@@ -251,6 +251,8 @@ int32_t agp_laplace_f_and_lml(agp_ctx* ctx, const agp_laplace_problem* problem, 
  *        5 = B_ch.L (n x n column-major); 7 = loglik (1 double, owned caches only)              */
 int32_t agp_laplace_cache_fetch(agp_laplace_cache* cache, int32_t field, double* host_out);
 int32_t agp_laplace_cache_destroy(agp_laplace_cache* cache);
+/* Number of latent values n of a cache (or callback view): the length of its vector fields. */
+int32_t agp_laplace_cache_n(agp_laplace_cache* cache);
 /* Replaces the prediction methods of ApproxPosteriorGP{<:LaplaceApproximation} -- Laplace.jl:425-463
  * (_laplace_predict_intermediates, mean_and_var, mean_and_cov, mean, var, cov(f, x), cov(f, x, y)) on a cache
  * returned by agp_laplace_f_and_lml: kernel / Xtrain (host, point-major n x D) describe prior_at_x.  Any of
