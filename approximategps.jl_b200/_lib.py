@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("AGP_B200_LIB") or os.path.join(HERE, "libagp_b200.so"
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_NOT_PD, ERR_DOMAIN, ERR_CUDA, ERR_NCCL, ERR_ALLOC = range(8)
 
 KERNEL_SE, KERNEL_MATERN32, KERNEL_MATERN52, KERNEL_LINEAR = range(4)
-LIK_GAUSSIAN, LIK_BERNOULLI_LOGIT, LIK_POISSON_EXP = range(3)
+LIK_GAUSSIAN, LIK_BERNOULLI_LOGIT, LIK_POISSON_EXP, LIK_EXPONENTIAL_EXP, LIK_GAMMA_EXP = range(5)
 EXPECT_DEFAULT, EXPECT_ANALYTIC, EXPECT_GAUSS_HERMITE, EXPECT_MONTE_CARLO = range(4)
 NONCENTERED, CENTERED = 0, 1
 POINT_MAJOR, FEATURE_MAJOR = 0, 1

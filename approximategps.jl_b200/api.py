@@ -131,6 +131,28 @@ class PoissonLikelihood:
 
 
 @dataclass
+class ExponentialLikelihood:
+    """``ExponentialLikelihood()`` with the exp link: ``Exponential(scale = exp(f))``."""
+
+    sigma2: float = 0.0
+    kind: int = L.LIK_EXPONENTIAL_EXP
+
+
+class GammaLikelihood:
+    """``GammaLikelihood(alpha)`` with the exp link: ``Gamma(alpha, scale = exp(f))``.  The shape travels in the ABI's scalar
+    likelihood-parameter slot (``sigma2``); its gradient comes back in ``ELBOGradient.lik_sigma2``."""
+
+    kind = L.LIK_GAMMA_EXP
+
+    def __init__(self, alpha: float = 1.0):
+        self.alpha = float(alpha)
+
+    @property
+    def sigma2(self) -> float:
+        return self.alpha
+
+
+@dataclass
 class DefaultExpectationMethod:
     pass
 

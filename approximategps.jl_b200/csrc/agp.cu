@@ -650,7 +650,7 @@ static int32_t resolve_params(const agp_svgp_params* p, SvgpState& st) {
   if (p->kernel.kind < AGP_KERNEL_SE || p->kernel.kind > AGP_KERNEL_LINEAR) return fail(AGP_ERR_UNSUPPORTED, "unsupported kernel kind %d", p->kernel.kind);
   if (p->kernel.n_scale != 1 && p->kernel.n_scale != p->D) return fail(AGP_ERR_INVALID, "kernel.n_scale must be 1 or D");
   if (!p->kernel.inv_lengthscale) return fail(AGP_ERR_INVALID, "kernel.inv_lengthscale is NULL");
-  if (p->lik.kind < AGP_LIK_GAUSSIAN || p->lik.kind > AGP_LIK_POISSON_EXP) return fail(AGP_ERR_UNSUPPORTED, "unsupported likelihood kind %d", p->lik.kind);
+  if (p->lik.kind < AGP_LIK_GAUSSIAN || p->lik.kind > AGP_LIK_GAMMA_EXP) return fail(AGP_ERR_UNSUPPORTED, "unsupported likelihood kind %d", p->lik.kind);
   if (p->parametrization != AGP_NONCENTERED && p->parametrization != AGP_CENTERED) return fail(AGP_ERR_INVALID, "unknown parametrization");
   st.M = p->M;
   st.D = p->D;
@@ -673,7 +673,7 @@ static int32_t resolve_params(const agp_svgp_params* p, SvgpState& st) {
   int method = p->expect.method;
   if (method == AGP_EXPECT_DEFAULT) {
     // GPLikelihoods.DefaultExpectationMethod: analytic for Gaussian and Poisson-exp, else Gauss-Hermite(20)
-    method = (p->lik.kind == AGP_LIK_GAUSSIAN || p->lik.kind == AGP_LIK_POISSON_EXP) ? AGP_EXPECT_ANALYTIC : AGP_EXPECT_GAUSS_HERMITE;
+    method = (p->lik.kind != AGP_LIK_BERNOULLI_LOGIT) ? AGP_EXPECT_ANALYTIC : AGP_EXPECT_GAUSS_HERMITE;
   }
   if (method == AGP_EXPECT_ANALYTIC && p->lik.kind == AGP_LIK_BERNOULLI_LOGIT)
     return fail(AGP_ERR_UNSUPPORTED, "no analytic expectation for the Bernoulli likelihood");
@@ -692,6 +692,7 @@ static int32_t resolve_params(const agp_svgp_params* p, SvgpState& st) {
     return fail(AGP_ERR_UNSUPPORTED, "unsupported expectation method %d", method);
   }
   if (p->lik.kind == AGP_LIK_GAUSSIAN && !(p->lik.sigma2 > 0)) return fail(AGP_ERR_INVALID, "GaussianLikelihood needs sigma2 > 0");
+  if (p->lik.kind == AGP_LIK_GAMMA_EXP && !(p->lik.sigma2 > 0)) return fail(AGP_ERR_INVALID, "GammaLikelihood needs alpha > 0");
   return AGP_OK;
 }
 

@@ -116,22 +116,53 @@ __device__ __forceinline__ double logistic(double x) {
   return e / (1.0 + e);
 }
 
-// log p(y | f) and d/df (closed forms of Distributions.logpdf for the three likelihoods; the
-// Bernoulli form is the overflow-free -softplus(-+f), an intentional divergence from the
-// reference's log(logistic(f)) which returns -Inf for |f| > 36.7)
-__device__ __forceinline__ void loglik_d1(const LikParams& lp, double f, double y, double lg_y1, double& ll, double& dll) {
+// digamma(x), x > 0: recurrence up to x >= 10, then the asymptotic series (error < 1e-15)
+__device__ __forceinline__ double digamma(double x) {
+  double r = 0.0;
+  while (x < 10.0) {
+    r -= 1.0 / x;
+    x += 1.0;
+  }
+  const double i = 1.0 / x, i2 = i * i;
+  const double ser = i2 * (1.0 / 12.0 - i2 * (1.0 / 120.0 - i2 * (1.0 / 252.0 - i2 * (1.0 / 240.0 - i2 * (1.0 / 132.0 - i2 * (691.0 / 32760.0))))));
+  return r + log(x) - 0.5 * i - ser;
+}
+
+// the part of log p(y | f) that does not depend on f
+__device__ __forceinline__ double loglik_const(const LikParams& lp, double y) {
+  if (lp.kind == AGP_LIK_POISSON_EXP) return -lgamma(y + 1.0);
+  if (lp.kind == AGP_LIK_GAMMA_EXP) return (lp.sigma2 - 1.0) * log(y) - lgamma(lp.sigma2);
+  if (lp.kind == AGP_LIK_GAUSSIAN) return -0.5 * (1.8378770664093453 + log(lp.sigma2));
+  return 0.0;
+}
+
+// log p(y | f), d/df and d/d(likelihood parameter) (closed forms of Distributions.logpdf; the Bernoulli form is the
+// overflow-free -softplus(-+f), an intentional divergence from the reference's log(logistic(f)) which returns -Inf for
+// |f| > 36.7).  cst = loglik_const(lp, y).
+__device__ __forceinline__ void loglik_d1(const LikParams& lp, double f, double y, double cst, double& ll, double& dll, double& dpar) {
+  dpar = 0.0;
   if (lp.kind == AGP_LIK_BERNOULLI_LOGIT) {
     const bool one = y > 0.5;
     ll = -softplus(one ? -f : f);
     dll = (one ? 1.0 : 0.0) - logistic(f);
   } else if (lp.kind == AGP_LIK_POISSON_EXP) {
     const double lam = exp(f);
-    ll = y * f - lam - lg_y1;
+    ll = y * f - lam + cst;
     dll = y - lam;
+  } else if (lp.kind == AGP_LIK_EXPONENTIAL_EXP) {  // Exponential(scale = exp(f)): -f - y exp(-f)
+    const double t = y * exp(-f);
+    ll = -f - t;
+    dll = -1.0 + t;
+  } else if (lp.kind == AGP_LIK_GAMMA_EXP) {  // Gamma(alpha, scale = exp(f)): (alpha-1) log y - y exp(-f) - alpha f - lgamma(alpha)
+    const double t = y * exp(-f);
+    ll = cst - t - lp.sigma2 * f;
+    dll = -lp.sigma2 + t;
+    dpar = -f;  // + log y - digamma(alpha), added once per point by the caller
   } else {
     const double r = y - f;
-    ll = -0.5 * (1.8378770664093453 + log(lp.sigma2)) - 0.5 * r * r / lp.sigma2;
+    ll = cst - 0.5 * r * r / lp.sigma2;
     dll = r / lp.sigma2;
+    dpar = -0.5 / lp.sigma2 + 0.5 * r * r / (lp.sigma2 * lp.sigma2);
   }
 }
 
@@ -144,26 +175,24 @@ __device__ __forceinline__ void expected_loglik(const LikParams& lp, double mu, 
   if (lp.method == AGP_EXPECT_MONTE_CARLO) {
     // GPLikelihoods.MonteCarloExpectation(n): mean over n reparameterised samples f = mu + sd * eps of log p(y | f); the
     // derivatives are those of this finite sum (what Zygote differentiates), eps held fixed.
-    const double lg_y1 = (lp.kind == AGP_LIK_POISSON_EXP) ? lgamma(y + 1.0) : 0.0;
+    const double cst = loglik_const(lp, y);
+    const double par0 = (lp.kind == AGP_LIK_GAMMA_EXP) ? log(y) - digamma(lp.sigma2) : 0.0;
     double sE = 0.0, sM = 0.0, sS = 0.0, sG = 0.0;
     for (int k = 0; k < lp.ngh; k++) {
       const double eps = philox_normal(lp.seed, point, k);
       const double f = fma(sd, eps, mu);
-      double ll, dll;
-      loglik_d1(lp, f, y, lg_y1, ll, dll);
+      double ll, dll, dpar;
+      loglik_d1(lp, f, y, cst, ll, dll, dpar);
       sE += ll;
       sM += dll;
       sS = fma(dll, eps, sS);
-      if (lp.kind == AGP_LIK_GAUSSIAN) {
-        const double r = y - f;
-        sG += -0.5 / lp.sigma2 + 0.5 * r * r / (lp.sigma2 * lp.sigma2);
-      }
+      sG += dpar;
     }
     const double inv = 1.0 / (double)lp.ngh;
     E = sE * inv;
     dmu = sM * inv;
     dvar = sS * inv / (2.0 * sd);
-    ds2 = sG * inv;
+    ds2 = sG * inv + par0;
     return;
   }
   if (lp.method == AGP_EXPECT_ANALYTIC) {
@@ -174,35 +203,42 @@ __device__ __forceinline__ void expected_loglik(const LikParams& lp, double mu, 
       dmu = r / s2;
       dvar = -0.5 / s2;
       ds2 = -0.5 / s2 + 0.5 * (r * r + v) / (s2 * s2);
-    } else {  // Poisson, exp link
+    } else if (lp.kind == AGP_LIK_POISSON_EXP) {
       const double e = exp(mu + 0.5 * v);
       E = y * mu - e - lgamma(y + 1.0);
       dmu = y - e;
       dvar = -0.5 * e;
+    } else {  // Exponential / Gamma with exp link: E[exp(-f)] = exp(-mu + v/2)
+      const double alpha = (lp.kind == AGP_LIK_GAMMA_EXP) ? lp.sigma2 : 1.0;
+      const double t = y * exp(-mu + 0.5 * v);
+      E = loglik_const(lp, y) - t - alpha * mu;
+      dmu = -alpha + t;
+      dvar = -0.5 * t;
+      if (lp.kind == AGP_LIK_GAMMA_EXP) ds2 = log(y) - digamma(alpha) - mu;
     }
     return;
   }
-  const double lg_y1 = (lp.kind == AGP_LIK_POISSON_EXP) ? lgamma(y + 1.0) : 0.0;
+  const double cst = loglik_const(lp, y);
   const double sq2sd = 1.4142135623730951 * sd;
   double sE = 0.0, sM = 0.0, sS = 0.0, sG = 0.0;
   for (int k = 0; k < lp.ngh; k++) {
     const double x = c_gh_x[k], w = c_gh_w[k];
     const double f = mu + sq2sd * x;
-    double ll, dll;
-    loglik_d1(lp, f, y, lg_y1, ll, dll);
+    double ll, dll, dpar;
+    loglik_d1(lp, f, y, cst, ll, dll, dpar);
     sE += w * ll;
     sM += w * dll;
     sS += w * dll * (1.4142135623730951 * x);
-    if (lp.kind == AGP_LIK_GAUSSIAN) {
-      const double r = y - f;
-      sG += w * (-0.5 / lp.sigma2 + 0.5 * r * r / (lp.sigma2 * lp.sigma2));
-    }
+    sG += w * dpar;
   }
   const double isp = 0.5641895835477563;  // 1/sqrt(pi)
+  double wsum = 0.0;
+  if (lp.kind == AGP_LIK_GAMMA_EXP)
+    for (int k = 0; k < lp.ngh; k++) wsum += c_gh_w[k];
   E = isp * sE;
   dmu = isp * sM;
   dvar = isp * sS / (2.0 * sd);
-  ds2 = isp * sG;
+  ds2 = isp * sG + ((lp.kind == AGP_LIK_GAMMA_EXP) ? isp * wsum * (log(y) - digamma(lp.sigma2)) : 0.0);
 }
 
 }  // namespace agp

@@ -53,6 +53,13 @@ __global__ void __launch_bounds__(256) lap_derivs_kernel(LapDerivArgs a) {
         d1 = y - lam;
         W = lam;
         d3 = -lam;
+      } else if (a.lp.kind == AGP_LIK_EXPONENTIAL_EXP || a.lp.kind == AGP_LIK_GAMMA_EXP) {
+        const double alpha = (a.lp.kind == AGP_LIK_GAMMA_EXP) ? a.lp.sigma2 : 1.0;
+        const double t = y * exp(-f);  // Exponential / Gamma with scale exp(f)
+        ll = loglik_const(a.lp, y) - t - alpha * f;
+        d1 = -alpha + t;
+        W = t;
+        d3 = t;
       } else {
         const double r = y - f, s2 = a.lp.sigma2;
         ll = -0.5 * (1.8378770664093453 + log(s2)) - 0.5 * r * r / s2;

@@ -43,6 +43,8 @@ extern "C" {
 #define AGP_LIK_GAUSSIAN 0        /* GaussianLikelihood(sigma2)                                  */
 #define AGP_LIK_BERNOULLI_LOGIT 1 /* BernoulliLikelihood() (logistic link)                       */
 #define AGP_LIK_POISSON_EXP 2     /* PoissonLikelihood() (exp link)                              */
+#define AGP_LIK_EXPONENTIAL_EXP 3 /* ExponentialLikelihood() (exp link): Exponential(scale = exp(f)) */
+#define AGP_LIK_GAMMA_EXP 4       /* GammaLikelihood(alpha) (exp link): Gamma(alpha, scale = exp(f)); alpha in `sigma2` */
 
 #define AGP_EXPECT_DEFAULT 0       /* GPLikelihoods.DefaultExpectationMethod()                   */
 #define AGP_EXPECT_ANALYTIC 1      /* AnalyticExpectation()                                      */
@@ -82,7 +84,7 @@ typedef struct {
 
 typedef struct {
   int32_t kind;
-  double sigma2; /* GaussianLikelihood only */
+  double sigma2; /* the likelihood's scalar parameter: GaussianLikelihood sigma2, GammaLikelihood alpha; ignored otherwise */
 } agp_likelihood;
 
 typedef struct {
@@ -122,7 +124,7 @@ typedef struct {
   double* dinv_lengthscale; /* n_scale                                       */
   double* dlinear_c;        /* 1                                             */
   double* dmean_const;      /* 1                                             */
-  double* dlik_sigma2;      /* 1                                             */
+  double* dlik_sigma2;      /* 1: d / d(likelihood parameter) (sigma2 or alpha)  */
 } agp_svgp_grads;
 
 /* ---- context ------------------------------------------------------------------------------- */

@@ -94,6 +94,8 @@ def _d3_loglik(lik: Likelihood, f, y):
         return -p * (1.0 - p) * (1.0 - 2.0 * p)
     if lik.kind == POISSON_EXP:
         return -np.exp(f)
+    if lik.kind in ("exponential_exp", "gamma_exp"):
+        return y * np.exp(-f)
     raise ValueError(lik.kind)
 
 

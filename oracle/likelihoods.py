@@ -26,6 +26,7 @@ import numpy as np
 from scipy.special import gammaln, xlogy
 
 GAUSSIAN, BERNOULLI_LOGIT, POISSON_EXP = "gaussian", "bernoulli_logit", "poisson_exp"
+EXPONENTIAL_EXP, GAMMA_EXP = "exponential_exp", "gamma_exp"  # Exponential / Gamma(alpha) with scale exp(f); alpha rides in sigma2
 ANALYTIC, GAUSS_HERMITE, MONTE_CARLO = "analytic", "gauss_hermite", "monte_carlo"
 
 _LOG2PI = np.log(2.0 * np.pi)
@@ -50,7 +51,7 @@ class Expectation:
     def resolve(self, lik: Likelihood) -> "Expectation":
         if self.method != "default":
             return self
-        if lik.kind in (GAUSSIAN, POISSON_EXP):
+        if lik.kind in (GAUSSIAN, POISSON_EXP, EXPONENTIAL_EXP, GAMMA_EXP):
             return Expectation(ANALYTIC, 0)
         return Expectation(GAUSS_HERMITE, 20)
 
@@ -116,7 +117,28 @@ def loglik_and_derivs(lik: Likelihood, f, y):
     if lik.kind == POISSON_EXP:
         lam = np.exp(f)
         return xlogy(y, lam) - lam - gammaln(y + 1.0), y - lam, -lam
+    if lik.kind in (EXPONENTIAL_EXP, GAMMA_EXP):
+        # Distributions.logpdf(Gamma(alpha, theta), y) with theta = exp(f): (alpha-1) log y - y/theta - alpha log theta - loggamma(alpha);
+        # Exponential(theta) is alpha = 1
+        alpha = lik.sigma2 if lik.kind == GAMMA_EXP else 1.0
+        t = y * np.exp(-f)
+        cst = (alpha - 1.0) * np.log(y) - gammaln(alpha) if lik.kind == GAMMA_EXP else 0.0
+        return cst - t - alpha * f, -alpha + t, -t
     raise ValueError(lik.kind)
+
+
+def dloglik_dparam(lik: Likelihood, f, y):
+    """d log p(y|f) / d(likelihood parameter): sigma2 for the Gaussian, alpha for the Gamma likelihood, else 0."""
+    f = np.asarray(f, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    if lik.kind == GAUSSIAN:
+        r = y - f
+        return -0.5 / lik.sigma2 + 0.5 * r * r / lik.sigma2**2
+    if lik.kind == GAMMA_EXP:
+        from scipy.special import digamma
+
+        return np.log(y) - digamma(lik.sigma2) - f
+    return np.zeros(np.broadcast(f, y).shape)
 
 
 def expected_loglik_terms(exp_: Expectation, lik: Likelihood, mu, var, y, point0: int = 0):
@@ -141,6 +163,13 @@ def expected_loglik_terms(exp_: Expectation, lik: Likelihood, mu, var, y, point0
         if lik.kind == POISSON_EXP:
             e = np.exp(mu + v / 2.0)
             return y * mu - e - gammaln(y + 1.0), y - e, -0.5 * e, np.zeros_like(mu)
+        if lik.kind in (EXPONENTIAL_EXP, GAMMA_EXP):
+            # GPLikelihoods AnalyticExpectation for the exp link: E[exp(-f)] = exp(-mu + v/2)
+            alpha = lik.sigma2 if lik.kind == GAMMA_EXP else 1.0
+            t = y * np.exp(-mu + v / 2.0)
+            cst = (alpha - 1.0) * np.log(y) - gammaln(alpha) if lik.kind == GAMMA_EXP else 0.0
+            dpar = dloglik_dparam(lik, mu, y) if lik.kind == GAMMA_EXP else np.zeros_like(mu)
+            return cst - t - alpha * mu, -alpha + t, -0.5 * t, dpar
         raise ValueError(f"no analytic expectation for {lik.kind}")
     if exp_.method == MONTE_CARLO:
         # GPLikelihoods.MonteCarloExpectation(n): mean over n reparameterised samples; derivatives of that finite sum
@@ -150,11 +179,7 @@ def expected_loglik_terms(exp_: Expectation, lik: Likelihood, mu, var, y, point0
         E = ll.mean(axis=1)
         dmu = dll.mean(axis=1)
         dvar = (dll * eps).mean(axis=1) / (2.0 * std)
-        if lik.kind == GAUSSIAN:
-            r = y[:, None] - f
-            ds2 = (-0.5 / lik.sigma2 + 0.5 * r * r / lik.sigma2**2).mean(axis=1)
-        else:
-            ds2 = np.zeros_like(mu)
+        ds2 = dloglik_dparam(lik, f, y[:, None]).mean(axis=1)
         return E, dmu, dvar, ds2
     xs, ws = gausshermite(exp_.n_points)
     f = mu[:, None] + (_SQRT2 * std)[:, None] * xs[None, :]
@@ -163,9 +188,5 @@ def expected_loglik_terms(exp_: Expectation, lik: Likelihood, mu, var, y, point0
     dmu = _INVSQRTPI * (dll @ ws)
     dstd = _INVSQRTPI * ((dll * (_SQRT2 * xs)[None, :]) @ ws)
     dvar = dstd / (2.0 * std)
-    if lik.kind == GAUSSIAN:
-        r = y[:, None] - f
-        ds2 = _INVSQRTPI * ((-0.5 / lik.sigma2 + 0.5 * r * r / lik.sigma2**2) @ ws)
-    else:
-        ds2 = np.zeros_like(mu)
+    ds2 = _INVSQRTPI * (dloglik_dparam(lik, f, y[:, None]) @ ws)
     return E, dmu, dvar, ds2

@@ -23,13 +23,17 @@ def make_problem(seed=0, kind="se", N=300, M=20, D=2, centered=False, lik="gauss
         y = g + 0.3 * rng.normal(size=N)
     elif lik == "bernoulli_logit":
         y = (rng.random(N) < 1 / (1 + np.exp(-2 * g))).astype(np.float64)
+    elif lik == "exponential_exp":
+        y = rng.exponential(np.exp(0.5 * g))
+    elif lik == "gamma_exp":
+        y = rng.gamma(2.5, np.exp(0.5 * g))
     else:
         y = rng.poisson(np.exp(0.5 * g)).astype(np.float64)
     m = 0.1 * rng.normal(size=M)
     A = 0.5 * np.eye(M) + 0.01 * np.tril(rng.normal(size=(M, M)))
     A[np.diag_indices(M)] = np.abs(np.diag(A))
     return dict(X=X, y=y, Z=Z, m=m, A=A, kind=kind, variance=variance, inv=inv, c=0.4 if kind == "linear" else 0.0, centered=centered,
-                lik=lik, method=method, n_gh=n_gh, mean_const=mean_const, jitter=jitter, sigma2=0.3)
+                lik=lik, method=method, n_gh=n_gh, mean_const=mean_const, jitter=jitter, sigma2=2.5 if lik == "gamma_exp" else 0.3)
 
 
 def oracle_objects(p):
@@ -49,7 +53,8 @@ def agp_objects(agp, p, x=None):
     fz = f(p["Z"], p["jitter"])
     q = agp.MvNormal(p["m"], chol_lower=p["A"])
     sva = agp.SparseVariationalApproximation(agp.Centered() if p["centered"] else agp.NonCentered(), fz, q)
-    lik = {"gaussian": agp.GaussianLikelihood(p["sigma2"]), "bernoulli_logit": agp.BernoulliLikelihood(), "poisson_exp": agp.PoissonLikelihood()}[p["lik"]]
+    lik = {"gaussian": agp.GaussianLikelihood(p["sigma2"]), "bernoulli_logit": agp.BernoulliLikelihood(), "poisson_exp": agp.PoissonLikelihood(),
+           "exponential_exp": agp.ExponentialLikelihood(), "gamma_exp": agp.GammaLikelihood(p["sigma2"])}[p["lik"]]
     quad = {"default": agp.DefaultExpectationMethod(), "analytic": agp.AnalyticExpectation(), "gauss_hermite": agp.GaussHermiteExpectation(p["n_gh"]),
             "monte_carlo": agp.MonteCarloExpectation(p["n_gh"], p.get("mc_seed", 0))}[p["method"]]
     lfx = agp.LatentGP(f, lik, 1e-18)(p["X"] if x is None else x)
@@ -69,6 +74,6 @@ def compare_grads(g, rg, p):
         out["linear_c"] = rel_err(g.linear_c, rg.kernel.c)
     if p["mean_const"] != 0.0:
         out["mean_const"] = rel_err(g.mean_const, rg.mean_const)
-    if p["lik"] == "gaussian":
+    if p["lik"] in ("gaussian", "gamma_exp"):
         out["lik_sigma2"] = rel_err(g.lik_sigma2, rg.lik_sigma2)
     return out

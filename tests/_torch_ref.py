@@ -67,6 +67,10 @@ def t_expected_loglik(lik_kind, sigma2, method, n_points, mu, var, y):
             return torch.sum(-0.5 * (math.log(2 * math.pi) + torch.log(sigma2) + ((y - mu) ** 2 + v) / sigma2))
         if lik_kind == POISSON_EXP:
             return torch.sum(y * mu - torch.exp(mu + v / 2) - torch.lgamma(y + 1))
+        if lik_kind in ("exponential_exp", "gamma_exp"):
+            alpha = sigma2 if lik_kind == "gamma_exp" else torch.tensor(1.0, dtype=mu.dtype)
+            cst = (alpha - 1) * torch.log(y) - torch.lgamma(alpha) if lik_kind == "gamma_exp" else 0.0
+            return torch.sum(cst - y * torch.exp(-mu + v / 2) - alpha * mu)
         raise ValueError
     xs, ws = gausshermite(n_points)
     xs = torch.tensor(xs)
@@ -78,6 +82,10 @@ def t_expected_loglik(lik_kind, sigma2, method, n_points, mu, var, y):
     elif lik_kind == BERNOULLI_LOGIT:
         p = torch.sigmoid(f)
         ll = torch.where(yy > 0.5, torch.log(p), torch.log(1 - p))
+    elif lik_kind in ("exponential_exp", "gamma_exp"):
+        alpha = sigma2 if lik_kind == "gamma_exp" else torch.tensor(1.0, dtype=mu.dtype)
+        cst = (alpha - 1) * torch.log(yy) - torch.lgamma(alpha) if lik_kind == "gamma_exp" else 0.0
+        ll = cst - yy * torch.exp(-f) - alpha * f
     else:
         ll = yy * f - torch.exp(f) - torch.lgamma(yy + 1)
     return torch.sum((ll @ ws) / math.sqrt(math.pi))

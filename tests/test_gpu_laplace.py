@@ -39,7 +39,8 @@ def _build_latent_gp(agp, theta):
 
 
 def _lik(agp, name):
-    return {"gaussian": agp.GaussianLikelihood(0.01), "bernoulli_logit": agp.BernoulliLikelihood(), "poisson_exp": agp.PoissonLikelihood()}[name]
+    return {"gaussian": agp.GaussianLikelihood(0.01), "bernoulli_logit": agp.BernoulliLikelihood(), "poisson_exp": agp.PoissonLikelihood(),
+            "exponential_exp": agp.ExponentialLikelihood(), "gamma_exp": agp.GammaLikelihood(2.5)}[name]
 
 
 def _problem(seed, n, D, lik):
@@ -52,6 +53,10 @@ def _problem(seed, n, D, lik):
         y = (rng.random(n) < 1 / (1 + np.exp(-3 * g))).astype(np.float64)
     elif lik == "poisson_exp":
         y = rng.poisson(np.exp(g)).astype(np.float64)
+    elif lik == "exponential_exp":
+        y = rng.exponential(np.exp(g))
+    elif lik == "gamma_exp":
+        y = rng.gamma(2.5, np.exp(g))
     else:
         y = g + 0.1 * rng.normal(size=n)
     return X, k, K, y
@@ -216,3 +221,13 @@ def test_issue_109_smoke(agp):
     post = agp.posterior(agp.LaplaceApproximation(), lfx, y)
     mu, var = agp.mean_and_var(post, X)
     assert np.all(np.isfinite(mu)) and np.all(var > 0)
+
+
+@pytest.mark.parametrize("lik", ["exponential_exp", "gamma_exp"])
+def test_laplace_exponential_and_gamma(agp, lik):
+    X, k, K, y = _problem(33, 300, 2, lik)
+    olik = ol.Likelihood(lik, 2.5)
+    lml, Kbar, f_opt, steps = olap.lml_and_grad_K(olik, y, K)
+    r = agp.laplace_lml_and_grad_K(_lik(agp, lik), y, K)
+    assert r.steps == steps and r.converged
+    assert abs(r.lml - lml) < 1e-10 * abs(lml) and rel_err(r.f, f_opt) < 1e-10 and rel_err(r.dK, Kbar) < 1e-8

@@ -332,3 +332,11 @@ def test_abi_error_conventions(agp):
     ds.close()
     # the context is still usable after every error
     assert np.isfinite(agp.elbo(sva, lfx, p["y"]))
+
+
+@pytest.mark.parametrize("lik,method", [("exponential_exp", "default"), ("gamma_exp", "default"), ("gamma_exp", "gauss_hermite"), ("exponential_exp", "monte_carlo")])
+def test_exponential_and_gamma_likelihoods(agp, lik, method):
+    """ExponentialLikelihood / GammaLikelihood(alpha) with the exp link: analytic (the GPLikelihoods default), Gauss-Hermite and
+    Monte-Carlo expectations, including d/d alpha."""
+    p = make_problem(seed=91, kind="matern52", N=600, M=25, D=3, lik=lik, method=method, n_gh=20)
+    _run_case(agp, p, num_data=6000.0)

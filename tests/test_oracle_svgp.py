@@ -89,6 +89,9 @@ CASES = [
     dict(kind="matern32", D=1, centered=True, lik="poisson_exp", method="default"),
     dict(kind="se", D=4, centered=True, lik="poisson_exp", method="gauss_hermite", ard=True, mean_const=0.3),
     dict(kind="linear", D=3, centered=False, lik="gaussian", method="gauss_hermite", jitter=1e-3, zdist="random", lengthscale=1.5, M=3),
+    dict(kind="matern52", D=2, centered=False, lik="gamma_exp", method="default"),
+    dict(kind="se", D=2, centered=False, lik="gamma_exp", method="gauss_hermite"),
+    dict(kind="matern32", D=3, centered=False, lik="exponential_exp", method="default"),
 ]
 
 
@@ -108,7 +111,7 @@ def test_reverse_pass_matches_autograd(case):
         assert rel_err(g.kernel.c, tg["c"]) < 1e-9
     if p["mean_const"] != 0.0:
         assert rel_err(g.mean_const, tg["mean_const"]) < 1e-9
-    if p["lik"] == "gaussian":
+    if p["lik"] in ("gaussian", "gamma_exp"):
         assert rel_err(g.lik_sigma2, tg["lik_sigma2"]) < 1e-9
 
 
