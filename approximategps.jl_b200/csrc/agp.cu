@@ -849,7 +849,13 @@ static int32_t ensure_sweep_workspace(agp_ctx* c, int64_t cols, bool grad) {
     OK(c->As.ensure((int64_t)Mp * cc));
     OK(c->gpart.ensure((cc / BN) * Mp));
     const int ntiles = nb * (nb + 1);
-    c->nsplit = std::max(1, (2 * c->sms) / ntiles);
+    // K-splits of the SYRK: about eight waves of CTAs so that the cheap diagonal tiles (3/8 and 7/8 of a full tile's MMAs)
+    // are balanced by the block scheduler (measured at C4: 4 splits / one wave 113 ms per 3e6 points, 32 splits 105 ms);
+    // the per-split partial G slices are capped at 512 MB.
+    const int by_waves = (8 * 2 * c->sms + ntiles - 1) / ntiles;
+    const int by_mem = (int)std::max<int64_t>(1, ((int64_t)512 << 20) / (MM * 8));
+    c->nsplit = std::max(1, std::min(std::min(by_waves, by_mem), 32));
+    if (const char* e = getenv("AGP_SYRK_SPLIT")) c->nsplit = std::max(1, atoi(e));  // tuning knob
     OK(c->Gpart.ensure((int64_t)c->nsplit * MM));
     c->nslab = (int)std::max<int64_t>((cc + 2047) / 2048, (Mp + 2047) / 2048);
     OK(c->kpart.ensure((int64_t)c->nslab * Mp * (2 * D + 3)));
