@@ -20,10 +20,13 @@ from .laplace_api import (  # noqa: F401
     LaplaceObjectiveCache,
     LaplacePosterior,
     LaplaceResult,
+    LaplaceStepResult,
     build_laplace_objective,
     build_laplace_objective_,
     laplace_approx_lml_and_gradient,
     laplace_f_and_lml,
+    laplace_f_cov,
+    laplace_steps,
     laplace_lml,
     laplace_lml_and_grad_K,
 )

@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("AGP_B200_LIB") or os.path.join(HERE, "libagp_b200.so"
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_NOT_PD, ERR_DOMAIN, ERR_CUDA, ERR_NCCL, ERR_ALLOC = range(8)
 
 KERNEL_SE, KERNEL_MATERN32, KERNEL_MATERN52, KERNEL_LINEAR = range(4)
-LIK_GAUSSIAN, LIK_BERNOULLI_LOGIT, LIK_POISSON_EXP, LIK_EXPONENTIAL_EXP, LIK_GAMMA_EXP = range(5)
+LIK_GAUSSIAN, LIK_BERNOULLI_LOGIT, LIK_POISSON_EXP, LIK_EXPONENTIAL_EXP, LIK_GAMMA_EXP, LIK_BERNOULLI_PROBIT = range(6)
 EXPECT_DEFAULT, EXPECT_ANALYTIC, EXPECT_GAUSS_HERMITE, EXPECT_MONTE_CARLO = range(4)
 NONCENTERED, CENTERED = 0, 1
 POINT_MAJOR, FEATURE_MAJOR = 0, 1
@@ -149,6 +149,8 @@ SYMBOLS = {
     "agp_laplace_cache_fetch": (C.c_int32, [_vp, C.c_int32, c_double_p]),
     "agp_laplace_cache_destroy": (C.c_int32, [_vp]),
     "agp_laplace_cache_n": (C.c_int32, [_vp]),
+    "agp_laplace_f_cov": (C.c_int32, [_vp, c_double_p]),
+    "agp_laplace_cache_lml": (C.c_int32, [_vp, c_double_p]),
 }
 
 

@@ -118,10 +118,29 @@ class GaussianLikelihood:
     kind: int = L.LIK_GAUSSIAN
 
 
-@dataclass
+class LogisticLink:
+    """``GPLikelihoods.LogisticLink()`` (the default link of ``BernoulliLikelihood``)."""
+
+
+class ProbitLink:
+    """``GPLikelihoods.ProbitLink()``: ``p = normcdf(f)``."""
+
+
 class BernoulliLikelihood:
-    sigma2: float = 0.0
-    kind: int = L.LIK_BERNOULLI_LOGIT
+    """``BernoulliLikelihood(l=logistic)``: ``Bernoulli(l(f))`` with the logistic (default) or the probit link."""
+
+    sigma2 = 0.0
+
+    def __init__(self, link=None):
+        if link is None or isinstance(link, LogisticLink) or link is LogisticLink or link == "logistic":
+            self.kind = L.LIK_BERNOULLI_LOGIT
+        elif isinstance(link, ProbitLink) or link is ProbitLink or link in ("probit", "normcdf"):
+            self.kind = L.LIK_BERNOULLI_PROBIT
+        else:
+            raise ValueError(f"ArgumentError: unsupported link {link!r} (no CPU fallback)")
+
+    def __repr__(self):
+        return f"BernoulliLikelihood({'ProbitLink' if self.kind == L.LIK_BERNOULLI_PROBIT else 'LogisticLink'}())"
 
 
 @dataclass
@@ -439,7 +458,7 @@ class _Packed:
         lik = lik or GaussianLikelihood(1.0)
         p.lik = L.AgpLikelihood(lik.kind, float(lik.sigma2))
         q = quadrature or DefaultExpectationMethod()
-        if isinstance(q, GaussHermiteExpectation) or (isinstance(q, DefaultExpectationMethod) and lik.kind == L.LIK_BERNOULLI_LOGIT):
+        if isinstance(q, GaussHermiteExpectation) or (isinstance(q, DefaultExpectationMethod) and lik.kind in (L.LIK_BERNOULLI_LOGIT, L.LIK_BERNOULLI_PROBIT)):
             gh = q if isinstance(q, GaussHermiteExpectation) else GaussHermiteExpectation(20)
             xs, ws = gh.nodes_weights()
             self.xs, self.ws = np.ascontiguousarray(xs), np.ascontiguousarray(ws)

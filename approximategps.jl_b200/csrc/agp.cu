@@ -148,6 +148,8 @@ struct agp_ctx {
   void* lap = nullptr;  // LapWork (laplace_host.inc)
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;                // trailing updates of the blocked Cholesky (look-ahead), see blocked_cholesky
+  cudaEvent_t ev_panel = nullptr, ev_trail = nullptr;
   int sms = 148;
   int64_t launches = 0;
   int64_t chunk_cols = 0;  // capacity of the per-chunk scratch (columns)
@@ -211,6 +213,9 @@ extern "C" int32_t agp_ctx_create(int32_t device, agp_ctx** out) {
   c->device = device;
   c->sms = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_trail, cudaEventDisableTiming));
   CU(cudaMalloc(&c->d_flags, 4 * sizeof(int)));
   CU(cudaMemset(c->d_flags, 0, 4 * sizeof(int)));
   *out = c;
@@ -230,6 +235,9 @@ extern "C" int32_t agp_ctx_destroy(agp_ctx* c) {
   lap_release(c);
   if (c->d_flags) cudaFree(c->d_flags);
   for (cudaEvent_t e : c->prof.pool) cudaEventDestroy(e);
+  if (c->ev_panel) cudaEventDestroy(c->ev_panel);
+  if (c->ev_trail) cudaEventDestroy(c->ev_trail);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
   delete c;
   return AGP_OK;
@@ -506,9 +514,23 @@ static int32_t transpose(agp_ctx* c, const double* in, double* out, int n, int64
 // Inner level: 128-blocks (diagonal kernel + panel GEMM + an update confined to the current 512-wide super-panel);
 // outer level: one trailing update per super-panel with K = 512, which quadruples the flop per byte of the
 // dominant GEMM compared with a rank-128 update.
+// Look-ahead: the factorisation of a super-panel is a chain of latency-bound launches (one CTA on the diagonal block,
+// then a few dozen GEMM tiles) that leaves the machine idle, while the trailing update is the only part with enough tiles
+// to fill it.  So the trailing update is split: the block columns of the NEXT super-panel are updated on the main stream
+// (the chain continues with them at once), the remaining columns on a second stream, concurrently with the next
+// super-panel's chain.  The arithmetic of every tile is unchanged (same k order), so the factor is bit-identical to the
+// single-stream schedule.
+struct StreamSwap {  // launch helpers use c->stream: point it at the second stream for a scope
+  agp_ctx* c;
+  cudaStream_t saved;
+  StreamSwap(agp_ctx* c_, cudaStream_t s) : c(c_), saved(c_->stream) { c->stream = s; }
+  ~StreamSwap() { c->stream = saved; }
+};
 static int32_t blocked_cholesky(agp_ctx* c, double* Kw, double* L, double* Lt, double* Ut, int nb, int64_t ld, int* info, int nvalid) {
   OK((ensure_smem<potrf_trinv128_kernel>(c, PT_SMEM_BYTES)));
   constexpr int OB = 4;  // inner blocks per super-panel
+  static const bool lookahead = !(getenv("AGP_CHOL_LOOKAHEAD") && atoi(getenv("AGP_CHOL_LOOKAHEAD")) == 0);  // tuning knob
+  bool trail_pending = false;  // a trailing update is in flight on stream2
   for (int J0 = 0; J0 < nb; J0 += OB) {
     const int J1 = std::min(nb, J0 + OB);  // super-panel = block columns [J0, J1)
     for (int J = J0; J < J1; J++) {
@@ -531,10 +553,31 @@ static int32_t blocked_cholesky(agp_ctx* c, double* Kw, double* L, double* Lt, d
     const int rem = nb - J1;
     if (rem <= 0) break;
     // trailing update with the whole super-panel: Kw[>=J1, >=J1] -= L[>=J1, J0..J1) L[>=J1, J0..J1)^T
+    const int K = (J1 - J0) * BM;
     const int64_t pnl = (int64_t)J0 * BM * ld + (int64_t)J1 * BM;
     const int64_t trl = (int64_t)J1 * BM * ld + (int64_t)J1 * BM;
-    OK((run_gemm<A_KM, B_KN>(c, rem, 2 * rem, L + pnl, ld, L + pnl, ld, (J1 - J0) * BM, KR_FULL, TS_NBLK_LE, epi_store(Kw + trl, ld, false, -1.0, 1.0))));
+    const int J2 = std::min(nb, J1 + OB), rem2 = nb - J2;  // [J1, J2) = the next super-panel
+    if (!lookahead || rem2 <= 0) {
+      if (trail_pending) CU(cudaStreamWaitEvent(c->stream, c->ev_trail, 0));
+      trail_pending = false;
+      OK((run_gemm<A_KM, B_KN>(c, rem, 2 * rem, L + pnl, ld, L + pnl, ld, K, KR_FULL, TS_NBLK_LE, epi_store(Kw + trl, ld, false, -1.0, 1.0))));
+      continue;
+    }
+    CU(cudaEventRecord(c->ev_panel, c->stream));  // block columns [J0, J1) of L are complete
+    // main stream: columns [J1, J2) only (they were last written by the previous trailing update on stream2)
+    if (trail_pending) CU(cudaStreamWaitEvent(c->stream, c->ev_trail, 0));
+    OK((run_gemm<A_KM, B_KN>(c, rem, 2 * (J2 - J1), L + pnl, ld, L + pnl, ld, K, KR_FULL, TS_NBLK_LE, epi_store(Kw + trl, ld, false, -1.0, 1.0))));
+    {  // second stream: columns >= J2 (stream order serialises successive trailing updates of the same tiles)
+      StreamSwap sw(c, c->stream2);
+      CU(cudaStreamWaitEvent(c->stream, c->ev_panel, 0));
+      const int64_t pnl2 = (int64_t)J0 * BM * ld + (int64_t)J2 * BM;
+      const int64_t trl2 = (int64_t)J2 * BM * ld + (int64_t)J2 * BM;
+      OK((run_gemm<A_KM, B_KN>(c, rem2, 2 * rem2, L + pnl2, ld, L + pnl2, ld, K, KR_FULL, TS_NBLK_LE, epi_store(Kw + trl2, ld, false, -1.0, 1.0))));
+      CU(cudaEventRecord(c->ev_trail, c->stream));
+      trail_pending = true;
+    }
   }
+  if (trail_pending) CU(cudaStreamWaitEvent(c->stream, c->ev_trail, 0));
   return AGP_OK;
 }
 
@@ -650,7 +693,7 @@ static int32_t resolve_params(const agp_svgp_params* p, SvgpState& st) {
   if (p->kernel.kind < AGP_KERNEL_SE || p->kernel.kind > AGP_KERNEL_LINEAR) return fail(AGP_ERR_UNSUPPORTED, "unsupported kernel kind %d", p->kernel.kind);
   if (p->kernel.n_scale != 1 && p->kernel.n_scale != p->D) return fail(AGP_ERR_INVALID, "kernel.n_scale must be 1 or D");
   if (!p->kernel.inv_lengthscale) return fail(AGP_ERR_INVALID, "kernel.inv_lengthscale is NULL");
-  if (p->lik.kind < AGP_LIK_GAUSSIAN || p->lik.kind > AGP_LIK_GAMMA_EXP) return fail(AGP_ERR_UNSUPPORTED, "unsupported likelihood kind %d", p->lik.kind);
+  if (p->lik.kind < AGP_LIK_GAUSSIAN || p->lik.kind > AGP_LIK_BERNOULLI_PROBIT) return fail(AGP_ERR_UNSUPPORTED, "unsupported likelihood kind %d", p->lik.kind);
   if (p->parametrization != AGP_NONCENTERED && p->parametrization != AGP_CENTERED) return fail(AGP_ERR_INVALID, "unknown parametrization");
   st.M = p->M;
   st.D = p->D;
@@ -673,9 +716,9 @@ static int32_t resolve_params(const agp_svgp_params* p, SvgpState& st) {
   int method = p->expect.method;
   if (method == AGP_EXPECT_DEFAULT) {
     // GPLikelihoods.DefaultExpectationMethod: analytic for Gaussian and Poisson-exp, else Gauss-Hermite(20)
-    method = (p->lik.kind != AGP_LIK_BERNOULLI_LOGIT) ? AGP_EXPECT_ANALYTIC : AGP_EXPECT_GAUSS_HERMITE;
+    method = (p->lik.kind != AGP_LIK_BERNOULLI_LOGIT && p->lik.kind != AGP_LIK_BERNOULLI_PROBIT) ? AGP_EXPECT_ANALYTIC : AGP_EXPECT_GAUSS_HERMITE;
   }
-  if (method == AGP_EXPECT_ANALYTIC && p->lik.kind == AGP_LIK_BERNOULLI_LOGIT)
+  if (method == AGP_EXPECT_ANALYTIC && (p->lik.kind == AGP_LIK_BERNOULLI_LOGIT || p->lik.kind == AGP_LIK_BERNOULLI_PROBIT))
     return fail(AGP_ERR_UNSUPPORTED, "no analytic expectation for the Bernoulli likelihood");
   st.lp.method = method;
   st.lp.ngh = 0;

@@ -116,6 +116,16 @@ __device__ __forceinline__ double logistic(double x) {
   return e / (1.0 + e);
 }
 
+// log Phi(z) and r(z) = phi(z) / Phi(z) for the probit link, overflow-free through erfcx: Phi(z) = erfc(t) / 2 with
+// t = -z / sqrt2, r = sqrt(2/pi) / erfcx(t).  (An intentional divergence like the logistic one above: the reference evaluates
+// log(normcdf(f)) / log(1 - normcdf(f)), which loses its digits once normcdf(f) rounds to 0 or 1.)
+__device__ __forceinline__ void log_ndtr_and_ratio(double z, double& lp, double& r) {
+  const double t = -0.7071067811865476 * z;
+  const double ex = erfcx(t);
+  r = 0.7978845608028654 / ex;
+  lp = (t > 0.0) ? log(0.5 * ex) - t * t : log1p(-0.5 * erfc(-t));
+}
+
 // digamma(x), x > 0: recurrence up to x >= 10, then the asymptotic series (error < 1e-15)
 __device__ __forceinline__ double digamma(double x) {
   double r = 0.0;
@@ -145,6 +155,11 @@ __device__ __forceinline__ void loglik_d1(const LikParams& lp, double f, double 
     const bool one = y > 0.5;
     ll = -softplus(one ? -f : f);
     dll = (one ? 1.0 : 0.0) - logistic(f);
+  } else if (lp.kind == AGP_LIK_BERNOULLI_PROBIT) {  // log Phi(s f), s = +-1
+    const double sg = (y > 0.5) ? 1.0 : -1.0;
+    double r;
+    log_ndtr_and_ratio(sg * f, ll, r);
+    dll = sg * r;
   } else if (lp.kind == AGP_LIK_POISSON_EXP) {
     const double lam = exp(f);
     ll = y * f - lam + cst;

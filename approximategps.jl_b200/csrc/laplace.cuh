@@ -47,6 +47,14 @@ __global__ void __launch_bounds__(256) lap_derivs_kernel(LapDerivArgs a) {
         d1 = (one ? 1.0 : 0.0) - p;
         W = p * (1.0 - p);
         d3 = -p * (1.0 - p) * (1.0 - 2.0 * p);
+      } else if (a.lp.kind == AGP_LIK_BERNOULLI_PROBIT) {
+        // l = log Phi(z), z = s f, r = phi(z) / Phi(z): d1 = s r, d2 = -r (z + r), d3 = s r ((z + r)(z + 2 r) - 1)
+        const double sg = (y > 0.5) ? 1.0 : -1.0, z = sg * f;
+        double r;
+        log_ndtr_and_ratio(z, ll, r);
+        d1 = sg * r;
+        W = r * (z + r);
+        d3 = sg * r * ((z + r) * (z + 2.0 * r) - 1.0);
       } else if (a.lp.kind == AGP_LIK_POISSON_EXP) {
         const double lam = exp(f);
         ll = y * f - lam - lgamma(y + 1.0);

@@ -33,6 +33,22 @@ class LaplaceCacheView:
             self._memo[name] = float(out[0]) if fld == 7 else out
         return self._memo[name]
 
+    def f_cov(self) -> np.ndarray:
+        """``laplace_f_cov(cache)`` (Laplace.jl:376-386), computed on the device (agp_laplace_f_cov)."""
+        if "f_cov" not in self._memo:
+            out = np.zeros((self.n, self.n), order="F")
+            L.check(self._lib.agp_laplace_f_cov(self._h, L.dptr(out)))
+            self._memo["f_cov"] = out
+        return self._memo["f_cov"]
+
+    def lml_approx(self) -> float:
+        """``_laplace_lml(cache.f, cache)`` (Laplace.jl:250-254)."""
+        if "lml" not in self._memo:
+            out = np.zeros(1)
+            L.check(self._lib.agp_laplace_cache_lml(self._h, L.dptr(out)))
+            self._memo["lml"] = float(out[0])
+        return self._memo["lml"]
+
     def close(self):
         if self._owning and self._h:
             self._lib.agp_laplace_cache_destroy(self._h)
@@ -150,6 +166,40 @@ def laplace_f_and_lml(lfx, ys, *, ctx=None, **newton_kwargs):
     """``laplace_f_and_lml(lfx, ys; newton_kwargs...)`` (Laplace.jl:140-145) -> (f_opt, lml)."""
     r = _run(ctx, **_check_laplace_inputs(lfx, ys, **newton_kwargs))
     return r.f, r.lml
+
+
+def laplace_f_cov(cache: LaplaceCacheView) -> np.ndarray:
+    """``laplace_f_cov(cache)`` (Laplace.jl:376-386): ``Wsqrt^-1 (I - B^-1) Wsqrt^-1``."""
+    return cache.f_cov()
+
+
+@dataclass
+class LaplaceStepResult:
+    """``LaplaceResult(fnew, cache)`` (Laplace.jl:388-395): one record per Newton step of ``laplace_steps``.  ``q`` is
+    ``MvNormal(cache.f, _symmetric(f_cov))``, kept as the pair ``(q_mean, q_cov)``."""
+
+    fnew: np.ndarray
+    f_cov: np.ndarray
+    q_mean: np.ndarray
+    q_cov: np.ndarray
+    lml_approx: float
+    cache: dict
+
+
+def laplace_steps(lfx, ys, *, ctx=None, **newton_kwargs):
+    """``laplace_steps(lfx, ys; newton_kwargs...)`` (Laplace.jl:409-421): the intermediate approximation of every
+    Newton step.  The callback's cache view is only valid during the step, so its fields are copied to the host."""
+    if "callback" in newton_kwargs:
+        raise TypeError("laplace_steps installs its own callback")  # the reference would hit a duplicate keyword
+    res_array = []
+
+    def store_result(fnew, cache):
+        f_cov = cache.f_cov()
+        fields = {k: np.array(getattr(cache, k)) for k in ("W", "Wsqrt", "d_loglik", "a", "f", "B_ch_L")}
+        res_array.append(LaplaceStepResult(np.array(fnew), f_cov, fields["f"], 0.5 * (f_cov + f_cov.T), cache.lml_approx(), fields))
+
+    _run(ctx, **_check_laplace_inputs(lfx, ys, **newton_kwargs, callback=store_result))
+    return res_array
 
 
 def laplace_lml(*args, ctx=None, f_init=None, maxiter=100, callback=None):

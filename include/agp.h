@@ -45,6 +45,7 @@ extern "C" {
 #define AGP_LIK_POISSON_EXP 2     /* PoissonLikelihood() (exp link)                              */
 #define AGP_LIK_EXPONENTIAL_EXP 3 /* ExponentialLikelihood() (exp link): Exponential(scale = exp(f)) */
 #define AGP_LIK_GAMMA_EXP 4       /* GammaLikelihood(alpha) (exp link): Gamma(alpha, scale = exp(f)); alpha in `sigma2` */
+#define AGP_LIK_BERNOULLI_PROBIT 5 /* BernoulliLikelihood(ProbitLink()): Bernoulli(normcdf(f))    */
 
 #define AGP_EXPECT_DEFAULT 0       /* GPLikelihoods.DefaultExpectationMethod()                   */
 #define AGP_EXPECT_ANALYTIC 1      /* AnalyticExpectation()                                      */
@@ -255,6 +256,11 @@ int32_t agp_laplace_cache_fetch(agp_laplace_cache* cache, int32_t field, double*
 int32_t agp_laplace_cache_destroy(agp_laplace_cache* cache);
 /* Number of latent values n of a cache (or callback view): the length of its vector fields. */
 int32_t agp_laplace_cache_n(agp_laplace_cache* cache);
+/* Replaces laplace_f_cov(cache) -- Laplace.jl:376-386: the covariance of q(f), Wsqrt^-1 (I - B^-1) Wsqrt^-1, column-major
+ * n x n, from an owned cache or from the view a Newton callback receives (laplace_steps, Laplace.jl:409-421).            */
+int32_t agp_laplace_f_cov(agp_laplace_cache* cache, double* cov_out);
+/* _laplace_lml(cache.f, cache) -- Laplace.jl:250-254 -- as LaplaceResult(fnew, cache) (:388-395) evaluates it per step. */
+int32_t agp_laplace_cache_lml(agp_laplace_cache* cache, double* lml_out);
 /* Replaces the prediction methods of ApproxPosteriorGP{<:LaplaceApproximation} -- Laplace.jl:425-463
  * (_laplace_predict_intermediates, mean_and_var, mean_and_cov, mean, var, cov(f, x), cov(f, x, y)) on a cache
  * returned by agp_laplace_f_and_lml: kernel / Xtrain (host, point-major n x D) describe prior_at_x.  Any of

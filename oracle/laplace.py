@@ -86,12 +86,39 @@ def laplace_f_and_lml(lik: Likelihood, y, K, f_init=None, maxiter=100, callback=
     return f_opt, laplace_lml(lik, y, K, f_opt), steps
 
 
+def laplace_f_cov(cache: LaplaceCache) -> np.ndarray:
+    """Laplace.jl:376-386: (K^-1 + W)^-1 = Wsqrt^-1 (I - B^-1) Wsqrt^-1."""
+    n = len(cache.f)
+    Binv = cho_solve((cache.B_L, True), np.eye(n))
+    wi = 1.0 / cache.Wsqrt
+    return wi[:, None] * (np.eye(n) - Binv) * wi[None, :]
+
+
+def laplace_steps(lik: Likelihood, y, K, f_init=None, maxiter=100):
+    """Laplace.jl:409-421 with LaplaceResult :388-395: one dict (fnew, f_cov, q_mean, q_cov, lml_approx, cache) per step."""
+    out = []
+
+    def store(fnew, cache):
+        fc = laplace_f_cov(cache)
+        out.append(dict(fnew=fnew.copy(), f_cov=fc, q_mean=cache.f.copy(), q_cov=0.5 * (fc + fc.T), lml_approx=_laplace_lml(cache.f, cache), cache=cache))
+
+    newton_inner_loop(lik, y, K, f_init, maxiter, callback=store)
+    return out
+
+
 def _d3_loglik(lik: Likelihood, f, y):
     if lik.kind == GAUSSIAN:
         return np.zeros_like(f)
     if lik.kind == BERNOULLI_LOGIT:
         p = logistic(f)
         return -p * (1.0 - p) * (1.0 - 2.0 * p)
+    if lik.kind == "bernoulli_probit":
+        from scipy.special import erfcx
+
+        sg = np.where(y > 0.5, 1.0, -1.0)
+        z = sg * f
+        r = np.sqrt(2.0 / np.pi) / erfcx(-z / np.sqrt(2.0))
+        return sg * r * ((z + r) * (z + 2.0 * r) - 1.0)
     if lik.kind == POISSON_EXP:
         return -np.exp(f)
     if lik.kind in ("exponential_exp", "gamma_exp"):

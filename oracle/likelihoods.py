@@ -26,6 +26,7 @@ import numpy as np
 from scipy.special import gammaln, xlogy
 
 GAUSSIAN, BERNOULLI_LOGIT, POISSON_EXP = "gaussian", "bernoulli_logit", "poisson_exp"
+BERNOULLI_PROBIT = "bernoulli_probit"  # BernoulliLikelihood(ProbitLink()): Bernoulli(normcdf(f))
 EXPONENTIAL_EXP, GAMMA_EXP = "exponential_exp", "gamma_exp"  # Exponential / Gamma(alpha) with scale exp(f); alpha rides in sigma2
 ANALYTIC, GAUSS_HERMITE, MONTE_CARLO = "analytic", "gauss_hermite", "monte_carlo"
 
@@ -114,6 +115,15 @@ def loglik_and_derivs(lik: Likelihood, f, y):
         with np.errstate(divide="ignore"):
             ll = np.where(y > 0.5, np.log(p), np.log(1.0 - p))  # Distributions.logpdf(Bernoulli(p), y)
         return ll, y - p, -p * (1.0 - p)
+    if lik.kind == BERNOULLI_PROBIT:
+        # logpdf(Bernoulli(normcdf(f)), y) = log Phi(s f), s = 2y - 1, in the overflow-free form (log_ndtr / erfcx); with
+        # r = phi(z) / Phi(z): d/df = s r, d2/df2 = -r (z + r)
+        from scipy.special import erfcx, log_ndtr
+
+        sg = np.where(y > 0.5, 1.0, -1.0)
+        z = sg * f
+        r = np.sqrt(2.0 / np.pi) / erfcx(-z / _SQRT2)
+        return log_ndtr(z), sg * r, -r * (z + r)
     if lik.kind == POISSON_EXP:
         lam = np.exp(f)
         return xlogy(y, lam) - lam - gammaln(y + 1.0), y - lam, -lam

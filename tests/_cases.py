@@ -21,7 +21,7 @@ def make_problem(seed=0, kind="se", N=300, M=20, D=2, centered=False, lik="gauss
     g = np.sin(X @ w)
     if lik == "gaussian":
         y = g + 0.3 * rng.normal(size=N)
-    elif lik == "bernoulli_logit":
+    elif lik in ("bernoulli_logit", "bernoulli_probit"):
         y = (rng.random(N) < 1 / (1 + np.exp(-2 * g))).astype(np.float64)
     elif lik == "exponential_exp":
         y = rng.exponential(np.exp(0.5 * g))
@@ -53,7 +53,7 @@ def agp_objects(agp, p, x=None):
     fz = f(p["Z"], p["jitter"])
     q = agp.MvNormal(p["m"], chol_lower=p["A"])
     sva = agp.SparseVariationalApproximation(agp.Centered() if p["centered"] else agp.NonCentered(), fz, q)
-    lik = {"gaussian": agp.GaussianLikelihood(p["sigma2"]), "bernoulli_logit": agp.BernoulliLikelihood(), "poisson_exp": agp.PoissonLikelihood(),
+    lik = {"gaussian": agp.GaussianLikelihood(p["sigma2"]), "bernoulli_logit": agp.BernoulliLikelihood(), "bernoulli_probit": agp.BernoulliLikelihood(agp.ProbitLink()), "poisson_exp": agp.PoissonLikelihood(),
            "exponential_exp": agp.ExponentialLikelihood(), "gamma_exp": agp.GammaLikelihood(p["sigma2"])}[p["lik"]]
     quad = {"default": agp.DefaultExpectationMethod(), "analytic": agp.AnalyticExpectation(), "gauss_hermite": agp.GaussHermiteExpectation(p["n_gh"]),
             "monte_carlo": agp.MonteCarloExpectation(p["n_gh"], p.get("mc_seed", 0))}[p["method"]]

@@ -82,6 +82,10 @@ def t_expected_loglik(lik_kind, sigma2, method, n_points, mu, var, y):
     elif lik_kind == BERNOULLI_LOGIT:
         p = torch.sigmoid(f)
         ll = torch.where(yy > 0.5, torch.log(p), torch.log(1 - p))
+    elif lik_kind == "bernoulli_probit":
+        # p = normcdf(f); logpdf(Bernoulli(p), y) = y ? log(p) : log(1 - p) = log Phi(+-f).  (torch.where over the literal
+        # log(p) / log(1 - p) pair back-propagates 0 * inf = NaN from the unselected branch once 1 - p rounds to 0.)
+        ll = torch.special.log_ndtr(torch.where(yy > 0.5, f, -f))
     elif lik_kind in ("exponential_exp", "gamma_exp"):
         alpha = sigma2 if lik_kind == "gamma_exp" else torch.tensor(1.0, dtype=mu.dtype)
         cst = (alpha - 1) * torch.log(yy) - torch.lgamma(alpha) if lik_kind == "gamma_exp" else 0.0

@@ -39,7 +39,7 @@ def _build_latent_gp(agp, theta):
 
 
 def _lik(agp, name):
-    return {"gaussian": agp.GaussianLikelihood(0.01), "bernoulli_logit": agp.BernoulliLikelihood(), "poisson_exp": agp.PoissonLikelihood(),
+    return {"gaussian": agp.GaussianLikelihood(0.01), "bernoulli_logit": agp.BernoulliLikelihood(), "bernoulli_probit": agp.BernoulliLikelihood("probit"), "poisson_exp": agp.PoissonLikelihood(),
             "exponential_exp": agp.ExponentialLikelihood(), "gamma_exp": agp.GammaLikelihood(2.5)}[name]
 
 
@@ -49,7 +49,7 @@ def _problem(seed, n, D, lik):
     k = ok.Kernel(ok.SE, 1.3, np.array([1.0 / 0.8]))
     K = ok.kernelmatrix(k, X) + 1e-6 * np.eye(n)
     g = np.sin(X @ rng.normal(size=D))
-    if lik == "bernoulli_logit":
+    if lik in ("bernoulli_logit", "bernoulli_probit"):
         y = (rng.random(n) < 1 / (1 + np.exp(-3 * g))).astype(np.float64)
     elif lik == "poisson_exp":
         y = rng.poisson(np.exp(g)).astype(np.float64)
@@ -223,7 +223,7 @@ def test_issue_109_smoke(agp):
     assert np.all(np.isfinite(mu)) and np.all(var > 0)
 
 
-@pytest.mark.parametrize("lik", ["exponential_exp", "gamma_exp"])
+@pytest.mark.parametrize("lik", ["exponential_exp", "gamma_exp", "bernoulli_probit"])
 def test_laplace_exponential_and_gamma(agp, lik):
     X, k, K, y = _problem(33, 300, 2, lik)
     olik = ol.Likelihood(lik, 2.5)
@@ -231,3 +231,38 @@ def test_laplace_exponential_and_gamma(agp, lik):
     r = agp.laplace_lml_and_grad_K(_lik(agp, lik), y, K)
     assert r.steps == steps and r.converged
     assert abs(r.lml - lml) < 1e-10 * abs(lml) and rel_err(r.f, f_opt) < 1e-10 and rel_err(r.dK, Kbar) < 1e-8
+
+
+@pytest.mark.parametrize("n,D", [(48, 1), (300, 2)])
+def test_laplace_steps_and_f_cov(agp, n, D):
+    """laplace_steps / LaplaceResult / laplace_f_cov (Laplace.jl:376-421, test :207-217) against the oracle: one record per
+    Newton step with fnew, q = MvNormal(cache.f, sym(f_cov)), lml_approx, and the cache fields."""
+    if n == 48:
+        X, y = olap.generate_data()
+        k = ok.Kernel(ok.SE, 1.3, np.array([1.0 / 0.9]))
+        jit = 1e-8
+    else:
+        X, k, _, y = _problem(11, n, D, "bernoulli_logit")
+        jit = 1e-6
+    K = ok.kernelmatrix(k, X) + jit * np.eye(n)
+    ref = olap.laplace_steps(ol.Likelihood(ol.BERNOULLI_LOGIT), y, K)
+    f = agp.GP(k.variance * agp.ScaleTransform(agp.SqExponentialKernel(), float(k.inv_lengthscale[0])))
+    lfx = agp.LatentGP(f, agp.BernoulliLikelihood(), jit)(X)
+    res = agp.laplace_steps(lfx, y)
+    assert len(res) == len(ref)
+    worst = 0.0
+    for a, b in zip(res, ref):
+        assert rel_err(a.fnew, b["fnew"]) < 1e-9
+        assert rel_err(a.q_mean, b["q_mean"]) < 1e-9
+        e = np.max(np.abs(a.f_cov - b["f_cov"])) / np.max(np.abs(b["f_cov"]))
+        worst = max(worst, e)
+        assert e < 1e-9
+        assert np.array_equal(a.q_cov, a.q_cov.T)
+        assert abs(a.lml_approx - b["lml_approx"]) <= 1e-10 * abs(b["lml_approx"])
+        assert rel_err(a.cache["W"], b["cache"].W) < 1e-9
+    print(f"\n[laplace_steps n={n}] {len(res)} steps, worst f_cov rel err {worst:.2e}")
+    # the owned cache of posterior(la, lfx, ys) gives the same covariance as the last step
+    post = agp.posterior(agp.LaplaceApproximation(), lfx, y)
+    fc = agp.laplace_f_cov(post.data)
+    assert np.max(np.abs(fc - ref[-1]["f_cov"])) / np.max(np.abs(ref[-1]["f_cov"])) < 1e-9
+    assert abs(post.data.lml_approx() - ref[-1]["lml_approx"]) <= 1e-10 * abs(ref[-1]["lml_approx"])

@@ -334,6 +334,13 @@ def test_abi_error_conventions(agp):
     assert np.isfinite(agp.elbo(sva, lfx, p["y"]))
 
 
+@pytest.mark.parametrize("method,centered", [("default", False), ("gauss_hermite", True), ("monte_carlo", False)])
+def test_bernoulli_probit_link(agp, method, centered):
+    """BernoulliLikelihood(ProbitLink()): Gauss-Hermite (the GPLikelihoods default for Bernoulli) and Monte-Carlo expectations."""
+    p = make_problem(seed=77, kind="se", N=700, M=30, D=3, lik="bernoulli_probit", method=method, n_gh=20, centered=centered)
+    _run_case(agp, p, num_data=3500.0)
+
+
 @pytest.mark.parametrize("lik,method", [("exponential_exp", "default"), ("gamma_exp", "default"), ("gamma_exp", "gauss_hermite"), ("exponential_exp", "monte_carlo")])
 def test_exponential_and_gamma_likelihoods(agp, lik, method):
     """ExponentialLikelihood / GammaLikelihood(alpha) with the exp link: analytic (the GPLikelihoods default), Gauss-Hermite and

@@ -92,3 +92,67 @@ def test_warm_start_saves_newton_steps():
         _, _, f, s = olap.objective_and_grad(t, X, y, f_init=f)
         warm += s
     assert warm < cold
+
+
+def test_laplace_f_cov_is_posterior_covariance_and_steps_record_every_iteration():
+    """laplace_f_cov (Laplace.jl:376-386) is (K^-1 + W)^-1 (checked against the direct inverse); laplace_steps
+    (:409-421, test :207-217) returns one LaplaceResult per Newton step, the last one at the mode."""
+    X, y = olap.generate_data()
+    K = ok.kernelmatrix(ok.Kernel(ok.SE, 1.3, np.array([1.0 / 0.9])), X) + 1e-8 * np.eye(len(y))
+    lik = ol.Likelihood(ol.BERNOULLI_LOGIT)
+    res = olap.laplace_steps(lik, y, K)
+    f_opt, lml, steps = olap.laplace_f_and_lml(lik, y, K)
+    assert len(res) == steps
+    last = res[-1]
+    assert np.allclose(last["q_mean"], f_opt, rtol=0, atol=1e-12)
+    assert abs(last["lml_approx"] - lml) < 1e-10 * abs(lml)
+    direct = np.linalg.inv(np.linalg.inv(K) + np.diag(last["cache"].W))
+    assert np.allclose(last["f_cov"], direct, rtol=0, atol=1e-7 * np.abs(direct).max())  # K^-1 with jitter 1e-8 is ill-conditioned
+    assert np.allclose(last["q_cov"], last["q_cov"].T, rtol=0, atol=0)
+    assert np.all(np.linalg.eigvalsh(last["q_cov"]) > -1e-10)
+    # Gaussian 'likelihood': q(f) is the exact GP posterior over f, K - K (K + s2 I)^-1 K
+    s2 = 0.3
+    yg = np.sin(X) + 0.1
+    resg = olap.laplace_steps(ol.Likelihood(ol.GAUSSIAN, s2), yg, K)
+    exact = K - K @ np.linalg.solve(K + s2 * np.eye(len(yg)), K)
+    assert np.allclose(resg[-1]["f_cov"], exact, rtol=0, atol=1e-10)
+
+
+def test_probit_link_derivatives():
+    """BernoulliLikelihood(ProbitLink()): the oracle's overflow-free log Phi(s f) and its closed-form derivatives against
+    (i) mpmath log(ncdf) at 50 digits, (ii) torch autograd through the reference's op sequence log(normcdf(f)) /
+    log(1 - normcdf(f)) where that is well conditioned, (iii) the third derivative by finite differences of the second,
+    and the Laplace gradient w.r.t. K by finite differences."""
+    import pytest
+    import torch
+
+    mp = pytest.importorskip("mpmath")
+    lik = ol.Likelihood("bernoulli_probit")
+    f = np.array([-9.0, -3.0, -0.7, 0.0, 0.4, 2.5, 6.0])
+    for yv in (0.0, 1.0):
+        y = np.full_like(f, yv)
+        ll, d1, d2 = ol.loglik_and_derivs(lik, f, y)
+        sg = 1.0 if yv > 0.5 else -1.0
+        with mp.workdps(50):
+            ref = np.array([float(mp.log(mp.ncdf(sg * v))) for v in f])
+        assert np.allclose(ll, ref, rtol=1e-14, atol=0)
+        sel = np.abs(f) < 5  # log(1 - normcdf(f)) is only accurate away from the saturated tail
+        ft = torch.tensor(f[sel], requires_grad=True)
+        p = torch.special.ndtr(ft)
+        lt = (torch.log(p) if yv > 0.5 else torch.log(1 - p)).sum()
+        (g1,) = torch.autograd.grad(lt, ft, create_graph=True)
+        (g2,) = torch.autograd.grad(g1.sum(), ft)
+        assert np.allclose(d1[sel], g1.detach().numpy(), rtol=1e-9) and np.allclose(d2[sel], g2.numpy(), rtol=1e-8)
+        h = 1e-4
+        d3 = olap._d3_loglik(lik, f, y)
+        fd = (ol.loglik_and_derivs(lik, f + h, y)[2] - ol.loglik_and_derivs(lik, f - h, y)[2]) / (2 * h)
+        assert np.allclose(d3, fd, rtol=1e-6, atol=1e-9)
+    X, y = olap.generate_data()
+    K = ok.kernelmatrix(ok.Kernel(ok.SE, 1.3, np.array([1.0 / 0.9])), X) + 1e-6 * np.eye(len(y))
+    lml, Kbar, _, _ = olap.lml_and_grad_K(lik, y, K)
+    rng = np.random.default_rng(0)
+    Dm = rng.normal(size=K.shape)
+    Dm = 0.5 * (Dm + Dm.T) * 1e-2
+    h = 1e-5
+    fd = (olap.laplace_f_and_lml(lik, y, K + h * Dm)[1] - olap.laplace_f_and_lml(lik, y, K - h * Dm)[1]) / (2 * h)
+    assert abs(fd - np.sum(Kbar * Dm)) < 1e-6 * max(1.0, abs(fd))

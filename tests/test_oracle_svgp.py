@@ -92,6 +92,8 @@ CASES = [
     dict(kind="matern52", D=2, centered=False, lik="gamma_exp", method="default"),
     dict(kind="se", D=2, centered=False, lik="gamma_exp", method="gauss_hermite"),
     dict(kind="matern32", D=3, centered=False, lik="exponential_exp", method="default"),
+    dict(kind="matern52", D=2, centered=False, lik="bernoulli_probit", method="default"),
+    dict(kind="se", D=3, centered=True, lik="bernoulli_probit", method="gauss_hermite", n_gh=32),
 ]
 
 
