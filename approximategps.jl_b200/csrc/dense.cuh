@@ -88,35 +88,40 @@ __global__ void cross_k_kernel(double* K, int64_t ld, const double* xs, const do
 constexpr int PT_LD = 129;
 constexpr int PT_SMEM_BYTES = (128 * PT_LD + 64 * 65 + 128) * 8;
 
-// Compile-time recursion over the 32 columns keeps every register-array index a constant (a plain doubly nested
-// `#pragma unroll` of the triangular loops is not fully unrolled by nvcc and the arrays fall into local memory).
-template <int J>
-struct PtPotrfCol {  // right-looking Cholesky step J of a 32 x 32 block: lane i holds row i in a[]
-  static __device__ __forceinline__ void run(double (&a)[32], int lane, double* rdiag, int col0, int* info) {
-    const double d = __shfl_sync(0xffffffffu, a[J], J);
+// Cholesky of a 32 x 32 diagonal block by one warp, in place in shared memory (lane i owns row i; left-looking: column J is
+// a_iJ - sum_{k<J} l_ik l_Jk, a dot product of the lane's own row with row J, which every lane reads as a broadcast).
+// This warp's per-column dependency chain (shuffle of the diagonal -> rsqrt -> corrections -> store) is the critical path of
+// the whole diagonal-block kernel: tools/pt_timing.cu measures ~14 us per 32-block (~850 cycles per column) for this loop,
+// for a fully unrolled right-looking register version (16 / 10 us cold / warm, ~25 KB of straight-line code) and for a variant
+// with the chain cut to rsqrt + one multiply and the k < J part of the next dot product issued under the rsqrt (14.6 us), so
+// the compact loop is kept (profiles/r03_pt_timing.txt).
+__device__ __forceinline__ void pt_potrf32(double* blk, int lane, double* rdiag, int col0, int* info) {
+  double* row = blk + lane * PT_LD;
+  for (int J = 0; J < 32; J++) {
+    const double* rJ = blk + J * PT_LD;
+    double acc0 = row[J], acc1 = 0.0;
+    int k = 0;
+    for (; k + 1 < J; k += 2) {
+      acc0 = fma(-row[k], rJ[k], acc0);
+      acc1 = fma(-row[k + 1], rJ[k + 1], acc1);
+    }
+    if (k < J) acc0 = fma(-row[k], rJ[k], acc0);
+    const double v = acc0 + acc1;
+    const double d = __shfl_sync(0xffffffffu, v, J);
     if (lane == 0 && !(d > 0.0)) atomicCAS(info, 0, col0 + J + 1);
-    // sqrt(d), 1/sqrt(d) and a/sqrt(d) from one rsqrt plus FMA corrections (the results agree with sqrt() and the
+    // sqrt(d), 1/sqrt(d) and v/sqrt(d) from one rsqrt plus FMA corrections (the results agree with sqrt() and the
     // true quotients to the last bit or one ulp; a dependent sqrt + two divisions cost 4x the latency per column)
     const double y = rsqrt(d);
     const double s0 = d * y;
     const double sq = fma(fma(-s0, s0, d), 0.5 * y, s0);
     const double inv = fma(fma(-sq, y, 1.0), y, y);
-    const double l0 = a[J] * inv;
-    const double lij = (lane == J) ? sq : fma(fma(-l0, sq, a[J]), inv, l0);
-    a[J] = (lane >= J) ? lij : 0.0;
+    const double l0 = v * inv;
+    const double lij = (lane == J) ? sq : fma(fma(-l0, sq, v), inv, l0);
+    if (lane >= J) row[J] = lij;  // rows above the diagonal keep the zero they were loaded with
     if (lane == J) rdiag[J] = inv;
-#pragma unroll
-    for (int k = J + 1; k < 32; k++) {
-      const double lkj = __shfl_sync(0xffffffffu, lij, k);
-      if (lane >= k) a[k] = fma(-lij, lkj, a[k]);
-    }
-    PtPotrfCol<J + 1>::run(a, lane, rdiag, col0, info);
+    __syncwarp();  // column J is read (as row J's entries) by every later column
   }
-};
-template <>
-struct PtPotrfCol<32> {
-  static __device__ __forceinline__ void run(double (&)[32], int, double*, int, int*) {}
-};
+}
 template <int J>
 struct PtSolveRow {  // x L_d^T = a for one row held in x[] (right-looking: x[J] is final, then x[k > J] -= x[J] L[k][J])
   static __device__ __forceinline__ void run(double (&x)[32], const double* Ld, const double* rdiag) {
@@ -227,15 +232,7 @@ __global__ void __launch_bounds__(256) potrf_trinv128_kernel(const double* src, 
   if (tid < N) rdiag[tid] = 1.0;
   __syncthreads();
   for (int o = 0; o < nact; o += 32) {
-    if (warp == 0) {  // diagonal 32 x 32 block: lane i holds row o + i in registers, columns exchanged by shuffles
-      double* row = s + (o + lane) * LD + o;
-      double a[32];
-#pragma unroll
-      for (int j = 0; j < 32; j++) a[j] = row[j];
-      PtPotrfCol<0>::run(a, lane, rdiag + o, col0 + o, info);
-#pragma unroll
-      for (int j = 0; j < 32; j++) row[j] = a[j];
-    }
+    if (warp == 0) pt_potrf32(s + o * LD + o, lane, rdiag + o, col0 + o, info);  // diagonal 32 x 32 block
     __syncthreads();
     if (o == 0) { PT_TICK(1) }
     const int T = nact - o - 32;  // rows below the diagonal block (rows >= nact are identity padding: zero below the diagonal)

@@ -241,19 +241,25 @@ __global__ void __launch_bounds__(256) trsv_bwd_chain_kernel(const double* L, co
   const int J = nb - 1 - blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, i = tid & 127, h = tid >> 7;
   if (tid < 128) colacc[tid] = 0.0;
   for (int Lb = nb - 1; Lb > J; Lb--) {
+    // (block Lb,J)^T x_Lb: column c of the block is contiguous over the rows; one warp handles 16 columns.  The block does
+    // not depend on x: fetch it into registers before waiting (the wait for x_{J+1} is the critical path of the chain)
+    double lv[16][4];
+#pragma unroll
+    for (int cc = 0; cc < 16; cc++) {
+      const double* Lp = L + (int64_t)(J * 128 + warp * 16 + cc) * ld + (int64_t)Lb * 128 + lane;
+#pragma unroll
+      for (int k = 0; k < 4; k++) lv[cc][k] = __ldg(Lp + 32 * k);
+    }
     trsv_wait(flags + Lb, epoch);
     if (tid < 128) xs[tid] = __ldcg(x + (int64_t)Lb * 128 + tid);
     __syncthreads();
     const double x0 = xs[lane], x1 = xs[lane + 32], x2 = xs[lane + 64], x3 = xs[lane + 96];
-    // (block Lb,J)^T x_Lb: column c of the block is contiguous over the rows; one warp handles 16 columns
-#pragma unroll 4
+#pragma unroll
     for (int cc = 0; cc < 16; cc++) {
-      const int c = warp * 16 + cc;
-      const double* Lp = L + (int64_t)(J * 128 + c) * ld + (int64_t)Lb * 128;
-      double acc = fma(Lp[lane], x0, fma(Lp[lane + 32], x1, fma(Lp[lane + 64], x2, Lp[lane + 96] * x3)));
+      double acc = fma(lv[cc][0], x0, fma(lv[cc][1], x1, fma(lv[cc][2], x2, lv[cc][3] * x3)));
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) colacc[c] += acc;
+      if (lane == 0) colacc[warp * 16 + cc] += acc;
     }
     __syncthreads();
   }

@@ -347,3 +347,57 @@ def test_exponential_and_gamma_likelihoods(agp, lik, method):
     Monte-Carlo expectations, including d/d alpha."""
     p = make_problem(seed=91, kind="matern52", N=600, M=25, D=3, lik=lik, method=method, n_gh=20)
     _run_case(agp, p, num_data=6000.0)
+
+
+def test_full_size_c4_properties(agp):
+    """BASELINE config 4 at its full size (Poisson, SE, N = 1e7, D = 8, M = 1024), where the NumPy oracle cannot run: size-independent
+    properties of the reference's formula.  With D(slice) = elbo(slice; num_data = 2 count) - elbo(slice; num_data = count)
+    = sum_{i in slice} E_q[log p(y_i | f_i)] (SVA.jl:354-359, the KL term cancels):
+      * additivity  D(all) = D(first 60 %) + D(rest), values and every gradient buffer (the sum over points is the only coupling);
+      * order independence: the reversed data set gives the same ELBO and gradients;
+      * the oracle on a 2048-point slice of the same resident data set equals the device value on that slice (offset view)."""
+    from oracle import kernels as ok, likelihoods as ol
+
+    N, M, D = 10_000_000, 1024, 8
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((N, D))
+    w = rng.standard_normal(D)
+    y = rng.poisson(np.exp(0.5 * np.sin(X @ w))).astype(np.float64)
+    Z = X[:M] + 1e-3 * rng.standard_normal((M, D))
+    m = 0.1 * rng.standard_normal(M)
+    A = 0.5 * np.eye(M) + 0.01 * np.tril(rng.standard_normal((M, M)))
+    A[np.diag_indices(M)] = np.abs(np.diag(A))
+    ls = np.sqrt(8.0)
+    f = agp.GP(1.0 * agp.with_lengthscale(agp.SqExponentialKernel(), ls))
+    sva = agp.SparseVariationalApproximation(f(Z, 1e-6), agp.MvNormal(m, chol_lower=A))
+    ctx = agp.default_context()
+    ds = agp.DeviceData(X, y, ctx=ctx)
+    lds = agp.LatentGP(f, agp.PoissonLikelihood(), 1e-18)(ds)
+
+    def data_term(offset, count):
+        v2, g2 = agp.elbo_and_gradient(sva, lds, None, num_data=2.0 * count, offset=offset, count=count)
+        v1, g1 = agp.elbo_and_gradient(sva, lds, None, num_data=1.0 * count, offset=offset, count=count)
+        return v2 - v1, {k: getattr(g2, k) - getattr(g1, k) for k in ("m", "Lq", "Z", "variance", "inv_lengthscale")}, (v1, g1)
+
+    cut = 6_000_000
+    d_all, g_all, (v_all, gv_all) = data_term(0, N)
+    d_a, g_a, _ = data_term(0, cut)
+    d_b, g_b, _ = data_term(cut, N - cut)
+    e = abs(d_all - (d_a + d_b)) / abs(d_all)
+    errs = {k: rel_err(g_a[k] + g_b[k], g_all[k]) for k in g_all}
+    print(f"\n[C4 full size] elbo={v_all:.6f} additivity rel={e:.1e} " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
+    assert e < 1e-12 and all(v < 1e-10 for v in errs.values()), (e, errs)
+    # oracle on a slice of the resident data set
+    lo, cnt = 7_654_321, 2048
+    s = osv.SVGP(ok.Kernel(ok.SE, 1.0, np.array([1.0 / ls])), Z, m, A, jitter=1e-6)
+    ref, rg = osv.elbo_and_grad(s, X[lo:lo + cnt], y[lo:lo + cnt], ol.Likelihood(ol.POISSON_EXP), ol.Expectation(), num_data=float(N))
+    val, g = agp.elbo_and_gradient(sva, lds, None, num_data=float(N), offset=lo, count=cnt)
+    assert abs(val - ref) < ELBO_TOL * abs(ref) and rel_err(g.Z, rg.Z) < GRAD_TOL and rel_err(g.Lq, rg.Lq) < GRAD_TOL
+    # order independence
+    ds.upload(X[::-1].copy(), y[::-1].copy())
+    v_rev, g_rev = agp.elbo_and_gradient(sva, lds, None, num_data=1.0 * N)
+    e_rev = abs(v_rev - v_all) / abs(v_all)
+    errs = {k: rel_err(getattr(g_rev, k), getattr(gv_all, k)) for k in ("m", "Lq", "Z", "variance", "inv_lengthscale")}
+    print(f"[C4 full size] reversed order rel={e_rev:.1e} " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
+    assert e_rev < 1e-12 and all(v < 1e-10 for v in errs.values()), (e_rev, errs)
+    ds.close()
