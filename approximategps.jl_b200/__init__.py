@@ -27,6 +27,9 @@ from .laplace_api import (  # noqa: F401
     laplace_f_and_lml,
     laplace_f_cov,
     laplace_steps,
+    newton_inner_loop,
+    rrule_newton_inner_loop,
+    frule_newton_inner_loop,
     laplace_lml,
     laplace_lml_and_grad_K,
 )

@@ -150,6 +150,8 @@ SYMBOLS = {
     "agp_laplace_cache_destroy": (C.c_int32, [_vp]),
     "agp_laplace_cache_n": (C.c_int32, [_vp]),
     "agp_laplace_f_cov": (C.c_int32, [_vp, c_double_p]),
+    "agp_laplace_newton_pullback": (C.c_int32, [_vp, c_double_p, c_double_p, c_double_p]),
+    "agp_laplace_newton_pushforward": (C.c_int32, [_vp, c_double_p, c_double_p]),
     "agp_laplace_cache_lml": (C.c_int32, [_vp, c_double_p]),
 }
 

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib as L
 
-_FIELDS = {"W": 0, "Wsqrt": 1, "d_loglik": 2, "a": 3, "f": 4, "B_ch_L": 5, "fnew": 6, "loglik": 7}
+_FIELDS = {"W": 0, "Wsqrt": 1, "d_loglik": 2, "a": 3, "f": 4, "B_ch_L": 5, "fnew": 6, "loglik": 7, "newton_Wsqrt": 8, "newton_d_loglik": 9}
 
 
 class LaplaceCacheView:
@@ -166,6 +166,41 @@ def laplace_f_and_lml(lfx, ys, *, ctx=None, **newton_kwargs):
     """``laplace_f_and_lml(lfx, ys; newton_kwargs...)`` (Laplace.jl:140-145) -> (f_opt, lml)."""
     r = _run(ctx, **_check_laplace_inputs(lfx, ys, **newton_kwargs))
     return r.f, r.lml
+
+
+def newton_inner_loop(lik, ys, K, *, f_init=None, maxiter=100, callback=None, ctx=None) -> np.ndarray:
+    """``newton_inner_loop(dist_y_given_f, ys, K; f_init, maxiter, callback)`` (Laplace.jl:304-307): the mode f_opt."""
+    return _run(ctx, K=K, y=ys, lik=lik, f_init=f_init, maxiter=maxiter, callback=callback).f
+
+
+def rrule_newton_inner_loop(lik, ys, K, *, f_init=None, maxiter=100, ctx=None):
+    """``ChainRulesCore.rrule(newton_inner_loop, dist_y_given_f, ys, K; kwargs...)`` (Laplace.jl:330-369): returns
+    ``(f_opt, newton_pullback)``; ``newton_pullback(df_opt)`` is the cotangent of K, ``(Wsqrt .* (B_ch \\ (df_opt ./ Wsqrt))) *
+    d_loglik'`` (the cotangents of the likelihood and of ys are ``@not_implemented`` in the reference)."""
+    r = _run(ctx, K=K, y=ys, lik=lik, f_init=f_init, maxiter=maxiter, want_cache=True)
+    n = len(r.f)
+
+    def newton_pullback(df_opt, dense=True):
+        df = np.ascontiguousarray(df_opt, dtype=np.float64)
+        assert df.shape == (n,)
+        u = np.zeros(n)
+        dK = np.zeros((n, n), order="F") if dense else None
+        L.check(r.cache._lib.agp_laplace_newton_pullback(r.cache._h, L.dptr(df), L.dptr(u), L.dptr(dK)))
+        return dK if dense else (u, np.array(r.cache.newton_d_loglik))
+
+    return r.f, newton_pullback
+
+
+def frule_newton_inner_loop(dK, lik, ys, K, *, f_init=None, maxiter=100, ctx=None):
+    """``ChainRulesCore.frule((_, _, _, dK), newton_inner_loop, dist_y_given_f, ys, K; kwargs...)`` (Laplace.jl:309-328):
+    returns ``(f_opt, fdot)`` with ``fdot = (B_ch \\ (Wsqrt .* (dK * d_loglik))) ./ Wsqrt``."""
+    r = _run(ctx, K=K, y=ys, lik=lik, f_init=f_init, maxiter=maxiter, want_cache=True)
+    n = len(r.f)
+    dK = np.asfortranarray(dK, dtype=np.float64)
+    assert dK.shape == (n, n)
+    fdot = np.zeros(n)
+    L.check(r.cache._lib.agp_laplace_newton_pushforward(r.cache._h, L.dptr(dK), L.dptr(fdot)))
+    return r.f, fdot
 
 
 def laplace_f_cov(cache: LaplaceCacheView) -> np.ndarray:

@@ -251,7 +251,8 @@ typedef struct {
 int32_t agp_laplace_f_and_lml(agp_ctx* ctx, const agp_laplace_problem* problem, agp_laplace_result* result,
                               agp_laplace_cache** cache_out);
 /* field: 0 = W, 1 = Wsqrt, 2 = d_loglik, 3 = a, 4 = f, 6 = fnew (callback view only) (n doubles each);
- *        5 = B_ch.L (n x n column-major); 7 = loglik (1 double, owned caches only)              */
+ *        5 = B_ch.L (n x n column-major); 7 = loglik (1 double, owned caches only);
+ *        8 = Wsqrt, 9 = d_loglik of the last Newton step (owned caches; they differ from 1 / 2 only after a maxiter-stopped loop) */
 int32_t agp_laplace_cache_fetch(agp_laplace_cache* cache, int32_t field, double* host_out);
 int32_t agp_laplace_cache_destroy(agp_laplace_cache* cache);
 /* Number of latent values n of a cache (or callback view): the length of its vector fields. */
@@ -261,6 +262,14 @@ int32_t agp_laplace_cache_n(agp_laplace_cache* cache);
 int32_t agp_laplace_f_cov(agp_laplace_cache* cache, double* cov_out);
 /* _laplace_lml(cache.f, cache) -- Laplace.jl:250-254 -- as LaplaceResult(fnew, cache) (:388-395) evaluates it per step. */
 int32_t agp_laplace_cache_lml(agp_laplace_cache* cache, double* lml_out);
+/* rrule(newton_inner_loop) -- Laplace.jl:330-369: newton_pullback(df_opt) = (Wsqrt .* (B_ch \ (df_opt ./ Wsqrt))) * d_loglik' on the
+ * cache returned by agp_laplace_f_and_lml (the fields of the last Newton step, as in the reference).  u_out (n) receives the left
+ * factor of the rank-1 cotangent, dK_out (column-major n x n) the dense matrix; either may be NULL.  The cotangents of the
+ * likelihood and of ys are @not_implemented in the reference (:352-358) and are not produced here either.                  */
+int32_t agp_laplace_newton_pullback(agp_laplace_cache* cache, const double* df_opt, double* u_out, double* dK_out);
+/* frule(newton_inner_loop) -- Laplace.jl:309-328: fdot = (B_ch \ (Wsqrt .* (dK * d_loglik))) ./ Wsqrt for a tangent dK (host,
+ * column-major n x n).                                                                                                    */
+int32_t agp_laplace_newton_pushforward(agp_laplace_cache* cache, const double* dK, double* fdot_out);
 /* Replaces the prediction methods of ApproxPosteriorGP{<:LaplaceApproximation} -- Laplace.jl:425-463
  * (_laplace_predict_intermediates, mean_and_var, mean_and_cov, mean, var, cov(f, x), cov(f, x, y)) on a cache
  * returned by agp_laplace_f_and_lml: kernel / Xtrain (host, point-major n x D) describe prior_at_x.  Any of

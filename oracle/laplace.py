@@ -86,6 +86,17 @@ def laplace_f_and_lml(lik: Likelihood, y, K, f_init=None, maxiter=100, callback=
     return f_opt, laplace_lml(lik, y, K, f_opt), steps
 
 
+def newton_pullback(cache: LaplaceCache, df_opt) -> np.ndarray:
+    """``newton_pullback`` of ``rrule(newton_inner_loop)`` (Laplace.jl:330-369): the cotangent of K."""
+    u = cache.Wsqrt * cho_solve((cache.B_L, True), np.asarray(df_opt, dtype=np.float64) / cache.Wsqrt)
+    return np.outer(u, cache.d_loglik)
+
+
+def newton_pushforward(cache: LaplaceCache, dK) -> np.ndarray:
+    """``frule(newton_inner_loop)`` (Laplace.jl:309-328): the tangent of f_opt for a tangent dK."""
+    return cho_solve((cache.B_L, True), cache.Wsqrt * (np.asarray(dK, dtype=np.float64) @ cache.d_loglik)) / cache.Wsqrt
+
+
 def laplace_f_cov(cache: LaplaceCache) -> np.ndarray:
     """Laplace.jl:376-386: (K^-1 + W)^-1 = Wsqrt^-1 (I - B^-1) Wsqrt^-1."""
     n = len(cache.f)

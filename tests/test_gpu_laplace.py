@@ -266,3 +266,34 @@ def test_laplace_steps_and_f_cov(agp, n, D):
     fc = agp.laplace_f_cov(post.data)
     assert np.max(np.abs(fc - ref[-1]["f_cov"])) / np.max(np.abs(ref[-1]["f_cov"])) < 1e-9
     assert abs(post.data.lml_approx() - ref[-1]["lml_approx"]) <= 1e-10 * abs(ref[-1]["lml_approx"])
+
+
+@pytest.mark.parametrize("n,D,maxiter", [(3, 1, 100), (300, 2, 100), (300, 2, 2)])
+def test_newton_inner_loop_rrule_and_frule(agp, n, D, maxiter):
+    """rrule / frule of newton_inner_loop (Laplace.jl:309-369; test :78-145) through the C ABI against the oracle, on the
+    reference's 3-point case (K = L'L), on a 300-point problem, and after a maxiter-stopped loop (where the rules use the
+    cache of the last Newton step, not the intermediates at f_opt)."""
+    rng = np.random.default_rng(54321)
+    lik_o, lik = ol.Likelihood(ol.BERNOULLI_LOGIT), agp.BernoulliLikelihood()
+    if n == 3:
+        ys = np.array([1.0, 1.0, 0.0])
+        Lm = rng.normal(size=(3, 3))
+        K = Lm.T @ Lm
+    else:
+        _, _, K, ys = _problem(7, n, D, "bernoulli_logit")
+    dK = rng.normal(size=(n, n))  # a general (non-symmetric) tangent
+    df = rng.normal(size=n)
+    f_ref, cache, steps = olap.newton_inner_loop(lik_o, ys, K, maxiter=maxiter)
+    assert (steps == maxiter) == (maxiter == 2)
+    f_opt, pullback = agp.rrule_newton_inner_loop(lik, ys, K, maxiter=maxiter)
+    assert rel_err(f_opt, f_ref) < 1e-10
+    assert np.array_equal(agp.newton_inner_loop(lik, ys, K, maxiter=maxiter), f_opt)
+    Kbar, Kbar_ref = pullback(df), olap.newton_pullback(cache, df)
+    u, dll = pullback(df, dense=False)
+    f2, fdot = agp.frule_newton_inner_loop(dK, lik, ys, K, maxiter=maxiter)
+    fdot_ref = olap.newton_pushforward(cache, dK)
+    print(f"\n[newton rules n={n} maxiter={maxiter}] steps={steps} rrule rel={rel_err(Kbar, Kbar_ref):.1e} frule rel={rel_err(fdot, fdot_ref):.1e}")
+    assert rel_err(Kbar, Kbar_ref) < 1e-9 and np.allclose(np.outer(u, dll), Kbar, rtol=0, atol=1e-14 * np.abs(Kbar).max())
+    assert rel_err(fdot, fdot_ref) < 1e-9 and np.array_equal(f2, f_opt)
+    adj = np.sum(Kbar * dK)
+    assert abs(adj - df @ fdot) < 1e-9 * max(1.0, abs(adj))  # <Kbar, dK> == <df, fdot>

@@ -156,3 +156,29 @@ def test_probit_link_derivatives():
     h = 1e-5
     fd = (olap.laplace_f_and_lml(lik, y, K + h * Dm)[1] - olap.laplace_f_and_lml(lik, y, K - h * Dm)[1]) / (2 * h)
     assert abs(fd - np.sum(Kbar * Dm)) < 1e-6 * max(1.0, abs(fd))
+
+
+def test_newton_inner_loop_chain_rules():
+    """test/LaplaceApproximationModule.jl:78-145 (test_frule / test_rrule of newton_inner_loop through K = L'L): the frule is
+    the finite-difference derivative of f_opt, and the rrule is its adjoint."""
+    xs = np.array([0.2, 0.3, 0.7])
+    ys = np.array([1.0, 1.0, 0.0])
+    rng = np.random.default_rng(54321)
+    Lm = rng.normal(size=(3, 3))
+    dL = rng.normal(size=(3, 3))
+    lik = ol.Likelihood(ol.BERNOULLI_LOGIT)
+    K = Lm.T @ Lm
+    dK = dL.T @ Lm + Lm.T @ dL
+    f_opt, cache, _ = olap.newton_inner_loop(lik, ys, K)
+    fdot = olap.newton_pushforward(cache, dK)
+    h = 1e-5
+    fp = olap.newton_inner_loop(lik, ys, (Lm + h * dL).T @ (Lm + h * dL))[0]
+    fm = olap.newton_inner_loop(lik, ys, (Lm - h * dL).T @ (Lm - h * dL))[0]
+    assert np.allclose(fdot, (fp - fm) / (2 * h), rtol=1e-6, atol=1e-9)
+    df = rng.normal(size=3)
+    Kbar = olap.newton_pullback(cache, df)
+    assert abs(np.sum(Kbar * dK) - df @ fdot) < 1e-12 * max(1.0, abs(df @ fdot))
+    # through L: Lbar = L (Kbar' + Kbar)  (:128)
+    Lbar = Lm @ (Kbar.T + Kbar)
+    assert abs(np.sum(Lbar * dL) - df @ fdot) < 1e-12 * max(1.0, abs(df @ fdot))
+    assert xs.shape == ys.shape
