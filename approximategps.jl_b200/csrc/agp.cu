@@ -212,8 +212,12 @@ extern "C" int32_t agp_ctx_create(int32_t device, agp_ctx** out) {
   agp_ctx* c = new agp_ctx();
   c->device = device;
   c->sms = prop.multiProcessorCount;
-  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  // the main stream outranks the look-ahead stream: the latency-bound chain of the blocked Cholesky must get the first CTA
+  // slot that the trailing update frees (blocked_cholesky)
+  int prio_lo = 0, prio_hi = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
+  CU(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));
   CU(cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_trail, cudaEventDisableTiming));
   CU(cudaMalloc(&c->d_flags, 4 * sizeof(int)));
@@ -572,7 +576,15 @@ static int32_t blocked_cholesky(agp_ctx* c, double* Kw, double* L, double* Lt, d
       CU(cudaStreamWaitEvent(c->stream, c->ev_panel, 0));
       const int64_t pnl2 = (int64_t)J0 * BM * ld + (int64_t)J2 * BM;
       const int64_t trl2 = (int64_t)J2 * BM * ld + (int64_t)J2 * BM;
-      OK((run_gemm<A_KM, B_KN>(c, rem2, 2 * rem2, L + pnl2, ld, L + pnl2, ld, K, KR_FULL, TS_NBLK_LE, epi_store(Kw + trl2, ld, false, -1.0, 1.0))));
+      {  // 2-stage instantiation (51 KB per CTA): a finished CTA leaves room for the diagonal kernel (166 KB) on its SM
+        constexpr int S2 = 2;
+        using Cfg = StageCfg<A_KM, B_KN>;
+        GemmArgs g{L + pnl2, ld, L + pnl2, ld, K, KR_FULL, TS_NBLK_LE};
+        OK((ensure_smem<gemm_kernel<A_KM, B_KN, EpiStore, S2>>(c, S2 * Cfg::bytes)));
+        gemm_kernel<A_KM, B_KN, EpiStore, S2><<<dim3(rem2, 2 * rem2), NTHREADS, S2 * Cfg::bytes, c->stream>>>(g, epi_store(Kw + trl2, ld, false, -1.0, 1.0));
+        LAUNCHED(c);
+        KCHECK();
+      }
       CU(cudaEventRecord(c->ev_trail, c->stream));
       trail_pending = true;
     }

@@ -34,13 +34,12 @@ struct GemmArgs {
 // skips every MMA of this warp (SYRK tiles above the diagonal).
 constexpr int TRI_NONE = 0, TRI_LOWER = 1, TRI_UPPER = 2;
 
-template <int LA, int LB>
+template <int LA, int LB, int S = StageCfg<LA, LB>::stages>
 __device__ __forceinline__ void gemm_mainloop(Acc& acc, double* smem, const double* __restrict__ gA, int64_t lda,
                                               const double* __restrict__ gB, int64_t ldb, int nsteps,
                                               const ThreadMap& tm, int tri = TRI_NONE, int diag_step = 0,
                                               bool whole_active = true) {
   using Cfg = StageCfg<LA, LB>;
-  constexpr int S = Cfg::stages;
   const int tid = threadIdx.x;
   const int64_t a_step = (LA == A_KM) ? (int64_t)BK * lda : (int64_t)BK;
   const int64_t b_step = (LB == B_KN) ? (int64_t)BK * ldb : (int64_t)BK;
@@ -87,7 +86,9 @@ __device__ __forceinline__ void gemm_mainloop(Acc& acc, double* smem, const doub
   __syncthreads();  // smem is free for the epilogue
 }
 
-template <int LA, int LB, class Epi>
+// S: pipeline stages (shared memory = S * 25.6 KB).  The 2-stage instantiation exists for the look-ahead trailing update of
+// the blocked Cholesky: one such CTA (51 KB) leaves room for the 166 KB diagonal-block kernel on the same SM.
+template <int LA, int LB, class Epi, int S = StageCfg<LA, LB>::stages>
 __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(GemmArgs g, Epi epi) {
   extern __shared__ __align__(128) double smem[];
   ThreadMap tm;
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(GemmArgs g, Epi epi) 
   } else if (g.kmode == KR_UPPER) {
     tri = TRI_UPPER;
   }
-  gemm_mainloop<LA, LB>(acc, smem, gA, g.lda, gB, g.ldb, nsteps, tm, tri, diag_step);
+  gemm_mainloop<LA, LB, S>(acc, smem, gA, g.lda, gB, g.ldb, nsteps, tm, tri, diag_step);
   epi(acc, tm, m0, n0, smem);
 }
 
