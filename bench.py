@@ -56,6 +56,11 @@ WORKLOADS = {
     # BASELINE.json configs[3] (the configuration `metric` is quoted on)
     "c4": dict(label="C4 SVGP Poisson(exp) analytic, SqExponential, N=1e7, D=8, M=1024, FP64", N=10_000_000, D=8, M=1024, kind="se",
                lik="poisson_exp", method="default", seed=4, lengthscale=math.sqrt(8.0), variance=1.0, jitter=1e-6),
+    # SURVEY.md section 8(d) variants of C4: Gauss-Hermite(20) instead of the analytic Poisson expectation; Matern52 kernel
+    "c4gh": dict(label="C4 variant: SVGP Poisson(exp) Gauss-Hermite(20), SqExponential, N=1e7, D=8, M=1024, FP64", N=10_000_000, D=8, M=1024,
+                 kind="se", lik="poisson_exp", method="gauss_hermite", seed=4, lengthscale=math.sqrt(8.0), variance=1.0, jitter=1e-6),
+    "c4m52": dict(label="C4 variant: SVGP Poisson(exp) analytic, Matern52, N=1e7, D=8, M=1024, FP64", N=10_000_000, D=8, M=1024,
+                  kind="matern52", lik="poisson_exp", method="default", seed=4, lengthscale=math.sqrt(8.0), variance=1.0, jitter=1e-6),
     # BASELINE.json configs[1]
     "c2": dict(label="C2 SVGP Bernoulli GH-20, Matern52, N=1e6, D=8, M=512, FP64", N=1_000_000, D=8, M=512, kind="matern52",
                lik="bernoulli_logit", method="default", seed=2, lengthscale=math.sqrt(8.0), variance=1.0, jitter=1e-6),
@@ -306,7 +311,7 @@ def main():
     lik = {"gaussian": agp.GaussianLikelihood(0.01), "bernoulli_logit": agp.BernoulliLikelihood(), "poisson_exp": agp.PoissonLikelihood()}[w["lik"]]
     from agp_b200.api import _Packed
 
-    pk = _Packed(sva, lik, None)
+    pk = _Packed(sva, lik, agp.GaussHermiteExpectation(20) if w["method"] == "gauss_hermite" else None)
     g_m, g_Lq, g_Z = np.zeros(M), np.zeros((M, M), order="F"), np.zeros((M, D))
     sc = np.zeros(4)
     g_ils = np.zeros(1)
