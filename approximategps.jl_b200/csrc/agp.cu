@@ -457,12 +457,13 @@ static int32_t launch_trsm(agp_ctx* c, const TrsmArgs& a, int tiles_n) {
   return launch_trsm_s<MODE, 4>(c, a, tiles_n);
 }
 
-template <int LA, int LB, class Epi>
+template <int LA, int LB, int S = StageCfg<LA, LB>::stages, class Epi>
 static int32_t run_gemm(agp_ctx* c, int tiles_m, int tiles_n, const double* A, int64_t lda, const double* B, int64_t ldb, int K,
                         int kmode, int tmode, const Epi& epi) {
   using Cfg = StageCfg<LA, LB>;
+  constexpr int smem_bytes = S * Cfg::bytes;
   GemmArgs g{A, lda, B, ldb, K, kmode, tmode};
-  OK((ensure_smem<gemm_kernel<LA, LB, Epi>>(c, Cfg::smem_bytes)));
+  OK((ensure_smem<gemm_kernel<LA, LB, Epi, S>>(c, smem_bytes)));
   dim3 grid(tiles_m, tiles_n);
   if ((kmode == KR_LOWER || kmode == KR_UPPER) && tmode == TS_ALL && tiles_m > 1) {
     static const int env_g = getenv("AGP_SWIZZLE") ? atoi(getenv("AGP_SWIZZLE")) : 0;  // tuning knob
@@ -471,7 +472,7 @@ static int32_t run_gemm(agp_ctx* c, int tiles_m, int tiles_n, const double* A, i
     g.tiles_n = tiles_n;
     grid = dim3(tiles_m * tiles_n, 1);
   }
-  gemm_kernel<LA, LB, Epi><<<grid, NTHREADS, Cfg::smem_bytes, c->stream>>>(g, epi);
+  gemm_kernel<LA, LB, Epi, S><<<grid, NTHREADS, smem_bytes, c->stream>>>(g, epi);
   LAUNCHED(c);
   KCHECK();
   return AGP_OK;
@@ -535,6 +536,19 @@ static int32_t blocked_cholesky(agp_ctx* c, double* Kw, double* L, double* Lt, d
   constexpr int OB = 4;  // inner blocks per super-panel
   static const bool lookahead = !(getenv("AGP_CHOL_LOOKAHEAD") && atoi(getenv("AGP_CHOL_LOOKAHEAD")) == 0);  // tuning knob
   bool trail_pending = false;  // a trailing update is in flight on stream2
+  // development aid (AGP_CHOL_TRACE=1): device timestamps of the phases of one large factorisation, printed to stderr
+  static int trace_left = (getenv("AGP_CHOL_TRACE") && nb >= 32) ? 1 : 0;
+  const bool trace = trace_left > 0 && nb >= 32;
+  struct Mark { const char* what; int s; cudaEvent_t e; };
+  std::vector<Mark> marks;
+  auto mark = [&](const char* what, int s, cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    marks.push_back({what, s, e});
+  };
+  mark("start", 0, c->stream);
   for (int J0 = 0; J0 < nb; J0 += OB) {
     const int J1 = std::min(nb, J0 + OB);  // super-panel = block columns [J0, J1)
     for (int J = J0; J < J1; J++) {
@@ -568,28 +582,38 @@ static int32_t blocked_cholesky(agp_ctx* c, double* Kw, double* L, double* Lt, d
       continue;
     }
     CU(cudaEventRecord(c->ev_panel, c->stream));  // block columns [J0, J1) of L are complete
+    mark("factor_done", J0 / OB, c->stream);
     // main stream: columns [J1, J2) only (they were last written by the previous trailing update on stream2)
     if (trail_pending) CU(cudaStreamWaitEvent(c->stream, c->ev_trail, 0));
+    mark("prio_start", J0 / OB, c->stream);
     OK((run_gemm<A_KM, B_KN>(c, rem, 2 * (J2 - J1), L + pnl, ld, L + pnl, ld, K, KR_FULL, TS_NBLK_LE, epi_store(Kw + trl, ld, false, -1.0, 1.0))));
+    mark("prio_done", J0 / OB, c->stream);
     {  // second stream: columns >= J2 (stream order serialises successive trailing updates of the same tiles)
       StreamSwap sw(c, c->stream2);
       CU(cudaStreamWaitEvent(c->stream, c->ev_panel, 0));
+      mark("trail_start", J0 / OB, c->stream);
       const int64_t pnl2 = (int64_t)J0 * BM * ld + (int64_t)J2 * BM;
       const int64_t trl2 = (int64_t)J2 * BM * ld + (int64_t)J2 * BM;
-      {  // 2-stage instantiation (51 KB per CTA): a finished CTA leaves room for the diagonal kernel (166 KB) on its SM
-        constexpr int S2 = 2;
-        using Cfg = StageCfg<A_KM, B_KN>;
-        GemmArgs g{L + pnl2, ld, L + pnl2, ld, K, KR_FULL, TS_NBLK_LE};
-        OK((ensure_smem<gemm_kernel<A_KM, B_KN, EpiStore, S2>>(c, S2 * Cfg::bytes)));
-        gemm_kernel<A_KM, B_KN, EpiStore, S2><<<dim3(rem2, 2 * rem2), NTHREADS, S2 * Cfg::bytes, c->stream>>>(g, epi_store(Kw + trl2, ld, false, -1.0, 1.0));
-        LAUNCHED(c);
-        KCHECK();
-      }
+      // 2-stage instantiation (51 KB per CTA): a finished CTA leaves room for the diagonal kernel (166 KB) on its SM
+      OK((run_gemm<A_KM, B_KN, 2>(c, rem2, 2 * rem2, L + pnl2, ld, L + pnl2, ld, K, KR_FULL, TS_NBLK_LE, epi_store(Kw + trl2, ld, false, -1.0, 1.0))));
       CU(cudaEventRecord(c->ev_trail, c->stream));
+      mark("trail_done", J0 / OB, c->stream);
       trail_pending = true;
     }
   }
   if (trail_pending) CU(cudaStreamWaitEvent(c->stream, c->ev_trail, 0));
+  if (trace) {
+    mark("end", 0, c->stream);
+    trace_left = 0;
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->stream2);
+    for (const Mark& m : marks) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, marks[0].e, m.e);
+      fprintf(stderr, "[chol trace] %-12s s=%2d t=%9.1f us\n", m.what, m.s, 1e3 * ms);
+    }
+    for (const Mark& m : marks) cudaEventDestroy(m.e);
+  }
   return AGP_OK;
 }
 
