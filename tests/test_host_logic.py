@@ -72,3 +72,38 @@ def test_two_rank_gloo_allreduce_equals_single_process(tmp_path):
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     got, ref = np.load(out)
     assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6)) < 1e-9
+
+
+def test_reference_interface_objects_without_a_device():
+    """Host mirror of the reference's constructors (no device call): likelihood / link resolution, kernel composition,
+    SparseVariationalApproximation defaults, argument errors that must be raised before anything crosses the C ABI."""
+    import agp_b200 as agp
+    from agp_b200 import _lib as L
+
+    assert agp.BernoulliLikelihood().kind == L.LIK_BERNOULLI_LOGIT
+    assert agp.BernoulliLikelihood(agp.LogisticLink()).kind == L.LIK_BERNOULLI_LOGIT
+    assert agp.BernoulliLikelihood(agp.ProbitLink()).kind == agp.BernoulliLikelihood("probit").kind == L.LIK_BERNOULLI_PROBIT
+    with pytest.raises(ValueError):
+        agp.BernoulliLikelihood("cloglog")  # unsupported link: ArgumentError, there is no CPU fallback
+    assert agp.GammaLikelihood(2.5).sigma2 == 2.5 and agp.ExponentialLikelihood().kind == L.LIK_EXPONENTIAL_EXP
+    # variance * (k o ScaleTransform(1 / l)): KernelFunctions composition
+    k = 1.3 * agp.with_lengthscale(agp.Matern52Kernel(), 0.5)
+    assert k.kind == L.KERNEL_MATERN52 and k.variance == 1.3 and np.allclose(k.inv_lengthscale, [2.0])
+    k2 = agp.ARDTransform(agp.SqExponentialKernel(), [1.0, 2.0, 4.0])
+    assert np.allclose(k2.inv_lengthscale, [1.0, 2.0, 4.0])
+    f = agp.GP(k)
+    z = np.linspace(-1, 1, 5)
+    sva = agp.SparseVariationalApproximation(f(z, 1e-6), agp.MvNormal(np.zeros(5), chol_lower=np.eye(5)))
+    assert not sva.centered  # NonCentered is the default (SVA.jl:93)
+    assert agp.SparseVariationalApproximation(agp.Centered(), f(z, 1e-6), agp.MvNormal(np.zeros(5), chol_lower=np.eye(5))).centered
+    # laplace_steps installs its own Newton callback (Laplace.jl:409-421)
+    lfx = agp.LatentGP(f, agp.BernoulliLikelihood(), 1e-8)(z)
+    with pytest.raises(TypeError):
+        agp.laplace_steps(lfx, np.ones(5), callback=lambda *a: None)
+    # _check_laplace_inputs (Laplace.jl:167-179): zero prior mean, matching lengths
+    from agp_b200.laplace_api import _check_laplace_inputs
+
+    with pytest.raises(AssertionError):
+        _check_laplace_inputs(lfx, np.ones(4))
+    with pytest.raises(AssertionError):
+        _check_laplace_inputs(agp.LatentGP(agp.GP(0.5, k), agp.BernoulliLikelihood(), 1e-8)(z), np.ones(5))
