@@ -134,6 +134,11 @@ SYMBOLS = {
         [_vp, _vp, C.c_int64, C.c_int64, C.POINTER(AgpSvgpParams), C.c_double, C.c_int64, c_double_p, C.POINTER(AgpSvgpGrads)],
     ),
     "agp_svgp_elbo": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int64, C.POINTER(AgpSvgpParams), C.c_double, C.c_int64, c_double_p]),
+    "agp_svgp_flat_size": (C.c_int32, [C.POINTER(AgpSvgpParams), C.POINTER(C.c_int64)]),
+    "agp_svgp_elbo_grad_flat": (
+        C.c_int32,
+        [_vp, _vp, C.c_int64, C.c_int64, C.POINTER(AgpSvgpParams), c_double_p, C.c_double, C.c_int64, c_double_p, c_double_p],
+    ),
     "agp_svgp_sweep": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int64, C.POINTER(AgpSvgpParams), C.c_double, C.c_int64, C.c_int32]),
     "agp_svgp_reduce_buffer": (C.c_int32, [_vp, C.POINTER(_vp), C.POINTER(C.c_int64)]),
     "agp_svgp_finish": (C.c_int32, [_vp, c_double_p, C.POINTER(AgpSvgpGrads)]),

@@ -560,6 +560,53 @@ def elbo_and_gradient(sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx:
             ds.close()
 
 
+class FlatELBO:
+    """``flatten`` / ``unflatten`` of the trainable parameters of ``elbo(sva, l_fx, y)`` and the objective on the flat vector
+    (the role of ``ParameterHandling.flatten`` + ``Optim`` in examples/b-classification/script.jl:102-142): ``x0`` is the current
+    parameter vector, ``value_and_gradient(x)`` evaluates ELBO and gradient through ``agp_svgp_elbo_grad_flat`` (one pointer in,
+    one out), ``unflatten(x)`` gives back a dict of named views.  Layout: include/agp.h ``agp_svgp_elbo_grad_flat``."""
+
+    def __init__(self, sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx: Context | None = None, offset=0, count=None, global_batch=0):
+        self.ctx = ctx or default_context()
+        fx, lik = _resolve_lik(sva, l_fx)
+        self._ds, self._own = _dataset_for(fx, y, self.ctx)
+        self._pk = _Packed(sva, lik, quadrature)
+        self._count = int(count if count is not None else len(self._ds) - offset)
+        self._offset, self._num_data, self._gb = int(offset), float(num_data or 0.0), int(global_batch)
+        pk = self._pk
+        self.n_scale, self.M, self.D = pk.ils.size, pk.M, pk.D
+        n = C.c_int64()
+        L.check(self.ctx.lib.agp_svgp_flat_size(C.byref(pk.p), C.byref(n)))
+        self.size = int(n.value)
+        k = sva.fz.f.kernel
+        self.x0 = np.concatenate([[k.variance], pk.ils, [k.c, sva.fz.f.mean_const, float(lik.sigma2)], pk.Z.ravel(), pk.m, pk.Lq.ravel(order="F")])
+        assert self.x0.size == self.size
+
+    def unflatten(self, x) -> dict:
+        x = np.asarray(x)
+        ns, M, D = self.n_scale, self.M, self.D
+        o = 4 + ns
+        return dict(variance=x[0], inv_lengthscale=x[1:1 + ns], linear_c=x[1 + ns], mean_const=x[2 + ns], lik_param=x[3 + ns],
+                    Z=x[o:o + M * D].reshape(M, D), m=x[o + M * D:o + M * D + M], Lq=x[o + M * D + M:].reshape(M, M, order="F"))
+
+    def value_and_gradient(self, x, want_grad=True):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.shape == (self.size,)
+        out = C.c_double()
+        g = np.zeros(self.size) if want_grad else None
+        L.check(self.ctx.lib.agp_svgp_elbo_grad_flat(self.ctx.h, self._ds.h, self._offset, self._count, C.byref(self._pk.p), L.dptr(x), self._num_data,
+                                                     self._gb, C.byref(out), L.dptr(g)))
+        return out.value, g
+
+    def __call__(self, x):
+        return self.value_and_gradient(x, want_grad=False)[0]
+
+    def close(self):
+        if self._own and self._ds is not None:
+            self._ds.close()
+        self._ds = None
+
+
 def approx_lml(approx, l_fx, ys=None, **kwargs):
     """``API.approx_lml`` -- SVA.jl:276-280 (alias of elbo) / Laplace.jl:58-60."""
     if isinstance(approx, SparseVariationalApproximation):

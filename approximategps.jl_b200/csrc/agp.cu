@@ -1346,6 +1346,48 @@ extern "C" int32_t agp_svgp_elbo_grad(agp_ctx* c, agp_dataset* ds, int64_t offse
   return agp_svgp_finish(c, elbo_out, go);
 }
 
+// Flat-vector form: [variance | inv_lengthscale (n_scale) | linear_c | mean_const | lik parameter |
+// Z (M*D, point-major) | m (M) | Lq (M*M, column-major)] in, the gradient in the same layout out.
+static int64_t flat_size(const agp_svgp_params* p) {
+  if (!p || p->M < 1 || p->D < 1 || p->kernel.n_scale < 1) return 0;
+  return 4 + (int64_t)p->kernel.n_scale + (int64_t)p->M * p->D + p->M + (int64_t)p->M * p->M;
+}
+extern "C" int32_t agp_svgp_flat_size(const agp_svgp_params* p, int64_t* n_out) {
+  const int64_t n = flat_size(p);
+  if (n == 0 || !n_out) return fail(AGP_ERR_INVALID, "agp_svgp_flat_size: template needs M, D and kernel.n_scale");
+  *n_out = n;
+  return AGP_OK;
+}
+extern "C" int32_t agp_svgp_elbo_grad_flat(agp_ctx* c, agp_dataset* ds, int64_t offset, int64_t count, const agp_svgp_params* tmpl,
+                                           const double* flat, double num_data, int64_t global_batch, double* elbo_out, double* flat_grad) {
+  if (!tmpl || !flat) return fail(AGP_ERR_INVALID, "agp_svgp_elbo_grad_flat: NULL argument");
+  if (flat_size(tmpl) == 0) return fail(AGP_ERR_INVALID, "agp_svgp_elbo_grad_flat: template needs M, D and kernel.n_scale");
+  agp_svgp_params p = *tmpl;
+  const int ns = p.kernel.n_scale, M = p.M, D = p.D;
+  const double* f = flat;
+  p.kernel.variance = f[0];
+  p.kernel.inv_lengthscale = f + 1;
+  p.kernel.linear_c = f[1 + ns];
+  p.mean_const = f[2 + ns];
+  p.lik.sigma2 = f[3 + ns];
+  p.Z = f + 4 + ns;
+  p.m = p.Z + (int64_t)M * D;
+  p.Lq = p.m + M;
+  p.ldLq = M;
+  if (!flat_grad) return agp_svgp_elbo(c, ds, offset, count, &p, num_data, global_batch, elbo_out);
+  double* g = flat_grad;
+  agp_svgp_grads go{};
+  go.dvariance = g;
+  go.dinv_lengthscale = g + 1;
+  go.dlinear_c = g + 1 + ns;
+  go.dmean_const = g + 2 + ns;
+  go.dlik_sigma2 = g + 3 + ns;
+  go.dZ = g + 4 + ns;
+  go.dm = go.dZ + (int64_t)M * D;
+  go.dLq = go.dm + M;
+  return agp_svgp_elbo_grad(c, ds, offset, count, &p, num_data, global_batch, elbo_out, &go);
+}
+
 extern "C" int32_t agp_svgp_elbo(agp_ctx* c, agp_dataset* ds, int64_t offset, int64_t count, const agp_svgp_params* p,
                                  double num_data, int64_t global_batch, double* elbo_out) {
   OK(agp_svgp_sweep(c, ds, offset, count, p, num_data, global_batch, 0));

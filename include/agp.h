@@ -178,6 +178,15 @@ int32_t agp_svgp_elbo(agp_ctx* ctx, agp_dataset* ds, int64_t offset, int64_t cou
                       const agp_svgp_params* p, double num_data, int64_t global_batch,
                       double* elbo_out);
 
+/* Flat-vector form for optimisers that work on one parameter vector (ParameterHandling.flatten + Optim in
+ * examples/b-classification/script.jl:102-142, Flux.params in examples/a-regression/script.jl:188): `tmpl` fixes everything that is
+ * not optimised (kernel kind, n_scale, M, D, jitter, parametrization, likelihood kind, expectation method); `flat` holds
+ *   [variance | inv_lengthscale (n_scale) | linear_c | mean_const | likelihood parameter | Z (M*D point-major) | m (M) | Lq (M*M column-major)]
+ * (agp_svgp_flat_size doubles) and `flat_grad` (same layout, or NULL for the value only) receives the gradient: one pointer in, one out. */
+int32_t agp_svgp_flat_size(const agp_svgp_params* tmpl, int64_t* n_doubles);
+int32_t agp_svgp_elbo_grad_flat(agp_ctx* ctx, agp_dataset* ds, int64_t offset, int64_t count, const agp_svgp_params* tmpl,
+                                const double* flat, double num_data, int64_t global_batch, double* elbo_out, double* flat_grad);
+
 /* Split-phase form of agp_svgp_elbo_grad for hosts that own the collective (torch.distributed,
  * MPI.jl): sweep -> caller all-reduces the packed float64 buffer in place (sum) -> finish.     */
 int32_t agp_svgp_sweep(agp_ctx* ctx, agp_dataset* ds, int64_t offset, int64_t count,

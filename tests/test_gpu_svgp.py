@@ -401,3 +401,41 @@ def test_full_size_c4_properties(agp):
     print(f"[C4 full size] reversed order rel={e_rev:.1e} " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
     assert e_rev < 1e-12 and all(v < 1e-10 for v in errs.values()), (e_rev, errs)
     ds.close()
+
+
+@pytest.mark.parametrize("centered,lik", [(False, "poisson_exp"), (True, "gaussian")])
+def test_flat_vector_interface(agp, centered, lik):
+    """agp_svgp_elbo_grad_flat: one flat parameter vector in, the gradient in the same layout out; equal to the
+    struct interface, and usable as a scipy.optimize objective (a few L-BFGS steps increase the ELBO)."""
+    from scipy.optimize import minimize
+
+    p = make_problem(seed=17, kind="se", N=500, M=12, D=2, lik=lik, centered=centered, ard=True)
+    sva, lfx, quad, _ = agp_objects(agp, p)
+    val, g = agp.elbo_and_gradient(sva, lfx, p["y"], num_data=2000.0, quadrature=quad)
+    fo = agp.FlatELBO(sva, lfx, p["y"], num_data=2000.0, quadrature=quad)
+    assert fo.size == 4 + 2 + 12 * 2 + 12 + 144
+    v2, gf = fo.value_and_gradient(fo.x0)
+    u = fo.unflatten(gf)
+    assert v2 == val and fo(fo.x0) == pytest.approx(val, rel=1e-12)
+    assert np.array_equal(u["m"], g.m) and np.array_equal(u["Lq"], g.Lq) and np.array_equal(u["Z"], g.Z)
+    assert u["variance"] == g.variance and np.array_equal(u["inv_lengthscale"], g.inv_lengthscale) and u["lik_param"] == g.lik_sigma2
+    x0 = fo.unflatten(fo.x0)
+    assert np.array_equal(x0["Z"], p["Z"]) and np.array_equal(x0["Lq"], p["A"]) and np.allclose(x0["inv_lengthscale"], p["inv"])
+    # optimise the variational mean only (the positive parameters and diag(Lq) would need the examples' softplus re-parametrisation;
+    # a non-positive diag(Lq) is a DomainError here as `logdet` is in the reference)
+    o, e = 4 + 2 + 24, 4 + 2 + 24 + 12
+
+    def neg(xm):
+        x = fo.x0.copy()
+        x[o:e] = xm
+        v, gg = fo.value_and_gradient(x)
+        return -v, -gg[o:e].copy()
+
+    res = minimize(neg, fo.x0[o:e], jac=True, method="L-BFGS-B", options=dict(maxiter=15))
+    bad = fo.x0.copy()
+    bad[e] = -1.0  # Lq[0, 0]
+    with pytest.raises(agp.DomainError):
+        fo.value_and_gradient(bad)
+    print(f"\n[flat interface] elbo {val:.4f} -> {-res.fun:.4f} after {res.nit} L-BFGS iterations")
+    assert -res.fun > val
+    fo.close()
