@@ -127,6 +127,7 @@ SYMBOLS = {
     "agp_comm_destroy": (C.c_int32, [_vp]),
     "agp_dataset_create": (C.c_int32, [_vp, C.c_int64, C.c_int32, C.POINTER(_vp)]),
     "agp_dataset_upload": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int64, C.c_int32, _vp, C.c_int32, C.c_int32]),
+    "agp_dataset_upload_f32": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int64, C.c_int32, _vp, C.c_int32, C.c_int32]),
     "agp_dataset_size": (C.c_int32, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "agp_dataset_destroy": (C.c_int32, [_vp]),
     "agp_svgp_elbo_grad": (

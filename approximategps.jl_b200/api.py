@@ -390,9 +390,10 @@ class DeviceData:
     def __init__(self, x=None, y=None, *, capacity=None, D=None, ctx: Context | None = None):
         self.ctx = ctx or default_context()
         if x is not None:
-            x = _points(x)
+            if not (isinstance(x, np.ndarray) and x.dtype == np.float32):  # Float32 points are uploaded as they are
+                x = _points(x)
             capacity = capacity or x.shape[0]
-            D = x.shape[1]
+            D = 1 if x.ndim == 1 else x.shape[1]
         h = C.c_void_p()
         L.check(self.ctx.lib.agp_dataset_create(self.ctx.h, int(capacity), int(D), C.byref(h)))
         self.h, self.D, self.N = h, int(D), 0
@@ -400,7 +401,8 @@ class DeviceData:
             self.upload(x, y)
 
     def upload(self, x, y=None):
-        x = _points(x)
+        x32 = isinstance(x, np.ndarray) and x.dtype == np.float32
+        x = np.ascontiguousarray(x.reshape(len(x), -1)) if x32 else _points(x)
         yp, yt = None, L.Y_F64
         if y is not None:
             y = np.ascontiguousarray(y)
@@ -408,7 +410,8 @@ class DeviceData:
                 y = y.astype(np.float64)
             yt = _YTYPES[y.dtype]
             yp = y.ctypes.data_as(C.c_void_p)
-        L.check(self.ctx.lib.agp_dataset_upload(self.h, x.ctypes.data_as(C.c_void_p), x.shape[0], x.shape[1], L.POINT_MAJOR, yp, yt, L.HOST))
+        up = self.ctx.lib.agp_dataset_upload_f32 if x32 else self.ctx.lib.agp_dataset_upload  # Float32 inputs travel as Float32
+        L.check(up(self.h, x.ctypes.data_as(C.c_void_p), x.shape[0], x.shape[1], L.POINT_MAJOR, yp, yt, L.HOST))
         self.N = x.shape[0]
 
     def upload_device(self, x_ptr: int, n: int, y_ptr: int | None, layout=L.POINT_MAJOR, ldx=0, ytype=L.Y_F64):

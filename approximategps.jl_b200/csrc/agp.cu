@@ -357,6 +357,32 @@ extern "C" int32_t agp_dataset_create(agp_ctx* c, int64_t capacity, int32_t D, a
   return AGP_OK;
 }
 
+// observations: F64 as is, F32 / I64 / U8 (Bool) widened on the device
+static int32_t upload_y(agp_dataset* ds, const void* y, int64_t N, int32_t ytype, int32_t location) {
+  agp_ctx* c = ds->ctx;
+  const cudaMemcpyKind kind = location == AGP_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (y) {
+    if (ytype == AGP_Y_F64) {
+      CU(cudaMemcpyAsync(ds->y, y, sizeof(double) * N, kind, c->stream));
+    } else {
+      const size_t esz = ytype == AGP_Y_F32 ? 4 : ytype == AGP_Y_I64 ? 8 : ytype == AGP_Y_U8 ? 1 : 0;
+      if (!esz) return fail(AGP_ERR_INVALID, "unknown ytype %d", ytype);
+      const void* src = y;
+      if (location == AGP_HOST) {
+        OK(ds->stage.ensure((int64_t)((esz * N + 7) / 8) + 1));
+        CU(cudaMemcpyAsync(ds->stage.p, y, esz * N, cudaMemcpyHostToDevice, c->stream));
+        src = ds->stage.p;
+      }
+      if (ytype == AGP_Y_F32) convert_y_kernel<float><<<1024, 256, 0, c->stream>>>((const float*)src, ds->y, N);
+      if (ytype == AGP_Y_I64) convert_y_kernel<long long><<<1024, 256, 0, c->stream>>>((const long long*)src, ds->y, N);
+      if (ytype == AGP_Y_U8) convert_y_kernel<unsigned char><<<1024, 256, 0, c->stream>>>((const unsigned char*)src, ds->y, N);
+      LAUNCHED(c);
+      KCHECK();
+    }
+  }
+  return AGP_OK;
+}
+
 extern "C" int32_t agp_dataset_upload(agp_dataset* ds, const void* X, int64_t N, int64_t ldx, int32_t layout, const void* y,
                                       int32_t ytype, int32_t location) {
   if (!ds || !X || N < 0 || N > ds->cap) return fail(AGP_ERR_INVALID, "agp_dataset_upload: bad arguments (N=%lld, cap=%lld)", (long long)N, ds ? (long long)ds->cap : -1LL);
@@ -384,25 +410,42 @@ extern "C" int32_t agp_dataset_upload(agp_dataset* ds, const void* X, int64_t N,
   } else {
     return fail(AGP_ERR_INVALID, "unknown layout %d", layout);
   }
-  if (y) {
-    if (ytype == AGP_Y_F64) {
-      CU(cudaMemcpyAsync(ds->y, y, sizeof(double) * N, kind, c->stream));
-    } else {
-      const size_t esz = ytype == AGP_Y_F32 ? 4 : ytype == AGP_Y_I64 ? 8 : ytype == AGP_Y_U8 ? 1 : 0;
-      if (!esz) return fail(AGP_ERR_INVALID, "unknown ytype %d", ytype);
-      const void* src = y;
-      if (location == AGP_HOST) {
-        OK(ds->stage.ensure((int64_t)((esz * N + 7) / 8) + 1));
-        CU(cudaMemcpyAsync(ds->stage.p, y, esz * N, cudaMemcpyHostToDevice, c->stream));
-        src = ds->stage.p;
-      }
-      if (ytype == AGP_Y_F32) convert_y_kernel<float><<<1024, 256, 0, c->stream>>>((const float*)src, ds->y, N);
-      if (ytype == AGP_Y_I64) convert_y_kernel<long long><<<1024, 256, 0, c->stream>>>((const long long*)src, ds->y, N);
-      if (ytype == AGP_Y_U8) convert_y_kernel<unsigned char><<<1024, 256, 0, c->stream>>>((const unsigned char*)src, ds->y, N);
-      LAUNCHED(c);
-      KCHECK();
-    }
+  OK(upload_y(ds, y, N, ytype, location));
+  CU(cudaStreamSynchronize(c->stream));
+  ds->N = N;
+  return AGP_OK;
+}
+
+// Float32 inputs (a Float32 caller's ColVecs / RowVecs): half the PCIe bytes; widened to the FP64 the kernels compute in.
+__global__ void widen_x_kernel(const float* in, int64_t ldx, int layout, double* out, int64_t N, int D) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N * D; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / D;
+    const int d = (int)(i % D);
+    out[i] = (double)(layout == AGP_FEATURE_MAJOR ? in[(int64_t)d * ldx + n] : in[n * ldx + d]);
   }
+}
+extern "C" int32_t agp_dataset_upload_f32(agp_dataset* ds, const float* X, int64_t N, int64_t ldx, int32_t layout, const void* y,
+                                          int32_t ytype, int32_t location) {
+  if (!ds || !X || N < 0 || N > ds->cap) return fail(AGP_ERR_INVALID, "agp_dataset_upload_f32: bad arguments (N=%lld, cap=%lld)", (long long)N, ds ? (long long)ds->cap : -1LL);
+  if (layout != AGP_POINT_MAJOR && layout != AGP_FEATURE_MAJOR) return fail(AGP_ERR_INVALID, "unknown layout %d", layout);
+  agp_ctx* c = ds->ctx;
+  CU(cudaSetDevice(c->device));
+  const int D = ds->D;
+  if (ldx <= 0) ldx = layout == AGP_POINT_MAJOR ? D : N;
+  const int64_t nflt = layout == AGP_POINT_MAJOR ? N * ldx : (int64_t)D * ldx;
+  const float* src = X;
+  if (location == AGP_HOST && N > 0) {
+    OK(ds->stage.ensure((nflt + 1) / 2 + 1));
+    CU(cudaMemcpyAsync(ds->stage.p, X, sizeof(float) * nflt, cudaMemcpyHostToDevice, c->stream));
+    src = reinterpret_cast<const float*>(ds->stage.p);
+  }
+  if (N > 0) {
+    widen_x_kernel<<<1024, 256, 0, c->stream>>>(src, ldx, layout, ds->X, N, D);
+    LAUNCHED(c);
+    KCHECK();
+  }
+  CU(cudaStreamSynchronize(c->stream));  // the staging buffer is reused for the observations
+  OK(upload_y(ds, y, N, ytype, location));
   CU(cudaStreamSynchronize(c->stream));
   ds->N = N;
   return AGP_OK;

@@ -159,6 +159,10 @@ int32_t agp_dataset_create(agp_ctx* ctx, int64_t capacity, int32_t D, agp_datase
 /* (Re)fill from host or device memory; N <= capacity.  location: AGP_HOST | AGP_DEVICE.        */
 int32_t agp_dataset_upload(agp_dataset* ds, const void* X, int64_t N, int64_t ldx, int32_t layout,
                            const void* y, int32_t ytype, int32_t location);
+/* The same for Float32 inputs (a Float32 caller's ColVecs / RowVecs / Vector): half the bytes over PCIe; the points are widened
+ * to the Float64 the kernels compute in (the Float32 *arithmetic* mode of north_star is not built).        */
+int32_t agp_dataset_upload_f32(agp_dataset* ds, const float* X, int64_t N, int64_t ldx, int32_t layout,
+                               const void* y, int32_t ytype, int32_t location);
 int32_t agp_dataset_size(agp_dataset* ds, int64_t* N, int32_t* D);
 int32_t agp_dataset_destroy(agp_dataset* ds);
 

@@ -439,3 +439,26 @@ def test_flat_vector_interface(agp, centered, lik):
     print(f"\n[flat interface] elbo {val:.4f} -> {-res.fun:.4f} after {res.nit} L-BFGS iterations")
     assert -res.fun > val
     fo.close()
+
+
+def test_float32_inputs_are_uploaded_as_float32(agp):
+    """agp_dataset_upload_f32: a Float32 caller's points (point-major and RowVecs layouts) and Float32 observations are widened on the
+    device; the result equals the Float64 interface on the same (Float32-representable) values bit for bit."""
+    import ctypes as C
+
+    from agp_b200 import _lib as L
+
+    p = make_problem(seed=5, kind="matern32", N=333, M=11, D=3, lik="gaussian")
+    X32, y32 = p["X"].astype(np.float32), p["y"].astype(np.float32)
+    sva, _, quad, f = agp_objects(agp, p)
+    ctx = agp.default_context()
+    lik = agp.GaussianLikelihood(p["sigma2"])
+    ref, rg = agp.elbo_and_gradient(sva, agp.LatentGP(f, lik, 1e-18)(X32.astype(np.float64)), y32.astype(np.float64), num_data=999.0)
+    ds = agp.DeviceData(X32, y32, ctx=ctx)
+    val, g = agp.elbo_and_gradient(sva, agp.LatentGP(f, lik, 1e-18)(ds), None, num_data=999.0)
+    assert val == ref and np.array_equal(g.Z, rg.Z) and np.array_equal(g.Lq, rg.Lq)
+    Xf = np.asfortranarray(X32)  # RowVecs(N x D) of Float32
+    L.check(ctx.lib.agp_dataset_upload_f32(ds.h, Xf.ctypes.data_as(C.c_void_p), 333, 333, L.FEATURE_MAJOR, y32.ctypes.data_as(C.c_void_p), L.Y_F32, L.HOST))
+    val2, _ = agp.elbo_and_gradient(sva, agp.LatentGP(f, lik, 1e-18)(ds), None, num_data=999.0)
+    assert val2 == ref
+    ds.close()
