@@ -147,6 +147,8 @@ SYMBOLS = {
     "agp_svgp_posterior": (C.c_int32, [_vp, C.POINTER(AgpSvgpParams), c_double_p, c_double_p, c_double_p]),
     "agp_svgp_mean_and_var": (C.c_int32, [_vp, C.POINTER(AgpSvgpParams), c_double_p, C.c_int64, c_double_p, c_double_p]),
     "agp_svgp_mean_and_cov": (C.c_int32, [_vp, C.POINTER(AgpSvgpParams), c_double_p, C.c_int64, c_double_p, C.c_int64, c_double_p, c_double_p]),
+    "agp_kernel_matrix": (C.c_int32, [_vp, C.POINTER(AgpKernel), C.c_int32, c_double_p, C.c_int64, c_double_p, C.c_int64, c_double_p]),
+    "agp_fp64_peak": (C.c_int32, [_vp, C.c_int32, c_double_p]),
     "agp_laplace_predict": (
         C.c_int32,
         [_vp, C.POINTER(AgpKernel), c_double_p, C.c_int32, c_double_p, C.c_int64, c_double_p, C.c_int64, c_double_p, c_double_p, c_double_p],
@@ -215,5 +217,5 @@ def check(status: int):
 def dptr(a: np.ndarray | None):
     if a is None:
         return None
-    assert a.dtype == np.float64 and a.flags.c_contiguous or a.flags.f_contiguous
+    assert a.dtype == np.float64 and (a.flags.c_contiguous or a.flags.f_contiguous), "float64, contiguous"
     return a.ctypes.data_as(c_double_p)

@@ -355,6 +355,15 @@ class Context:
         L.check(self.lib.agp_ctx_profile_read(self.h, 64, ms, cnt, C.byref(n)))
         return {self.lib.agp_profile_class_name(i).decode(): (ms[i], cnt[i]) for i in range(n.value)}
 
+    def fp64_peak(self) -> dict:
+        """Achieved TFLOP/s of register-resident DMMA.8x8x4 and DFMA chains on this device, measured now (agp_fp64_peak)."""
+        out = {}
+        v = C.c_double()
+        for i, name in enumerate(("dmma", "dfma")):
+            L.check(self.lib.agp_fp64_peak(self.h, i, C.byref(v)))
+            out[name] = v.value
+        return out
+
     def stream(self) -> int:
         s = C.c_void_p()
         L.check(self.lib.agp_ctx_stream(self.h, C.byref(s)))
@@ -372,6 +381,20 @@ class Context:
 
 
 _default_ctx: dict[int, Context] = {}
+
+
+def kernelmatrix(k, x, y=None, *, ctx: "Context | None" = None) -> np.ndarray:
+    """``KernelFunctions.kernelmatrix(k, x[, y])`` = ``cov(GP(k), x[, y])`` evaluated on the device (agp_kernel_matrix)."""
+    ctx = ctx or default_context()
+    k = _as_kernel(k)
+    x = _points(x)
+    yy = None if y is None else _points(y)
+    n1, n2 = len(x), (len(x) if yy is None else len(yy))
+    ils = np.ascontiguousarray(k.inv_lengthscale, dtype=np.float64)
+    kk = L.AgpKernel(k.kind, ils.size, k.variance, L.dptr(ils), k.c)
+    out = np.zeros((n1, n2), order="F")
+    L.check(ctx.lib.agp_kernel_matrix(ctx.h, C.byref(kk), x.shape[1], L.dptr(x), n1, L.dptr(yy), n2, L.dptr(out)))
+    return out
 
 
 def default_context(device: int = 0) -> Context:

@@ -105,6 +105,7 @@ static int32_t load_nccl() {
 // Everything the sweep needs that depends on one agp_svgp_params (uploaded once per step).
 struct SvgpState {
   bool valid = false;
+  bool sweep_pending = false;  // agp_svgp_sweep has filled the reduce buffer and agp_svgp_finish has not consumed it yet
   int M = 0, Mp = 0, D = 0, nb = 0;
   int n_scale = 1;
   bool centered = false;
@@ -159,7 +160,7 @@ struct agp_ctx {
   // per-chunk scratch [Mp][chunk_cols]
   DevBuf A, C, Ab, As, saa, sam, scc_part, dmu, dv, sc_part;
   // accumulators
-  DevBuf gpart, Gpart, kpart, red, small;
+  DevBuf gpart, Gpart, kpart, red, small, ghbuf;
   int* d_flags = nullptr;  // [0] potrf info, [1] domain flag
   SvgpState st;
   ncclComm_t comm = nullptr;
@@ -233,7 +234,7 @@ extern "C" int32_t agp_ctx_destroy(agp_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   DevBuf* bufs[] = {&c->z, &c->zs, &c->zn, &c->zsp, &c->mvec, &c->mt, &c->Lq, &c->Kw, &c->Lk, &c->Lt, &c->Ut, &c->Bt_cm, &c->Bt_rm,
                     &c->W1, &c->W2, &c->W3, &c->W4, &c->vec64, &c->vec64b, &c->A, &c->C, &c->Ab, &c->As, &c->saa, &c->sam,
-                    &c->scc_part, &c->dmu, &c->dv, &c->sc_part, &c->gpart, &c->Gpart, &c->kpart, &c->red, &c->small,
+                    &c->scc_part, &c->dmu, &c->dv, &c->sc_part, &c->gpart, &c->Gpart, &c->kpart, &c->red, &c->small, &c->ghbuf,
                     &c->mu_out, &c->var_out, &c->px1, &c->px2, &c->pxs1, &c->pxn1, &c->pxs2, &c->pxn2, &c->pcov};
   for (DevBuf* b : bufs) b->release();
   lap_release(c);
@@ -802,6 +803,7 @@ static int32_t resolve_params(const agp_svgp_params* p, SvgpState& st) {
   st.lp.method = method;
   st.lp.ngh = 0;
   st.lp.seed = 0;
+  st.lp.gh = nullptr;
   if (method == AGP_EXPECT_GAUSS_HERMITE) {
     if (p->expect.n_points < 1 || p->expect.n_points > AGP_MAX_GH_POINTS || !p->expect.nodes || !p->expect.weights)
       return fail(AGP_ERR_INVALID, "Gauss-Hermite needs 1..%d nodes and weights from the caller", AGP_MAX_GH_POINTS);
@@ -822,6 +824,7 @@ static int32_t resolve_params(const agp_svgp_params* p, SvgpState& st) {
 static int32_t prepare_step(agp_ctx* c, const agp_svgp_params* p) {
   SvgpState& st = c->st;
   st.valid = false;
+  st.sweep_pending = false;
   OK(resolve_params(p, st));
   CU(cudaSetDevice(c->device));
   const int M = st.M, Mp = st.Mp, D = st.D, nb = st.nb;
@@ -854,8 +857,10 @@ static int32_t prepare_step(agp_ctx* c, const agp_svgp_params* p) {
   LAUNCHED(c);
   KCHECK();
   if (st.lp.method == AGP_EXPECT_GAUSS_HERMITE && st.lp.ngh > 0) {
-    CU(cudaMemcpyToSymbolAsync(c_gh_x, p->expect.nodes, sizeof(double) * st.lp.ngh, 0, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyToSymbolAsync(c_gh_w, p->expect.weights, sizeof(double) * st.lp.ngh, 0, cudaMemcpyHostToDevice, c->stream));
+    OK(c->ghbuf.ensure(2 * AGP_MAX_GH_POINTS));
+    CU(cudaMemcpyAsync(c->ghbuf.p, p->expect.nodes, sizeof(double) * st.lp.ngh, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->ghbuf.p + AGP_MAX_GH_POINTS, p->expect.weights, sizeof(double) * st.lp.ngh, cudaMemcpyHostToDevice, c->stream));
+    st.lp.gh = c->ghbuf.p;
   }
   CU(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int), c->stream));
   prep_z_kernel<<<(Mp + 127) / 128, 128, 0, c->stream>>>(c->z.p, c->zs.p, c->zn.p, c->zsp.p, Mp, st.kp);
@@ -927,6 +932,8 @@ static int32_t check_step_flags(agp_ctx* c, bool domain) {
 // ---------------------------------------------------------------------------------------------------
 // SVGP: the data sweep
 // ---------------------------------------------------------------------------------------------------
+// slot of the scalar segment (between NSC and the start of g) in which a rank that failed before the collective reports itself
+constexpr int SC_PEER_FAILED = NSC + 1;
 // layout of the packed reduce buffer
 struct RedLayout {
   int64_t scal, g, G, dZ, theta, total;
@@ -1049,6 +1056,13 @@ static int32_t finish_kgrad(agp_ctx* c, int nslab, double zfac, double* dZ, doub
   return AGP_OK;
 }
 
+// Stage-order de-phasing of the Kuf-generating solve (StepIter::late): CTA b uses the late order when (b / #SMs) is odd, i.e.
+// the two CTAs that the block scheduler places on one SM run different orders.  AGP_S1_DEPHASE=0 disables it (tuning knob).
+static int s1_dephase(agp_ctx* c) {
+  static const int on = getenv("AGP_S1_DEPHASE") ? atoi(getenv("AGP_S1_DEPHASE")) : 1;
+  return on ? c->sms : 0;
+}
+
 // forward (+ backward) sweep over points [offset, offset+count) of ds.  predict != 0: only S1-S3 writing mu/var.
 static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_t count, bool grad, bool predict, double* mu_out,
                             double* var_out) {
@@ -1086,6 +1100,7 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
     t1.saa = c->saa.p;
     t1.sam = c->sam.p;
     t1.kp = st.kp;
+    t1.dephase = s1_dephase(c);
     {
       ProfScope ps(c, PC_TRSM_FWD);
       OK(launch_trsm<TR_KUF_FWD>(c, t1, tiles_n));
@@ -1190,7 +1205,9 @@ static int32_t check_dataset(agp_ctx* c, agp_dataset* ds, int64_t offset, int64_
   if (!c || !ds) return fail(AGP_ERR_INVALID, "NULL context or dataset");
   if (ds->ctx != c) return fail(AGP_ERR_INVALID, "dataset belongs to another context");
   if (ds->D != D) return fail(AGP_ERR_INVALID, "dataset dimension %d != params.D %d", ds->D, D);
-  if (offset < 0 || count < 1 || offset + count > ds->N)
+  // an empty shard (count == 0) is legal for a rank of a data-parallel job with fewer points than ranks: it contributes zeros
+  const int64_t min_count = (c->comm && c->nranks > 1) ? 0 : 1;
+  if (offset < 0 || count < min_count || offset + count > ds->N)
     return fail(AGP_ERR_INVALID, "points [%lld, %lld) outside the dataset (N=%lld)", (long long)offset, (long long)(offset + count), (long long)ds->N);
   return AGP_OK;
 }
@@ -1198,6 +1215,9 @@ static int32_t check_dataset(agp_ctx* c, agp_dataset* ds, int64_t offset, int64_
 extern "C" int32_t agp_svgp_sweep(agp_ctx* c, agp_dataset* ds, int64_t offset, int64_t count, const agp_svgp_params* p,
                                   double num_data, int64_t global_batch, int32_t want_grad) {
   if (!c || !p) return fail(AGP_ERR_INVALID, "agp_svgp_sweep: NULL argument");
+  if (c->comm && c->nranks > 1 && global_batch <= 0)
+    return fail(AGP_ERR_INVALID, "with a communicator attached global_batch (the batch size summed over all ranks) is required: "
+                                 "num_data / count of one shard would scale the ELBO by the number of ranks");
   OK(check_dataset(c, ds, offset, count, p->D));
   {
     ProfScope ps(c, PC_PREPARE);
@@ -1209,14 +1229,15 @@ extern "C" int32_t agp_svgp_sweep(agp_ctx* c, agp_dataset* ds, int64_t offset, i
   st.want_grad = want_grad;
   st.point_base = offset + ((long long)c->rank << 40);  // distinct Monte-Carlo streams per rank
   OK(sweep_points(c, ds->X + offset * ds->D, ds->y + offset, count, want_grad != 0, false, nullptr, nullptr));
+  st.sweep_pending = true;
   return AGP_OK;
 }
 
 extern "C" int32_t agp_svgp_reduce_buffer(agp_ctx* c, void** dptr, int64_t* n) {
-  if (!c || !c->st.valid) return fail(AGP_ERR_INVALID, "agp_svgp_reduce_buffer: no sweep pending");
+  if (!c || !c->st.valid || !c->st.sweep_pending) return fail(AGP_ERR_INVALID, "agp_svgp_reduce_buffer: no sweep pending");
   RedLayout rl(c->st.Mp, c->st.D);
   if (dptr) *dptr = c->red.p;
-  if (n) *n = c->st.want_grad ? rl.total : NSC;
+  if (n) *n = c->st.want_grad ? rl.total : rl.g;
   CU(cudaStreamSynchronize(c->stream));  // the caller's collective runs on its own stream
   return AGP_OK;
 }
@@ -1225,7 +1246,9 @@ extern "C" int32_t agp_svgp_reduce_buffer(agp_ctx* c, void** dptr, int64_t* n) {
 // SVGP: replicated epilogue (KL, Cholesky pullback, Kuu part of dZ / dtheta)
 // ---------------------------------------------------------------------------------------------------
 extern "C" int32_t agp_svgp_finish(agp_ctx* c, double* elbo_out, agp_svgp_grads* go) {
-  if (!c || !c->st.valid) return fail(AGP_ERR_INVALID, "agp_svgp_finish: no sweep pending");
+  // (st.valid alone is also set by prior_kl / posterior / mean_and_var, whose prepare_step leaves no reduce buffer behind)
+  if (!c || !c->st.valid || !c->st.sweep_pending) return fail(AGP_ERR_INVALID, "agp_svgp_finish: no sweep pending");
+  c->st.sweep_pending = false;
   CU(cudaSetDevice(c->device));
   ProfScope ps_finish(c, PC_FINISH);
   SvgpState& st = c->st;
@@ -1235,13 +1258,14 @@ extern "C" int32_t agp_svgp_finish(agp_ctx* c, double* elbo_out, agp_svgp_grads*
   double* red = c->red.p;
   double* small = c->small.p;  // [0] KL, [1] sum(mbar) (centered)
   OK(run_kl(c, small));
-  std::vector<double> h_scal(NSC), h_small(4, 0.0);
+  std::vector<double> h_scal(rl.g), h_small(4, 0.0);
   if (!st.want_grad || !go) {
-    CU(cudaMemcpyAsync(h_scal.data(), red + rl.scal, sizeof(double) * NSC, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(h_scal.data(), red + rl.scal, sizeof(double) * rl.g, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(h_small.data(), small, sizeof(double) * 1, cudaMemcpyDeviceToHost, c->stream));
     int h_flags[4];
     CU(cudaMemcpyAsync(h_flags, c->d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if (h_scal[SC_PEER_FAILED] != 0.0) return fail(AGP_ERR_NCCL, "%d peer rank(s) failed before the all-reduce; the result is invalid", (int)h_scal[SC_PEER_FAILED]);
     if (h_flags[0] != 0) return fail(AGP_ERR_NOT_PD, "PosDefException: cov(fz) is not positive definite; Cholesky failed at column %d", h_flags[0]);
     if (h_flags[1] != 0) return fail(AGP_ERR_DOMAIN, "DomainError: a marginal variance is not positive");
     if (elbo_out) *elbo_out = h_scal[SC_E] * st.scale - h_small[0];
@@ -1329,7 +1353,7 @@ extern "C" int32_t agp_svgp_finish(agp_ctx* c, double* elbo_out, agp_svgp_grads*
   // outputs
   std::vector<double> h_theta(2 + D), h_dZ((int64_t)Mp * D), h_vec(2 * (int64_t)Mp), h_g(Mp);
   std::vector<double> h_dLq;
-  CU(cudaMemcpyAsync(h_scal.data(), red + rl.scal, sizeof(double) * NSC, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(h_scal.data(), red + rl.scal, sizeof(double) * rl.g, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(h_small.data(), small, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(h_theta.data(), theta, sizeof(double) * (2 + D), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(h_dZ.data(), dZ, sizeof(double) * Mp * D, cudaMemcpyDeviceToHost, c->stream));
@@ -1348,6 +1372,7 @@ extern "C" int32_t agp_svgp_finish(agp_ctx* c, double* elbo_out, agp_svgp_grads*
 #if defined(AGP_EXP_NOGEN) || defined(AGP_EXP_NOEXP) || defined(AGP_EXP_WAIT2)
   h_flags[0] = h_flags[1] = 0;  // timing experiments (tools/s1_experiments.sh) produce garbage on purpose
 #endif
+  if (h_scal[SC_PEER_FAILED] != 0.0) return fail(AGP_ERR_NCCL, "%d peer rank(s) failed before the all-reduce; the result is invalid", (int)h_scal[SC_PEER_FAILED]);
   if (h_flags[0] != 0) return fail(AGP_ERR_NOT_PD, "PosDefException: cov(fz) is not positive definite; Cholesky failed at column %d", h_flags[0]);
   if (h_flags[1] != 0) return fail(AGP_ERR_DOMAIN, "DomainError: a marginal variance is not positive");
   if (elbo_out) *elbo_out = h_scal[SC_E] * st.scale - h_small[0];
@@ -1375,16 +1400,39 @@ extern "C" int32_t agp_svgp_finish(agp_ctx* c, double* elbo_out, agp_svgp_grads*
 static int32_t allreduce_if_needed(agp_ctx* c) {
   if (!c->comm || c->nranks == 1) return AGP_OK;
   RedLayout rl(c->st.Mp, c->st.D);
-  const size_t n = c->st.want_grad ? (size_t)rl.total : (size_t)NSC;
+  const size_t n = c->st.want_grad ? (size_t)rl.total : (size_t)rl.g;
   ProfScope ps(c, PC_ALLREDUCE);
   ncclResult_t r = g_nccl.AllReduce(c->red.p, c->red.p, n, ncclDouble, ncclSum, c->comm, c->stream);
   if (r != ncclSuccess) return fail(AGP_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   return AGP_OK;
 }
 
+// A rank whose sweep failed locally (allocation, CUDA error, a bad shard) must still enter the collective, or its peers block
+// in ncclAllReduce forever: it contributes a zero buffer with SC_PEER_FAILED = 1, the peers see the non-zero slot in
+// agp_svgp_finish and fail with AGP_ERR_NCCL, and this rank returns its own error.  (Argument errors that every rank detects
+// identically -- NULL pointers, global_batch <= 0 -- return before the collective on all of them.)
+static void signal_failure_to_peers(agp_ctx* c, const agp_svgp_params* p, bool want_grad) {
+  if (!c || !c->comm || c->nranks < 2 || !p || p->M < 1 || p->D < 1 || p->D > MAXD) return;
+  const std::string saved = g_err;
+  const int Mp = (int)round_up(p->M, BM);
+  RedLayout rl(Mp, p->D);
+  if (cudaSetDevice(c->device) == cudaSuccess && c->red.ensure(rl.total) == AGP_OK) {
+    const double one = 1.0;
+    cudaMemsetAsync(c->red.p, 0, sizeof(double) * rl.total, c->stream);
+    cudaMemcpyAsync(c->red.p + SC_PEER_FAILED, &one, sizeof one, cudaMemcpyHostToDevice, c->stream);
+    g_nccl.AllReduce(c->red.p, c->red.p, want_grad ? (size_t)rl.total : (size_t)rl.g, ncclDouble, ncclSum, c->comm, c->stream);
+    cudaStreamSynchronize(c->stream);
+  }
+  g_err = saved;
+}
+
 extern "C" int32_t agp_svgp_elbo_grad(agp_ctx* c, agp_dataset* ds, int64_t offset, int64_t count, const agp_svgp_params* p,
                                       double num_data, int64_t global_batch, double* elbo_out, agp_svgp_grads* go) {
-  OK(agp_svgp_sweep(c, ds, offset, count, p, num_data, global_batch, go ? 1 : 0));
+  const int32_t s = agp_svgp_sweep(c, ds, offset, count, p, num_data, global_batch, go ? 1 : 0);
+  if (s != AGP_OK) {
+    if (c && !(c->comm && c->nranks > 1 && global_batch <= 0)) signal_failure_to_peers(c, p, go != nullptr);
+    return s;
+  }
   OK(allreduce_if_needed(c));
   return agp_svgp_finish(c, elbo_out, go);
 }
@@ -1433,7 +1481,11 @@ extern "C" int32_t agp_svgp_elbo_grad_flat(agp_ctx* c, agp_dataset* ds, int64_t 
 
 extern "C" int32_t agp_svgp_elbo(agp_ctx* c, agp_dataset* ds, int64_t offset, int64_t count, const agp_svgp_params* p,
                                  double num_data, int64_t global_batch, double* elbo_out) {
-  OK(agp_svgp_sweep(c, ds, offset, count, p, num_data, global_batch, 0));
+  const int32_t s = agp_svgp_sweep(c, ds, offset, count, p, num_data, global_batch, 0);
+  if (s != AGP_OK) {
+    if (c && !(c->comm && c->nranks > 1 && global_batch <= 0)) signal_failure_to_peers(c, p, false);
+    return s;
+  }
   OK(allreduce_if_needed(c));
   return agp_svgp_finish(c, elbo_out, nullptr);
 }
@@ -1517,6 +1569,7 @@ static int32_t project_points(agp_ctx* c, const double* X_dev, int n, int ncols,
   t1.saa = c->saa.p;
   t1.sam = c->sam.p;
   t1.kp = st.kp;
+  t1.dephase = s1_dephase(c);
   OK(launch_trsm<TR_KUF_FWD>(c, t1, ncols / BN));
   EpiS2 e2{Cbuf, ldc, c->scc_part.p, ldc};
   OK((run_gemm<A_KM, B_KN>(c, st.nb, ncols / BN, c->Bt_rm.p, st.Mp, Abuf, ldc, st.Mp, KR_UPPER, TS_ALL, e2)));
@@ -1604,6 +1657,115 @@ extern "C" int32_t agp_svgp_mean_and_cov(agp_ctx* c, const agp_svgp_params* p, c
   OK((run_gemm<A_KM, B_KN>(c, n1p / BM, n2p / BN, c->C.p, ldc, C2, ldc, Mp, KR_FULL, TS_ALL, epi_store(c->pcov.p, n1p, false, 1.0, 1.0))));
   CU(cudaMemcpy2DAsync(cov_out, sizeof(double) * n1, c->pcov.p, sizeof(double) * n1p, sizeof(double) * n1, n2, cudaMemcpyDeviceToHost, c->stream));
   return check_step_flags(c, false);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// prior covariance matrices and the in-run FP64 peak measurement
+// ---------------------------------------------------------------------------------------------------
+extern "C" int32_t agp_kernel_matrix(agp_ctx* c, const agp_kernel* k, int32_t D, const double* X1, int64_t n1, const double* X2, int64_t n2,
+                                     double* K_out) {
+  if (!c || !k || !X1 || !K_out || n1 < 1 || D < 1) return fail(AGP_ERR_INVALID, "agp_kernel_matrix: bad arguments");
+  if (D > MAXD) return fail(AGP_ERR_UNSUPPORTED, "input dimension %d > %d is not supported on device", D, MAXD);
+  if (k->kind < AGP_KERNEL_SE || k->kind > AGP_KERNEL_LINEAR) return fail(AGP_ERR_UNSUPPORTED, "unsupported kernel kind %d", k->kind);
+  if ((k->n_scale != 1 && k->n_scale != D) || !k->inv_lengthscale) return fail(AGP_ERR_INVALID, "kernel.n_scale must be 1 or D");
+  const bool cross = X2 != nullptr;
+  if (!cross) n2 = n1;
+  if (n2 < 1 || n1 > AGP_MAX_COV_POINTS || n2 > AGP_MAX_COV_POINTS) return fail(AGP_ERR_INVALID, "agp_kernel_matrix: 1 <= n <= %lld", (long long)AGP_MAX_COV_POINTS);
+  CU(cudaSetDevice(c->device));
+  KernelParams kp;
+  memset(&kp, 0, sizeof kp);
+  kp.kind = k->kind;
+  kp.D = D;
+  kp.ard = k->n_scale != 1;
+  kp.variance = k->variance;
+  kp.c = k->linear_c;
+  for (int d = 0; d < D; d++) kp.s[d] = k->inv_lengthscale[k->n_scale == 1 ? 0 : d];
+  OK(c->px1.ensure(n1 * D));
+  OK(c->pxs1.ensure(n1 * D));
+  OK(c->pxn1.ensure(n1));
+  OK(c->pcov.ensure(n1 * n2));
+  CU(cudaMemcpyAsync(c->px1.p, X1, sizeof(double) * n1 * D, cudaMemcpyHostToDevice, c->stream));
+  kp.M = (int)n1;
+  prep_z_kernel<<<(int)((n1 + 127) / 128), 128, 0, c->stream>>>(c->px1.p, c->pxs1.p, c->pxn1.p, nullptr, (int)n1, kp);
+  LAUNCHED(c);
+  KCHECK();
+  if (cross) {
+    OK(c->px2.ensure(n2 * D));
+    OK(c->pxs2.ensure(n2 * D));
+    OK(c->pxn2.ensure(n2));
+    CU(cudaMemcpyAsync(c->px2.p, X2, sizeof(double) * n2 * D, cudaMemcpyHostToDevice, c->stream));
+    KernelParams ky = kp;
+    ky.M = (int)n2;
+    prep_z_kernel<<<(int)((n2 + 127) / 128), 128, 0, c->stream>>>(c->px2.p, c->pxs2.p, c->pxn2.p, nullptr, (int)n2, ky);
+    LAUNCHED(c);
+    KCHECK();
+    cross_k_kernel<<<dim3((int)((n1 + 127) / 128), (int)n2), 128, 0, c->stream>>>(c->pcov.p, n1, c->pxs1.p, c->pxn1.p, (int)n1, c->pxs2.p, c->pxn2.p, (int)n2, (int)n1, kp);
+  } else {
+    build_kuu_kernel<<<dim3((int)((n1 + 127) / 128), (int)n1), 128, 0, c->stream>>>(c->pcov.p, (int)n1, c->pxs1.p, c->pxn1.p, 0.0, kp);
+  }
+  LAUNCHED(c);
+  KCHECK();
+  CU(cudaMemcpyAsync(K_out, c->pcov.p, sizeof(double) * n1 * n2, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return AGP_OK;
+}
+
+// FP64 issue-rate microbenchmarks (the roofline denominators bench.py prints next to every FP64 fraction): register-resident
+// DMMA.8x8x4 chains (16 independent accumulators per warp) and DFMA chains (8 per thread), 1024 threads x 2 blocks per SM.
+__global__ void __launch_bounds__(1024) peak_dmma_kernel(double* out, int iters, double s) {
+  double acc[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc[i][0] = acc[i][1] = 0.0;
+  const double a = s + threadIdx.x * 1e-12, b = 1e-3 * s;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) dmma884(acc[i], a, b);
+  }
+  double r = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) r += acc[i][0] + acc[i][1];
+  out[blockIdx.x * (int64_t)blockDim.x + threadIdx.x] = r;
+}
+__global__ void __launch_bounds__(1024) peak_dfma_kernel(double* out, int iters, double s) {
+  double acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = threadIdx.x * 1e-9 + i;
+  const double a = s, b = 1.0 - s;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = fma(acc[i], a, b);
+  }
+  double r = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r += acc[i];
+  out[blockIdx.x * (int64_t)blockDim.x + threadIdx.x] = r;
+}
+extern "C" int32_t agp_fp64_peak(agp_ctx* c, int32_t which, double* tflops_out) {
+  if (!c || !tflops_out || which < 0 || which > 1) return fail(AGP_ERR_INVALID, "agp_fp64_peak: bad arguments");
+  CU(cudaSetDevice(c->device));
+  const int threads = 1024, blocks = 2 * c->sms, iters = 20000;
+  OK(c->pcov.ensure((int64_t)threads * blocks));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {  // rep 0 warms up the clocks
+    CU(cudaEventRecord(e0, c->stream));
+    if (which == 0) peak_dmma_kernel<<<blocks, threads, 0, c->stream>>>(c->pcov.p, iters, 0.5);
+    else peak_dfma_kernel<<<blocks, threads, 0, c->stream>>>(c->pcov.p, iters, 0.5);
+    LAUNCHED(c);
+    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  KCHECK();
+  const double flop = which == 0 ? 2.0 * 256 * 16 * (double)iters * (threads / 32) * blocks : 2.0 * 8 * (double)iters * threads * blocks;
+  *tflops_out = flop / (best * 1e-3) / 1e12;
+  return AGP_OK;
 }
 
 #include "laplace_host.inc"

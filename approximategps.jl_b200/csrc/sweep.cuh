@@ -39,21 +39,38 @@ struct TrsmArgs {
   const double* rowscale;  // TR_KUF_FWD_SCALED: [Mp]
   const double* dvec;      // TR_KUF_FWD_SCALED: [Mp]
   double* skd;             // TR_KUF_FWD_SCALED: [ldx]
+  int dephase;             // > 0: CTAs with (blockIdx.x / dephase) odd use the late stage order (StepIter); = SM count
   KernelParams kp;
 };
 
 struct StepIter {
   int J, q, kk, cnt, nb;
   bool fwd;
-  __device__ __forceinline__ void init(bool f, int nb_) {
+  // late (forward only): the diagonal-block slot of a block row -- for the Kuf generator the eight stages that need generated
+  // rows -- is moved from the front of the row's stage sequence to its last-but-one position,
+  //   early: [diag, L = 0 .. J-1]      late (J >= 2): [L = 0 .. J-2, diag, L = J-1]
+  // so that the two CTAs sharing an SM (which start together and run the same schedule) are not in their generator phase at
+  // the same time: one of them always has plain DMMA stages to issue.  L = J-1 stays last in both orders (it was written by
+  // this CTA's previous row epilogue and is prefetched three stages ahead).  A sum over k-blocks in another order: both
+  // orders are fixed functions of blockIdx, so the result stays bit-reproducible.
+  bool late;
+  __device__ __forceinline__ void init(bool f, int nb_, bool late_ = false) {
     fwd = f;
     nb = nb_;
+    late = late_;
     J = f ? 0 : nb_ - 1;
     q = 0;
     kk = 0;
     cnt = 1 + (f ? J : nb - 1 - J);
   }
-  __device__ __forceinline__ int src() const { return q == 0 ? J : (fwd ? q - 1 : nb - q); }
+  __device__ __forceinline__ int dslot() const { return (late && J >= 2) ? J - 1 : 0; }
+  __device__ __forceinline__ bool is_diag() const { return q == dslot(); }
+  __device__ __forceinline__ int src() const {
+    const int d = dslot();
+    if (q == d) return J;
+    if (!fwd) return nb - q;
+    return q < d ? q : q - 1;
+  }
   __device__ __forceinline__ bool last_in_row() const { return q == cnt - 1 && kk == BM / BK - 1; }
   __device__ __forceinline__ void next() {
     if (++kk == BM / BK) {
@@ -183,9 +200,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
 
   double pkd[2] = {0.0, 0.0};  // SCALED: partial k' * dvec of this thread's 2 columns
   StepIter it_issue, it_cons, it_gen;
-  it_issue.init(MODE != TR_RHS_BWD, a.nb);
-  it_cons.init(MODE != TR_RHS_BWD, a.nb);
-  it_gen.init(true, a.nb);
+  const bool late = FWD && a.dephase > 0 && ((blockIdx.x / a.dephase) & 1);
+  it_issue.init(MODE != TR_RHS_BWD, a.nb, late);
+  it_cons.init(MODE != TR_RHS_BWD, a.nb, late);
+  it_gen.init(true, a.nb, late);
   const int total = (BM / BK) * a.nb * (a.nb + 1) / 2;
 
   ALoad<A_KM> la;
@@ -196,7 +214,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
     double* st = smem + slot * stage_elems;
     const int J = it_issue.J, L = it_issue.src(), kk = it_issue.kk;
     la.load(st, a.T + (int64_t)(L * BM + kk * BK) * a.ldt + J * BM);
-    if (FWD && it_issue.q == 0) {
+    if (FWD && it_issue.is_diag()) {
       // z slab of the 16 inducing rows this stage turns into Kuf rows (contiguous in the padded copy)
       const double* zsrc = a.zsp + (int64_t)(J * BM + kk * BK) * Sx;
       for (int ch = tid; ch < BK * Sx / 2; ch += NTHREADS) cp_async16(st + Cfg::elems + ch * 2, zsrc + ch * 2);
@@ -212,9 +230,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
 
   Acc acc;
   acc_zero(acc);
-  double paa[4][2], pam[4][2];
-#pragma unroll
-  for (int ni = 0; ni < 4; ni++) paa[ni][0] = paa[ni][1] = pam[ni][0] = pam[ni][1] = 0.0;
+  // column sums a^T a and a^T mt: after every block row the 32 x 32 warp tile is folded over its rows with a halving shuffle
+  // tree (7 shuffles per quantity), so that a lane carries ONE column -- ni = 2 (g >> 2 & 1) + (g >> 1 & 1), e = g & 1 -- in two
+  // registers instead of the eight (ni, e) partial sums per quantity a plain per-thread accumulation would hold
+  double caa = 0.0, cam = 0.0;
 
 #pragma unroll
   for (int s = 0; s < S - 1; s++) {
@@ -241,15 +260,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
     if (step + S - 1 < total) issue((step + S - 1) % S);
     cp_async_commit();
     const double* st = smem + (step % S) * stage_elems;
-    // q == 0 is the (triangular) inverse diagonal block: skip the k-steps in which this warp's rows are all zero
-    const bool active = it_cons.q != 0 || ((MODE == TR_RHS_BWD) ? tm.tri_active_upper(it_cons.kk * BK) : tm.tri_active_lower(it_cons.kk * BK));
+    // the diagonal slot is the (triangular) inverse diagonal block: skip the k-steps in which this warp's rows are all zero
+    const bool active = !it_cons.is_diag() || ((MODE == TR_RHS_BWD) ? tm.tri_active_upper(it_cons.kk * BK) : tm.tri_active_lower(it_cons.kk * BK));
     if (active) mma_stage<A_KM, B_KN>(acc, st, st + Cfg::a_elems, tm);
     if (FWD) {
-      if (step + 1 < total && it_gen.q == 0) gen((step + 1) % S);
+      if (step + 1 < total && it_gen.is_diag()) gen((step + 1) % S);
       it_gen.next();
     }
     if (it_cons.last_in_row()) {
       const int J = it_cons.J;
+      double qa[8], qm[8];  // index c = 2 ni + e
+#pragma unroll
+      for (int c = 0; c < 8; c++) qa[c] = qm[c] = 0.0;
 #pragma unroll
       for (int mi = 0; mi < 4; mi++) {
         const int row = J * BM + tm.row(mi);
@@ -260,11 +282,31 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
           const double v0 = acc[mi][ni][0], v1 = acc[mi][ni][1];
           *reinterpret_cast<double2*>(xr + tm.col(ni, 0)) = make_double2(v0, v1);
           if (FWD) {
-            paa[ni][0] = fma(v0, v0, paa[ni][0]);
-            paa[ni][1] = fma(v1, v1, paa[ni][1]);
-            pam[ni][0] = fma(v0, mtr, pam[ni][0]);
-            pam[ni][1] = fma(v1, mtr, pam[ni][1]);
+            qa[2 * ni] = fma(v0, v0, qa[2 * ni]);
+            qa[2 * ni + 1] = fma(v1, v1, qa[2 * ni + 1]);
+            qm[2 * ni] = fma(v0, mtr, qm[2 * ni]);
+            qm[2 * ni + 1] = fma(v1, mtr, qm[2 * ni + 1]);
           }
+        }
+      }
+      if (FWD) {
+        const bool b2 = tm.g & 4, b1 = tm.g & 2, b0 = tm.g & 1;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {  // fold c bit 2 over lane bit 4
+          const double sa = b2 ? qa[j] : qa[j + 4], sm = b2 ? qm[j] : qm[j + 4];
+          qa[j] = (b2 ? qa[j + 4] : qa[j]) + __shfl_xor_sync(0xffffffffu, sa, 16);
+          qm[j] = (b2 ? qm[j + 4] : qm[j]) + __shfl_xor_sync(0xffffffffu, sm, 16);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {  // c bit 1 over lane bit 3
+          const double sa = b1 ? qa[j] : qa[j + 2], sm = b1 ? qm[j] : qm[j + 2];
+          qa[j] = (b1 ? qa[j + 2] : qa[j]) + __shfl_xor_sync(0xffffffffu, sa, 8);
+          qm[j] = (b1 ? qm[j + 2] : qm[j]) + __shfl_xor_sync(0xffffffffu, sm, 8);
+        }
+        {  // c bit 0 over lane bit 2
+          const double sa = b0 ? qa[0] : qa[1], sm = b0 ? qm[0] : qm[1];
+          caa += (b0 ? qa[1] : qa[0]) + __shfl_xor_sync(0xffffffffu, sa, 4);
+          cam += (b0 ? qm[1] : qm[0]) + __shfl_xor_sync(0xffffffffu, sm, 4);
         }
       }
       acc_zero(acc);
@@ -276,21 +318,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
   if (FWD) {
     __syncthreads();
     double* sred = smem;  // [2][4 m-warps][64]
-#pragma unroll
-    for (int ni = 0; ni < 4; ni++)
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        double v = paa[ni][e], w = pam[ni][e];
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-          v += __shfl_xor_sync(0xffffffffu, v, o);
-          w += __shfl_xor_sync(0xffffffffu, w, o);
-        }
-        if (tm.g == 0) {
-          sred[(tm.warp & 3) * 64 + tm.col(ni, e)] = v;
-          sred[256 + (tm.warp & 3) * 64 + tm.col(ni, e)] = w;
-        }
-      }
+    {
+      const int col = tm.wn + (((tm.g >> 2) & 1) * 2 + ((tm.g >> 1) & 1)) * 8 + 2 * tm.t + (tm.g & 1);
+      sred[(tm.wm >> 5) * 64 + col] = caa;
+      sred[256 + (tm.wm >> 5) * 64 + col] = cam;
+    }
     __syncthreads();
     if (tid < BN) {
       a.saa[n0 + tid] = ((sred[tid] + sred[64 + tid]) + sred[128 + tid]) + sred[192 + tid];

@@ -119,10 +119,18 @@ def _run(ctx, *, K=None, kernel=None, X=None, jitter=0.0, y, lik, f_init=None, m
     if maxiter < 1:
         raise AssertionError("maxiter >= 1")  # Laplace.jl:257
     pr.maxiter = int(maxiter)
+    cb_error = []
     if callback is not None:
         def _cb(user, it, handle):
-            view = LaplaceCacheView(lib, C.c_void_p(handle), n, owning=False)
-            callback(view.fnew, view)
+            # an exception raised by the user's callback propagates out of the Newton loop in the reference (Laplace.jl:263-265);
+            # ctypes would print and swallow it, so it is captured here, the loop is stopped (non-zero status) and it is
+            # re-raised once agp_laplace_f_and_lml has returned
+            try:
+                view = LaplaceCacheView(lib, C.c_void_p(handle), n, owning=False)
+                callback(view.fnew, view)
+            except BaseException as e:  # noqa: BLE001
+                cb_error.append(e)
+                return 1
             return 0
 
         cb = L.NEWTON_CALLBACK(_cb)
@@ -141,7 +149,10 @@ def _run(ctx, *, K=None, kernel=None, X=None, jitter=0.0, y, lik, f_init=None, m
         rs.dvariance, rs.dlinear_c = sc[0:1].ctypes.data_as(L.c_double_p), sc[1:2].ctypes.data_as(L.c_double_p)
         rs.dinv_lengthscale, rs.dX = L.dptr(dils), L.dptr(dX)
     h = C.c_void_p()
-    L.check(lib.agp_laplace_f_and_lml(ctx.h, C.byref(pr), C.byref(rs), C.byref(h) if want_cache else None))
+    status = lib.agp_laplace_f_and_lml(ctx.h, C.byref(pr), C.byref(rs), C.byref(h) if want_cache else None)
+    if cb_error:
+        raise cb_error[0]
+    L.check(status)
     if want_grad:
         grad = LaplaceGradient(float(sc[0]), dils, float(sc[1]), dX)
     cache = LaplaceCacheView(lib, h, n, owning=True) if want_cache else None
@@ -317,15 +328,24 @@ class _LaplaceObjective:
     def __init__(self, cache, build_latent_gp, xs, ys, newton_warmstart, newton_callback, newton_maxiter, ctx):
         self.cache, self._build, self._xs, self._ys = cache, build_latent_gp, xs, ys
         self._warm, self._cb, self._maxiter, self._ctx = newton_warmstart, newton_callback, newton_maxiter, ctx
+        self._initialize_f = True  # Laplace.jl:104
         self.newton_steps = 0
 
     def _eval(self, args, want_grad):
         lfx = self._build(*args)(self._xs)  # Laplace.jl:107-108
-        f_init = self.cache.f if (self._warm and self.cache.f is not None) else None  # :109-118 (zeros otherwise)
-        r = _run(self._ctx, want_grad=want_grad, **_check_laplace_inputs(lfx, self._ys, f_init, self._maxiter, self._cb))
+        n = len(lfx.fx)
+        # :109-118 -- `cache.f === nothing` -> mean(lfx.fx) (zeros: _check_laplace_inputs asserts the zero mean); while
+        # `initialize_f` is still true (no warm-start store has happened yet) a caller-supplied vector is overwritten IN PLACE
+        # with mean(lfx.fx) as well, so build_laplace_objective!(f_init, ...) only fixes the storage, not the first start
+        if self.cache.f is None:
+            self.cache.f = np.zeros(n)
+        elif self._initialize_f:
+            self.cache.f[...] = 0.0
+        r = _run(self._ctx, want_grad=want_grad, **_check_laplace_inputs(lfx, self._ys, self.cache.f, self._maxiter, self._cb))
         self.newton_steps += r.steps
         if self._warm:
-            self.cache.f = r.f  # :122-127
+            self.cache.f[...] = r.f  # :122-127 `cache.f .= f_opt` (in place: the caller's vector sees the mode)
+            self._initialize_f = False
         return r
 
     def __call__(self, *args):
@@ -347,5 +367,7 @@ def build_laplace_objective(build_latent_gp, xs, ys, *, newton_warmstart=True, n
 def build_laplace_objective_(cache, build_latent_gp, xs, ys, *, newton_warmstart=True, newton_callback=None, newton_maxiter=100, ctx=None):
     """``build_laplace_objective!(f_init | cache, ...)`` (Laplace.jl:95-132)."""
     if not isinstance(cache, LaplaceObjectiveCache):
-        cache = LaplaceObjectiveCache(np.array(cache, dtype=np.float64))
+        # build_laplace_objective!(f_init::Vector, ...) (Laplace.jl:85-89): the caller's vector IS the cache storage
+        f = cache if (isinstance(cache, np.ndarray) and cache.dtype == np.float64 and cache.flags.c_contiguous) else np.array(cache, dtype=np.float64)
+        cache = LaplaceObjectiveCache(f)
     return _LaplaceObjective(cache, build_latent_gp, xs, ys, newton_warmstart, newton_callback, newton_maxiter, ctx)

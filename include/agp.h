@@ -67,7 +67,7 @@ extern "C" {
 #define AGP_DEVICE 1
 
 #define AGP_MAX_GH_POINTS 128
-#define AGP_MAX_D 64
+#define AGP_MAX_D 32 /* compile-time bound of the device code (kfun.cuh MAXD): larger D is AGP_ERR_UNSUPPORTED */
 
 typedef struct agp_ctx agp_ctx;
 typedef struct agp_dataset agp_dataset;
@@ -218,6 +218,16 @@ int32_t agp_svgp_mean_and_var(agp_ctx* ctx, const agp_svgp_params* p, const doub
  * column-major n1 x n2.  Dense output: at most 16384 points per argument (AGP_ERR_UNSUPPORTED beyond).        */
 int32_t agp_svgp_mean_and_cov(agp_ctx* ctx, const agp_svgp_params* p, const double* X1, int64_t n1,
                               const double* X2, int64_t n2, double* mu1_out, double* cov_out);
+
+/* Replaces cov(f.prior, x) / cov(f.prior, x, y), i.e. KernelFunctions.kernelmatrix(k, x[, y]) as the reference reaches it at
+ * SVA.jl:216, :227, :263 and Laplace.jl:174, :427 (without any observation noise): X1 / X2 host point-major n x D, X2 == NULL ->
+ * the one-argument form with an exactly zero-distance diagonal; K_out host column-major n1 x n2 (n <= 16384).                */
+int32_t agp_kernel_matrix(agp_ctx* ctx, const agp_kernel* kernel, int32_t D, const double* X1, int64_t n1, const double* X2,
+                          int64_t n2, double* K_out);
+
+/* Measurement aid (bench.py): achieved FP64 TFLOP/s of a register-resident instruction chain on this device, now --
+ * which = 0: DMMA.8x8x4 (the tensor-path roofline denominator), 1: DFMA.  No reference counterpart.                          */
+int32_t agp_fp64_peak(agp_ctx* ctx, int32_t which, double* tflops_out);
 
 /* ---- Laplace --------------------------------------------------------------------------------- */
 /* Newton callback(fnew, cache) of _newton_inner_loop (Laplace.jl:263-265): called after every Newton

@@ -5,6 +5,14 @@ from oracle import kernels as ok, likelihoods as ol, svgp as osv
 
 KIND_NAMES = {"se": 0, "matern32": 1, "matern52": 2, "linear": 3}
 
+# measured parity errors of the GPU tests (case label -> {quantity: relative error, "tol": asserted tolerance}); conftest.py writes
+# them to gpurun_out/parity_errors.json at the end of a GPU session, the tracked copy is profiles/parity_errors.json
+PARITY_ERRORS = {}
+
+
+def record_parity(label, errs, **extra):
+    PARITY_ERRORS[label] = {**{k: float(v) for k, v in errs.items()}, **extra}
+
 
 def make_problem(seed=0, kind="se", N=300, M=20, D=2, centered=False, lik="gaussian", method="default", n_gh=20, ard=False,
                  mean_const=0.0, jitter=1e-6, lengthscale=None, variance=1.3, zdist="data"):

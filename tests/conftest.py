@@ -25,3 +25,23 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Write the measured GPU-vs-oracle errors collected by tests/_cases.record_parity (GPU sessions only)."""
+    cases = sys.modules.get("_cases")
+    rec = getattr(cases, "PARITY_ERRORS", None)
+    if not rec:
+        return
+    import json
+
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    worst = {}
+    for errs in rec.values():
+        for k, v in errs.items():
+            if isinstance(v, float) and k != "tol" and v == v:
+                worst[k] = max(worst.get(k, 0.0), v)
+    with open(os.path.join(out, "parity_errors.json"), "w") as fh:
+        json.dump({"what": "max-abs error of the CUDA path against the NumPy oracle, relative to the max-abs entry of the oracle's array "
+                           "(scalars: relative); every case is one GPU test through the C ABI", "worst_per_quantity": worst, "cases": rec}, fh, indent=1)

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from _cases import rel_err  # noqa: E402
+from _cases import record_parity, rel_err  # noqa: E402
 
 from oracle import kernels as ok, laplace as olap, likelihoods as ol  # noqa: E402
 
@@ -70,11 +70,38 @@ def test_matrix_form_value_and_dK(agp, lik, n, D):
     lml, Kbar, f_opt, steps = olap.lml_and_grad_K(olik, y, K)
     r = agp.laplace_lml_and_grad_K(_lik(agp, lik), y, K)
     print(f"\n[laplace {lik} n={n}] lml={r.lml:.10f} rel={abs(r.lml - lml) / abs(lml):.1e} steps={r.steps}/{steps} f={rel_err(r.f, f_opt):.1e} dK={rel_err(r.dK, Kbar):.1e}")
+    record_parity(f"laplace {lik} n={n} D={D} (matrix form)", dict(lml=abs(r.lml - lml) / abs(lml), f_opt=rel_err(r.f, f_opt), dK=rel_err(r.dK, Kbar)), tol=1e-8)
     assert r.steps == steps and r.converged
     assert abs(r.lml - lml) < 1e-10 * abs(lml)
     assert rel_err(r.f, f_opt) < 1e-10
     assert rel_err(r.dK, Kbar) < 1e-8
     assert abs(agp.laplace_lml(_lik(agp, lik), y, K) - lml) < 1e-10 * abs(lml)
+
+
+def test_c3_full_size(agp):
+    """BASELINE.json configs[2] at its full size (N = 8192: 64 diagonal blocks, 16 super-panels and the two-stream look-ahead of
+    the blocked Cholesky, none of which the n <= 1000 cases reach) against the oracle's result on the same inputs, stored in
+    tests/golden/laplace_c3_golden.npz (tests/golden/make_c3_golden.py; AGP_C3_ORACLE=1 re-runs the oracle here, ~70 s).
+    Reference: _newton_inner_loop / _laplace_train_intermediates / _laplace_lml, Laplace.jl:201-276, and their reverse pass."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_c3_golden import c3_oracle, c3_problem
+
+    X, y = c3_problem()
+    gold = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "laplace_c3_golden.npz")))
+    assert np.array_equal(gold["x_checksum"], np.array([X.sum(), y.sum()]))  # same inputs as the fixture
+    if os.environ.get("AGP_C3_ORACLE") == "1":
+        gold = c3_oracle(X, y)
+    f = agp.GP(1.0 * agp.with_lengthscale(agp.SqExponentialKernel(), 1.0))
+    lfx = agp.LatentGP(f, agp.BernoulliLikelihood(), 1e-8)(X)
+    r = agp.laplace_approx_lml_and_gradient(agp.LaplaceApproximation(maxiter=100), lfx, y)
+    lml = float(gold["lml"])
+    errs = dict(lml=abs(r.lml - lml) / abs(lml), f_opt=rel_err(r.f, gold["f_opt"]), dvariance=rel_err(r.grad.variance, gold["dvariance"]),
+                dinv_lengthscale=rel_err(r.grad.inv_lengthscale, gold["dinv_lengthscale"]), dX=rel_err(r.grad.X, gold["dX"]))
+    print(f"\n[laplace C3 n=8192] lml={r.lml:.10f} steps={r.steps}/{int(gold['steps'])} " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
+    record_parity("laplace C3 bernoulli_logit se n=8192 D=2", errs, tol=1e-8)
+    assert r.steps == int(gold["steps"]) and r.converged
+    assert errs["lml"] < 1e-10 and errs["f_opt"] < 1e-10
+    assert errs["dvariance"] < 1e-8 and errs["dinv_lengthscale"] < 1e-8 and errs["dX"] < 1e-8
 
 
 def test_not_converged_uses_newton_cache(agp):
@@ -146,10 +173,37 @@ def test_warmstart_and_callback(agp):
         vals[warm] = [obj(*th) for th in thetas]
         counts[warm] = obj.newton_steps
         assert n_cb[0] == obj.newton_steps
-        assert (obj.cache.f is not None) == warm
+        # Laplace.jl:109-127: without warm start cache.f stays mean(lfx.fx) = zeros, with it cache.f holds the last mode
+        assert obj.cache.f is not None and (np.any(obj.cache.f != 0.0) == warm)
     print("\n[laplace warm start] newton steps cold/warm:", counts[False], counts[True])
     assert counts[True] < counts[False]
     assert np.allclose(vals[True], vals[False], rtol=1e-9)
+
+
+def test_objective_cache_semantics_and_callback_errors(agp):
+    """build_laplace_objective!(f_init, ...) (Laplace.jl:85-132): while `initialize_f` is true the caller's vector is overwritten
+    in place with mean(lfx.fx) = 0 (so it does NOT choose the first Newton start), afterwards it carries the mode in place; an
+    exception thrown by newton_callback propagates to the caller of the objective."""
+    X, y = olap.generate_data()
+    f0 = np.full(48, 3.0)
+    obj = agp.build_laplace_objective_(f0, lambda *th: _build_latent_gp(agp, np.array(th)), X, y)
+    cold = agp.build_laplace_objective(lambda *th: _build_latent_gp(agp, np.array(th)), X, y)
+    v, vc = obj(5.0, 1.0), cold(5.0, 1.0)
+    assert obj.cache.f is f0 and np.all(f0 != 3.0)  # the storage is the caller's, now holding f_opt
+    assert v == vc and obj.newton_steps == cold.newton_steps  # same start (zeros) as a fresh objective
+    f_after = f0.copy()
+    obj(5.05, 1.05)  # second call warm-starts from f_after
+    assert obj.cache.f is f0 and np.any(f0 != f_after)
+
+    class Boom(RuntimeError):
+        pass
+
+    def cb(fnew, cache):
+        raise Boom("from the callback")
+
+    bad = agp.build_laplace_objective(lambda *th: _build_latent_gp(agp, np.array(th)), X, y, newton_callback=cb)
+    with pytest.raises(Boom):
+        bad(5.0, 1.0)
 
 
 def test_gaussian_laplace_equals_exact_gpr(agp):

@@ -1,10 +1,10 @@
 """GPU parity: the CUDA path (through the C ABI) against the NumPy oracle on the same seeded inputs.
 
-Tolerances: north_star asks for relative 1e-10 on the ELBO and gradients in Float64.  The ELBO is
-asserted at 1e-10.  Gradient arrays are asserted at 1e-9 relative to their max-abs entry: with
-jitter 1e-6 the Cholesky factor of Kuu has condition number 1e3-1e4, so two backward-stable float64
-evaluations of the same formula (the oracle's LAPACK order vs the blocked device order) already
-differ by ~1e-11..1e-10; the measured errors are printed with -s.
+Tolerances: north_star asks for relative 1e-10 on the ELBO and gradients in Float64, and that is what is asserted: ELBO at 1e-10,
+every gradient array at 1e-10 of its max-abs entry (scalars: relative).  Exceptions are named where they are made
+(`grad_tol=`): problems whose Kuu has a condition number of 1e6 and more, where two backward-stable float64 evaluations of the
+same formula (the oracle's LAPACK order, the blocked device order) already differ by cond * eps.  The measured errors of every
+case are collected (tests/_cases.record_parity) and tracked in profiles/parity_errors.json.
 """
 import os
 import sys
@@ -13,14 +13,14 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from _cases import agp_objects, compare_grads, make_problem, oracle_objects, rel_err  # noqa: E402
+from _cases import agp_objects, compare_grads, make_problem, oracle_objects, record_parity, rel_err  # noqa: E402
 
-from oracle import svgp as osv  # noqa: E402
+from oracle import kernels as ok, svgp as osv  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
 ELBO_TOL = 1e-10
-GRAD_TOL = 1e-9
+GRAD_TOL = 1e-10
 
 
 @pytest.fixture(scope="module")
@@ -38,8 +38,9 @@ def _run_case(agp, p, num_data=None, grad_tol=GRAD_TOL):
     fwd = agp.elbo(sva, lfx, p["y"], num_data=num_data, quadrature=quad)
     e_val = abs(val - ref) / abs(ref)
     errs = compare_grads(g, rg, p)
-    print(f"\n[{p['kind']} D={p['X'].shape[1]} M={len(p['m'])} N={len(p['y'])} cent={p['centered']} {p['lik']}/{p['method']}] "
-          f"elbo={val:.10f} rel={e_val:.1e} " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
+    label = f"{p['kind']} D={p['X'].shape[1]} M={len(p['m'])} N={len(p['y'])} cent={p['centered']} {p['lik']}/{p['method']}" + (" ard" if p["inv"].size > 1 else "")
+    print(f"\n[{label}] elbo={val:.10f} rel={e_val:.1e} " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
+    record_parity(label, {"elbo": e_val, **errs}, tol=grad_tol)
     assert e_val < ELBO_TOL, (val, ref)
     assert abs(fwd - val) <= 1e-12 * abs(val), (fwd, val)
     assert np.all(np.triu(g.Lq, 1) == 0.0)
@@ -54,7 +55,9 @@ def test_gaussian_small(agp, kind, centered):
     # d/dvariance is then a difference of terms 1e4 times larger than itself and two correct FP64 Cholesky orderings differ by
     # ~1e-8 on it.  A shorter length scale keeps the case a test of the kernels rather than of the conditioning.
     ls = 0.7 if (centered and kind == "se") else None
-    _run_case(agp, make_problem(seed=1, kind=kind, N=300, M=20, D=2, centered=centered, lik="gaussian", lengthscale=ls))
+    # named exception: Centered + SE, cond(Kuu) ~ 1e5 even with the shorter length scale (measured 7e-10 on dZ, 3e-10 on dvariance)
+    tol = 1e-9 if (centered and kind == "se") else GRAD_TOL
+    _run_case(agp, make_problem(seed=1, kind=kind, N=300, M=20, D=2, centered=centered, lik="gaussian", lengthscale=ls), grad_tol=tol)
 
 
 @pytest.mark.parametrize("D", [1, 3, 8])
@@ -72,7 +75,9 @@ def test_multi_block_M(agp, centered):
     # (Centered with an un-whitened random q has huge marginal variances; the oracle's faithful log(logistic(f)) then overflows to
     #  -inf where the device's softplus form stays finite -- an intentional divergence -- so that case uses the Gaussian likelihood.)
     lik = "gaussian" if centered else "bernoulli_logit"
-    _run_case(agp, make_problem(seed=3, kind="se", N=1500, M=300, D=4, centered=centered, lik=lik, zdist="random", lengthscale=1.0), num_data=1e5)
+    # named exception: 300 random inducing points under an SE kernel in D = 4, cond(Kuu) ~ 1e6-1e7 at jitter 1e-6: gradients at 1e-8
+    _run_case(agp, make_problem(seed=3, kind="se", N=1500, M=300, D=4, centered=centered, lik=lik, zdist="random", lengthscale=1.0), num_data=1e5,
+              grad_tol=1e-8)
 
 
 def test_ard_and_mean(agp):
@@ -462,3 +467,32 @@ def test_float32_inputs_are_uploaded_as_float32(agp):
     val2, _ = agp.elbo_and_gradient(sva, agp.LatentGP(f, lik, 1e-18)(ds), None, num_data=999.0)
     assert val2 == ref
     ds.close()
+
+
+@pytest.mark.parametrize("kind", ["se", "matern32", "matern52", "linear"])
+def test_kernel_function_values(agp, kind):
+    """cov(f.prior, x) / cov(f.prior, x, y) on the device (agp_kernel_matrix) against the oracle's kernelmatrix, including pairs so far
+    apart that exp(-u/2) underflows and coincident points: the table-driven exponential of kfun.cuh (exp_nonpos) stays within
+    1e-15 relative of the library exponential the oracle uses."""
+    rng = np.random.default_rng(31)
+    D = 3
+    X = np.concatenate([rng.normal(size=(150, D)), 30.0 * rng.normal(size=(40, D)), 200.0 * rng.normal(size=(10, D))])
+    Y = np.concatenate([X[:7], rng.normal(size=(60, D)), 1e-9 + X[7:9]])
+    inv = np.array([0.9, 1.1, 0.7])
+    k = ok.Kernel(kind, 1.3, inv, 0.4 if kind == "linear" else 0.0)
+    kb = agp.LinearKernel(0.4) if kind == "linear" else {"se": agp.SqExponentialKernel, "matern32": agp.Matern32Kernel, "matern52": agp.Matern52Kernel}[kind]()
+    kd = 1.3 * agp.ARDTransform(kb, inv)
+    for args in ((X,), (X, Y)):
+        ref = ok.kernelmatrix(k, *args)
+        got = agp.kernelmatrix(kd, *args)
+        # the squared distance itself (GEMM form, as Distances.jl computes it) carries an absolute error of eps * |x|^2; compare the
+        # exponentials where that is negligible (|x| = O(1)) relatively, everywhere else absolutely against the prior variance
+        err_abs = np.max(np.abs(got - ref)) / np.max(np.abs(ref))
+        core = (slice(0, 150), slice(0, 150)) if len(args) == 1 else (slice(0, 150), slice(7, 67))
+        big = np.abs(ref[core]) > 1e-280
+        err_rel = np.max(np.abs(got[core][big] - ref[core][big]) / np.abs(ref[core][big]))
+        print(f"\n[kernelmatrix {kind} {'cross' if len(args) == 2 else 'self'}] abs={err_abs:.1e} rel(core)={err_rel:.1e}")
+        record_parity(f"kernelmatrix {kind} {'cross' if len(args) == 2 else 'self'}", dict(abs=err_abs, rel_core=err_rel), tol=1e-13)
+        assert err_abs < 1e-13 and err_rel < 1e-12
+        if len(args) == 1 and kind != "linear":
+            assert np.all(np.diag(got) == 1.3)  # exactly zero distances on the diagonal

@@ -4,6 +4,7 @@ import os
 import sys
 
 import numpy as np
+import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
@@ -182,3 +183,26 @@ def test_newton_inner_loop_chain_rules():
     Lbar = Lm @ (Kbar.T + Kbar)
     assert abs(np.sum(Lbar * dL) - df @ fdot) < 1e-12 * max(1.0, abs(df @ fdot))
     assert xs.shape == ys.shape
+
+
+def test_third_party_pin_scikit_learn_gpc():
+    """Independent implementation of the same algorithm: scikit-learn's GaussianProcessClassifier is Rasmussen & Williams
+    Alg. 3.1 (Newton mode finding) and Alg. 5.1 (log marginal likelihood and its total derivative, implicit part through f-hat
+    included) with the logistic link -- what Laplace.jl:201-276 / :330-369 implement.  On the reference's 48-point fixture
+    (src/TestUtils.jl:13-28) the oracle's lml and d lml / d log(theta) agree with it to 1e-10 (measured 1e-12 .. 1e-14): the oracle's
+    Laplace value AND gradient are pinned by a second, unrelated code base, not only by the reference's golden optimum."""
+    skl = pytest.importorskip("sklearn.gaussian_process")
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel, WhiteKernel
+
+    X, y = olap.generate_data()
+    for var, ls in [(1.7, 2.3), (5.0067, 1.3133), (0.6, 0.9)]:
+        kern = ConstantKernel(var) * RBF(ls) + WhiteKernel(1e-8, noise_level_bounds="fixed")
+        gpc = skl.GaussianProcessClassifier(kernel=kern, optimizer=None, max_iter_predict=1000).fit(X[:, None], y)
+        lml_s, g_s = gpc.log_marginal_likelihood(gpc.kernel_.theta, eval_gradient=True)  # gradient w.r.t. log(variance), log(lengthscale)
+        k = ok.Kernel(ok.SE, var, np.array([1.0 / ls]))
+        K = ok.kernelmatrix(k, X) + 1e-8 * np.eye(len(y))
+        lml, Kbar, _, _ = olap.lml_and_grad_K(ol.Likelihood("bernoulli_logit"), y, K)
+        _, _, kg = ok.kernelmatrix_pullback(k, X, None, Kbar)
+        g = np.array([kg.variance * var, kg.inv_lengthscale[0] * (-1.0 / ls**2) * ls])
+        assert abs(lml - lml_s) < 1e-10 * abs(lml_s)
+        assert np.max(np.abs(g - g_s) / np.abs(g_s)) < 1e-10

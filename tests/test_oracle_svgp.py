@@ -229,3 +229,46 @@ def test_monte_carlo_stream_and_expectation():
     fd_mu = (L.expected_loglik_terms(ex, lik, mu + h, var, y)[0] - L.expected_loglik_terms(ex, lik, mu - h, var, y)[0]) / (2 * h)
     fd_var = (L.expected_loglik_terms(ex, lik, mu, var + h, y)[0] - L.expected_loglik_terms(ex, lik, mu, var - h, y)[0]) / (2 * h)
     assert abs(fd_mu[0] - dmu[0]) < 1e-8 and abs(fd_var[0] - dvar[0]) < 1e-8
+
+
+def test_third_party_pin_scikit_learn_kernels_and_gpr():
+    """Third-party pins for what no reference test constrains (SURVEY.md section 8c "parity unpinned"): the covariance functions on
+    D > 1 inputs and the Gaussian SVGP bound.  scikit-learn's kernels are an unrelated implementation of the same definitions
+    (KernelFunctions: SqExponential exp(-d^2/2), Matern32 (1+sqrt3 d) exp(-sqrt3 d), Matern52 (1+sqrt5 d+5d^2/3) exp(-sqrt5 d),
+    Linear x.y + c; scale transforms multiply the inputs by 1/lengthscale): values AND hyper-parameter gradients agree to 1e-12,
+    for isotropic and ARD length scales, D = 8.  And with Z = X and the optimal q the ELBO equals scikit-learn's exact GPR log
+    marginal likelihood up to the jitter (test/SparseVariationalApproximationModule.jl:126-133 states the same about AbstractGPs)."""
+    skl = pytest.importorskip("sklearn.gaussian_process")
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel, DotProduct, Matern, WhiteKernel
+
+    rng = np.random.default_rng(11)
+    X, Z = rng.normal(size=(40, 8)), rng.normal(size=(13, 8))
+    for ard in (False, True):
+        ls = rng.uniform(1.5, 3.0, size=8) if ard else np.array([2.2])
+        for kind, sk in ((ok.SE, RBF(ls if ard else ls[0])), (ok.MATERN32, Matern(ls if ard else ls[0], nu=1.5)), (ok.MATERN52, Matern(ls if ard else ls[0], nu=2.5))):
+            k = ok.Kernel(kind, 1.7, 1.0 / ls)
+            full = ConstantKernel(1.7) * sk
+            assert np.max(np.abs(ok.kernelmatrix(k, X, Z) - full(X, Z))) < 1e-13
+            Kx, dK = full(X, eval_gradient=True)  # dK[..., j]: derivative w.r.t. log(theta_j), theta = (variance, lengthscales)
+            assert np.max(np.abs(ok.kernelmatrix(k, X) - Kx)) < 1e-13
+            W = rng.normal(size=Kx.shape)
+            W = W + W.T
+            _, _, kg = ok.kernelmatrix_pullback(k, X, None, W)
+            g_sk = np.einsum("ij,ijp->p", W, dK)
+            g_or = np.concatenate([[kg.variance * 1.7], kg.inv_lengthscale * (-1.0 / ls**2) * ls])
+            assert np.max(np.abs(g_or - g_sk)) < 1e-11 * np.max(np.abs(g_sk))
+    klin = ok.Kernel(ok.LINEAR, 1.0, np.array([1.0]), 0.4)
+    assert np.max(np.abs(ok.kernelmatrix(klin, X, Z) - DotProduct(sigma_0=np.sqrt(0.4))(X, Z))) < 1e-13
+    # Gaussian SVGP bound at Z = X with the optimal q  ==  exact GPR log marginal likelihood (scikit-learn), D = 3, Matern52
+    n, s2 = 30, 0.3
+    X = rng.normal(size=(n, 3))
+    y = np.sin(X @ rng.normal(size=3)) + 0.3 * rng.normal(size=n)
+    k = ok.Kernel(ok.MATERN52, 1.3, np.array([1.0 / 1.4]))
+    gpr = skl.GaussianProcessRegressor(kernel=ConstantKernel(1.3) * Matern(1.4, nu=2.5) + WhiteKernel(s2), optimizer=None).fit(X, y)
+    K = ok.kernelmatrix(k, X)
+    S = K - K @ np.linalg.solve(K + s2 * np.eye(n), K)
+    mq = K @ np.linalg.solve(K + s2 * np.eye(n), y)
+    S = 0.5 * (S + S.T) + 1e-12 * np.eye(n)
+    s = osv.SVGP(k, X, mq, np.linalg.cholesky(S), jitter=1e-10, centered=True)
+    val = osv.elbo(s, X, y, ol.Likelihood("gaussian", s2), ol.Expectation())
+    assert abs(val - gpr.log_marginal_likelihood_value_) < 1e-5
