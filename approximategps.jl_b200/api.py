@@ -500,6 +500,9 @@ class _Packed:
         self.p, self.M, self.D = p, M, D
 
 
+PackedParams = _Packed  # public name: the agp_svgp_params struct of one (sva, likelihood, quadrature) plus the buffers it points into
+
+
 @dataclass
 class ELBOGradient:
     """Structural tangent of ``elbo`` (what the new ``rrule`` returns)."""
@@ -592,7 +595,11 @@ class FlatELBO:
     parameter vector, ``value_and_gradient(x)`` evaluates ELBO and gradient through ``agp_svgp_elbo_grad_flat`` (one pointer in,
     one out), ``unflatten(x)`` gives back a dict of named views.  Layout: include/agp.h ``agp_svgp_elbo_grad_flat``."""
 
-    def __init__(self, sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx: Context | None = None, offset=0, count=None, global_batch=0):
+    def __init__(self, sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx: Context | None = None, offset=0, count=None, global_batch=0,
+                 resident=True):
+        """``resident=True`` evaluates through an optimiser-step handle (``agp_svgp_stepper_*``): parameter / result buffers,
+        workspace and quadrature table stay on the device side between calls and a small problem (a minibatch of the
+        a-regression example) costs ONE kernel launch; ``resident=False`` calls ``agp_svgp_elbo_grad_flat`` every time."""
         self.ctx = ctx or default_context()
         fx, lik = _resolve_lik(sva, l_fx)
         self._ds, self._own = _dataset_for(fx, y, self.ctx)
@@ -607,6 +614,11 @@ class FlatELBO:
         k = sva.fz.f.kernel
         self.x0 = np.concatenate([[k.variance], pk.ils, [k.c, sva.fz.f.mean_const, float(lik.sigma2)], pk.Z.ravel(), pk.m, pk.Lq.ravel(order="F")])
         assert self.x0.size == self.size
+        self._stepper = None
+        if resident:
+            h = C.c_void_p()
+            L.check(self.ctx.lib.agp_svgp_stepper_create(self.ctx.h, C.byref(pk.p), C.byref(h)))
+            self._stepper = h
 
     def unflatten(self, x) -> dict:
         x = np.asarray(x)
@@ -615,22 +627,46 @@ class FlatELBO:
         return dict(variance=x[0], inv_lengthscale=x[1:1 + ns], linear_c=x[1 + ns], mean_const=x[2 + ns], lik_param=x[3 + ns],
                     Z=x[o:o + M * D].reshape(M, D), m=x[o + M * D:o + M * D + M], Lq=x[o + M * D + M:].reshape(M, M, order="F"))
 
-    def value_and_gradient(self, x, want_grad=True):
+    def value_and_gradient(self, x, want_grad=True, offset=None, count=None, out_grad=None):
+        """ELBO and gradient at the flat vector ``x`` over points ``[offset, offset+count)`` of the resident data set (default: the
+        range given at construction -- pass another one per call for minibatching, examples/a-regression/script.jl:176-194)."""
         x = np.ascontiguousarray(x, dtype=np.float64)
         assert x.shape == (self.size,)
         out = C.c_double()
-        g = np.zeros(self.size) if want_grad else None
-        L.check(self.ctx.lib.agp_svgp_elbo_grad_flat(self.ctx.h, self._ds.h, self._offset, self._count, C.byref(self._pk.p), L.dptr(x), self._num_data,
-                                                     self._gb, C.byref(out), L.dptr(g)))
+        g = (out_grad if out_grad is not None else np.zeros(self.size)) if want_grad else None
+        off = self._offset if offset is None else int(offset)
+        cnt = self._count if count is None else int(count)
+        if self._stepper is not None:
+            L.check(self.ctx.lib.agp_svgp_stepper_eval(self._stepper, self._ds.h, off, cnt, L.dptr(x), self._num_data, self._gb, C.byref(out), L.dptr(g)))
+        else:
+            L.check(self.ctx.lib.agp_svgp_elbo_grad_flat(self.ctx.h, self._ds.h, off, cnt, C.byref(self._pk.p), L.dptr(x), self._num_data,
+                                                         self._gb, C.byref(out), L.dptr(g)))
         return out.value, g
+
+    def path_counts(self) -> tuple:
+        """(evaluations that took the one-launch small-problem kernel, evaluations that took the throughput path)."""
+        if self._stepper is None:
+            return (0, 0)
+        a, b = C.c_int64(), C.c_int64()
+        L.check(self.ctx.lib.agp_svgp_stepper_counts(self._stepper, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def __call__(self, x):
         return self.value_and_gradient(x, want_grad=False)[0]
 
     def close(self):
+        if getattr(self, "_stepper", None) is not None:
+            self.ctx.lib.agp_svgp_stepper_destroy(self._stepper)
+            self._stepper = None
         if self._own and self._ds is not None:
             self._ds.close()
         self._ds = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def approx_lml(approx, l_fx, ys=None, **kwargs):

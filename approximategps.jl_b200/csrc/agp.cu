@@ -1056,13 +1056,6 @@ static int32_t finish_kgrad(agp_ctx* c, int nslab, double zfac, double* dZ, doub
   return AGP_OK;
 }
 
-// Stage-order de-phasing of the Kuf-generating solve (StepIter::late): CTA b uses the late order when (b / #SMs) is odd, i.e.
-// the two CTAs that the block scheduler places on one SM run different orders.  AGP_S1_DEPHASE=0 disables it (tuning knob).
-static int s1_dephase(agp_ctx* c) {
-  static const int on = getenv("AGP_S1_DEPHASE") ? atoi(getenv("AGP_S1_DEPHASE")) : 1;
-  return on ? c->sms : 0;
-}
-
 // forward (+ backward) sweep over points [offset, offset+count) of ds.  predict != 0: only S1-S3 writing mu/var.
 static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_t count, bool grad, bool predict, double* mu_out,
                             double* var_out) {
@@ -1100,7 +1093,6 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
     t1.saa = c->saa.p;
     t1.sam = c->sam.p;
     t1.kp = st.kp;
-    t1.dephase = s1_dephase(c);
     {
       ProfScope ps(c, PC_TRSM_FWD);
       OK(launch_trsm<TR_KUF_FWD>(c, t1, tiles_n));
@@ -1569,7 +1561,6 @@ static int32_t project_points(agp_ctx* c, const double* X_dev, int n, int ncols,
   t1.saa = c->saa.p;
   t1.sam = c->sam.p;
   t1.kp = st.kp;
-  t1.dephase = s1_dephase(c);
   OK(launch_trsm<TR_KUF_FWD>(c, t1, ncols / BN));
   EpiS2 e2{Cbuf, ldc, c->scc_part.p, ldc};
   OK((run_gemm<A_KM, B_KN>(c, st.nb, ncols / BN, c->Bt_rm.p, st.Mp, Abuf, ldc, st.Mp, KR_UPPER, TS_ALL, e2)));
@@ -1711,19 +1702,19 @@ extern "C" int32_t agp_kernel_matrix(agp_ctx* c, const agp_kernel* k, int32_t D,
 }
 
 // FP64 issue-rate microbenchmarks (the roofline denominators bench.py prints next to every FP64 fraction): register-resident
-// DMMA.8x8x4 chains (16 independent accumulators per warp) and DFMA chains (8 per thread), 1024 threads x 2 blocks per SM.
+// DMMA.8x8x4 chains (8 independent accumulators per warp) and DFMA chains (8 per thread), 1024 threads x 2 blocks per SM.
 __global__ void __launch_bounds__(1024) peak_dmma_kernel(double* out, int iters, double s) {
-  double acc[16][2];
+  double acc[8][2];  // 8 independent accumulators per warp: 37.1 TFLOP/s on B200; 16 measure lower (28.6, profiles/r01_fp64_peak.jsonl)
 #pragma unroll
-  for (int i = 0; i < 16; i++) acc[i][0] = acc[i][1] = 0.0;
+  for (int i = 0; i < 8; i++) acc[i][0] = acc[i][1] = 0.0;
   const double a = s + threadIdx.x * 1e-12, b = 1e-3 * s;
   for (int it = 0; it < iters; it++) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) dmma884(acc[i], a, b);
+    for (int i = 0; i < 8; i++) dmma884(acc[i], a, b);
   }
   double r = 0.0;
 #pragma unroll
-  for (int i = 0; i < 16; i++) r += acc[i][0] + acc[i][1];
+  for (int i = 0; i < 8; i++) r += acc[i][0] + acc[i][1];
   out[blockIdx.x * (int64_t)blockDim.x + threadIdx.x] = r;
 }
 __global__ void __launch_bounds__(1024) peak_dfma_kernel(double* out, int iters, double s) {
@@ -1763,9 +1754,10 @@ extern "C" int32_t agp_fp64_peak(agp_ctx* c, int32_t which, double* tflops_out) 
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   KCHECK();
-  const double flop = which == 0 ? 2.0 * 256 * 16 * (double)iters * (threads / 32) * blocks : 2.0 * 8 * (double)iters * threads * blocks;
+  const double flop = which == 0 ? 2.0 * 256 * 8 * (double)iters * (threads / 32) * blocks : 2.0 * 8 * (double)iters * threads * blocks;
   *tflops_out = flop / (best * 1e-3) / 1e12;
   return AGP_OK;
 }
 
+#include "small_host.inc"
 #include "laplace_host.inc"

@@ -1,0 +1,727 @@
+// small.cuh -- the latency path: one `elbo` + all gradients of a SMALL problem in ONE kernel launch of ONE CTA.
+//
+// BASELINE.json configs[0] (examples/a-regression/script.jl:170-194) evaluates the ELBO on minibatches of 100 points with
+// M = 20 inducing points, 30 000 times.  The throughput path of sweep.cuh needs ~50 launches and ~15 small copies for one such
+// step (0.5 ms: slower than OpenBLAS on the host); here the whole step -- Kuu, its Cholesky and inverse, the Kuf tile, the
+// marginals, the expected log-likelihood, the reverse pass and the O(M^3) epilogue -- runs as one CTA of 1024 threads over an
+// L1-resident workspace, reads its parameters straight from the caller's (mapped, pinned) flat vector and writes ELBO and the
+// gradient back into mapped pinned memory: one launch + one stream synchronisation per optimiser step.
+//
+// Same mathematics, in the same whitened variables, as the throughput path (agp_svgp_finish), i.e. the
+// reference's posterior(sva) / mean_and_var / expected_loglikelihood / _prior_kl (SVA.jl:115-187, :246-253, :340-373) and their
+// Zygote pullbacks.  The one structural difference: with M <= 128 the triangular solves go through the explicit inverse of the
+// Cholesky factor (a column per thread, no barriers), so that everything else is a small dense product parallel over its outputs.
+#pragma once
+#include "kfun.cuh"
+
+namespace agp {
+
+constexpr int SM_THREADS = 1024;
+constexpr int SM_MAXM = 128;
+constexpr int SM_TILE = 256;  // points per pass
+
+struct SmallArgs {
+  const double* flat;  // [variance | inv_lengthscale (n_scale) | linear_c | mean_const | lik parameter | Z (M*D) | m (M) | Lq (M*M col-major)]
+  double* out;         // [elbo | gradient in the same flat layout | status, info]  (mapped pinned host memory)
+  const double* X;     // device: points [count][D] (already offset)
+  const double* y;     // device: [count]
+  int count;
+  double scale;        // num_data / count
+  int M, D, n_scale, kind, centered;
+  double jitter;
+  LikParams lp;        // kind, method, ngh, seed, gh table; sigma2 is read from flat
+  long long point_base;
+  double* ws;          // device workspace (small_ws_doubles)
+  int want_grad;
+  int ldb;             // min(count, SM_TILE) rounded up to 32
+  int smem_doubles;    // dynamic shared memory given to the kernel, in doubles
+};
+
+__host__ __device__ inline int64_t small_ws_doubles(int M, int D) {
+  const int64_t MM = (int64_t)M * M, MB = (int64_t)M * SM_TILE;
+  return (int64_t)M * D * 5 + 9 * (int64_t)M + 11 * MM + (int64_t)SM_TILE * (D + 8) + 5 * MB + 64 + 2 * MAXD + 128;  // (+ rounding of each array to 2)
+}
+
+// deterministic block reduction of one value per thread (all threads must call); result broadcast to every thread
+__device__ __forceinline__ double sm_block_sum(double v, double* sred /* >= 33 */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) sred[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double r = (lane < (int)(blockDim.x >> 5)) ? sred[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if (lane == 0) sred[32] = r;
+  }
+  __syncthreads();
+  return sred[32];
+}
+
+__global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) {
+  __shared__ double sred[40];
+  __shared__ double s_scale[MAXD];
+  __shared__ double s_par[8];  // variance, c, mean_const, likpar
+  __shared__ int s_status[2];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int M = a.M, D = a.D, ns = a.n_scale, kind = a.kind;
+  const bool centered = a.centered != 0, linear = kind == AGP_KERNEL_LINEAR, direct = D == 1 && !linear;
+  const int64_t MM = (int64_t)M * M;
+  // ---- workspace carve-up: shared memory first (in order of access frequency), the global workspace for what does not fit ----
+  // A phase of this kernel is "read what the previous phase wrote, one FMA chain, write": with the operands in global memory
+  // every phase pays an L2 round trip (~1.5 us measured per phase); in shared memory it pays ~0.3 us.
+  extern __shared__ __align__(16) double sm_pool[];
+  double* w = a.ws;
+  int64_t sm_left = a.smem_doubles, sm_used = 0;
+  auto take = [&](int64_t n) -> double* {
+    n = (n + 1) & ~(int64_t)1;
+    if (n <= sm_left) {
+      double* p = sm_pool + sm_used;
+      sm_used += n;
+      sm_left -= n;
+      return p;
+    }
+    double* p = w;
+    w += n;
+    return p;
+  };
+  const int LDB = a.ldb;  // row length of the per-point matrices: the tile size rounded up to 32
+  const int64_t MB = (int64_t)M * LDB;
+  // vectors and the factorisation's operands first
+  double* zs = take((int64_t)M * D);  // scaled Z
+  double* zn = take(M);
+  double* mt = take(M);   // whitened mean
+  double* ipiv = take(M);  // 1 / Lk_jj
+  double* Lk = take(MM);   // all M x M matrices column-major: X[i + j*M]
+  double* W1 = take(MM);   // (the residual rows Y of the inverse during the factorisation)
+  double* Li = take(MM);   // Lk^-1 (lower)
+  double* Bt = take(MM);
+  double* A = take(MB);    // per-point matrices [i][n], n contiguous (ld = LDB)
+  double* Cm = take(MB);
+  double* Kuf = take(MB);
+  double* G = take(MM);
+  double* W2 = take(MM);
+  double* W3 = take(MM);
+  double* W4 = take(MM);
+  double* LiT = take(MM);  // transposed copies: coalesced access when the thread index runs over the column
+  double* LkT = take(MM);
+  double* Ab = take(MB);
+  double* DK = take(MB);
+  double* Lq = take(MM);
+  double* xs = take((int64_t)LDB * D);  // scaled points of the tile [n][D]
+  double* xn = take(LDB);
+  double* pdmu = take(LDB);
+  double* pdv = take(LDB);
+  double* zr = take((int64_t)M * D);  // raw Z
+  double* dZ = take((int64_t)M * D);
+  double* wx = take((int64_t)M * D);  // kernel-gradient partial sums (kgrad_kernel's wx / wxx)
+  double* wxx = take((int64_t)M * D);
+  double* mv = take(M);   // m
+  double* g = take(M);
+  double* rs = take(M);
+  double* dvr = take(M);
+  double* dcc = take(M);
+  double* mbar = take(M);
+  double* acc = take(64 + 2 * MAXD);  // scalar accumulators: [0] E [1] dmu [2] dkxx [3] ds2 [4] dc [8..8+D) ds_lin [8+MAXD .. ) theta
+  const double* f = a.flat;
+  const double* fZ = f + 4 + ns;
+  const double* fm = fZ + (int64_t)M * D;
+  const double* fLq = fm + M;
+
+  // ---- P0: parameters ------------------------------------------------------------------------------------------------
+  if (tid == 0) {
+    s_par[0] = f[0];
+    s_par[1] = f[1 + ns];
+    s_par[2] = f[2 + ns];
+    s_par[3] = f[3 + ns];
+    s_status[0] = 0;
+    s_status[1] = 0;
+  }
+  if (tid < D) s_scale[tid] = f[1 + (ns == 1 ? 0 : tid)];
+  for (int i = tid; i < 64 + 2 * MAXD; i += nt) acc[i] = 0.0;
+  for (int64_t i = tid; i < (int64_t)M * D; i += nt) {
+    zr[i] = fZ[i];
+    dZ[i] = wx[i] = wxx[i] = 0.0;
+  }
+  for (int i = tid; i < M; i += nt) {
+    mv[i] = fm[i];
+    g[i] = rs[i] = dvr[i] = dcc[i] = 0.0;
+  }
+  for (int64_t i = tid; i < MM; i += nt) {
+    const int r = (int)(i % M), c = (int)(i / M);
+    Lq[i] = (r >= c) ? fLq[i] : 0.0;  // LowerTriangular(A) view, utils.jl:18
+    G[i] = 0.0;
+  }
+  __syncthreads();
+  const double variance = s_par[0], lin_c = s_par[1], mean_const = s_par[2];
+  LikParams lp = a.lp;
+  lp.sigma2 = s_par[3];
+  for (int i = tid; i < M; i += nt) {
+    double nrm = 0.0;
+    for (int d = 0; d < D; d++) {
+      const double v = zr[(int64_t)i * D + d] * s_scale[d];
+      zs[(int64_t)i * D + d] = v;
+      nrm = fma(v, v, nrm);
+    }
+    zn[i] = nrm;
+    if (!(Lq[i + (int64_t)i * M] > 0.0)) atomicExch(&s_status[0], AGP_ERR_DOMAIN);  // logdet(q.Sigma) would throw
+  }
+  __syncthreads();
+  // ---- P1: Kuu (lower triangle; build_kuu_kernel's operation order) ------------------------------------------------------
+  for (int64_t i = tid; i < MM; i += nt) {
+    const int r = (int)(i % M), c = (int)(i / M);
+    double v = 0.0;
+    if (r >= c) {
+      double u;
+      if (r == c && !linear) u = 0.0;
+      else if (direct) {
+        const double df = zs[r] - zs[c];
+        u = df * df;
+      } else {
+        double dot = 0.0;
+        for (int d = 0; d < D; d++) dot = fma(zs[(int64_t)c * D + d], zs[(int64_t)r * D + d], dot);  // lo = c, hi = r
+        u = u_from_dot(kind, zn[c], zn[r], dot);
+      }
+      v = variance * kappa(kind, u, lin_c);
+      if (r == c) v += a.jitter;
+    }
+    Lk[i] = v;
+  }
+  __syncthreads();
+  // ---- P2 + P3: Cholesky and the inverse of the factor in one right-looking sweep, ONE barrier per column ------------------
+  // Unscaled (LDL^T-style) columns: with d_j the pivot, L[i][j] = K(j)[i][j] / sqrt(d_j) is only formed at the end, so that a
+  // step reads column j and writes columns > j (no intra-step hazard):   K[i][k] -= K[i][j] K[k][j] / d_j   (i >= k > j).
+  // The forward substitution L X = I rides along: residual rows Y (= I at the start), Y[i][c] -= K[i][j] Y[j][c] / d_j for
+  // i > j, c <= j; X[j][c] = Y[j][c] / sqrt(d_j).
+  double* Y = W1;
+  for (int64_t i = tid; i < MM; i += nt) Y[i] = ((i % M) == (i / M)) ? 1.0 : 0.0;
+  __syncthreads();
+  for (int j = 0; j < M; j++) {
+    const double d = Lk[j + (int64_t)j * M];
+    if (!(d > 0.0)) {
+      if (tid == 0 && s_status[0] == 0) {
+        s_status[0] = AGP_ERR_NOT_PD;
+        s_status[1] = j + 1;
+      }
+      break;  // uniform: every thread reads the same d
+    }
+    const double invd = 1.0 / d;
+    if (tid == 0) ipiv[j] = 1.0 / sqrt(d);
+    const int rem = M - 1 - j;  // rows / columns below / right of the pivot
+    const int nk = rem * rem, ny = rem * (j + 1);
+    for (int e = tid; e < nk + ny; e += nt) {
+      if (e < nk) {
+        const int i = j + 1 + e % rem, k = j + 1 + e / rem;
+        if (i >= k) Lk[i + (int64_t)k * M] = fma(-Lk[i + (int64_t)j * M] * invd, Lk[k + (int64_t)j * M], Lk[i + (int64_t)k * M]);
+      } else {
+        const int q = e - nk, i = j + 1 + q % rem, c = q / rem;
+        Y[i + (int64_t)c * M] = fma(-Lk[i + (int64_t)j * M] * invd, Y[j + (int64_t)c * M], Y[i + (int64_t)c * M]);
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (s_status[0] != 0) {
+    if (tid == 0) {
+      const int64_t nflat = 4 + ns + (int64_t)M * D + M + MM;
+      a.out[1 + nflat] = (double)s_status[0];
+      a.out[2 + nflat] = (double)s_status[1];
+    }
+    return;
+  }
+  for (int64_t e = tid; e < MM; e += nt) {
+    const int i = (int)(e % M), j = (int)(e / M);
+    double l = 0.0, x = 0.0;
+    if (i >= j) {
+      l = (i == j) ? 1.0 / ipiv[j] : Lk[e] * ipiv[j];
+      x = Y[e] * ipiv[i];
+    }
+    Li[e] = x;
+    LiT[j + (int64_t)i * M] = x;
+    LkT[j + (int64_t)i * M] = l;
+    W2[e] = l;  // (Lk itself is rewritten after the barrier: other threads still read the unscaled column entries above)
+  }
+  __syncthreads();
+  for (int64_t e = tid; e < MM; e += nt) Lk[e] = W2[e];
+  __syncthreads();
+  // ---- P4: whitened variables ---------------------------------------------------------------------------------------------
+  if (!centered) {
+    for (int i = tid; i < M; i += nt) mt[i] = mv[i];
+    for (int64_t i = tid; i < MM; i += nt) Bt[i] = Lq[i];
+  } else {
+    for (int i = tid; i < M; i += nt) {
+      double s = 0.0;
+      for (int k = 0; k <= i; k++) s = fma(Li[i + (int64_t)k * M], mv[k] - mean_const, s);
+      mt[i] = s;
+    }
+    for (int64_t e = tid; e < MM; e += nt) {
+      const int i = (int)(e % M), j = (int)(e / M);
+      double s = 0.0;
+      for (int k = j; k <= i; k++) s = fma(Li[i + (int64_t)k * M], Lq[k + (int64_t)j * M], s);
+      Bt[e] = s;
+    }
+  }
+  __syncthreads();
+
+  // ---- P5: the points, SM_TILE at a time -------------------------------------------------------------------------------------
+  for (int t0 = 0; t0 < a.count; t0 += SM_TILE) {
+    const int nb = min(SM_TILE, a.count - t0);
+    for (int n = tid; n < nb; n += nt) {
+      double nrm = 0.0;
+      for (int d = 0; d < D; d++) {
+        const double v = a.X[(int64_t)(t0 + n) * D + d] * s_scale[d];
+        xs[n * D + d] = v;
+        nrm = fma(v, v, nrm);
+      }
+      xn[n] = nrm;
+    }
+    __syncthreads();
+    for (int e = tid; e < M * nb; e += nt) {
+      const int l = e / nb, n = e % nb;
+      double u;
+      if (direct) {
+        const double df = xs[n] - zs[l];
+        u = df * df;
+      } else {
+        double dot = 0.0;
+        for (int d = 0; d < D; d++) dot = fma(zs[(int64_t)l * D + d], xs[n * D + d], dot);
+        u = u_from_dot(kind, xn[n], zn[l], dot);
+      }
+      double k, dk;
+      kappa_and_du(kind, u, lin_c, k, dk);
+      Kuf[l * LDB + n] = variance * k;
+      DK[l * LDB + n] = variance * dk;
+    }
+    __syncthreads();
+    for (int e = tid; e < M * nb; e += nt) {  // A = Li Kuf
+      const int i = e / nb, n = e % nb;
+      double s = 0.0;
+      for (int j = 0; j <= i; j++) s = fma(Li[i + (int64_t)j * M], Kuf[j * LDB + n], s);
+      A[i * LDB + n] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < M * nb; e += nt) {  // C = Bt^T A
+      const int j = e / nb, n = e % nb;
+      double s = 0.0;
+      for (int i = j; i < M; i++) s = fma(Bt[i + (int64_t)j * M], A[i * LDB + n], s);
+      Cm[j * LDB + n] = s;
+    }
+    __syncthreads();
+    // marginals + expected log-likelihood, one point per thread (all threads take part in the reductions)
+    {
+      double E = 0.0, dmu = 0.0, dvar = 0.0, ds2 = 0.0, kf = 0.0;
+      const int n = tid;
+      if (n < nb) {
+        double saa = 0.0, sam = 0.0, scc = 0.0;
+        for (int i = 0; i < M; i++) {
+          const double av = A[i * LDB + n], cv = Cm[i * LDB + n];
+          saa = fma(av, av, saa);
+          sam = fma(av, mt[i], sam);
+          scc = fma(cv, cv, scc);
+        }
+        kf = linear ? xn[n] + lin_c : 1.0;
+        const double mu = mean_const + sam;
+        const double var = variance * kf - saa + scc + 1e-18;  // AbstractGPs default jitter of f_post(x), SVA.jl:354
+        if (!(var > 0.0)) atomicExch(&s_status[0], AGP_ERR_DOMAIN);
+        expected_loglik(lp, mu, var, a.y[t0 + n], E, dmu, dvar, ds2, a.point_base + t0 + n);
+        dmu *= a.scale;
+        dvar *= a.scale;
+        ds2 *= a.scale;
+        pdmu[n] = dmu;
+        pdv[n] = dvar;
+      }
+      // (SM_TILE <= blockDim.x: every point of the tile has its own thread)
+      const double r0 = sm_block_sum(E, sred), r1 = sm_block_sum(dmu, sred), r2 = sm_block_sum(dvar * kf, sred), r3 = sm_block_sum(ds2, sred);
+      const double r4 = linear ? sm_block_sum(dvar, sred) : 0.0;
+      if (tid == 0) {
+        acc[0] += r0;
+        acc[1] += r1;
+        acc[2] += r2;
+        acc[3] += r3;
+        acc[4] += linear ? r4 * variance : 0.0;
+      }
+      if (linear && a.want_grad) {
+        for (int d = 0; d < D; d++) {
+          double t = 0.0;
+          if (n < nb) {
+            const double x = a.X[(int64_t)(t0 + n) * D + d];
+            t = dvar * 2.0 * variance * s_scale[d] * x * x;
+          }
+          const double r = sm_block_sum(t, sred);
+          if (tid == 0) acc[8 + d] += r;
+        }
+      }
+    }
+    __syncthreads();
+    if (!a.want_grad) continue;
+    for (int e = tid; e < M * nb; e += nt) {  // Ab = dmu (x) mt + 2 dv (Bt C - A)
+      const int i = e / nb, n = e % nb;
+      double s = 0.0;
+      for (int j = 0; j <= i; j++) s = fma(Bt[i + (int64_t)j * M], Cm[j * LDB + n], s);
+      Ab[i * LDB + n] = fma(pdmu[n], mt[i], 2.0 * pdv[n] * (s - A[i * LDB + n]));
+    }
+    __syncthreads();
+    for (int e = tid; e < M * nb; e += nt) {  // Kb = Li^T Ab  (into Cm)
+      const int j = e / nb, n = e % nb;
+      double s = 0.0;
+      for (int i = j; i < M; i++) s = fma(Li[i + (int64_t)j * M], Ab[i * LDB + n], s);
+      Cm[j * LDB + n] = s;
+    }
+    // G += (dv A) A^T (lower), g += A dmu: one warp per output, lanes over the points (coalesced rows of A), fixed-order
+    // shuffle tree -- independent of Kb, so no barrier is needed before
+    {
+      const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+      const int npair = M * (M + 1) / 2;
+      for (int p = warp; p < npair + M; p += nw) {
+        double v = 0.0;
+        int i = 0, j = 0;
+        if (p < npair) {
+          i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+          while ((i + 1) * (i + 2) / 2 <= p) i++;
+          while (i * (i + 1) / 2 > p) i--;
+          j = p - i * (i + 1) / 2;
+          for (int n = lane; n < nb; n += 32) v = fma(pdv[n] * A[i * LDB + n], A[j * LDB + n], v);
+        } else {
+          i = p - npair;
+          for (int n = lane; n < nb; n += 32) v = fma(pdmu[n], A[i * LDB + n], v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) {
+          if (p < npair) G[i + (int64_t)j * M] += v;
+          else g[i] += v;
+        }
+      }
+    }
+    __syncthreads();
+    // kernel-gradient partial sums of this tile (kgrad_kernel's quantities): W = Kb * variance * kappa'(u); one warp per (row, d)
+    {
+      const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+      for (int e = warp; e < M * (D + 1); e += nw) {
+        const int l = e / (D + 1), q = e % (D + 1);
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+        if (q == D) {
+          for (int n = lane; n < nb; n += 32) {
+            const double kb = Cm[l * LDB + n];
+            v0 = fma(kb, DK[l * LDB + n], v0);
+            v1 = fma(kb, Kuf[l * LDB + n], v1);
+            v2 += kb;
+          }
+        } else {
+          for (int n = lane; n < nb; n += 32) {
+            const double W = Cm[l * LDB + n] * DK[l * LDB + n];
+            const double x = xs[n * D + q];
+            const double wxd = W * x;
+            v0 += wxd;
+            v1 = fma(wxd, x, v1);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+          v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+          v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+        }
+        if (lane == 0) {
+          if (q == D) {
+            rs[l] += v0;
+            dvr[l] += v1 / variance;  // sum Kb kappa(u)
+            dcc[l] += v2;
+          } else {
+            wx[(int64_t)l * D + q] += v0;
+            wxx[(int64_t)l * D + q] += v1;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int64_t nflat = 4 + ns + (int64_t)M * D + M + MM;
+  double* out = a.out;
+  // ---- KL ---------------------------------------------------------------------------------------------------------------
+  double kl;
+  {
+    double tr = 0.0, mm = 0.0, ldq = 0.0, ldk = 0.0;
+    for (int64_t i = tid; i < MM; i += nt) tr = fma(Bt[i], Bt[i], tr);
+    for (int j = tid; j < M; j += nt) {
+      mm = fma(mt[j], mt[j], mm);
+      ldq += log(Lq[j + (int64_t)j * M]);
+      if (centered) ldk += log(Lk[j + (int64_t)j * M]);
+    }
+    const double s0 = sm_block_sum(tr, sred), s1 = sm_block_sum(mm, sred), s2 = sm_block_sum(ldq, sred), s3 = sm_block_sum(ldk, sred);
+    kl = 0.5 * (s0 + s1 - (double)M) + s3 - s2;
+  }
+  if (!a.want_grad) {
+    if (tid == 0) {
+      out[0] = acc[0] * a.scale - kl;
+      out[1 + nflat] = (double)s_status[0];
+      out[2 + nflat] = 0.0;
+    }
+    return;
+  }
+  // ---- P6: replicated epilogue (agp_svgp_finish) -----------------------------------------------------------------------------
+  // data part of dZ / theta from the accumulated partial sums (kgrad_finish_kernel, zfac = 1)
+  double* theta = acc + 8 + MAXD;  // [0] dvariance [1] dc [2 + d] ds_d
+  {
+    double tv = 0.0, tc = 0.0;
+    for (int l = tid; l < M; l += nt) {
+      tv += dvr[l];
+      tc += dcc[l];
+    }
+    const double r0 = sm_block_sum(tv, sred), r1 = sm_block_sum(tc, sred);
+    if (tid == 0) {
+      theta[0] = r0;
+      theta[1] = linear ? variance * r1 : 0.0;
+    }
+    for (int d = 0; d < D; d++) {
+      double v = 0.0;
+      for (int l = tid; l < M; l += nt) {
+        const double z = zs[(int64_t)l * D + d], sx = wx[(int64_t)l * D + d], sxx = wxx[(int64_t)l * D + d];
+        v += linear ? z * sx : fma(z, fma(z, rs[l], -2.0 * sx), sxx);
+      }
+      const double r = sm_block_sum(v, sred);
+      if (tid == 0) theta[2 + d] = (s_scale[d] != 0.0) ? 2.0 / s_scale[d] * r : 0.0;
+    }
+    for (int64_t i = tid; i < (int64_t)M * D; i += nt) {
+      const int l = (int)(i / D), d = (int)(i % D);
+      const double sd = s_scale[d];
+      dZ[i] = linear ? sd * wx[i] : 2.0 * sd * (zs[i] * rs[l] - wx[i]);
+    }
+  }
+  __syncthreads();
+  // G: lower -> symmetric
+  for (int64_t e = tid; e < MM; e += nt) {
+    const int i = (int)(e % M), j = (int)(e / M);
+    if (i < j) G[e] = G[j + (int64_t)i * M];
+  }
+  __syncthreads();
+  // W1 = P1 = Bt Bt^T - I
+  for (int64_t e = tid; e < MM; e += nt) {
+    const int i = (int)(e % M), j = (int)(e / M);
+    double s = (i == j) ? -1.0 : 0.0;
+    const int kmax = min(i, j);
+    for (int k = 0; k <= kmax; k++) s = fma(Bt[i + (int64_t)k * M], Bt[j + (int64_t)k * M], s);
+    W1[e] = s;
+  }
+  __syncthreads();
+  // W2 = Asum = mt g^T + 2 P1 G ;  W3 = Bt-bar = tril(2 G Bt) [- Bt]
+  for (int64_t e = tid; e < MM; e += nt) {
+    const int i = (int)(e % M), j = (int)(e / M);
+    double s = 0.0, t = 0.0;
+    for (int k = 0; k < M; k++) s = fma(W1[i + (int64_t)k * M], G[k + (int64_t)j * M], s);
+    W2[e] = fma(mt[i], g[j], 2.0 * s);
+    if (i >= j) {
+      for (int k = j; k < M; k++) t = fma(G[i + (int64_t)k * M], Bt[k + (int64_t)j * M], t);
+      t = 2.0 * t - (centered ? Bt[e] : 0.0);
+    }
+    W3[e] = t;
+  }
+  __syncthreads();
+  // W4 = V = Li^T Asum
+  for (int64_t e = tid; e < MM; e += nt) {
+    const int i = (int)(e % M), j = (int)(e / M);
+    double s = 0.0;
+    for (int k = i; k < M; k++) s = fma(LiT[i + (int64_t)k * M], W2[k + (int64_t)j * M], s);
+    W4[e] = s;
+  }
+  double summbar = 0.0;
+  if (centered) {
+    // mbar = Li^T (g - mt)
+    for (int i = tid; i < M; i += nt) {
+      double s = 0.0;
+      for (int k = i; k < M; k++) s = fma(LiT[i + (int64_t)k * M], g[k] - mt[k], s);
+      mbar[i] = s;
+    }
+    __syncthreads();
+    double v = 0.0;
+    for (int i = tid; i < M; i += nt) v += mbar[i];
+    summbar = sm_block_sum(v, sred);
+    // W1 = Y = Li^T Bt-bar  (P1 is no longer needed: Asum has been formed)
+    for (int64_t e = tid; e < MM; e += nt) {
+      const int i = (int)(e % M), j = (int)(e / M);
+      double s = 0.0;
+      for (int k = max(i, j); k < M; k++) s = fma(LiT[i + (int64_t)k * M], W3[k + (int64_t)j * M], s);
+      W1[e] = s;
+    }
+    __syncthreads();
+    // W2 = X2 = Y Bt^T + mbar mt^T   (Asum is no longer needed: V has been formed)
+    for (int64_t e = tid; e < MM; e += nt) {
+      const int i = (int)(e % M), j = (int)(e / M);
+      double s = mbar[i] * mt[j];
+      for (int k = 0; k <= j; k++) s = fma(W1[i + (int64_t)k * M], Bt[j + (int64_t)k * M], s);
+      W2[e] = s;
+    }
+  }
+  __syncthreads();
+  // dLq, dm, scalars: everything that does not depend on the Cholesky pullback
+  {
+    const double* src = centered ? W1 : W3;
+    double* oLq = out + 1 + 4 + ns + (int64_t)M * D + M;
+    for (int64_t e = tid; e < MM; e += nt) {
+      const int r = (int)(e % M), c = (int)(e / M);
+      double v = 0.0;
+      if (r >= c) {
+        v = src[e] - (centered ? 0.0 : Lq[e]);
+        if (r == c) v += 1.0 / Lq[e];
+      }
+      oLq[e] = v;
+    }
+    double* om = out + 1 + 4 + ns + (int64_t)M * D;
+    for (int i = tid; i < M; i += nt) om[i] = centered ? mbar[i] : g[i] - mv[i];
+  }
+  // G <- Lbar = -tril(V) [- tril(X2) - diag(1 / Lk_jj)]     (G is no longer needed)
+  for (int64_t e = tid; e < MM; e += nt) {
+    const int r = (int)(e % M), c = (int)(e / M);
+    double v = 0.0;
+    if (r >= c) {
+      v = -W4[e];
+      if (centered) {
+        v -= W2[e];
+        if (r == c) v -= 1.0 / Lk[e];
+      }
+    }
+    G[e] = v;
+  }
+  __syncthreads();
+  // W3 = Phi(Lk^T Lbar): lower, diagonal halved
+  for (int64_t e = tid; e < MM; e += nt) {
+    const int i = (int)(e % M), j = (int)(e / M);
+    double s = 0.0;
+    if (i >= j) {
+      for (int k = i; k < M; k++) s = fma(LkT[i + (int64_t)k * M], G[k + (int64_t)j * M], s);
+      if (i == j) s *= 0.5;
+    }
+    W3[e] = s;
+  }
+  __syncthreads();
+  // W4 = Y1 = Li^T Phi ;  W2 = Y2 = Li^T Y1^T ;  G = Kuu-bar = (Y2 + Y2^T) / 2
+  for (int64_t e = tid; e < MM; e += nt) {
+    const int i = (int)(e % M), j = (int)(e / M);
+    double s = 0.0;
+    for (int k = max(i, j); k < M; k++) s = fma(LiT[i + (int64_t)k * M], W3[k + (int64_t)j * M], s);
+    W4[e] = s;
+  }
+  __syncthreads();
+  for (int64_t e = tid; e < MM; e += nt) {
+    const int i = (int)(e % M), j = (int)(e / M);
+    double s = 0.0;
+    for (int k = i; k < M; k++) s = fma(LiT[i + (int64_t)k * M], W4[j + (int64_t)k * M], s);  // Y1^T[k][j] = Y1[j][k]
+    W2[e] = s;
+  }
+  __syncthreads();
+  for (int64_t e = tid; e < MM; e += nt) {
+    const int i = (int)(e % M), j = (int)(e / M);
+    G[e] = 0.5 * (W2[e] + W2[j + (int64_t)i * M]);
+  }
+  __syncthreads();
+  // Kuu part of dZ / theta: contraction of Kuu-bar with the derivatives of k(z_l, z_n); both arguments move -> zfac = 2.
+  // W3 = Kuu-bar .* variance kappa'(u), W4 = kappa(u) (both symmetric), then the same per-row sums as for the data part.
+  for (int64_t e = tid; e < MM; e += nt) {
+    const int l = (int)(e % M), n = (int)(e / M);
+    double u;
+    if (direct) {
+      const double df = zs[n] - zs[l];
+      u = df * df;
+    } else {
+      double dot = 0.0;
+      const int lo = min(l, n), hi = max(l, n);
+      for (int d = 0; d < D; d++) dot = fma(zs[(int64_t)lo * D + d], zs[(int64_t)hi * D + d], dot);
+      u = u_from_dot(kind, zn[lo], zn[hi], dot);
+    }
+    double k, dk;
+    kappa_and_du(kind, u, lin_c, k, dk);
+    W3[e] = G[e] * variance * dk;
+    W4[e] = k;
+  }
+  __syncthreads();
+  {
+    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    for (int e = warp; e < M * (D + 1); e += nw) {
+      const int l = e / (D + 1), q = e % (D + 1);
+      double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+      if (q == D) {
+        for (int n = lane; n < M; n += 32) {
+          const double kb = G[n + (int64_t)l * M];
+          v0 += W3[n + (int64_t)l * M];
+          v1 = fma(kb, W4[n + (int64_t)l * M], v1);
+          v2 += kb;
+        }
+      } else {
+        for (int n = lane; n < M; n += 32) {
+          const double x = zs[(int64_t)n * D + q];
+          const double wxd = W3[n + (int64_t)l * M] * x;
+          v0 += wxd;
+          v1 = fma(wxd, x, v1);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+      }
+      if (lane == 0) {
+        if (q == D) {
+          rs[l] = v0;
+          dvr[l] = v1;
+          dcc[l] = v2;
+        } else {
+          wx[(int64_t)l * D + q] = v0;
+          wxx[(int64_t)l * D + q] = v1;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  {
+    double tv = 0.0, tc = 0.0;
+    for (int l = tid; l < M; l += nt) {
+      tv += dvr[l];
+      tc += dcc[l];
+    }
+    const double r0 = sm_block_sum(tv, sred), r1 = sm_block_sum(tc, sred);
+    if (tid == 0) {
+      theta[0] += r0;
+      theta[1] += linear ? variance * r1 : 0.0;
+    }
+    for (int d = 0; d < D; d++) {
+      double v = 0.0;
+      for (int l = tid; l < M; l += nt) {
+        const double z = zs[(int64_t)l * D + d], sx = wx[(int64_t)l * D + d], sxx = wxx[(int64_t)l * D + d];
+        v += linear ? z * sx : fma(z, fma(z, rs[l], -2.0 * sx), sxx);
+      }
+      const double r = sm_block_sum(v, sred);
+      if (tid == 0) theta[2 + d] += (s_scale[d] != 0.0) ? 2.0 / s_scale[d] * r : 0.0;
+    }
+    for (int64_t i = tid; i < (int64_t)M * D; i += nt) {
+      const int l = (int)(i / D), d = (int)(i % D);
+      const double sd = s_scale[d];
+      dZ[i] += 2.0 * (linear ? sd * wx[i] : 2.0 * sd * (zs[i] * rs[l] - wx[i]));
+    }
+  }
+  __syncthreads();
+  {
+    double* oZ = out + 1 + 4 + ns;
+    for (int64_t i = tid; i < (int64_t)M * D; i += nt) oZ[i] = dZ[i];
+    if (tid == 0) {
+      out[0] = acc[0] * a.scale - kl;
+      out[1 + 0] = theta[0] + acc[2];                 // dvariance
+      out[1 + 1 + ns] = theta[1] + acc[4];            // dlinear_c
+      out[1 + 2 + ns] = acc[1] - (centered ? summbar : 0.0);  // dmean_const
+      out[1 + 3 + ns] = acc[3];                       // d likelihood parameter
+      if (ns == 1) {
+        double s = 0.0;
+        for (int d = 0; d < D; d++) s += theta[2 + d] + (linear ? acc[8 + d] : 0.0);
+        out[1 + 1] = s;
+      } else {
+        for (int d = 0; d < D; d++) out[1 + 1 + d] = theta[2 + d] + (linear ? acc[8 + d] : 0.0);
+      }
+      out[1 + nflat] = (double)s_status[0];
+      out[2 + nflat] = 0.0;
+    }
+  }
+}
+
+}  // namespace agp

@@ -39,38 +39,22 @@ struct TrsmArgs {
   const double* rowscale;  // TR_KUF_FWD_SCALED: [Mp]
   const double* dvec;      // TR_KUF_FWD_SCALED: [Mp]
   double* skd;             // TR_KUF_FWD_SCALED: [ldx]
-  int dephase;             // > 0: CTAs with (blockIdx.x / dephase) odd use the late stage order (StepIter); = SM count
   KernelParams kp;
 };
 
 struct StepIter {
   int J, q, kk, cnt, nb;
   bool fwd;
-  // late (forward only): the diagonal-block slot of a block row -- for the Kuf generator the eight stages that need generated
-  // rows -- is moved from the front of the row's stage sequence to its last-but-one position,
-  //   early: [diag, L = 0 .. J-1]      late (J >= 2): [L = 0 .. J-2, diag, L = J-1]
-  // so that the two CTAs sharing an SM (which start together and run the same schedule) are not in their generator phase at
-  // the same time: one of them always has plain DMMA stages to issue.  L = J-1 stays last in both orders (it was written by
-  // this CTA's previous row epilogue and is prefetched three stages ahead).  A sum over k-blocks in another order: both
-  // orders are fixed functions of blockIdx, so the result stays bit-reproducible.
-  bool late;
-  __device__ __forceinline__ void init(bool f, int nb_, bool late_ = false) {
+  __device__ __forceinline__ void init(bool f, int nb_) {
     fwd = f;
     nb = nb_;
-    late = late_;
     J = f ? 0 : nb_ - 1;
     q = 0;
     kk = 0;
     cnt = 1 + (f ? J : nb - 1 - J);
   }
-  __device__ __forceinline__ int dslot() const { return (late && J >= 2) ? J - 1 : 0; }
-  __device__ __forceinline__ bool is_diag() const { return q == dslot(); }
-  __device__ __forceinline__ int src() const {
-    const int d = dslot();
-    if (q == d) return J;
-    if (!fwd) return nb - q;
-    return q < d ? q : q - 1;
-  }
+  __device__ __forceinline__ bool is_diag() const { return q == 0; }
+  __device__ __forceinline__ int src() const { return q == 0 ? J : (fwd ? q - 1 : nb - q); }
   __device__ __forceinline__ bool last_in_row() const { return q == cnt - 1 && kk == BM / BK - 1; }
   __device__ __forceinline__ void next() {
     if (++kk == BM / BK) {
@@ -200,10 +184,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
 
   double pkd[2] = {0.0, 0.0};  // SCALED: partial k' * dvec of this thread's 2 columns
   StepIter it_issue, it_cons, it_gen;
-  const bool late = FWD && a.dephase > 0 && ((blockIdx.x / a.dephase) & 1);
-  it_issue.init(MODE != TR_RHS_BWD, a.nb, late);
-  it_cons.init(MODE != TR_RHS_BWD, a.nb, late);
-  it_gen.init(true, a.nb, late);
+  it_issue.init(MODE != TR_RHS_BWD, a.nb);
+  it_cons.init(MODE != TR_RHS_BWD, a.nb);
+  it_gen.init(true, a.nb);
   const int total = (BM / BK) * a.nb * (a.nb + 1) / 2;
 
   ALoad<A_KM> la;

@@ -1,0 +1,280 @@
+// tf32x3.cuh -- the Float32 fast mode's GEMM engine: 3xTF32 split products on the 5th-generation tensor cores.
+//
+//   D[128 x 128] (FP32, in TMEM)  =  sum_k  Ah Bh^T + Ah Bl^T + Al Bh^T        x = xh + xl,  xh = tf32(x),  xl = tf32(x - xh)
+//
+// i.e. an FP32-accurate product (22 mantissa bits per operand, FP32 accumulation) at a third of the TF32 rate -- still ~10x the
+// FP64 DMMA rate that bounds the reference-precision path.  One CTA computes one 128 x 128 output tile:
+//   warp 0      TMA producer: cp.async.bulk.tensor (128-byte swizzle) of the four operand tiles of a k-block into a 3-stage ring
+//   warp 1      allocates TMEM, issues tcgen05.mma.kind::tf32 (one elected thread), commits stages back to the producer
+//   warps 2..5  epilogue: tcgen05.ld of the accumulator (one TMEM lane = one output row per thread), functor, global stores
+// Operands are read in place from the hi / lo FP32 planes the producing kernels write; both K-major (k contiguous) and MN-major
+// (m / n contiguous) operands are supported, so that one point-major copy of every intermediate serves all four sweep stages
+// (DESIGN.md section 8).  SASS: UTCHMMA-class tensor instructions, LDTM, UTMALDG.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace agp {
+namespace t5 {
+
+constexpr int TM = 128;      // output rows per CTA = TMEM lanes
+constexpr int TN = 128;      // output columns per CTA = TMEM columns
+constexpr int TK = 32;       // k per pipeline stage: 32 floats = one 128-byte swizzle row
+constexpr int UK = 8;        // k of one tcgen05.mma.kind::tf32
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = TM * TK * 4;        // 16 KB: one operand plane of one stage
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // Ah | Al | Bh | Bl
+constexpr int T5_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+
+// k-range of an output tile
+constexpr int KM_FULL = 0;     // [0, K)
+constexpr int KM_FROM_N = 1;   // [tile_n * TN, K)          the N-side operand is lower triangular stored as [n][k], k >= n
+constexpr int KM_UPTO_N = 2;   // [0, (tile_n + 1) * TN)    ...                                                       k <= n
+constexpr int KM_SPLIT = 3;    // [z * kchunk, min(K, (z + 1) * kchunk)), z = blockIdx.z
+
+struct Args {
+  int K;
+  int kmode;
+  int kchunk;
+  int lower_only;  // 1: skip tiles with tile_n > tile_m (symmetric output)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst), "l"(map),
+               "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init_u32(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, one 128 x 128 x 8 TF32 MMA issued by the calling thread
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, "
+      "%22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+        "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+        "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128-byte swizzle, version 1
+//   K-major  tile [rows][32 floats]: rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (1)
+//   MN-major tile: 4 boxes of [32 k][32 floats of m / n]: LBO = 4096 B between the 32-wide m / n groups, SBO = 1024 B between 8-k groups
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
+  const uint64_t lbo = mn_major ? (4096 >> 4) : 1, sbo = 1024 >> 4;
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, M = 128, N = 128, dense, no negate
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+// Epi: __device__ void operator()(int tile_m, int tile_n, int z, int row, int c0, const float (&v)[32]) const
+//      called by the thread that owns output row `row` (0..127 of the tile) for the column chunks c0 = 0, 32, 64, 96 in order;
+//      `begin(tile_m, tile_n, z, row)` / `end(...)` bracket the four calls (per-row reductions).
+template <bool AMN, bool BMN, class Epi>
+__global__ void __launch_bounds__(T5_THREADS, 1)
+tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl, const __grid_constant__ CUtensorMap mBh,
+                   const __grid_constant__ CUtensorMap mBl, Args g, Epi epi) {
+  extern __shared__ uint8_t t5_smem_raw[];
+  const int tile_m = blockIdx.x, tile_n = blockIdx.y, z = blockIdx.z;
+  if (g.lower_only && tile_n > tile_m) return;
+  int kb = 0, ke = g.K;
+  if (g.kmode == KM_FROM_N) kb = tile_n * TN;
+  if (g.kmode == KM_UPTO_N) ke = min(g.K, (tile_n + 1) * TN);
+  if (g.kmode == KM_SPLIT) {
+    kb = z * g.kchunk;
+    ke = min(g.K, kb + g.kchunk);
+  }
+  const int nk = (ke - kb + TK - 1) / TK;
+
+  const uint32_t base = (smem_u32(t5_smem_raw) + 1023u) & ~1023u;  // the 128-byte swizzle pattern repeats every 1024 B
+  const uint32_t bars = base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(t5_smem_raw + (tmem_slot - smem_u32(t5_smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init_u32(full_bar(s), 1);
+      mbar_init_u32(empty_bar(s), 1);
+    }
+    mbar_init_u32(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tmem_slot), "r"((uint32_t)TN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0 && nk > 0) {
+      // ---- TMA producer ---------------------------------------------------------------------------------------------
+      for (int i = 0; i < nk; i++) {
+        const int s = i % STAGES;
+        if (i >= STAGES) mbar_wait_u32(empty_bar(s), ((i / STAGES) - 1) & 1);
+        const uint32_t st = base + s * STAGE_BYTES;
+        mbar_expect_tx_u32(full_bar(s), STAGE_BYTES);
+        const int k0 = kb + i * TK;
+        if (AMN) {
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            tma_load_2d(st + b * 4096, &mAh, full_bar(s), tile_m * TM + 32 * b, k0);
+            tma_load_2d(st + TILE_BYTES + b * 4096, &mAl, full_bar(s), tile_m * TM + 32 * b, k0);
+          }
+        } else {
+          tma_load_2d(st, &mAh, full_bar(s), k0, tile_m * TM);
+          tma_load_2d(st + TILE_BYTES, &mAl, full_bar(s), k0, tile_m * TM);
+        }
+        if (BMN) {
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            tma_load_2d(st + 2 * TILE_BYTES + b * 4096, &mBh, full_bar(s), tile_n * TN + 32 * b, k0);
+            tma_load_2d(st + 3 * TILE_BYTES + b * 4096, &mBl, full_bar(s), tile_n * TN + 32 * b, k0);
+          }
+        } else {
+          tma_load_2d(st + 2 * TILE_BYTES, &mBh, full_bar(s), k0, tile_n * TN);
+          tma_load_2d(st + 3 * TILE_BYTES, &mBl, full_bar(s), k0, tile_n * TN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nk > 0) {
+      // ---- MMA issuer -------------------------------------------------------------------------------------------------
+      constexpr uint32_t idesc = make_idesc(AMN, BMN);
+      constexpr uint32_t a_step = AMN ? 1024 : UK * 4, b_step = BMN ? 1024 : UK * 4;  // bytes per k-step of 8
+      for (int i = 0; i < nk; i++) {
+        const int s = i % STAGES;
+        mbar_wait_u32(full_bar(s), (i / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t st = base + s * STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < TK / UK; k++) {
+          const uint64_t ah = make_desc(st + k * a_step, AMN), al = make_desc(st + TILE_BYTES + k * a_step, AMN);
+          const uint64_t bh = make_desc(st + 2 * TILE_BYTES + k * b_step, BMN), bl = make_desc(st + 3 * TILE_BYTES + k * b_step, BMN);
+          tc_mma_tf32(tmem_d, al, bh, idesc, (i | k) != 0);  // the small terms first
+          tc_mma_tf32(tmem_d, ah, bl, idesc, 1);
+          tc_mma_tf32(tmem_d, ah, bh, idesc, 1);
+        }
+        tc_commit(empty_bar(s));  // the stage may be refilled once these MMAs have read it
+      }
+      tc_commit(tmem_full_bar);
+    }
+  } else {
+    // ---- epilogue: warp w may only touch TMEM lanes 32 (w % 4) .. 32 (w % 4) + 31 ----------------------------------------
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    float v[32];
+    if (nk > 0) {
+      mbar_wait_u32(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    epi.begin(tile_m, tile_n, z, row);
+#pragma unroll 1
+    for (int c0 = 0; c0 < TN; c0 += 32) {
+      if (nk > 0) {
+        tc_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = 0.f;
+      }
+      epi(tile_m, tile_n, z, row, c0, v);
+    }
+    epi.end(tile_m, tile_n, z, row);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"((uint32_t)TN) : "memory");
+  }
+}
+
+// ---- host side: tensor maps -----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// FP32 matrix with `inner` contiguous elements per row and `outer` rows (row pitch `ld` elements); a box is 32 inner elements
+// (128 bytes, the swizzle width) x box_outer rows.  K-major operand: inner = k, box_outer = 128.  MN-major: inner = m / n, 32.
+inline bool make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {32, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// x -> (tf32(x), tf32(x - tf32(x))): both parts exactly representable in TF32 (round to nearest), so the tensor core's truncation
+// of the low 13 mantissa bits loses nothing
+__device__ __forceinline__ void split_tf32(double x, float& hi, float& lo) {
+  const float f = (float)x;
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(h) : "f"(f));
+  hi = __uint_as_float(h);
+  const float r = (float)(x - (double)hi);
+  uint32_t l;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(l) : "f"(r));
+  lo = __uint_as_float(l);
+}
+
+}  // namespace t5
+}  // namespace agp

@@ -191,6 +191,21 @@ int32_t agp_svgp_flat_size(const agp_svgp_params* tmpl, int64_t* n_doubles);
 int32_t agp_svgp_elbo_grad_flat(agp_ctx* ctx, agp_dataset* ds, int64_t offset, int64_t count, const agp_svgp_params* tmpl,
                                 const double* flat, double num_data, int64_t global_batch, double* elbo_out, double* flat_grad);
 
+/* Optimiser-step handle (the training loops of examples/a-regression/script.jl:176-194 -- 30 000
+ * ELBO+gradient evaluations on minibatches of 100 points with M = 20 -- and examples/b-classification/script.jl:124-142):
+ * `tmpl` fixes what an optimiser does not change, as for agp_svgp_elbo_grad_flat; every eval takes the current parameters as one
+ * flat vector (same layout) and returns the gradient in that layout.  What a step needs stays resident behind the handle
+ * (pinned parameter / result buffers the kernel reads and writes directly, workspace, quadrature table); a small problem
+ * (M <= 128 and M^2 * count <= 4e6, no communicator) is evaluated by ONE kernel launch of one CTA, anything else by the
+ * throughput path.  flat_grad == NULL -> value only.                                                                    */
+typedef struct agp_svgp_stepper agp_svgp_stepper;
+int32_t agp_svgp_stepper_create(agp_ctx* ctx, const agp_svgp_params* tmpl, agp_svgp_stepper** out);
+int32_t agp_svgp_stepper_flat_size(agp_svgp_stepper* s, int64_t* n_doubles);
+int32_t agp_svgp_stepper_eval(agp_svgp_stepper* s, agp_dataset* ds, int64_t offset, int64_t count, const double* flat,
+                              double num_data, int64_t global_batch, double* elbo_out, double* flat_grad);
+int32_t agp_svgp_stepper_counts(agp_svgp_stepper* s, int64_t* n_small, int64_t* n_large);
+int32_t agp_svgp_stepper_destroy(agp_svgp_stepper* s);
+
 /* Split-phase form of agp_svgp_elbo_grad for hosts that own the collective (torch.distributed,
  * MPI.jl): sweep -> caller all-reduces the packed float64 buffer in place (sum) -> finish.     */
 int32_t agp_svgp_sweep(agp_ctx* ctx, agp_dataset* ds, int64_t offset, int64_t count,

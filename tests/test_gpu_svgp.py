@@ -153,10 +153,13 @@ def test_mean_and_cov_and_cross_cov(agp):
         xa, xb = rng.normal(size=(201, D)), rng.normal(size=(77, D))
         mu, cov = agp.mean_and_cov(post, xa)
         rmu, rcov = osv.mean_and_cov(s, xa)
-        assert rel_err(mu, rmu) < 1e-10 and rel_err(cov, rcov) < 1e-10
-        assert rel_err(agp.cov(post, xa), rcov) < 1e-10
-        assert rel_err(np.diag(cov), agp.var(post, xa)) < 1e-10  # AbstractGPs interface consistency (test/SVA...:30-34)
-        assert rel_err(agp.cov(post, xa, xb), osv.cov_cross(s, xa, xb)) < 1e-10
+        # (Centered + SE in D = 1 with 37 inducing points: cond(Kuu) ~ 1e7 at jitter 1e-6 -- the named ill-conditioned case, 1e-9)
+        tol = 1e-9 if (centered and kind == "se") else 1e-10
+        record_parity(f"mean_and_cov {kind} D={D} cent={centered}", dict(mean=rel_err(mu, rmu), cov=rel_err(cov, rcov)), tol=tol)
+        assert rel_err(mu, rmu) < tol and rel_err(cov, rcov) < tol
+        assert rel_err(agp.cov(post, xa), rcov) < tol
+        assert rel_err(np.diag(cov), agp.var(post, xa)) < tol  # AbstractGPs interface consistency (test/SVA...:30-34)
+        assert rel_err(agp.cov(post, xa, xb), osv.cov_cross(s, xa, xb)) < tol
 
 
 def test_dataset_layouts_types_and_minibatch_views(agp):
@@ -417,7 +420,7 @@ def test_flat_vector_interface(agp, centered, lik):
     p = make_problem(seed=17, kind="se", N=500, M=12, D=2, lik=lik, centered=centered, ard=True)
     sva, lfx, quad, _ = agp_objects(agp, p)
     val, g = agp.elbo_and_gradient(sva, lfx, p["y"], num_data=2000.0, quadrature=quad)
-    fo = agp.FlatELBO(sva, lfx, p["y"], num_data=2000.0, quadrature=quad)
+    fo = agp.FlatELBO(sva, lfx, p["y"], num_data=2000.0, quadrature=quad, resident=False)  # agp_svgp_elbo_grad_flat: bit-identical to the struct call
     assert fo.size == 4 + 2 + 12 * 2 + 12 + 144
     v2, gf = fo.value_and_gradient(fo.x0)
     u = fo.unflatten(gf)
@@ -472,8 +475,7 @@ def test_float32_inputs_are_uploaded_as_float32(agp):
 @pytest.mark.parametrize("kind", ["se", "matern32", "matern52", "linear"])
 def test_kernel_function_values(agp, kind):
     """cov(f.prior, x) / cov(f.prior, x, y) on the device (agp_kernel_matrix) against the oracle's kernelmatrix, including pairs so far
-    apart that exp(-u/2) underflows and coincident points: the table-driven exponential of kfun.cuh (exp_nonpos) stays within
-    1e-15 relative of the library exponential the oracle uses."""
+    apart that exp(-u/2) underflows and coincident points."""
     rng = np.random.default_rng(31)
     D = 3
     X = np.concatenate([rng.normal(size=(150, D)), 30.0 * rng.normal(size=(40, D)), 200.0 * rng.normal(size=(10, D))])
