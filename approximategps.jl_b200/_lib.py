@@ -144,6 +144,7 @@ SYMBOLS = {
     "agp_svgp_stepper_flat_size": (C.c_int32, [_vp, C.POINTER(C.c_int64)]),
     "agp_svgp_stepper_eval": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int64, c_double_p, C.c_double, C.c_int64, c_double_p, c_double_p]),
     "agp_svgp_stepper_counts": (C.c_int32, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "agp_svgp_stepper_phase_ticks": (C.c_int32, [_vp, c_double_p]),
     "agp_svgp_stepper_destroy": (C.c_int32, [_vp]),
     "agp_svgp_sweep": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int64, C.POINTER(AgpSvgpParams), C.c_double, C.c_int64, C.c_int32]),
     "agp_svgp_reduce_buffer": (C.c_int32, [_vp, C.POINTER(_vp), C.POINTER(C.c_int64)]),

@@ -16,7 +16,7 @@
 
 namespace agp {
 
-constexpr int SM_THREADS = 1024;
+constexpr int SM_THREADS = 512;  // 128 registers per thread: the ~35 array pointers of the workspace stay in registers
 constexpr int SM_MAXM = 128;
 constexpr int SM_TILE = 256;  // points per pass
 
@@ -34,12 +34,18 @@ struct SmallArgs {
   double* ws;          // device workspace (small_ws_doubles)
   int want_grad;
   int ldb;             // min(count, SM_TILE) rounded up to 32
-  int smem_doubles;    // dynamic shared memory given to the kernel, in doubles
 };
 
 __host__ __device__ inline int64_t small_ws_doubles(int M, int D) {
   const int64_t MM = (int64_t)M * M, MB = (int64_t)M * SM_TILE;
-  return (int64_t)M * D * 5 + 9 * (int64_t)M + 11 * MM + (int64_t)SM_TILE * (D + 8) + 5 * MB + 64 + 2 * MAXD + 128;  // (+ rounding of each array to 2)
+  return (int64_t)M * D * 5 + 9 * (int64_t)M + 11 * MM + (int64_t)SM_TILE * (D + 8) + 6 * MB + 64 + 2 * MAXD + 128;  // (+ rounding of each array to 2)
+}
+
+// exact footprint for a given tile row length (the kernel's `take` sequence)
+__host__ __device__ inline int64_t small_doubles_exact(int M, int D, int ldb) {
+  auto r2 = [](int64_t n) { return (n + 1) & ~(int64_t)1; };
+  const int64_t MM = (int64_t)M * M, MB = (int64_t)M * ldb, MD = (int64_t)M * D;
+  return 5 * r2(MD) + 9 * r2(M) + 11 * r2(MM) + 6 * r2(MB) + r2((int64_t)ldb * D) + 3 * r2(ldb) + r2(64 + 2 * MAXD);
 }
 
 // deterministic block reduction of one value per thread (all threads must call); result broadcast to every thread
@@ -60,6 +66,19 @@ __device__ __forceinline__ double sm_block_sum(double v, double* sred /* >= 33 *
   return sred[32];
 }
 
+// development aid (-DAGP_SMALL_TIMING, tools/c1_phases.py): %globaltimer at the phase boundaries, returned behind the status words
+#ifdef AGP_SMALL_TIMING
+#define SM_TICK(k)                                                                    \
+  if (threadIdx.x == 0) {                                                             \
+    unsigned long long t_;                                                            \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                            \
+    a.out[3 + (4 + a.n_scale + (int64_t)a.M * a.D + a.M + (int64_t)a.M * a.M) + (k)] = (double)t_; \
+  }
+#else
+#define SM_TICK(k)
+#endif
+
+template <bool ALLSMEM>
 __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) {
   __shared__ double sred[40];
   __shared__ double s_scale[MAXD];
@@ -68,29 +87,22 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
   const int tid = threadIdx.x, nt = blockDim.x;
   const int M = a.M, D = a.D, ns = a.n_scale, kind = a.kind;
   const bool centered = a.centered != 0, linear = kind == AGP_KERNEL_LINEAR, direct = D == 1 && !linear;
-  const int64_t MM = (int64_t)M * M;
-  // ---- workspace carve-up: shared memory first (in order of access frequency), the global workspace for what does not fit ----
-  // A phase of this kernel is "read what the previous phase wrote, one FMA chain, write": with the operands in global memory
-  // every phase pays an L2 round trip (~1.5 us measured per phase); in shared memory it pays ~0.3 us.
+  const int MM = M * M;
+  // ---- workspace carve-up ------------------------------------------------------------------------------------------------------
+  // ALLSMEM: every array lives in shared memory (32-bit shared addresses: the ~35 array pointers cost one register each and a
+  // phase -- "read what the previous phase wrote, one FMA chain, write" -- pays a shared-memory round trip instead of an L1 / L2
+  // one); otherwise (M too large for 227 KB) every array lives in the global workspace.
   extern __shared__ __align__(16) double sm_pool[];
-  double* w = a.ws;
-  int64_t sm_left = a.smem_doubles, sm_used = 0;
-  auto take = [&](int64_t n) -> double* {
-    n = (n + 1) & ~(int64_t)1;
-    if (n <= sm_left) {
-      double* p = sm_pool + sm_used;
-      sm_used += n;
-      sm_left -= n;
-      return p;
-    }
+  double* w = ALLSMEM ? sm_pool : a.ws;
+  auto take = [&](int n) -> double* {
     double* p = w;
-    w += n;
+    w += (n + 1) & ~1;
     return p;
   };
   const int LDB = a.ldb;  // row length of the per-point matrices: the tile size rounded up to 32
-  const int64_t MB = (int64_t)M * LDB;
+  const int MB = M * LDB;
   // vectors and the factorisation's operands first
-  double* zs = take((int64_t)M * D);  // scaled Z
+  double* zs = take(M * D);  // scaled Z
   double* zn = take(M);
   double* mt = take(M);   // whitened mean
   double* ipiv = take(M);  // 1 / Lk_jj
@@ -100,6 +112,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
   double* Bt = take(MM);
   double* A = take(MB);    // per-point matrices [i][n], n contiguous (ld = LDB)
   double* Cm = take(MB);
+  double* At = take(MB);   // A transposed, [n][i] (ld = M): the reduction over the points of G / g runs with i contiguous
   double* Kuf = take(MB);
   double* G = take(MM);
   double* W2 = take(MM);
@@ -110,14 +123,14 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
   double* Ab = take(MB);
   double* DK = take(MB);
   double* Lq = take(MM);
-  double* xs = take((int64_t)LDB * D);  // scaled points of the tile [n][D]
+  double* xs = take(LDB * D);  // scaled points of the tile [n][D]
   double* xn = take(LDB);
   double* pdmu = take(LDB);
   double* pdv = take(LDB);
-  double* zr = take((int64_t)M * D);  // raw Z
-  double* dZ = take((int64_t)M * D);
-  double* wx = take((int64_t)M * D);  // kernel-gradient partial sums (kgrad_kernel's wx / wxx)
-  double* wxx = take((int64_t)M * D);
+  double* zr = take(M * D);  // raw Z
+  double* dZ = take(M * D);
+  double* wx = take(M * D);  // kernel-gradient partial sums (kgrad_kernel's wx / wxx)
+  double* wxx = take(M * D);
   double* mv = take(M);   // m
   double* g = take(M);
   double* rs = take(M);
@@ -127,9 +140,10 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
   double* acc = take(64 + 2 * MAXD);  // scalar accumulators: [0] E [1] dmu [2] dkxx [3] ds2 [4] dc [8..8+D) ds_lin [8+MAXD .. ) theta
   const double* f = a.flat;
   const double* fZ = f + 4 + ns;
-  const double* fm = fZ + (int64_t)M * D;
+  const double* fm = fZ + M * D;
   const double* fLq = fm + M;
 
+  SM_TICK(0)
   // ---- P0: parameters ------------------------------------------------------------------------------------------------
   if (tid == 0) {
     s_par[0] = f[0];
@@ -141,7 +155,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
   }
   if (tid < D) s_scale[tid] = f[1 + (ns == 1 ? 0 : tid)];
   for (int i = tid; i < 64 + 2 * MAXD; i += nt) acc[i] = 0.0;
-  for (int64_t i = tid; i < (int64_t)M * D; i += nt) {
+  for (int i = tid; i < M * D; i += nt) {
     zr[i] = fZ[i];
     dZ[i] = wx[i] = wxx[i] = 0.0;
   }
@@ -149,7 +163,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
     mv[i] = fm[i];
     g[i] = rs[i] = dvr[i] = dcc[i] = 0.0;
   }
-  for (int64_t i = tid; i < MM; i += nt) {
+  for (int i = tid; i < MM; i += nt) {
     const int r = (int)(i % M), c = (int)(i / M);
     Lq[i] = (r >= c) ? fLq[i] : 0.0;  // LowerTriangular(A) view, utils.jl:18
     G[i] = 0.0;
@@ -161,16 +175,17 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
   for (int i = tid; i < M; i += nt) {
     double nrm = 0.0;
     for (int d = 0; d < D; d++) {
-      const double v = zr[(int64_t)i * D + d] * s_scale[d];
-      zs[(int64_t)i * D + d] = v;
+      const double v = zr[i * D + d] * s_scale[d];
+      zs[i * D + d] = v;
       nrm = fma(v, v, nrm);
     }
     zn[i] = nrm;
-    if (!(Lq[i + (int64_t)i * M] > 0.0)) atomicExch(&s_status[0], AGP_ERR_DOMAIN);  // logdet(q.Sigma) would throw
+    if (!(Lq[i + i * M] > 0.0)) atomicExch(&s_status[0], AGP_ERR_DOMAIN);  // logdet(q.Sigma) would throw
   }
   __syncthreads();
+  SM_TICK(1)
   // ---- P1: Kuu (lower triangle; build_kuu_kernel's operation order) ------------------------------------------------------
-  for (int64_t i = tid; i < MM; i += nt) {
+  for (int i = tid; i < MM; i += nt) {
     const int r = (int)(i % M), c = (int)(i / M);
     double v = 0.0;
     if (r >= c) {
@@ -181,7 +196,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
         u = df * df;
       } else {
         double dot = 0.0;
-        for (int d = 0; d < D; d++) dot = fma(zs[(int64_t)c * D + d], zs[(int64_t)r * D + d], dot);  // lo = c, hi = r
+        for (int d = 0; d < D; d++) dot = fma(zs[c * D + d], zs[r * D + d], dot);  // lo = c, hi = r
         u = u_from_dot(kind, zn[c], zn[r], dot);
       }
       v = variance * kappa(kind, u, lin_c);
@@ -190,16 +205,17 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
     Lk[i] = v;
   }
   __syncthreads();
+  SM_TICK(2)
   // ---- P2 + P3: Cholesky and the inverse of the factor in one right-looking sweep, ONE barrier per column ------------------
   // Unscaled (LDL^T-style) columns: with d_j the pivot, L[i][j] = K(j)[i][j] / sqrt(d_j) is only formed at the end, so that a
   // step reads column j and writes columns > j (no intra-step hazard):   K[i][k] -= K[i][j] K[k][j] / d_j   (i >= k > j).
   // The forward substitution L X = I rides along: residual rows Y (= I at the start), Y[i][c] -= K[i][j] Y[j][c] / d_j for
   // i > j, c <= j; X[j][c] = Y[j][c] / sqrt(d_j).
   double* Y = W1;
-  for (int64_t i = tid; i < MM; i += nt) Y[i] = ((i % M) == (i / M)) ? 1.0 : 0.0;
+  for (int i = tid; i < MM; i += nt) Y[i] = ((i % M) == (i / M)) ? 1.0 : 0.0;
   __syncthreads();
   for (int j = 0; j < M; j++) {
-    const double d = Lk[j + (int64_t)j * M];
+    const double d = Lk[j + j * M];
     if (!(d > 0.0)) {
       if (tid == 0 && s_status[0] == 0) {
         s_status[0] = AGP_ERR_NOT_PD;
@@ -207,17 +223,24 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
       }
       break;  // uniform: every thread reads the same d
     }
-    const double invd = 1.0 / d;
-    if (tid == 0) ipiv[j] = 1.0 / sqrt(d);
-    const int rem = M - 1 - j;  // rows / columns below / right of the pivot
-    const int nk = rem * rem, ny = rem * (j + 1);
-    for (int e = tid; e < nk + ny; e += nt) {
-      if (e < nk) {
-        const int i = j + 1 + e % rem, k = j + 1 + e / rem;
-        if (i >= k) Lk[i + (int64_t)k * M] = fma(-Lk[i + (int64_t)j * M] * invd, Lk[k + (int64_t)j * M], Lk[i + (int64_t)k * M]);
-      } else {
-        const int q = e - nk, i = j + 1 + q % rem, c = q / rem;
-        Y[i + (int64_t)c * M] = fma(-Lk[i + (int64_t)j * M] * invd, Y[j + (int64_t)c * M], Y[i + (int64_t)c * M]);
+    const double invd = __drcp_rn(d);
+    if (tid == 0) ipiv[j] = rsqrt(d);
+    // one warp per column (columns j+1 .. M-1 of the trailing matrix, then columns 0 .. j of Y), lanes over the rows
+    {
+      const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+      const double* colj = Lk + j * M;
+      for (int c = warp; c < M; c += nw) {
+        if (c < M - 1 - j) {
+          const int k = j + 1 + c;
+          const double f = colj[k] * invd;
+          double* col = Lk + k * M;
+          for (int i = k + lane; i < M; i += 32) col[i] = fma(-colj[i], f, col[i]);
+        } else {
+          const int cy = c - (M - 1 - j);  // 0 .. j
+          double* col = Y + cy * M;
+          const double f = col[j] * invd;
+          for (int i = j + 1 + lane; i < M; i += 32) col[i] = fma(-colj[i], f, col[i]);
+        }
       }
     }
     __syncthreads();
@@ -225,13 +248,13 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
   __syncthreads();
   if (s_status[0] != 0) {
     if (tid == 0) {
-      const int64_t nflat = 4 + ns + (int64_t)M * D + M + MM;
+      const int nflat = 4 + ns + M * D + M + MM;
       a.out[1 + nflat] = (double)s_status[0];
       a.out[2 + nflat] = (double)s_status[1];
     }
     return;
   }
-  for (int64_t e = tid; e < MM; e += nt) {
+  for (int e = tid; e < MM; e += nt) {
     const int i = (int)(e % M), j = (int)(e / M);
     double l = 0.0, x = 0.0;
     if (i >= j) {
@@ -239,39 +262,41 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
       x = Y[e] * ipiv[i];
     }
     Li[e] = x;
-    LiT[j + (int64_t)i * M] = x;
-    LkT[j + (int64_t)i * M] = l;
+    LiT[j + i * M] = x;
+    LkT[j + i * M] = l;
     W2[e] = l;  // (Lk itself is rewritten after the barrier: other threads still read the unscaled column entries above)
   }
   __syncthreads();
-  for (int64_t e = tid; e < MM; e += nt) Lk[e] = W2[e];
+  for (int e = tid; e < MM; e += nt) Lk[e] = W2[e];
   __syncthreads();
+  SM_TICK(3)
   // ---- P4: whitened variables ---------------------------------------------------------------------------------------------
   if (!centered) {
     for (int i = tid; i < M; i += nt) mt[i] = mv[i];
-    for (int64_t i = tid; i < MM; i += nt) Bt[i] = Lq[i];
+    for (int i = tid; i < MM; i += nt) Bt[i] = Lq[i];
   } else {
     for (int i = tid; i < M; i += nt) {
       double s = 0.0;
-      for (int k = 0; k <= i; k++) s = fma(Li[i + (int64_t)k * M], mv[k] - mean_const, s);
+      for (int k = 0; k <= i; k++) s = fma(Li[i + k * M], mv[k] - mean_const, s);
       mt[i] = s;
     }
-    for (int64_t e = tid; e < MM; e += nt) {
+    for (int e = tid; e < MM; e += nt) {
       const int i = (int)(e % M), j = (int)(e / M);
       double s = 0.0;
-      for (int k = j; k <= i; k++) s = fma(Li[i + (int64_t)k * M], Lq[k + (int64_t)j * M], s);
+      for (int k = j; k <= i; k++) s = fma(Li[i + k * M], Lq[k + j * M], s);
       Bt[e] = s;
     }
   }
   __syncthreads();
 
+  SM_TICK(4)
   // ---- P5: the points, SM_TILE at a time -------------------------------------------------------------------------------------
   for (int t0 = 0; t0 < a.count; t0 += SM_TILE) {
     const int nb = min(SM_TILE, a.count - t0);
     for (int n = tid; n < nb; n += nt) {
       double nrm = 0.0;
       for (int d = 0; d < D; d++) {
-        const double v = a.X[(int64_t)(t0 + n) * D + d] * s_scale[d];
+        const double v = a.X[(t0 + n) * D + d] * s_scale[d];
         xs[n * D + d] = v;
         nrm = fma(v, v, nrm);
       }
@@ -286,7 +311,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
         u = df * df;
       } else {
         double dot = 0.0;
-        for (int d = 0; d < D; d++) dot = fma(zs[(int64_t)l * D + d], xs[n * D + d], dot);
+        for (int d = 0; d < D; d++) dot = fma(zs[l * D + d], xs[n * D + d], dot);
         u = u_from_dot(kind, xn[n], zn[l], dot);
       }
       double k, dk;
@@ -298,17 +323,19 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
     for (int e = tid; e < M * nb; e += nt) {  // A = Li Kuf
       const int i = e / nb, n = e % nb;
       double s = 0.0;
-      for (int j = 0; j <= i; j++) s = fma(Li[i + (int64_t)j * M], Kuf[j * LDB + n], s);
+      for (int j = 0; j <= i; j++) s = fma(Li[i + j * M], Kuf[j * LDB + n], s);
       A[i * LDB + n] = s;
+      At[n * M + i] = s;
     }
     __syncthreads();
     for (int e = tid; e < M * nb; e += nt) {  // C = Bt^T A
       const int j = e / nb, n = e % nb;
       double s = 0.0;
-      for (int i = j; i < M; i++) s = fma(Bt[i + (int64_t)j * M], A[i * LDB + n], s);
+      for (int i = j; i < M; i++) s = fma(Bt[i + j * M], A[i * LDB + n], s);
       Cm[j * LDB + n] = s;
     }
     __syncthreads();
+    SM_TICK(5)
     // marginals + expected log-likelihood, one point per thread (all threads take part in the reductions)
     {
       double E = 0.0, dmu = 0.0, dvar = 0.0, ds2 = 0.0, kf = 0.0;
@@ -333,6 +360,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
         pdv[n] = dvar;
       }
       // (SM_TILE <= blockDim.x: every point of the tile has its own thread)
+      static_assert(SM_TILE <= SM_THREADS, "one thread per point of a tile");
       const double r0 = sm_block_sum(E, sred), r1 = sm_block_sum(dmu, sred), r2 = sm_block_sum(dvar * kf, sred), r3 = sm_block_sum(ds2, sred);
       const double r4 = linear ? sm_block_sum(dvar, sred) : 0.0;
       if (tid == 0) {
@@ -346,7 +374,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
         for (int d = 0; d < D; d++) {
           double t = 0.0;
           if (n < nb) {
-            const double x = a.X[(int64_t)(t0 + n) * D + d];
+            const double x = a.X[(t0 + n) * D + d];
             t = dvar * 2.0 * variance * s_scale[d] * x * x;
           }
           const double r = sm_block_sum(t, sred);
@@ -355,47 +383,46 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
       }
     }
     __syncthreads();
+    SM_TICK(6)
     if (!a.want_grad) continue;
     for (int e = tid; e < M * nb; e += nt) {  // Ab = dmu (x) mt + 2 dv (Bt C - A)
       const int i = e / nb, n = e % nb;
       double s = 0.0;
-      for (int j = 0; j <= i; j++) s = fma(Bt[i + (int64_t)j * M], Cm[j * LDB + n], s);
+      for (int j = 0; j <= i; j++) s = fma(Bt[i + j * M], Cm[j * LDB + n], s);
       Ab[i * LDB + n] = fma(pdmu[n], mt[i], 2.0 * pdv[n] * (s - A[i * LDB + n]));
     }
     __syncthreads();
     for (int e = tid; e < M * nb; e += nt) {  // Kb = Li^T Ab  (into Cm)
       const int j = e / nb, n = e % nb;
       double s = 0.0;
-      for (int i = j; i < M; i++) s = fma(Li[i + (int64_t)j * M], Ab[i * LDB + n], s);
+      for (int i = j; i < M; i++) s = fma(Li[i + j * M], Ab[i * LDB + n], s);
       Cm[j * LDB + n] = s;
     }
-    // G += (dv A) A^T (lower), g += A dmu: one warp per output, lanes over the points (coalesced rows of A), fixed-order
-    // shuffle tree -- independent of Kb, so no barrier is needed before
-    {
-      const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-      const int npair = M * (M + 1) / 2;
-      for (int p = warp; p < npair + M; p += nw) {
-        double v = 0.0;
-        int i = 0, j = 0;
-        if (p < npair) {
-          i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
-          while ((i + 1) * (i + 2) / 2 <= p) i++;
-          while (i * (i + 1) / 2 > p) i--;
-          j = p - i * (i + 1) / 2;
-          for (int n = lane; n < nb; n += 32) v = fma(pdv[n] * A[i * LDB + n], A[j * LDB + n], v);
-        } else {
-          i = p - npair;
-          for (int n = lane; n < nb; n += 32) v = fma(pdmu[n], A[i * LDB + n], v);
+    SM_TICK(7)
+    // G += (dv A) A^T (lower), g += A dmu: one thread per output, i contiguous across the threads (rows of the transposed copy);
+    // independent of Kb, so no barrier is needed before
+    for (int e = tid; e < MM + M; e += nt) {
+      if (e < MM) {
+        const int i = e % M, j = e / M;
+        if (i >= j) {
+          double s0 = 0.0, s1 = 0.0;
+          int n = 0;
+          for (; n + 1 < nb; n += 2) {
+            s0 = fma(pdv[n] * At[n * M + i], At[n * M + j], s0);
+            s1 = fma(pdv[n + 1] * At[(n + 1) * M + i], At[(n + 1) * M + j], s1);
+          }
+          if (n < nb) s0 = fma(pdv[n] * At[n * M + i], At[n * M + j], s0);
+          G[e] += s0 + s1;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) {
-          if (p < npair) G[i + (int64_t)j * M] += v;
-          else g[i] += v;
-        }
+      } else {
+        const int i = e - MM;
+        double s0 = 0.0;
+        for (int n = 0; n < nb; n++) s0 = fma(pdmu[n], At[n * M + i], s0);
+        g[i] += s0;
       }
     }
     __syncthreads();
+    SM_TICK(8)
     // kernel-gradient partial sums of this tile (kgrad_kernel's quantities): W = Kb * variance * kappa'(u); one warp per (row, d)
     {
       const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
@@ -430,25 +457,26 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
             dvr[l] += v1 / variance;  // sum Kb kappa(u)
             dcc[l] += v2;
           } else {
-            wx[(int64_t)l * D + q] += v0;
-            wxx[(int64_t)l * D + q] += v1;
+            wx[l * D + q] += v0;
+            wxx[l * D + q] += v1;
           }
         }
       }
     }
     __syncthreads();
   }
-  const int64_t nflat = 4 + ns + (int64_t)M * D + M + MM;
+  const int nflat = 4 + ns + M * D + M + MM;
   double* out = a.out;
+  SM_TICK(9)
   // ---- KL ---------------------------------------------------------------------------------------------------------------
   double kl;
   {
     double tr = 0.0, mm = 0.0, ldq = 0.0, ldk = 0.0;
-    for (int64_t i = tid; i < MM; i += nt) tr = fma(Bt[i], Bt[i], tr);
+    for (int i = tid; i < MM; i += nt) tr = fma(Bt[i], Bt[i], tr);
     for (int j = tid; j < M; j += nt) {
       mm = fma(mt[j], mt[j], mm);
-      ldq += log(Lq[j + (int64_t)j * M]);
-      if (centered) ldk += log(Lk[j + (int64_t)j * M]);
+      ldq += log(Lq[j + j * M]);
+      if (centered) ldk += log(Lk[j + j * M]);
     }
     const double s0 = sm_block_sum(tr, sred), s1 = sm_block_sum(mm, sred), s2 = sm_block_sum(ldq, sred), s3 = sm_block_sum(ldk, sred);
     kl = 0.5 * (s0 + s1 - (double)M) + s3 - s2;
@@ -461,6 +489,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
     }
     return;
   }
+  SM_TICK(10)
   // ---- P6: replicated epilogue (agp_svgp_finish) -----------------------------------------------------------------------------
   // data part of dZ / theta from the accumulated partial sums (kgrad_finish_kernel, zfac = 1)
   double* theta = acc + 8 + MAXD;  // [0] dvariance [1] dc [2 + d] ds_d
@@ -478,52 +507,53 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
     for (int d = 0; d < D; d++) {
       double v = 0.0;
       for (int l = tid; l < M; l += nt) {
-        const double z = zs[(int64_t)l * D + d], sx = wx[(int64_t)l * D + d], sxx = wxx[(int64_t)l * D + d];
+        const double z = zs[l * D + d], sx = wx[l * D + d], sxx = wxx[l * D + d];
         v += linear ? z * sx : fma(z, fma(z, rs[l], -2.0 * sx), sxx);
       }
       const double r = sm_block_sum(v, sred);
       if (tid == 0) theta[2 + d] = (s_scale[d] != 0.0) ? 2.0 / s_scale[d] * r : 0.0;
     }
-    for (int64_t i = tid; i < (int64_t)M * D; i += nt) {
+    for (int i = tid; i < M * D; i += nt) {
       const int l = (int)(i / D), d = (int)(i % D);
       const double sd = s_scale[d];
       dZ[i] = linear ? sd * wx[i] : 2.0 * sd * (zs[i] * rs[l] - wx[i]);
     }
   }
   __syncthreads();
+  SM_TICK(11)
   // G: lower -> symmetric
-  for (int64_t e = tid; e < MM; e += nt) {
+  for (int e = tid; e < MM; e += nt) {
     const int i = (int)(e % M), j = (int)(e / M);
-    if (i < j) G[e] = G[j + (int64_t)i * M];
+    if (i < j) G[e] = G[j + i * M];
   }
   __syncthreads();
   // W1 = P1 = Bt Bt^T - I
-  for (int64_t e = tid; e < MM; e += nt) {
+  for (int e = tid; e < MM; e += nt) {
     const int i = (int)(e % M), j = (int)(e / M);
     double s = (i == j) ? -1.0 : 0.0;
     const int kmax = min(i, j);
-    for (int k = 0; k <= kmax; k++) s = fma(Bt[i + (int64_t)k * M], Bt[j + (int64_t)k * M], s);
+    for (int k = 0; k <= kmax; k++) s = fma(Bt[i + k * M], Bt[j + k * M], s);
     W1[e] = s;
   }
   __syncthreads();
   // W2 = Asum = mt g^T + 2 P1 G ;  W3 = Bt-bar = tril(2 G Bt) [- Bt]
-  for (int64_t e = tid; e < MM; e += nt) {
+  for (int e = tid; e < MM; e += nt) {
     const int i = (int)(e % M), j = (int)(e / M);
     double s = 0.0, t = 0.0;
-    for (int k = 0; k < M; k++) s = fma(W1[i + (int64_t)k * M], G[k + (int64_t)j * M], s);
+    for (int k = 0; k < M; k++) s = fma(W1[i + k * M], G[k + j * M], s);
     W2[e] = fma(mt[i], g[j], 2.0 * s);
     if (i >= j) {
-      for (int k = j; k < M; k++) t = fma(G[i + (int64_t)k * M], Bt[k + (int64_t)j * M], t);
+      for (int k = j; k < M; k++) t = fma(G[i + k * M], Bt[k + j * M], t);
       t = 2.0 * t - (centered ? Bt[e] : 0.0);
     }
     W3[e] = t;
   }
   __syncthreads();
   // W4 = V = Li^T Asum
-  for (int64_t e = tid; e < MM; e += nt) {
+  for (int e = tid; e < MM; e += nt) {
     const int i = (int)(e % M), j = (int)(e / M);
     double s = 0.0;
-    for (int k = i; k < M; k++) s = fma(LiT[i + (int64_t)k * M], W2[k + (int64_t)j * M], s);
+    for (int k = i; k < M; k++) s = fma(LiT[i + k * M], W2[k + j * M], s);
     W4[e] = s;
   }
   double summbar = 0.0;
@@ -531,7 +561,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
     // mbar = Li^T (g - mt)
     for (int i = tid; i < M; i += nt) {
       double s = 0.0;
-      for (int k = i; k < M; k++) s = fma(LiT[i + (int64_t)k * M], g[k] - mt[k], s);
+      for (int k = i; k < M; k++) s = fma(LiT[i + k * M], g[k] - mt[k], s);
       mbar[i] = s;
     }
     __syncthreads();
@@ -539,27 +569,28 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
     for (int i = tid; i < M; i += nt) v += mbar[i];
     summbar = sm_block_sum(v, sred);
     // W1 = Y = Li^T Bt-bar  (P1 is no longer needed: Asum has been formed)
-    for (int64_t e = tid; e < MM; e += nt) {
+    for (int e = tid; e < MM; e += nt) {
       const int i = (int)(e % M), j = (int)(e / M);
       double s = 0.0;
-      for (int k = max(i, j); k < M; k++) s = fma(LiT[i + (int64_t)k * M], W3[k + (int64_t)j * M], s);
+      for (int k = max(i, j); k < M; k++) s = fma(LiT[i + k * M], W3[k + j * M], s);
       W1[e] = s;
     }
     __syncthreads();
     // W2 = X2 = Y Bt^T + mbar mt^T   (Asum is no longer needed: V has been formed)
-    for (int64_t e = tid; e < MM; e += nt) {
+    for (int e = tid; e < MM; e += nt) {
       const int i = (int)(e % M), j = (int)(e / M);
       double s = mbar[i] * mt[j];
-      for (int k = 0; k <= j; k++) s = fma(W1[i + (int64_t)k * M], Bt[j + (int64_t)k * M], s);
+      for (int k = 0; k <= j; k++) s = fma(W1[i + k * M], Bt[j + k * M], s);
       W2[e] = s;
     }
   }
   __syncthreads();
+  SM_TICK(12)
   // dLq, dm, scalars: everything that does not depend on the Cholesky pullback
   {
     const double* src = centered ? W1 : W3;
-    double* oLq = out + 1 + 4 + ns + (int64_t)M * D + M;
-    for (int64_t e = tid; e < MM; e += nt) {
+    double* oLq = out + 1 + 4 + ns + M * D + M;
+    for (int e = tid; e < MM; e += nt) {
       const int r = (int)(e % M), c = (int)(e / M);
       double v = 0.0;
       if (r >= c) {
@@ -568,11 +599,11 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
       }
       oLq[e] = v;
     }
-    double* om = out + 1 + 4 + ns + (int64_t)M * D;
+    double* om = out + 1 + 4 + ns + M * D;
     for (int i = tid; i < M; i += nt) om[i] = centered ? mbar[i] : g[i] - mv[i];
   }
   // G <- Lbar = -tril(V) [- tril(X2) - diag(1 / Lk_jj)]     (G is no longer needed)
-  for (int64_t e = tid; e < MM; e += nt) {
+  for (int e = tid; e < MM; e += nt) {
     const int r = (int)(e % M), c = (int)(e / M);
     double v = 0.0;
     if (r >= c) {
@@ -586,39 +617,40 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
   }
   __syncthreads();
   // W3 = Phi(Lk^T Lbar): lower, diagonal halved
-  for (int64_t e = tid; e < MM; e += nt) {
+  for (int e = tid; e < MM; e += nt) {
     const int i = (int)(e % M), j = (int)(e / M);
     double s = 0.0;
     if (i >= j) {
-      for (int k = i; k < M; k++) s = fma(LkT[i + (int64_t)k * M], G[k + (int64_t)j * M], s);
+      for (int k = i; k < M; k++) s = fma(LkT[i + k * M], G[k + j * M], s);
       if (i == j) s *= 0.5;
     }
     W3[e] = s;
   }
   __syncthreads();
   // W4 = Y1 = Li^T Phi ;  W2 = Y2 = Li^T Y1^T ;  G = Kuu-bar = (Y2 + Y2^T) / 2
-  for (int64_t e = tid; e < MM; e += nt) {
+  for (int e = tid; e < MM; e += nt) {
     const int i = (int)(e % M), j = (int)(e / M);
     double s = 0.0;
-    for (int k = max(i, j); k < M; k++) s = fma(LiT[i + (int64_t)k * M], W3[k + (int64_t)j * M], s);
+    for (int k = max(i, j); k < M; k++) s = fma(LiT[i + k * M], W3[k + j * M], s);
     W4[e] = s;
   }
   __syncthreads();
-  for (int64_t e = tid; e < MM; e += nt) {
+  for (int e = tid; e < MM; e += nt) {
     const int i = (int)(e % M), j = (int)(e / M);
     double s = 0.0;
-    for (int k = i; k < M; k++) s = fma(LiT[i + (int64_t)k * M], W4[j + (int64_t)k * M], s);  // Y1^T[k][j] = Y1[j][k]
+    for (int k = i; k < M; k++) s = fma(LiT[i + k * M], W4[j + k * M], s);  // Y1^T[k][j] = Y1[j][k]
     W2[e] = s;
   }
   __syncthreads();
-  for (int64_t e = tid; e < MM; e += nt) {
+  for (int e = tid; e < MM; e += nt) {
     const int i = (int)(e % M), j = (int)(e / M);
-    G[e] = 0.5 * (W2[e] + W2[j + (int64_t)i * M]);
+    G[e] = 0.5 * (W2[e] + W2[j + i * M]);
   }
   __syncthreads();
+  SM_TICK(13)
   // Kuu part of dZ / theta: contraction of Kuu-bar with the derivatives of k(z_l, z_n); both arguments move -> zfac = 2.
   // W3 = Kuu-bar .* variance kappa'(u), W4 = kappa(u) (both symmetric), then the same per-row sums as for the data part.
-  for (int64_t e = tid; e < MM; e += nt) {
+  for (int e = tid; e < MM; e += nt) {
     const int l = (int)(e % M), n = (int)(e / M);
     double u;
     if (direct) {
@@ -627,7 +659,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
     } else {
       double dot = 0.0;
       const int lo = min(l, n), hi = max(l, n);
-      for (int d = 0; d < D; d++) dot = fma(zs[(int64_t)lo * D + d], zs[(int64_t)hi * D + d], dot);
+      for (int d = 0; d < D; d++) dot = fma(zs[lo * D + d], zs[hi * D + d], dot);
       u = u_from_dot(kind, zn[lo], zn[hi], dot);
     }
     double k, dk;
@@ -643,15 +675,15 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
       double v0 = 0.0, v1 = 0.0, v2 = 0.0;
       if (q == D) {
         for (int n = lane; n < M; n += 32) {
-          const double kb = G[n + (int64_t)l * M];
-          v0 += W3[n + (int64_t)l * M];
-          v1 = fma(kb, W4[n + (int64_t)l * M], v1);
+          const double kb = G[n + l * M];
+          v0 += W3[n + l * M];
+          v1 = fma(kb, W4[n + l * M], v1);
           v2 += kb;
         }
       } else {
         for (int n = lane; n < M; n += 32) {
-          const double x = zs[(int64_t)n * D + q];
-          const double wxd = W3[n + (int64_t)l * M] * x;
+          const double x = zs[n * D + q];
+          const double wxd = W3[n + l * M] * x;
           v0 += wxd;
           v1 = fma(wxd, x, v1);
         }
@@ -668,8 +700,8 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
           dvr[l] = v1;
           dcc[l] = v2;
         } else {
-          wx[(int64_t)l * D + q] = v0;
-          wxx[(int64_t)l * D + q] = v1;
+          wx[l * D + q] = v0;
+          wxx[l * D + q] = v1;
         }
       }
     }
@@ -689,22 +721,23 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
     for (int d = 0; d < D; d++) {
       double v = 0.0;
       for (int l = tid; l < M; l += nt) {
-        const double z = zs[(int64_t)l * D + d], sx = wx[(int64_t)l * D + d], sxx = wxx[(int64_t)l * D + d];
+        const double z = zs[l * D + d], sx = wx[l * D + d], sxx = wxx[l * D + d];
         v += linear ? z * sx : fma(z, fma(z, rs[l], -2.0 * sx), sxx);
       }
       const double r = sm_block_sum(v, sred);
       if (tid == 0) theta[2 + d] += (s_scale[d] != 0.0) ? 2.0 / s_scale[d] * r : 0.0;
     }
-    for (int64_t i = tid; i < (int64_t)M * D; i += nt) {
+    for (int i = tid; i < M * D; i += nt) {
       const int l = (int)(i / D), d = (int)(i % D);
       const double sd = s_scale[d];
       dZ[i] += 2.0 * (linear ? sd * wx[i] : 2.0 * sd * (zs[i] * rs[l] - wx[i]));
     }
   }
   __syncthreads();
+  SM_TICK(14)
   {
     double* oZ = out + 1 + 4 + ns;
-    for (int64_t i = tid; i < (int64_t)M * D; i += nt) oZ[i] = dZ[i];
+    for (int i = tid; i < M * D; i += nt) oZ[i] = dZ[i];
     if (tid == 0) {
       out[0] = acc[0] * a.scale - kl;
       out[1 + 0] = theta[0] + acc[2];                 // dvariance
@@ -722,6 +755,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
       out[2 + nflat] = 0.0;
     }
   }
+  SM_TICK(15)
 }
 
 }  // namespace agp

@@ -36,12 +36,6 @@ constexpr int KM_FROM_N = 1;   // [tile_n * TN, K)          the N-side operand i
 constexpr int KM_UPTO_N = 2;   // [0, (tile_n + 1) * TN)    ...                                                       k <= n
 constexpr int KM_SPLIT = 3;    // [z * kchunk, min(K, (z + 1) * kchunk)), z = blockIdx.z
 
-struct Args {
-  int K;
-  int kmode;
-  int kchunk;
-  int lower_only;  // 1: skip tiles with tile_n > tile_m (symmetric output)
-};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -98,12 +92,26 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128-byte swizzle, version 1
-//   K-major  tile [rows][32 floats]: rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (1)
-//   MN-major tile: 4 boxes of [32 k][32 floats of m / n]: LBO = 4096 B between the 32-wide m / n groups, SBO = 1024 B between 8-k groups
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
-  const uint64_t lbo = mn_major ? (4096 >> 4) : 1, sbo = 1024 >> 4;
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), version 1
+//   K-major  tile [rows][32 floats], 128-byte swizzle (layout type 2): rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (1)
+//   MN-major tile: 4 boxes of [32 k][32 floats of m / n].  For 32-bit operands the only MN-major layout the tensor core accepts is
+//            the 128-byte swizzle with a 32-byte atom (layout type 1, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; CUTLASS
+//            Layout_MN_SW128_32B_Atom): swizzle atoms of 4 k-rows x 128 B, so SBO = 512 B between the 4-k groups and
+//            LBO = 4096 B between the 32-wide m / n groups (one TMA box each)
+struct MnDesc {
+  uint32_t lbo16 = 4096 >> 4, sbo16 = 512 >> 4, layout = 1;
+};
+struct Args {
+  int K;
+  int kmode;
+  int kchunk;
+  int lower_only;  // 1: skip tiles with tile_n > tile_m (symmetric output)
+  MnDesc mn;       // descriptor fields of MN-major operands (fixed; a parameter only so that tools/tf32x3_test.cu can probe them)
+};
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major, const MnDesc& mn) {
+  const uint64_t lbo = mn_major ? mn.lbo16 : 1, sbo = mn_major ? mn.sbo16 : (1024 >> 4), lt = mn_major ? mn.layout : 2;
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (lt << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, M = 128, N = 128, dense, no negate
 __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
@@ -198,8 +206,8 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
         const uint32_t st = base + s * STAGE_BYTES;
 #pragma unroll
         for (int k = 0; k < TK / UK; k++) {
-          const uint64_t ah = make_desc(st + k * a_step, AMN), al = make_desc(st + TILE_BYTES + k * a_step, AMN);
-          const uint64_t bh = make_desc(st + 2 * TILE_BYTES + k * b_step, BMN), bl = make_desc(st + 3 * TILE_BYTES + k * b_step, BMN);
+          const uint64_t ah = make_desc(st + k * a_step, AMN, g.mn), al = make_desc(st + TILE_BYTES + k * a_step, AMN, g.mn);
+          const uint64_t bh = make_desc(st + 2 * TILE_BYTES + k * b_step, BMN, g.mn), bl = make_desc(st + 3 * TILE_BYTES + k * b_step, BMN, g.mn);
           tc_mma_tf32(tmem_d, al, bh, idesc, (i | k) != 0);  // the small terms first
           tc_mma_tf32(tmem_d, ah, bl, idesc, 1);
           tc_mma_tf32(tmem_d, ah, bh, idesc, 1);
@@ -252,15 +260,16 @@ inline EncodeTiledFn encode_tiled_fn() {
 }
 // FP32 matrix with `inner` contiguous elements per row and `outer` rows (row pitch `ld` elements); a box is 32 inner elements
 // (128 bytes, the swizzle width) x box_outer rows.  K-major operand: inner = k, box_outer = 128.  MN-major: inner = m / n, 32.
-inline bool make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
+inline bool make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer, bool mn_major = false) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {ld * sizeof(float)};
   cuuint32_t box[2] = {32, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // x -> (tf32(x), tf32(x - tf32(x))): both parts exactly representable in TF32 (round to nearest), so the tensor core's truncation

@@ -204,6 +204,8 @@ int32_t agp_svgp_stepper_flat_size(agp_svgp_stepper* s, int64_t* n_doubles);
 int32_t agp_svgp_stepper_eval(agp_svgp_stepper* s, agp_dataset* ds, int64_t offset, int64_t count, const double* flat,
                               double num_data, int64_t global_batch, double* elbo_out, double* flat_grad);
 int32_t agp_svgp_stepper_counts(agp_svgp_stepper* s, int64_t* n_small, int64_t* n_large);
+/* development aid: 16 phase time stamps (ns) of the last one-launch evaluation; zeros unless the library was built with -DAGP_SMALL_TIMING */
+int32_t agp_svgp_stepper_phase_ticks(agp_svgp_stepper* s, double* ticks16);
 int32_t agp_svgp_stepper_destroy(agp_svgp_stepper* s);
 
 /* Split-phase form of agp_svgp_elbo_grad for hosts that own the collective (torch.distributed,
