@@ -462,10 +462,21 @@ class DeviceData:
 # ---------------------------------------------------------------------------------------------
 
 
+def _compute_dtype(dtype) -> int:
+    """None / "f64" / np.float64 -> AGP_COMPUTE_F64; "f32" / np.float32 -> AGP_COMPUTE_F32 (the Float32 fast mode)."""
+    if dtype is None or dtype in ("f64", "float64", np.float64):
+        return L.COMPUTE_F64
+    if dtype in ("f32", "float32", np.float32):
+        return L.COMPUTE_F32
+    if dtype in ("f32_tc_solve",):
+        return L.COMPUTE_F32_TC_SOLVE
+    raise ValueError(f"ArgumentError: unsupported compute dtype {dtype!r}")
+
+
 class _Packed:
     """Keeps the numpy buffers alive next to the ctypes struct that points into them."""
 
-    def __init__(self, sva: SparseVariationalApproximation, lik=None, quadrature=None):
+    def __init__(self, sva: SparseVariationalApproximation, lik=None, quadrature=None, dtype=None):
         k = sva.fz.f.kernel
         Z = _points(sva.fz.x)
         M, D = Z.shape
@@ -497,6 +508,7 @@ class _Packed:
             p.expect = L.AgpExpectation(L.EXPECT_MONTE_CARLO, int(q.n_samples), None, None, int(q.seed))
         else:
             raise ValueError(f"unsupported expectation method {q!r}")
+        p.compute_dtype = _compute_dtype(dtype)
         self.p, self.M, self.D = p, M, D
 
 
@@ -547,14 +559,16 @@ def _dataset_for(fx: FiniteGP, y, ctx: Context):
     return DeviceData(fx.x, y, ctx=ctx), True
 
 
-def elbo(sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx: Context | None = None, offset=0, count=None, global_batch=0) -> float:
+def elbo(sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx: Context | None = None, offset=0, count=None, global_batch=0, dtype=None) -> float:
     """``AbstractGPs.elbo(sva, fx | lfx, y; num_data, quadrature)`` -- SVA.jl:307-360.
 
     ``offset`` / ``count`` select a minibatch view of a device-resident data set.  With a communicator attached to ``ctx``
     (``attach_communicator``) every rank passes its own shard and ``global_batch`` = the number of points over all ranks; the
-    partial sums are all-reduced once inside the library and every rank returns the same value."""
+    partial sums are all-reduced once inside the library and every rank returns the same value.  ``dtype="f32"`` selects the Float32
+    fast mode (what a Float32 GP is in the type-generic reference): the GEMM-shaped sweep stages run as 3xTF32 split products on
+    the tcgen05 tensor cores, parity target 1e-4 against the Float64 result."""
     fx, lik = _resolve_lik(sva, l_fx)  # argument errors first: they never cross the ABI
-    pk = _Packed(sva, lik, quadrature)
+    pk = _Packed(sva, lik, quadrature, dtype)
     ctx = ctx or default_context()
     ds, own = _dataset_for(fx, y, ctx)
     try:
@@ -567,10 +581,10 @@ def elbo(sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx: Context | No
             ds.close()
 
 
-def elbo_and_gradient(sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx: Context | None = None, offset=0, count=None, global_batch=0):
+def elbo_and_gradient(sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx: Context | None = None, offset=0, count=None, global_batch=0, dtype=None):
     """Value and gradient of ``elbo``: the forward + pullback of the new ``ChainRulesCore.rrule`` (same keywords as ``elbo``)."""
     fx, lik = _resolve_lik(sva, l_fx)
-    pk = _Packed(sva, lik, quadrature)
+    pk = _Packed(sva, lik, quadrature, dtype)
     ctx = ctx or default_context()
     ds, own = _dataset_for(fx, y, ctx)
     try:

@@ -16,6 +16,7 @@
 
 #include "../../include/agp.h"
 #include "dense.cuh"
+#include "f32sweep.cuh"
 #include "gemm.cuh"
 #include "kfun.cuh"
 #include "laplace.cuh"
@@ -106,6 +107,8 @@ static int32_t load_nccl() {
 struct SvgpState {
   bool valid = false;
   bool sweep_pending = false;  // agp_svgp_sweep has filled the reduce buffer and agp_svgp_finish has not consumed it yet
+  bool f32 = false;            // params.compute_dtype != AGP_COMPUTE_F64: S2 / S4 / S6 on the tcgen05 3xTF32 path (f32sweep.cuh)
+  bool f32_tc_solve = false;   // AGP_COMPUTE_F32_TC_SOLVE: the reverse-pass solve S5 as a 3xTF32 product with the explicit inverse as well
   int M = 0, Mp = 0, D = 0, nb = 0;
   int n_scale = 1;
   bool centered = false;
@@ -119,9 +122,9 @@ struct SvgpState {
 
 // Optional per-kernel-class timing with CUDA events on the context's stream (agp_ctx_profile*):
 // this is how bench.py measures the launch durations behind its roofline figures.
-enum { PC_TRSM_FWD = 0, PC_GEMM_BTA, PC_PERPOINT, PC_GEMM_BC, PC_TRSM_BWD, PC_SYRK, PC_KGRAD, PC_PREPARE, PC_FINISH, PC_ALLREDUCE, PC_LAPLACE, PC_COUNT };
+enum { PC_TRSM_FWD = 0, PC_GEMM_BTA, PC_PERPOINT, PC_GEMM_BC, PC_TRSM_BWD, PC_SYRK, PC_KGRAD, PC_PREPARE, PC_FINISH, PC_ALLREDUCE, PC_LAPLACE, PC_F32_AUX, PC_COUNT };
 static const char* const kProfNames[PC_COUNT] = {"trsm_kuf_fwd", "gemm_BtA", "perpoint", "gemm_BC", "trsm_bwd", "syrk_G", "kgrad",
-                                                 "prepare_step", "finish_epilogue", "allreduce", "laplace"};
+                                                 "prepare_step", "finish_epilogue", "allreduce", "laplace", "f32_planes_gvec"};
 struct ProfRec {
   int cls;
   cudaEvent_t a, b;
@@ -161,6 +164,8 @@ struct agp_ctx {
   DevBuf A, C, Ab, As, saa, sam, scc_part, dmu, dv, sc_part;
   // accumulators
   DevBuf gpart, Gpart, kpart, red, small, ghbuf;
+  // Float32 mode: hi | lo FP32 planes (each DevBuf holds both: 2 x count floats = count doubles)
+  DevBuf fA, fC, fAb, fAs, fBtc, fBtr, fLi;
   int* d_flags = nullptr;  // [0] potrf info, [1] domain flag
   SvgpState st;
   ncclComm_t comm = nullptr;
@@ -234,7 +239,7 @@ extern "C" int32_t agp_ctx_destroy(agp_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   DevBuf* bufs[] = {&c->z, &c->zs, &c->zn, &c->zsp, &c->mvec, &c->mt, &c->Lq, &c->Kw, &c->Lk, &c->Lt, &c->Ut, &c->Bt_cm, &c->Bt_rm,
                     &c->W1, &c->W2, &c->W3, &c->W4, &c->vec64, &c->vec64b, &c->A, &c->C, &c->Ab, &c->As, &c->saa, &c->sam,
-                    &c->scc_part, &c->dmu, &c->dv, &c->sc_part, &c->gpart, &c->Gpart, &c->kpart, &c->red, &c->small, &c->ghbuf,
+                    &c->scc_part, &c->dmu, &c->dv, &c->sc_part, &c->gpart, &c->Gpart, &c->kpart, &c->red, &c->small, &c->ghbuf, &c->fA, &c->fC, &c->fAb, &c->fAs, &c->fBtc, &c->fBtr, &c->fLi,
                     &c->mu_out, &c->var_out, &c->px1, &c->px2, &c->pxs1, &c->pxn1, &c->pxs2, &c->pxn2, &c->pcov};
   for (DevBuf* b : bufs) b->release();
   lap_release(c);
@@ -740,6 +745,10 @@ __global__ void build_Lbar_kernel(const double* V, const double* X2, const doubl
   out[(int64_t)r * Mp + cidx] = v;
 }
 
+__global__ void set_diag_kernel(double* A, int n, int64_t ld, double v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) A[(int64_t)i * ld + i] = v;
+}
 __global__ void axpby_kernel(double a, const double* x, double b, const double* y, double* out, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = a * x[i] + (y ? b * y[i] : 0.0);
@@ -791,6 +800,9 @@ static int32_t resolve_params(const agp_svgp_params* p, SvgpState& st) {
   st.kp.variance = p->kernel.variance;
   st.kp.c = p->kernel.linear_c;
   for (int d = 0; d < p->D; d++) st.kp.s[d] = p->kernel.inv_lengthscale[p->kernel.n_scale == 1 ? 0 : d];
+  if (p->compute_dtype < AGP_COMPUTE_F64 || p->compute_dtype > AGP_COMPUTE_F32_TC_SOLVE) return fail(AGP_ERR_INVALID, "unknown compute_dtype %d", p->compute_dtype);
+  st.f32 = p->compute_dtype != AGP_COMPUTE_F64;
+  st.f32_tc_solve = p->compute_dtype == AGP_COMPUTE_F32_TC_SOLVE;
   st.lp.kind = p->lik.kind;
   st.lp.sigma2 = p->lik.sigma2;
   int method = p->expect.method;
@@ -817,6 +829,45 @@ static int32_t resolve_params(const agp_svgp_params* p, SvgpState& st) {
   }
   if (p->lik.kind == AGP_LIK_GAUSSIAN && !(p->lik.sigma2 > 0)) return fail(AGP_ERR_INVALID, "GaussianLikelihood needs sigma2 > 0");
   if (p->lik.kind == AGP_LIK_GAMMA_EXP && !(p->lik.sigma2 > 0)) return fail(AGP_ERR_INVALID, "GammaLikelihood needs alpha > 0");
+  return AGP_OK;
+}
+
+// Float32 mode: hi / lo planes of the once-per-step operands of the tcgen05 stages -- Bt (column-major memory = the [j][l] operand of
+// S2, row-major memory = the [i][j] operand of S4) and the explicit inverse Linv = Lk^-1 (a block TRSM on the identity, as the Laplace
+// pullback builds B^-1), transposed to the [j][i] operand of S5.
+static int32_t prepare_f32_operands(agp_ctx* c) {
+  SvgpState& st = c->st;
+  const int Mp = st.Mp, nb = st.nb;
+  const int64_t MM = (int64_t)Mp * Mp;
+  if (!t5::encode_tiled_fn()) return fail(AGP_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver (Float32 mode needs TMA tensor maps)");
+  DevBuf* planes[] = {&c->fBtc, &c->fBtr, &c->fLi};
+  for (DevBuf* b : planes) OK(b->ensure(MM));
+  OK(c->W1.ensure(MM));
+  OK(c->W2.ensure(MM));
+  auto split = [&](const double* in, DevBuf& out) -> int32_t {
+    float* hi = reinterpret_cast<float*>(out.p);
+    t5::split_planes_kernel<<<1024, 256, 0, c->stream>>>(in, hi, hi + MM, MM);
+    LAUNCHED(c);
+    KCHECK();
+    return AGP_OK;
+  };
+  OK(split(c->Bt_cm.p, c->fBtc));
+  OK(split(c->Bt_rm.p, c->fBtr));
+  // W1 (row-major) = I, W1 <- Lk^-1 W1, W2 = W1^T
+  OK(fill(c, c->W1.p, MM, 0.0));
+  set_diag_kernel<<<(Mp + 255) / 256, 256, 0, c->stream>>>(c->W1.p, Mp, Mp, 1.0);
+  LAUNCHED(c);
+  KCHECK();
+  TrsmArgs a{};
+  a.T = c->Lt.p;
+  a.ldt = Mp;
+  a.nb = nb;
+  a.X = c->W1.p;
+  a.ldx = Mp;
+  a.kp = st.kp;
+  OK(launch_trsm<TR_RHS_FWD>(c, a, Mp / BN));
+  OK(transpose(c, c->W1.p, c->W2.p, Mp, Mp));
+  OK(split(c->W2.p, c->fLi));
   return AGP_OK;
 }
 
@@ -901,6 +952,7 @@ static int32_t prepare_step(agp_ctx* c, const agp_svgp_params* p) {
     OK(launch_trsm<TR_RHS_FWD>(c, a, Mp / BN));
     OK(transpose(c, c->Bt_rm.p, c->Bt_cm.p, Mp, Mp));
   }
+  if (st.f32) OK(prepare_f32_operands(c));
   st.valid = true;
   return AGP_OK;
 }
@@ -955,7 +1007,7 @@ static int64_t pick_chunk_cols(agp_ctx* c, int64_t count) {
   const int64_t by_mem = (int64_t)8e9 / (4 * 8 * std::max(c->st.Mp, BM)) / wave;
   int64_t cap = std::min<int64_t>(8, std::max<int64_t>(2, by_mem)) * wave;
   if (const char* e = getenv("AGP_CHUNK_COLS")) cap = std::max<int64_t>(BN, round_up(atoll(e), BN));
-  return std::min<int64_t>(cap, round_up(std::max<int64_t>(count, 1), BN));
+  return std::min<int64_t>(cap, round_up(std::max<int64_t>(count, 1), 2 * BN));  // multiples of 128: the tcgen05 stages tile the points by 128
 }
 
 static int32_t ensure_sweep_workspace(agp_ctx* c, int64_t cols, bool grad) {
@@ -968,11 +1020,19 @@ static int32_t ensure_sweep_workspace(agp_ctx* c, int64_t cols, bool grad) {
   OK(c->C.ensure((int64_t)Mp * cc));
   OK(c->saa.ensure(cc));
   OK(c->sam.ensure(cc));
-  OK(c->scc_part.ensure((int64_t)nb * cc));
+  OK(c->scc_part.ensure((int64_t)2 * nb * cc));  // (Float32 mode: one partial per 64-column half of a 128-column tile)
   OK(c->dmu.ensure(cc));
   OK(c->dv.ensure(cc));
   OK(c->sc_part.ensure((cc / 256 + 2) * NSC));
   OK(c->red.ensure(RedLayout(Mp, D).total));
+  if (st.f32) {
+    OK(c->fA.ensure((int64_t)Mp * cc));
+    OK(c->fC.ensure((int64_t)Mp * cc));
+    if (grad) {
+      OK(c->fAb.ensure((int64_t)Mp * cc));
+      OK(c->fAs.ensure((int64_t)Mp * cc));
+    }
+  }
   if (grad) {
     OK(c->Ab.ensure((int64_t)Mp * cc));
     OK(c->As.ensure((int64_t)Mp * cc));
@@ -1056,6 +1116,22 @@ static int32_t finish_kgrad(agp_ctx* c, int nslab, double zfac, double* dZ, doub
   return AGP_OK;
 }
 
+// One tcgen05 3xTF32 GEMM launch (tf32x3.cuh).  Operand planes: hi at p, lo at p + plane; K-major operand = [rows][inner = k],
+// MN-major operand = [k rows][inner = m / n].
+template <bool AMN, bool BMN, class Epi>
+static int32_t launch_t5(agp_ctx* c, dim3 grid, const float* A, int64_t planeA, uint64_t innerA, uint64_t outerA, const float* B, int64_t planeB,
+                         uint64_t innerB, uint64_t outerB, const t5::Args& g, const Epi& epi) {
+  CUtensorMap mah, mal, mbh, mbl;
+  const bool ok = t5::make_map(&mah, A, innerA, outerA, innerA, AMN ? 32 : 128, AMN) && t5::make_map(&mal, A + planeA, innerA, outerA, innerA, AMN ? 32 : 128, AMN) &&
+                  t5::make_map(&mbh, B, innerB, outerB, innerB, BMN ? 32 : 128, BMN) && t5::make_map(&mbl, B + planeB, innerB, outerB, innerB, BMN ? 32 : 128, BMN);
+  if (!ok) return fail(AGP_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  OK((ensure_smem<t5::tf32x3_gemm_kernel<AMN, BMN, Epi>>(c, t5::SMEM_BYTES)));
+  t5::tf32x3_gemm_kernel<AMN, BMN, Epi><<<grid, t5::T5_THREADS, t5::SMEM_BYTES, c->stream>>>(mah, mal, mbh, mbl, g, epi);
+  LAUNCHED(c);
+  KCHECK();
+  return AGP_OK;
+}
+
 // forward (+ backward) sweep over points [offset, offset+count) of ds.  predict != 0: only S1-S3 writing mu/var.
 static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_t count, bool grad, bool predict, double* mu_out,
                             double* var_out) {
@@ -1076,7 +1152,7 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
   }
   for (int64_t lo = 0; lo < count; lo += cols) {
     const int npts = (int)std::min<int64_t>(cols, count - lo);
-    const int ncols = (int)round_up(npts, BN);
+    const int ncols = (int)round_up(npts, st.f32 ? 2 * BN : BN);  // Float32 mode: the tcgen05 stages tile the points by 128
     const int tiles_n = ncols / BN;
     const double* pts = X + lo * D;
     // S1: A = Lk^-1 Kuf
@@ -1097,11 +1173,32 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
       ProfScope ps(c, PC_TRSM_FWD);
       OK(launch_trsm<TR_KUF_FWD>(c, t1, tiles_n));
     }
+    // Float32 mode: point-major hi / lo planes of A, then C = A Bt on the tcgen05 path (f32sweep.cuh)
+    const int64_t plane = (int64_t)Mp * ldc;  // floats per plane
+    float* fA = reinterpret_cast<float*>(c->fA.p);
+    float* fC = reinterpret_cast<float*>(c->fC.p);
+    float* fAb = reinterpret_cast<float*>(c->fAb.p);
+    float* fAs = reinterpret_cast<float*>(c->fAs.p);
+    const int64_t MMf = (int64_t)Mp * Mp;
+    const dim3 grid5(ncols / t5::TM, Mp / t5::TN, 1);
+    if (st.f32) {
+      {
+        ProfScope ps(c, PC_F32_AUX);
+        t5::transpose_split_kernel<<<dim3(ncols / 32, Mp / 32), 256, 0, c->stream>>>(c->A.p, ldc, Mp, ncols, fA, fA + plane, Mp);
+        LAUNCHED(c);
+        KCHECK();
+      }
+      ProfScope ps(c, PC_GEMM_BTA);
+      t5::EpiF2 e2{fC, fC + plane, Mp, c->scc_part.p, ldc};
+      t5::Args g{Mp, t5::KM_FROM_N, 0, 0, t5::MnDesc()};
+      OK((launch_t5<false, false>(c, grid5, fA, plane, Mp, ncols, reinterpret_cast<float*>(c->fBtc.p), MMf, Mp, Mp, g, e2)));
+    } else {
     // S2: C = Bt^T A  (A operand (m=j, k=l) = Bt[l][j] = Bt_rm[l*Mp + j]; nonzero for l >= j)
     EpiS2 e2{c->C.p, ldc, c->scc_part.p, ldc};
     {
       ProfScope ps(c, PC_GEMM_BTA);
       OK((run_gemm<A_KM, B_KN>(c, nb, tiles_n, c->Bt_rm.p, Mp, c->A.p, ldc, Mp, KR_UPPER, TS_ALL, e2)));
+    }
     }
     // S3: per-point stage
     PerPointArgs pp{};
@@ -1109,7 +1206,7 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
     pp.sam = c->sam.p;
     pp.scc_part = c->scc_part.p;
     pp.ldp = ldc;
-    pp.nb = nb;
+    pp.nb = st.f32 ? 2 * nb : nb;
     pp.pts = pts;
     pp.y = y ? y + lo : nullptr;
     pp.npts = npts;
@@ -1139,6 +1236,52 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
       KCHECK();
     }
     if (!grad) continue;
+    if (st.f32) {
+      const bool s5t = st.f32_tc_solve;
+      {
+        ProfScope ps(c, PC_GEMM_BC);
+        t5::Args g{Mp, t5::KM_UPTO_N, 0, 0, t5::MnDesc()};
+        if (s5t) {
+          t5::EpiF4<true> e4{fA, fA + plane, fAb, fAb + plane, fAs, fAs + plane, Mp, c->dmu.p, c->dv.p, c->mt.p, c->Ab.p, ldc};
+          OK((launch_t5<false, false>(c, grid5, fC, plane, Mp, ncols, reinterpret_cast<float*>(c->fBtr.p), MMf, Mp, Mp, g, e4)));
+        } else {
+          t5::EpiF4<false> e4{fA, fA + plane, fAb, fAb + plane, fAs, fAs + plane, Mp, c->dmu.p, c->dv.p, c->mt.p, c->Ab.p, ldc};
+          OK((launch_t5<false, false>(c, grid5, fC, plane, Mp, ncols, reinterpret_cast<float*>(c->fBtr.p), MMf, Mp, Mp, g, e4)));
+        }
+      }
+      if (s5t) {
+        ProfScope ps(c, PC_TRSM_BWD);
+        t5::EpiF5 e5{c->Ab.p, ldc};
+        t5::Args g{Mp, t5::KM_FROM_N, 0, 0, t5::MnDesc()};
+        OK((launch_t5<false, false>(c, grid5, fAb, plane, Mp, ncols, reinterpret_cast<float*>(c->fLi.p), MMf, Mp, Mp, g, e5)));
+      } else {
+        // Kb = Lk^-T Ab stays the FP64 triangular solve, in place on the FP64 inducing-major matrix the S4 epilogue wrote
+        TrsmArgs t5a{};
+        t5a.T = c->Ut.p;
+        t5a.ldt = Mp;
+        t5a.nb = nb;
+        t5a.X = c->Ab.p;
+        t5a.ldx = ldc;
+        t5a.kp = st.kp;
+        ProfScope ps(c, PC_TRSM_BWD);
+        OK(launch_trsm<TR_RHS_BWD>(c, t5a, tiles_n));
+      }
+      {
+        ProfScope ps(c, PC_SYRK);
+        const int kchunk = (int)round_up((ncols + c->nsplit - 1) / c->nsplit, t5::TM);
+        const int nz = (ncols + kchunk - 1) / kchunk;
+        t5::EpiF6 e6{c->Gpart.p, Mp};
+        t5::Args g{ncols, t5::KM_SPLIT, kchunk, 1, t5::MnDesc()};
+        OK((launch_t5<true, true>(c, dim3(Mp / t5::TM, Mp / t5::TN, nz), fAs, plane, Mp, ncols, fA, plane, Mp, ncols, g, e6)));
+      }
+      {
+        ProfScope ps(c, PC_F32_AUX);
+        const int slab = 512, nslab = (ncols + slab - 1) / slab;
+        t5::gvec_kernel<<<dim3((Mp / 4 + 255) / 256, nslab), 256, 0, c->stream>>>(fA, fA + plane, Mp, Mp, c->dmu.p, ncols, slab, c->gpart.p, Mp);
+        LAUNCHED(c);
+        KCHECK();
+      }
+    } else {
     // S4: Ab = dmu (x) mt + 2 dv (Bt C - A), As = dv A, g partial   (A operand (m=j,k=l) = Bt[j][l], l <= j)
     EpiS4 e4{c->A.p, c->Ab.p, c->As.p, ldc, c->dmu.p, c->dv.p, c->mt.p, c->gpart.p, Mp};
     {
@@ -1146,16 +1289,16 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
       OK((run_gemm<A_KM, B_KN>(c, nb, tiles_n, c->Bt_cm.p, Mp, c->C.p, ldc, Mp, KR_LOWER, TS_ALL, e4)));
     }
     // S5: Kb = Lk^-T Ab (in place)
-    TrsmArgs t5{};
-    t5.T = c->Ut.p;
-    t5.ldt = Mp;
-    t5.nb = nb;
-    t5.X = c->Ab.p;
-    t5.ldx = ldc;
-    t5.kp = st.kp;
+    TrsmArgs t5a{};
+    t5a.T = c->Ut.p;
+    t5a.ldt = Mp;
+    t5a.nb = nb;
+    t5a.X = c->Ab.p;
+    t5a.ldx = ldc;
+    t5a.kp = st.kp;
     {
       ProfScope ps(c, PC_TRSM_BWD);
-      OK(launch_trsm<TR_RHS_BWD>(c, t5, tiles_n));
+      OK(launch_trsm<TR_RHS_BWD>(c, t5a, tiles_n));
     }
     // S6: G += As A^T
     {
@@ -1174,6 +1317,7 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
       syrk_kernel<<<grid, NTHREADS, Cfg::smem_bytes, c->stream>>>(s);
       LAUNCHED(c);
       KCHECK();
+    }
     }
     // S7: contraction of Kb with the kernel derivatives
     {

@@ -5,8 +5,11 @@
 // i.e. an FP32-accurate product (22 mantissa bits per operand, FP32 accumulation) at a third of the TF32 rate -- still ~10x the
 // FP64 DMMA rate that bounds the reference-precision path.  One CTA computes one 128 x 128 output tile:
 //   warp 0      TMA producer: cp.async.bulk.tensor (128-byte swizzle) of the four operand tiles of a k-block into a 3-stage ring
-//   warp 1      allocates TMEM, issues tcgen05.mma.kind::tf32 (one elected thread), commits stages back to the producer
-//   warps 2..5  epilogue: tcgen05.ld of the accumulator (one TMEM lane = one output row per thread), functor, global stores
+//   warp 1      allocates TMEM (two 128-column buffers), issues tcgen05.mma.kind::tf32 (one elected thread) in groups of 64 k,
+//               alternating the buffers, commits stages back to the producer and groups to the epilogue
+//   warps 2..9  epilogue: tcgen05.ld of each finished group (one TMEM lane = one output row, 64 columns per thread), summed over
+//               the groups in FP64 registers (the tensor core's FP32 accumulator rounds toward zero: without this carry a k = 1024
+//               product has a systematic relative bias of 1e-5); then the functor and the global stores
 // Operands are read in place from the hi / lo FP32 planes the producing kernels write; both K-major (k contiguous) and MN-major
 // (m / n contiguous) operands are supported, so that one point-major copy of every intermediate serves all four sweep stages
 // (DESIGN.md section 8).  SASS: UTCHMMA-class tensor instructions, LDTM, UTMALDG.
@@ -27,7 +30,9 @@ constexpr int UK = 8;        // k of one tcgen05.mma.kind::tf32
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = TM * TK * 4;        // 16 KB: one operand plane of one stage
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // Ah | Al | Bh | Bl
-constexpr int T5_THREADS = 192;
+constexpr int EPI_WARPS = 8;      // two per TMEM lane quarter, 64 accumulator columns each
+constexpr int T5_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int GROUP_KB = 2;       // k-blocks per accumulation group (64 k = 24 accumulator updates), then carried over in FP64
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 
 // k-range of an output tile
@@ -92,6 +97,18 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, "
+      "%22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+        "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+        "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), version 1
 //   K-major  tile [rows][32 floats], 128-byte swizzle (layout type 2): rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (1)
 //   MN-major tile: 4 boxes of [32 k][32 floats of m / n].  For 32-bit operands the only MN-major layout the tensor core accepts is
@@ -118,9 +135,10 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
-// Epi: __device__ void operator()(int tile_m, int tile_n, int z, int row, int c0, const float (&v)[32]) const
-//      called by the thread that owns output row `row` (0..127 of the tile) for the column chunks c0 = 0, 32, 64, 96 in order;
-//      `begin(tile_m, tile_n, z, row)` / `end(...)` bracket the four calls (per-row reductions).
+// Epi: struct State (per-thread registers);  begin(State&, tile_m, tile_n, z, row, half);  end(State&, ..., half);
+//      operator()(State&, tile_m, tile_n, z, row, c0, const double (&v)[32]) -- a thread owns output row `row` (0..127 of the tile)
+//      and the column half `half` (0: columns 0..63, 1: 64..127); it is called for c0 = 64 half and 64 half + 32, bracketed by
+//      begin / end (per-row reductions: two partial results per row, one per half).
 template <bool AMN, bool BMN, class Epi>
 __global__ void __launch_bounds__(T5_THREADS, 1)
 tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl, const __grid_constant__ CUtensorMap mBh,
@@ -135,14 +153,16 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
     kb = z * g.kchunk;
     ke = min(g.K, kb + g.kchunk);
   }
-  const int nk = (ke - kb + TK - 1) / TK;
+  const int nk = (ke - kb + TK - 1) / TK;          // k-blocks of 32
+  const int ngroups = (nk + GROUP_KB - 1) / GROUP_KB;  // accumulation groups: one TMEM buffer each, carried over in FP64
 
   const uint32_t base = (smem_u32(t5_smem_raw) + 1023u) & ~1023u;  // the 128-byte swizzle pattern repeats every 1024 B
   const uint32_t bars = base + STAGES * STAGE_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bars + 8u * (2 * STAGES);
-  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 1);
+  auto tfull_bar = [&](int b) { return bars + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bars + 8u * (2 * STAGES + 2 + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(t5_smem_raw + (tmem_slot - smem_u32(t5_smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -151,11 +171,14 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
       mbar_init_u32(full_bar(s), 1);
       mbar_init_u32(empty_bar(s), 1);
     }
-    mbar_init_u32(tmem_full_bar, 1);
+    for (int b = 0; b < 2; b++) {
+      mbar_init_u32(tfull_bar(b), 1);
+      mbar_init_u32(tempty_bar(b), EPI_WARPS);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tmem_slot), "r"((uint32_t)TN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tmem_slot), "r"((uint32_t)(2 * TN)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   tc_fence_before();
@@ -196,53 +219,76 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0 && nk > 0) {
-      // ---- MMA issuer -------------------------------------------------------------------------------------------------
+      // ---- MMA issuer: group gi accumulates GROUP_KB k-blocks into TMEM buffer gi & 1, starting from zero ------------------
       constexpr uint32_t idesc = make_idesc(AMN, BMN);
       constexpr uint32_t a_step = AMN ? 1024 : UK * 4, b_step = BMN ? 1024 : UK * 4;  // bytes per k-step of 8
-      for (int i = 0; i < nk; i++) {
-        const int s = i % STAGES;
-        mbar_wait_u32(full_bar(s), (i / STAGES) & 1);
-        tc_fence_after();
-        const uint32_t st = base + s * STAGE_BYTES;
-#pragma unroll
-        for (int k = 0; k < TK / UK; k++) {
-          const uint64_t ah = make_desc(st + k * a_step, AMN, g.mn), al = make_desc(st + TILE_BYTES + k * a_step, AMN, g.mn);
-          const uint64_t bh = make_desc(st + 2 * TILE_BYTES + k * b_step, BMN, g.mn), bl = make_desc(st + 3 * TILE_BYTES + k * b_step, BMN, g.mn);
-          tc_mma_tf32(tmem_d, al, bh, idesc, (i | k) != 0);  // the small terms first
-          tc_mma_tf32(tmem_d, ah, bl, idesc, 1);
-          tc_mma_tf32(tmem_d, ah, bh, idesc, 1);
+      int i = 0;
+      for (int gi = 0; gi < ngroups; gi++) {
+        const int buf = gi & 1;
+        if (gi >= 2) {  // the epilogue warps have drained this buffer's previous group
+          mbar_wait_u32(tempty_bar(buf), ((gi >> 1) - 1) & 1);
+          tc_fence_after();
         }
-        tc_commit(empty_bar(s));  // the stage may be refilled once these MMAs have read it
+        const uint32_t dcol = tmem_d + (uint32_t)(buf * TN);
+        const int iend = min(nk, i + GROUP_KB);
+        for (bool first = true; i < iend; i++) {
+          const int s = i % STAGES;
+          mbar_wait_u32(full_bar(s), (i / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t st = base + s * STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < TK / UK; k++) {
+            const uint64_t ah = make_desc(st + k * a_step, AMN, g.mn), al = make_desc(st + TILE_BYTES + k * a_step, AMN, g.mn);
+            const uint64_t bh = make_desc(st + 2 * TILE_BYTES + k * b_step, BMN, g.mn), bl = make_desc(st + 3 * TILE_BYTES + k * b_step, BMN, g.mn);
+            tc_mma_tf32(dcol, al, bh, idesc, first ? 0u : 1u);  // the small terms first
+            tc_mma_tf32(dcol, ah, bl, idesc, 1);
+            tc_mma_tf32(dcol, ah, bh, idesc, 1);
+            first = false;
+          }
+          tc_commit(empty_bar(s));  // the stage may be refilled once these MMAs have read it
+        }
+        tc_commit(tfull_bar(buf));  // this group's partial sums are complete
       }
-      tc_commit(tmem_full_bar);
     }
   } else {
-    // ---- epilogue: warp w may only touch TMEM lanes 32 (w % 4) .. 32 (w % 4) + 31 ----------------------------------------
-    const int quarter = warp & 3;
+    // ---- epilogue: warp w may only touch TMEM lanes 32 (w % 4) .. 32 (w % 4) + 31; two warps share a lane quarter, 64 columns each.
+    // The FP32 accumulator of the tensor core rounds toward zero on every update (a relative bias of ~6e-8 per update, 1e-5 over
+    // the 384 updates of a k = 1024 product: measured as a systematic -1e-5 on |c|^2, i.e. on the marginal variances).  So a TMEM
+    // buffer only ever holds GROUP_KB * 12 updates; the groups are summed here in FP64 registers.
+    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
     const int row = quarter * 32 + lane;
-    float v[32];
-    if (nk > 0) {
-      mbar_wait_u32(tmem_full_bar, 0);
-      tc_fence_after();
-    }
-    epi.begin(tile_m, tile_n, z, row);
-#pragma unroll 1
-    for (int c0 = 0; c0 < TN; c0 += 32) {
-      if (nk > 0) {
-        tc_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-      } else {
+    double acc[64];
 #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = 0.f;
+    for (int j = 0; j < 64; j++) acc[j] = 0.0;
+    for (int gi = 0; gi < ngroups; gi++) {
+      const int buf = gi & 1;
+      mbar_wait_u32(tfull_bar(buf), (gi >> 1) & 1);
+      tc_fence_after();
+      float v0[32], v1[32];
+      const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TN + half * 64);
+      tc_ld32_nowait(taddr, v0);
+      tc_ld32_nowait(taddr + 32, v1);
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(tempty_bar(buf)) : "memory");
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        acc[j] += (double)v0[j];
+        acc[32 + j] += (double)v1[j];
       }
-      epi(tile_m, tile_n, z, row, c0, v);
     }
-    epi.end(tile_m, tile_n, z, row);
+    typename Epi::State st;
+    epi.begin(st, tile_m, tile_n, z, row, half);
+    epi(st, tile_m, tile_n, z, row, half * 64, *reinterpret_cast<const double(*)[32]>(acc));
+    epi(st, tile_m, tile_n, z, row, half * 64 + 32, *reinterpret_cast<const double(*)[32]>(acc + 32));
+    epi.end(st, tile_m, tile_n, z, row, half);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"((uint32_t)TN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"((uint32_t)(2 * TN)) : "memory");
   }
 }
 
@@ -282,6 +328,15 @@ __device__ __forceinline__ void split_tf32(double x, float& hi, float& lo) {
   const float r = (float)(x - (double)hi);
   uint32_t l;
   asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(l) : "f"(r));
+  lo = __uint_as_float(l);
+}
+
+// the same for an FP32 value (the accumulator of a previous product)
+__device__ __forceinline__ void split_tf32f(float x, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(l) : "f"(x - hi));
   lo = __uint_as_float(l);
 }
 

@@ -469,7 +469,8 @@ def run_svgp(args, w):
     f = agp.GP(w["variance"] * agp.with_lengthscale(base, w["lengthscale"]))
     sva = agp.SparseVariationalApproximation(f(Z, w["jitter"]), agp.MvNormal(m, chol_lower=A))
     lik = {"gaussian": agp.GaussianLikelihood(0.01), "bernoulli_logit": agp.BernoulliLikelihood(), "poisson_exp": agp.PoissonLikelihood()}[w["lik"]]
-    pk = agp.PackedParams(sva, lik, agp.GaussHermiteExpectation(20) if w["method"] == "gauss_hermite" else None)
+    pk = agp.PackedParams(sva, lik, agp.GaussHermiteExpectation(20) if w["method"] == "gauss_hermite" else None, args.dtype)
+    f32 = args.dtype != "f64"
     G, gb = grad_struct(L, M, D)
     out = C.c_double()
     num_data = float(w.get("num_data", N_total))
@@ -541,8 +542,8 @@ def run_svgp(args, w):
             correctness = {"what": f"rows [0,{n_check}) evaluated sharded over {world} ranks (one ncclAllReduce) vs by rank 0 alone, same C-ABI call",
                            "elbo_sharded": outs.value, "elbo_1rank": out1.value, "elbo_rel": abs(outs.value - out1.value) / abs(out1.value),
                            "grad_rel_to_max": errs, "grad_checksums_sharded": {k: float(np.sum(v)) for k, v in gs.items()},
-                           "grad_checksums_1rank": {k: float(np.sum(v)) for k, v in g1.items()}, "tol": 1e-12}
-            correctness["ok"] = bool(correctness["elbo_rel"] < 1e-12 and max(errs.values()) < 1e-12)
+                           "grad_checksums_1rank": {k: float(np.sum(v)) for k, v in g1.items()}, "tol": 1e-5 if f32 else 1e-12}
+            correctness["ok"] = bool(correctness["elbo_rel"] < correctness["tol"] and max(errs.values()) < correctness["tol"])
             ds1.close()
             ctx1.close()
         barrier()
@@ -596,8 +597,9 @@ def run_svgp(args, w):
                      "frac": pp_gbs / hbm_peak if pp_gbs else None,
                      "note": "two ~10 us launches per 151 552-point chunk (perpoint + fixed-order scalar reduce): launch-latency-bound, 0.1 % of the step; "
                              "the same kernel given one 1e7-point launch moves 5.0 TB/s (profiles/r02f_perpoint_standalone.jsonl)"}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f64",
+        line = {"metric": METRIC if not f32 else METRIC.replace("FP64", "Float32 fast mode: 3xTF32 tcgen05 stages, FP64 solve / reductions"), "value": value, "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": args.dtype,
                 "data": "synthetic" + (" (generated on the device)" if on_device else ""),
                 "config": svgp_config(w, N_total, world, n_local),
                 "elbo": val, "gpu_launches": launches, "clocks": clk, "roofline": roof, "per_point_stage": per_point, "kernels": kernels}
@@ -618,8 +620,8 @@ def run_svgp(args, w):
             errs = {"m": rel_to_max(gb["m"], rg.m), "Lq": rel_to_max(gb["Lq"], rg.Lq), "Z": rel_to_max(gb["Z"], rg.Z),
                     "variance": rel_to_max(gb["variance"], rg.kernel.variance), "inv_lengthscale": rel_to_max(gb["inv_lengthscale"], rg.kernel.inv_lengthscale)}
             line["correctness"] = {"what": f"CUDA path vs the CPU restatement on rows [0,{n_s}) (the cpu_baseline sample)", "elbo_cuda": out.value, "elbo_oracle": ref,
-                                   "elbo_rel": abs(out.value - ref) / abs(ref), "grad_rel_to_max": errs, "tol": 1e-10,
-                                   "ok": bool(abs(out.value - ref) / abs(ref) < 1e-10 and max(errs.values()) < 1e-10)}
+                                   "elbo_rel": abs(out.value - ref) / abs(ref), "grad_rel_to_max": errs, "tol": 1e-4 if f32 else 1e-10,
+                                   "ok": bool(abs(out.value - ref) / abs(ref) < (1e-4 if f32 else 1e-10) and max(errs.values()) < (1e-4 if f32 else 1e-10))}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -836,6 +838,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the N > 1 sharded-vs-single-rank correctness evaluation")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32", "f32_tc_solve"], help="f32: the Float32 fast mode (3xTF32 on tcgen05 for the GEMM-shaped sweep stages); "
+                                                                             "reported as its own line, never as the Float64 headline")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.n:

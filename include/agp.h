@@ -66,6 +66,15 @@ extern "C" {
 #define AGP_HOST 0
 #define AGP_DEVICE 1
 
+#define AGP_COMPUTE_F64 0 /* reference precision: every stage in Float64 (DMMA)                                   */
+#define AGP_COMPUTE_F32 1 /* "Float32 fast mode" (a Float32 GP in the reference, SVA.jl:59-62 is type-generic): the four
+                           * GEMM-shaped sweep stages run as 3xTF32 split products on the tcgen05 tensor path; Kuf + forward
+                           * solve, reverse-pass solve, per-point stage, reductions and the O(M^3) epilogue stay Float64; the
+                           * tensor-core partial sums are carried over in Float64 every 64 k.  Parity target 1e-4.          */
+#define AGP_COMPUTE_F32_TC_SOLVE 2 /* as AGP_COMPUTE_F32, with the reverse-pass solve Kb = Lk^-T Ab as a 3xTF32 product with the
+                           * explicit inverse too (1.2x faster again; its error on dZ / d theta grows with cond(Lk): 1.4e-4 at
+                           * the M = 1024 SqExponential twin of BASELINE config 4, below 1e-4 on the others)                */
+
 #define AGP_MAX_GH_POINTS 128
 #define AGP_MAX_D 32 /* compile-time bound of the device code (kfun.cuh MAXD): larger D is AGP_ERR_UNSUPPORTED */
 
@@ -113,6 +122,7 @@ typedef struct {
   int32_t parametrization;
   agp_likelihood lik;
   agp_expectation expect;
+  int32_t compute_dtype; /* AGP_COMPUTE_F64 (0, default) | AGP_COMPUTE_F32: arithmetic of elbo / elbo_grad; inputs and outputs stay Float64 */
 } agp_svgp_params;
 
 /* Gradient of the ELBO (unit cotangent); every pointer is a caller-allocated host buffer or NULL.

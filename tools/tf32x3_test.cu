@@ -13,14 +13,15 @@ __global__ void split_kernel(const double* in, float* hi, float* lo, int64_t n) 
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) split_tf32(in[i], hi[i], lo[i]);
 }
 struct EpiStoreF32 {
-  float* D;
+  double* D;
   int ld;
-  __device__ void begin(int, int, int, int) const {}
-  __device__ void end(int, int, int, int) const {}
-  __device__ void operator()(int tm, int tn, int z, int row, int c0, const float (&v)[32]) const {
-    float* d = D + (size_t)(tm * TM + row) * ld + tn * TN + c0;
+  struct State {};
+  __device__ void begin(State&, int, int, int, int, int) const {}
+  __device__ void end(State&, int, int, int, int, int) const {}
+  __device__ void operator()(State&, int tm, int tn, int z, int row, int c0, const double (&v)[32]) const {
+    double* d = D + (size_t)(tm * TM + row) * ld + tn * TN + c0;
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    for (int j = 0; j < 32; j += 2) *reinterpret_cast<double2*>(d + j) = make_double2(v[j], v[j + 1]);
   }
 };
 
@@ -53,7 +54,7 @@ static double run_case(const char* name, int M, int N, int K, int kmode, bool ti
   if (BMN) ok &= make_map(&mbh, pb.h, N, K, N, 32, atom32) && make_map(&mbl, pb.l, N, K, N, 32, atom32);
   else ok &= make_map(&mbh, pb.h, K, N, K, 128) && make_map(&mbl, pb.l, K, N, K, 128);
   if (!ok) { printf("%s: tensor map creation failed\n", name); return -1; }
-  float* D; CK(cudaMalloc(&D, (size_t)M * N * 4)); CK(cudaMemset(D, 0, (size_t)M * N * 4));
+  double* D; CK(cudaMalloc(&D, (size_t)M * N * 8)); CK(cudaMemset(D, 0, (size_t)M * N * 8));
   Args g{K, kmode, 0, 0, mn};
   EpiStoreF32 epi{D, N};
   auto kern = tf32x3_gemm_kernel<AMN, BMN, EpiStoreF32>;
@@ -62,9 +63,9 @@ static double run_case(const char* name, int M, int N, int K, int kmode, bool ti
   kern<<<grid, T5_THREADS, SMEM_BYTES>>>(mah, mal, mbh, mbl, g, epi);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
-  std::vector<float> Dh((size_t)M * N);
-  CK(cudaMemcpy(Dh.data(), D, Dh.size() * 4, cudaMemcpyDeviceToHost));
-  double maxerr = 0, maxref = 0;
+  std::vector<double> Dh((size_t)M * N);
+  CK(cudaMemcpy(Dh.data(), D, Dh.size() * 8, cudaMemcpyDeviceToHost));
+  double maxerr = 0, maxref = 0, bias = 0, cnt = 0;
   for (int m = 0; m < M; m += (timing ? 1237 : 1))  // (the large timing case is checked on a sample of rows)
     for (int n = 0; n < N; n++) {
       int kb = 0, ke = K;
@@ -73,9 +74,10 @@ static double run_case(const char* name, int M, int N, int K, int kmode, bool ti
       double s = 0;
       for (int k = kb; k < ke; k++) s += A[(size_t)m * K + k] * B[(size_t)n * K + k];
       maxerr = std::max(maxerr, std::fabs(s - (double)Dh[(size_t)m * N + n]));
+      bias += (std::fabs((double)Dh[(size_t)m * N + n]) - std::fabs(s)); cnt += std::fabs(s);
       maxref = std::max(maxref, std::fabs(s));
     }
-  printf("{\"case\": \"%s\", \"M\": %d, \"N\": %d, \"K\": %d, \"kmode\": %d, \"max_abs_err\": %.3e, \"max_ref\": %.3e, \"rel\": %.3e", name, M, N, K, kmode, maxerr, maxref, maxerr / maxref);
+  printf("{\"case\": \"%s\", \"M\": %d, \"N\": %d, \"K\": %d, \"kmode\": %d, \"max_abs_err\": %.3e, \"max_ref\": %.3e, \"rel\": %.3e, \"rel_bias_of_magnitude\": %.3e", name, M, N, K, kmode, maxerr, maxref, maxerr / maxref, bias / cnt);
   if (timing) {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int i = 0; i < 3; i++) kern<<<grid, T5_THREADS, SMEM_BYTES>>>(mah, mal, mbh, mbl, g, epi);
