@@ -118,6 +118,7 @@ SYMBOLS = {
     "agp_ctx_create": (C.c_int32, [C.c_int32, C.POINTER(_vp)]),
     "agp_ctx_destroy": (C.c_int32, [_vp]),
     "agp_last_error_string": (C.c_char_p, []),
+    "agp_last_error_info": (C.c_int32, []),
     "agp_build_arch": (C.c_int32, []),
     "agp_ctx_stream": (C.c_int32, [_vp, C.POINTER(_vp)]),
     "agp_ctx_launch_count": (C.c_int32, [_vp, C.POINTER(C.c_int64)]),
@@ -214,7 +215,9 @@ def check(status: int):
         return
     msg = load_library().agp_last_error_string().decode("utf-8", "replace")
     if status == ERR_NOT_PD:
-        raise PosDefException(status, msg)
+        e = PosDefException(status, msg)
+        e.info = int(load_library().agp_last_error_info())  # LinearAlgebra.PosDefException(info): the failing column
+        raise e
     if status == ERR_DOMAIN:
         raise DomainError(status, msg)
     if status in (ERR_INVALID, ERR_UNSUPPORTED):

@@ -28,6 +28,7 @@ using namespace agp;
 // error plumbing
 // ---------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
+static thread_local int32_t g_err_info = 0;  // PosDefException(info): the failing column of the last AGP_ERR_NOT_PD
 static int32_t fail(int32_t code, const char* fmt, ...) {
   char buf[1024];
   va_list ap;
@@ -48,7 +49,12 @@ static int32_t fail(int32_t code, const char* fmt, ...) {
     if (s_ != AGP_OK) return s_;   \
   } while (0)
 
+static int32_t fail_not_pd(const char* what, int column) {
+  g_err_info = column;
+  return fail(AGP_ERR_NOT_PD, "PosDefException: %s is not positive definite; Cholesky failed at column %d", what, column);
+}
 extern "C" const char* agp_last_error_string(void) { return g_err.c_str(); }
+extern "C" int32_t agp_last_error_info(void) { return g_err_info; }
 extern "C" int32_t agp_build_arch(void) { return 100; }
 
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
@@ -976,7 +982,7 @@ static int32_t check_step_flags(agp_ctx* c, bool domain) {
   int h_flags[4];
   CU(cudaMemcpyAsync(h_flags, c->d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  if (h_flags[0] != 0) return fail(AGP_ERR_NOT_PD, "PosDefException: cov(fz) is not positive definite; Cholesky failed at column %d", h_flags[0]);
+  if (h_flags[0] != 0) return fail_not_pd("cov(fz)", h_flags[0]);
   if (domain && h_flags[1] != 0) return fail(AGP_ERR_DOMAIN, "DomainError: a marginal variance is not positive");
   return AGP_OK;
 }
@@ -1402,7 +1408,7 @@ extern "C" int32_t agp_svgp_finish(agp_ctx* c, double* elbo_out, agp_svgp_grads*
     CU(cudaMemcpyAsync(h_flags, c->d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (h_scal[SC_PEER_FAILED] != 0.0) return fail(AGP_ERR_NCCL, "%d peer rank(s) failed before the all-reduce; the result is invalid", (int)h_scal[SC_PEER_FAILED]);
-    if (h_flags[0] != 0) return fail(AGP_ERR_NOT_PD, "PosDefException: cov(fz) is not positive definite; Cholesky failed at column %d", h_flags[0]);
+    if (h_flags[0] != 0) return fail_not_pd("cov(fz)", h_flags[0]);
     if (h_flags[1] != 0) return fail(AGP_ERR_DOMAIN, "DomainError: a marginal variance is not positive");
     if (elbo_out) *elbo_out = h_scal[SC_E] * st.scale - h_small[0];
     return AGP_OK;
@@ -1509,7 +1515,7 @@ extern "C" int32_t agp_svgp_finish(agp_ctx* c, double* elbo_out, agp_svgp_grads*
   h_flags[0] = h_flags[1] = 0;  // timing experiments (tools/s1_experiments.sh) produce garbage on purpose
 #endif
   if (h_scal[SC_PEER_FAILED] != 0.0) return fail(AGP_ERR_NCCL, "%d peer rank(s) failed before the all-reduce; the result is invalid", (int)h_scal[SC_PEER_FAILED]);
-  if (h_flags[0] != 0) return fail(AGP_ERR_NOT_PD, "PosDefException: cov(fz) is not positive definite; Cholesky failed at column %d", h_flags[0]);
+  if (h_flags[0] != 0) return fail_not_pd("cov(fz)", h_flags[0]);
   if (h_flags[1] != 0) return fail(AGP_ERR_DOMAIN, "DomainError: a marginal variance is not positive");
   if (elbo_out) *elbo_out = h_scal[SC_E] * st.scale - h_small[0];
   if (go->dm) {

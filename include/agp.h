@@ -142,6 +142,8 @@ typedef struct {
 int32_t agp_ctx_create(int32_t device, agp_ctx** out);
 int32_t agp_ctx_destroy(agp_ctx* ctx);
 const char* agp_last_error_string(void);
+/* `info` of the PosDefException behind the calling thread's last AGP_ERR_NOT_PD: the 1-based column at which cholesky failed. */
+int32_t agp_last_error_info(void);
 /* Version / build probe: returns the compute capability the kernels were built for (100). */
 int32_t agp_build_arch(void);
 /* The CUDA stream (cudaStream_t) every kernel of this context is launched on. */

@@ -39,6 +39,24 @@ def main():
         assert all(v < 1e-9 for v in errs.values()), errs
         assert all(v == vals[0] for v in vals), vals  # every rank returns the same numbers
         assert abs(fwd - val) <= 1e-12 * abs(val)
+    # a communicator without global_batch would silently scale the ELBO by the number of ranks: an argument error on every rank
+    try:
+        agp.elbo(sva, lds, None, num_data=1e5, quadrature=quad, ctx=ctx)
+        raise SystemExit("global_batch = 0 with a communicator must be rejected")
+    except ValueError:
+        pass
+    # fewer points than ranks: the ranks with an empty shard contribute zeros and still take part in the collective
+    n_tiny = world - 1
+    tlo, thi = agp.shard_range(n_tiny, rank, world)
+    dst = agp.DeviceData(capacity=1, D=3, ctx=ctx)
+    if thi > tlo:
+        dst.upload(p["X"][tlo:thi], p["y"][tlo:thi])
+    ldt = agp.LatentGP(f, agp.BernoulliLikelihood(), 1e-18)(dst)
+    vt, gt = agp.elbo_and_gradient(sva, ldt, None, num_data=1e5, quadrature=quad, ctx=ctx, global_batch=n_tiny, count=thi - tlo)
+    if rank == 0:
+        reft, rgt = osv.elbo_and_grad(s, p["X"][:n_tiny], p["y"][:n_tiny], lik, ex, num_data=1e5)
+        assert abs(vt - reft) < 1e-10 * abs(reft), (vt, reft)
+        assert all(v < 1e-9 for v in compare_grads(gt, rgt, p).values())
         print("DP_OK", world, val, flush=True)
     dist.barrier()
     dist.destroy_process_group()
