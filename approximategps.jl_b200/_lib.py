@@ -17,7 +17,8 @@ LIB_PATH = os.environ.get("AGP_B200_LIB") or os.path.join(HERE, "libagp_b200.so"
 # status codes (include/agp.h)
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_NOT_PD, ERR_DOMAIN, ERR_CUDA, ERR_NCCL, ERR_ALLOC = range(8)
 
-KERNEL_SE, KERNEL_MATERN32, KERNEL_MATERN52, KERNEL_LINEAR = range(4)
+KERNEL_SE, KERNEL_MATERN32, KERNEL_MATERN52, KERNEL_LINEAR, KERNEL_SUM, KERNEL_PRODUCT = range(6)
+MAX_COMPONENTS = 4
 LIK_GAUSSIAN, LIK_BERNOULLI_LOGIT, LIK_POISSON_EXP, LIK_EXPONENTIAL_EXP, LIK_GAMMA_EXP, LIK_BERNOULLI_PROBIT = range(6)
 EXPECT_DEFAULT, EXPECT_ANALYTIC, EXPECT_GAUSS_HERMITE, EXPECT_MONTE_CARLO = range(4)
 NONCENTERED, CENTERED = 0, 1
@@ -29,6 +30,10 @@ COMPUTE_F64, COMPUTE_F32, COMPUTE_F32_TC_SOLVE = 0, 1, 2
 c_double_p = C.POINTER(C.c_double)
 
 
+class AgpKernelComponent(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("variance", C.c_double), ("inv_lengthscale", C.c_double)]
+
+
 class AgpKernel(C.Structure):
     _fields_ = [
         ("kind", C.c_int32),
@@ -36,6 +41,8 @@ class AgpKernel(C.Structure):
         ("variance", C.c_double),
         ("inv_lengthscale", c_double_p),
         ("linear_c", C.c_double),
+        ("n_components", C.c_int32),
+        ("components", C.POINTER(AgpKernelComponent)),
     ]
 
 
@@ -75,6 +82,8 @@ class AgpSvgpGrads(C.Structure):
         ("dlinear_c", c_double_p),
         ("dmean_const", c_double_p),
         ("dlik_sigma2", c_double_p),
+        ("dcomp_variance", c_double_p),
+        ("dcomp_inv_lengthscale", c_double_p),
     ]
 
 
@@ -109,6 +118,8 @@ class AgpLaplaceResult(C.Structure):
         ("dinv_lengthscale", c_double_p),
         ("dlinear_c", c_double_p),
         ("dX", c_double_p),
+        ("dcomp_variance", c_double_p),
+        ("dcomp_inv_lengthscale", c_double_p),
     ]
 
 

@@ -40,8 +40,13 @@ class _BaseKernel:
     def __rmul__(self, variance):  # variance * kernel -> ScaledKernel
         return Kernel(self.kind, float(variance), np.ones(1), self.c)
 
-    def __mul__(self, variance):
-        return self.__rmul__(variance)
+    def __mul__(self, other):  # kernel * kernel -> KernelProduct
+        if isinstance(other, (_BaseKernel, Kernel)):
+            return _compose(L.KERNEL_PRODUCT, self, other)
+        return self.__rmul__(other)
+
+    def __add__(self, other):  # kernel + kernel -> KernelSum
+        return _compose(L.KERNEL_SUM, self, other)
 
 
 def SqExponentialKernel():
@@ -71,14 +76,70 @@ class Kernel:
     variance: float = 1.0
     inv_lengthscale: np.ndarray = field(default_factory=lambda: np.ones(1))
     c: float = 0.0
+    # kind == KERNEL_SUM / KERNEL_PRODUCT (``k1 + k2`` / ``k1 * k2``): ``variance * ((c_1 (+|*) c_2 ...) o Transform(inv_lengthscale))`` with
+    # components ``(kind_i, variance_i, inv_lengthscale_i)``: stationary kernels with scalar lengthscales under one shared outer transform
+    components: tuple = ()
 
     def __post_init__(self):
         self.inv_lengthscale = np.ascontiguousarray(np.atleast_1d(self.inv_lengthscale), dtype=np.float64)
+        self.components = tuple((int(q[0]), float(q[1]), float(q[2])) for q in self.components)
 
     def __rmul__(self, variance):
-        return Kernel(self.kind, self.variance * float(variance), self.inv_lengthscale, self.c)
+        return Kernel(self.kind, self.variance * float(variance), self.inv_lengthscale, self.c, self.components)
 
-    __mul__ = __rmul__
+    def __mul__(self, other):
+        if isinstance(other, (_BaseKernel, Kernel)):
+            return _compose(L.KERNEL_PRODUCT, self, other)
+        return self.__rmul__(other)
+
+    def __add__(self, other):
+        return _compose(L.KERNEL_SUM, self, other)
+
+
+def _compose(op: int, a, b) -> "Kernel":
+    """``KernelSum`` / ``KernelProduct`` of stationary kernels with scalar ScaleTransforms (each term keeps its own variance and
+    lengthscale; an outer ``variance * (...)`` / ``with_lengthscale(..., l)`` / ``ARDTransform`` then applies to the whole sum or product).
+    Nested sums of sums (products of products) flatten; anything else is not a device kernel (use the matrix-form Laplace interface)."""
+    terms = []
+    for k in (a, b):
+        k = _as_kernel(k)
+        if k.kind == op and k.variance == 1.0 and np.all(k.inv_lengthscale == 1.0):
+            terms.extend(k.components)
+        elif k.kind in (L.KERNEL_SE, L.KERNEL_MATERN32, L.KERNEL_MATERN52) and k.inv_lengthscale.size == 1:
+            terms.append((k.kind, k.variance, float(k.inv_lengthscale[0])))
+        else:
+            raise ValueError("ArgumentError: kernel sums / products on the device take stationary kernels (SqExponential, Matern32, Matern52) with "
+                             "scalar lengthscales; apply ARDTransform / variance to the whole sum or product")
+    if len(terms) > L.MAX_COMPONENTS:
+        raise ValueError(f"ArgumentError: at most {L.MAX_COMPONENTS} components")
+    return Kernel(op, 1.0, np.ones(1), 0.0, tuple(terms))
+
+
+def KernelSum(*ks) -> "Kernel":
+    out = ks[0]
+    for k in ks[1:]:
+        out = _compose(L.KERNEL_SUM, out, k)
+    return _as_kernel(out)
+
+
+def KernelProduct(*ks) -> "Kernel":
+    out = ks[0]
+    for k in ks[1:]:
+        out = _compose(L.KERNEL_PRODUCT, out, k)
+    return _as_kernel(out)
+
+
+def agp_kernel_struct(k: "Kernel"):
+    """(ctypes agp_kernel, keep-alive objects) of a host-mirror kernel."""
+    ils = np.ascontiguousarray(k.inv_lengthscale, dtype=np.float64)
+    kk = L.AgpKernel(k.kind, ils.size, k.variance, L.dptr(ils), k.c, 0, None)
+    keep = [ils]
+    if k.components:
+        arr = (L.AgpKernelComponent * len(k.components))(*[L.AgpKernelComponent(q[0], q[1], q[2]) for q in k.components])
+        kk.n_components = len(k.components)
+        kk.components = C.cast(arr, C.POINTER(L.AgpKernelComponent))
+        keep.append(arr)
+    return kk, keep
 
 
 def _as_kernel(k) -> Kernel:
@@ -92,19 +153,19 @@ def _as_kernel(k) -> Kernel:
 def with_lengthscale(k, lengthscale) -> Kernel:
     """``with_lengthscale(k, l) = k o ScaleTransform(1/l)`` (vector l -> ARDTransform(1 ./ l))."""
     k = _as_kernel(k)
-    return Kernel(k.kind, k.variance, k.inv_lengthscale * (1.0 / np.atleast_1d(np.asarray(lengthscale, dtype=np.float64))), k.c)
+    return Kernel(k.kind, k.variance, k.inv_lengthscale * (1.0 / np.atleast_1d(np.asarray(lengthscale, dtype=np.float64))), k.c, k.components)
 
 
 def ScaleTransform(k, s) -> Kernel:
     """``k o ScaleTransform(s)``."""
     k = _as_kernel(k)
-    return Kernel(k.kind, k.variance, k.inv_lengthscale * float(s), k.c)
+    return Kernel(k.kind, k.variance, k.inv_lengthscale * float(s), k.c, k.components)
 
 
 def ARDTransform(k, v) -> Kernel:
     """``k o ARDTransform(v)``."""
     k = _as_kernel(k)
-    return Kernel(k.kind, k.variance, k.inv_lengthscale * np.asarray(v, dtype=np.float64), k.c)
+    return Kernel(k.kind, k.variance, k.inv_lengthscale * np.asarray(v, dtype=np.float64), k.c, k.components)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -390,8 +451,7 @@ def kernelmatrix(k, x, y=None, *, ctx: "Context | None" = None) -> np.ndarray:
     x = _points(x)
     yy = None if y is None else _points(y)
     n1, n2 = len(x), (len(x) if yy is None else len(yy))
-    ils = np.ascontiguousarray(k.inv_lengthscale, dtype=np.float64)
-    kk = L.AgpKernel(k.kind, ils.size, k.variance, L.dptr(ils), k.c)
+    kk, _keep = agp_kernel_struct(k)
     out = np.zeros((n1, n2), order="F")
     L.check(ctx.lib.agp_kernel_matrix(ctx.h, C.byref(kk), x.shape[1], L.dptr(x), n1, L.dptr(yy), n2, L.dptr(out)))
     return out
@@ -484,9 +544,10 @@ class _Packed:
             raise ValueError("ARDTransform length must equal the input dimension")
         self.Z, self.m = Z, np.ascontiguousarray(sva.q.m, dtype=np.float64)
         self.Lq = np.asfortranarray(sva.q.Lq, dtype=np.float64)  # column-major
-        self.ils = np.ascontiguousarray(k.inv_lengthscale, dtype=np.float64)
         p = L.AgpSvgpParams()
-        p.kernel = L.AgpKernel(k.kind, self.ils.size, k.variance, L.dptr(self.ils), k.c)
+        p.kernel, self._kernel_keep = agp_kernel_struct(k)
+        self.ils = self._kernel_keep[0]
+        self.n_comp = len(k.components)
         p.mean_const = sva.fz.f.mean_const
         p.M, p.D = M, D
         p.Z, p.jitter = L.dptr(Z), float(sva.fz.Sigma_y)
@@ -527,6 +588,8 @@ class ELBOGradient:
     linear_c: float
     mean_const: float
     lik_sigma2: float
+    comp_variance: np.ndarray = field(default_factory=lambda: np.zeros(0))        # kernel sums / products: per component
+    comp_inv_lengthscale: np.ndarray = field(default_factory=lambda: np.zeros(0))
 
 
 def _resolve_lik(sva, l_fx):
@@ -594,6 +657,9 @@ def elbo_and_gradient(sva, l_fx, y=None, *, num_data=None, quadrature=None, ctx:
         sc = np.zeros(4)
         G = L.AgpSvgpGrads(L.dptr(g.m), L.dptr(g.Lq), L.dptr(g.Z), sc[0:1].ctypes.data_as(L.c_double_p), L.dptr(g.inv_lengthscale),
                            sc[1:2].ctypes.data_as(L.c_double_p), sc[2:3].ctypes.data_as(L.c_double_p), sc[3:4].ctypes.data_as(L.c_double_p))
+        if pk.n_comp:
+            g.comp_variance, g.comp_inv_lengthscale = np.zeros(pk.n_comp), np.zeros(pk.n_comp)
+            G.dcomp_variance, G.dcomp_inv_lengthscale = L.dptr(g.comp_variance), L.dptr(g.comp_inv_lengthscale)
         out = C.c_double()
         L.check(ctx.lib.agp_svgp_elbo_grad(ctx.h, ds.h, offset, count, C.byref(pk.p), float(num_data or 0), int(global_batch), C.byref(out), C.byref(G)))
         g.variance, g.linear_c, g.mean_const, g.lik_sigma2 = (float(v) for v in sc)
@@ -626,7 +692,9 @@ class FlatELBO:
         L.check(self.ctx.lib.agp_svgp_flat_size(C.byref(pk.p), C.byref(n)))
         self.size = int(n.value)
         k = sva.fz.f.kernel
-        self.x0 = np.concatenate([[k.variance], pk.ils, [k.c, sva.fz.f.mean_const, float(lik.sigma2)], pk.Z.ravel(), pk.m, pk.Lq.ravel(order="F")])
+        self.n_comp = pk.n_comp
+        self.x0 = np.concatenate([[k.variance], pk.ils, [k.c, sva.fz.f.mean_const, float(lik.sigma2)], pk.Z.ravel(), pk.m, pk.Lq.ravel(order="F"),
+                                  [q[1] for q in k.components], [q[2] for q in k.components]])
         assert self.x0.size == self.size
         self._stepper = None
         if resident:
@@ -638,8 +706,11 @@ class FlatELBO:
         x = np.asarray(x)
         ns, M, D = self.n_scale, self.M, self.D
         o = 4 + ns
+        e = o + M * D + M + M * M
+        nc = self.n_comp
         return dict(variance=x[0], inv_lengthscale=x[1:1 + ns], linear_c=x[1 + ns], mean_const=x[2 + ns], lik_param=x[3 + ns],
-                    Z=x[o:o + M * D].reshape(M, D), m=x[o + M * D:o + M * D + M], Lq=x[o + M * D + M:].reshape(M, M, order="F"))
+                    Z=x[o:o + M * D].reshape(M, D), m=x[o + M * D:o + M * D + M], Lq=x[o + M * D + M:e].reshape(M, M, order="F"),
+                    comp_variance=x[e:e + nc], comp_inv_lengthscale=x[e + nc:e + 2 * nc])
 
     def value_and_gradient(self, x, want_grad=True, offset=None, count=None, out_grad=None):
         """ELBO and gradient at the flat vector ``x`` over points ``[offset, offset+count)`` of the resident data set (default: the

@@ -168,6 +168,7 @@ struct agp_ctx {
   DevBuf z, zs, zn, zsp, mvec, mt, Lq, Kw, Lk, Lt, Ut, Bt_cm, Bt_rm, W1, W2, W3, W4, vec64, vec64b;
   // per-chunk scratch [Mp][chunk_cols]
   DevBuf A, C, Ab, As, saa, sam, scc_part, dmu, dv, sc_part;
+  DevBuf Kf, DKb;  // reverse pass, stationary kernels: Kuf and variance * kappa'(u) of the launch group, kept from S1 for S7
   // accumulators
   DevBuf gpart, Gpart, kpart, red, small, ghbuf;
   // Float32 mode: hi | lo FP32 planes (each DevBuf holds both: 2 x count floats = count doubles)
@@ -244,7 +245,7 @@ extern "C" int32_t agp_ctx_destroy(agp_ctx* c) {
   cudaStreamSynchronize(c->stream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   DevBuf* bufs[] = {&c->z, &c->zs, &c->zn, &c->zsp, &c->mvec, &c->mt, &c->Lq, &c->Kw, &c->Lk, &c->Lt, &c->Ut, &c->Bt_cm, &c->Bt_rm,
-                    &c->W1, &c->W2, &c->W3, &c->W4, &c->vec64, &c->vec64b, &c->A, &c->C, &c->Ab, &c->As, &c->saa, &c->sam,
+                    &c->W1, &c->W2, &c->W3, &c->W4, &c->vec64, &c->vec64b, &c->A, &c->C, &c->Ab, &c->As, &c->Kf, &c->DKb, &c->saa, &c->sam,
                     &c->scc_part, &c->dmu, &c->dv, &c->sc_part, &c->gpart, &c->Gpart, &c->kpart, &c->red, &c->small, &c->ghbuf, &c->fA, &c->fC, &c->fAb, &c->fAs, &c->fBtc, &c->fBtr, &c->fLi,
                     &c->mu_out, &c->var_out, &c->px1, &c->px2, &c->pxs1, &c->pxn1, &c->pxs2, &c->pxn2, &c->pcov};
   for (DevBuf* b : bufs) b->release();
@@ -506,6 +507,42 @@ static int32_t launch_trsm_s(agp_ctx* c, const TrsmArgs& a, int tiles_n) {
   return AGP_OK;
 }
 // 4 pipeline stages; the Kuf generator drops to 3 when the z slabs of a wide input (D > 8) would cost the second CTA per SM
+// S1 = cov(f.prior, z, x) + the forward solve (SVA.jl:216-217).  Default: kuf_gen_kernel writes the Kuf tile of the launch group into X
+// and the solve runs in place on it (TR_RHS_FWD_SUMS); AGP_S1_FUSED=1 selects the round-1 kernel that generates Kuf inside the DMMA
+// pipeline instead (kept for A/B measurements and used by the Laplace prediction path in its SCALED form).
+template <int MODE>
+static int32_t launch_trsm(agp_ctx* c, const TrsmArgs& a, int tiles_n);
+static bool s1_fused() {
+  static const bool fused = getenv("AGP_S1_FUSED") && atoi(getenv("AGP_S1_FUSED")) != 0;  // tuning knob
+  return fused;
+}
+// keep = true (reverse pass of a stationary kernel): Kuf goes to c->Kf and variance * kappa'(u) to c->DKb, the solve reads Kf and writes
+// t1.X; S7 then contracts the cotangent with the stored values (kgrad_kernel FAST) instead of recomputing distances and exp.
+static int32_t launch_s1(agp_ctx* c, const TrsmArgs& t1_in, int tiles_n, bool keep = false) {
+  if (s1_fused()) return launch_trsm<TR_KUF_FWD>(c, t1_in, tiles_n);
+  TrsmArgs t1 = t1_in;
+  KufGenArgs g{};
+  g.K = keep ? c->Kf.p : t1.X;
+  g.DK = keep ? c->DKb.p : nullptr;
+  if (keep) t1.RHS = c->Kf.p;
+  g.ldx = t1.ldx;
+  g.ncols = tiles_n * BN;
+  g.pts = t1.pts;
+  g.npts = t1.npts;
+  g.zsp = t1.zsp;
+  g.kp = t1.kp;
+  const int D = t1.kp.D;
+  const int smem = KG_ROWS * (kuf_dp(D) + 2) * (int)sizeof(double);
+  const dim3 grid((g.ncols + KG_COLS - 1) / KG_COLS, t1.nb * BM / KG_ROWS);
+  if (D <= 4) kuf_gen_kernel<4><<<grid, KG_COLS, smem, c->stream>>>(g);
+  else if (D <= 8) kuf_gen_kernel<8><<<grid, KG_COLS, smem, c->stream>>>(g);
+  else if (D <= 16) kuf_gen_kernel<16><<<grid, KG_COLS, smem, c->stream>>>(g);
+  else kuf_gen_kernel<32><<<grid, KG_COLS, smem, c->stream>>>(g);
+  LAUNCHED(c);
+  KCHECK();
+  return launch_trsm<TR_RHS_FWD_SUMS>(c, t1, tiles_n);
+}
+
 template <int MODE>
 static int32_t launch_trsm(agp_ctx* c, const TrsmArgs& a, int tiles_n) {
   if ((MODE == TR_KUF_FWD || MODE == TR_KUF_FWD_SCALED) && a.kp.D > 8) return launch_trsm_s<MODE, 3>(c, a, tiles_n);
@@ -781,13 +818,55 @@ __global__ void __launch_bounds__(256) vec_sum_kernel(const double* v, int n, do
 // ---------------------------------------------------------------------------------------------------
 // SVGP: per-step preparation
 // ---------------------------------------------------------------------------------------------------
+// agp_kernel -> KernelParams (validation shared by every entry point that takes a kernel)
+static int32_t fill_kernel_params(const agp_kernel* k, int D, int M, KernelParams& kp) {
+  if (!k) return fail(AGP_ERR_INVALID, "kernel is NULL");
+  if (k->kind < AGP_KERNEL_SE || k->kind > AGP_KERNEL_PRODUCT) return fail(AGP_ERR_UNSUPPORTED, "unsupported kernel kind %d", k->kind);
+  if ((k->n_scale != 1 && k->n_scale != D) || !k->inv_lengthscale) return fail(AGP_ERR_INVALID, "kernel.n_scale must be 1 or D");
+  memset(&kp, 0, sizeof kp);
+  kp.kind = k->kind;
+  kp.D = D;
+  kp.M = M;
+  kp.ard = k->n_scale != 1;
+  kp.variance = k->variance;
+  kp.c = k->linear_c;
+  kp.f0 = 1.0;
+  for (int d = 0; d < D; d++) kp.s[d] = k->inv_lengthscale[k->n_scale == 1 ? 0 : d];
+  if (kernel_is_composite(k->kind)) {
+    if (k->n_components < 1 || k->n_components > AGP_MAX_COMPONENTS || !k->components)
+      return fail(AGP_ERR_INVALID, "a kernel sum / product needs 1..%d components", AGP_MAX_COMPONENTS);
+    kp.ncomp = k->n_components;
+    kp.f0 = k->kind == AGP_KERNEL_SUM ? 0.0 : 1.0;
+    for (int i = 0; i < kp.ncomp; i++) {
+      const agp_kernel_component& q = k->components[i];
+      if (q.kind < AGP_KERNEL_SE || q.kind > AGP_KERNEL_MATERN52)
+        return fail(AGP_ERR_UNSUPPORTED, "component %d: only stationary kernels (SqExponential, Matern32, Matern52) can be summed / multiplied on the device", i);
+      kp.ckind[i] = q.kind;
+      kp.cv[i] = q.variance;
+      kp.ca[i] = q.inv_lengthscale * q.inv_lengthscale;
+      kp.f0 = k->kind == AGP_KERNEL_SUM ? kp.f0 + q.variance : kp.f0 * q.variance;
+    }
+  }
+  return AGP_OK;
+}
+
+// component gradients out of theta (kgrad_finish_kernel) plus the k(x, x) = variance F(0) term of the marginal variances
+// (dkxx_sum = sum_n dE/dvar_n * F(0), the SC_DKXX scalar; 0 where there is no such term)
+static void write_component_grads(const KernelParams& kp, const double* h_theta, int D, double dkxx_sum, double* dcv, double* dcs) {
+  for (int i = 0; i < kp.ncomp; i++) {
+    if (dcv) {
+      double extra = 0.0;
+      if (kp.f0 != 0.0) extra = (dkxx_sum / kp.f0) * kp.variance * (kp.kind == AGP_KERNEL_SUM ? 1.0 : (kp.cv[i] != 0.0 ? kp.f0 / kp.cv[i] : 0.0));
+      dcv[i] = h_theta[2 + D + i] + extra;
+    }
+    if (dcs) dcs[i] = h_theta[2 + D + MAXC + i];
+  }
+}
+
 static int32_t resolve_params(const agp_svgp_params* p, SvgpState& st) {
   if (!p) return fail(AGP_ERR_INVALID, "params is NULL");
   if (p->M < 1 || p->D < 1 || !p->Z || !p->m || !p->Lq) return fail(AGP_ERR_INVALID, "params: M, D, Z, m, Lq are required");
   if (p->D > MAXD) return fail(AGP_ERR_UNSUPPORTED, "input dimension %d > %d is not supported on device", p->D, MAXD);
-  if (p->kernel.kind < AGP_KERNEL_SE || p->kernel.kind > AGP_KERNEL_LINEAR) return fail(AGP_ERR_UNSUPPORTED, "unsupported kernel kind %d", p->kernel.kind);
-  if (p->kernel.n_scale != 1 && p->kernel.n_scale != p->D) return fail(AGP_ERR_INVALID, "kernel.n_scale must be 1 or D");
-  if (!p->kernel.inv_lengthscale) return fail(AGP_ERR_INVALID, "kernel.inv_lengthscale is NULL");
   if (p->lik.kind < AGP_LIK_GAUSSIAN || p->lik.kind > AGP_LIK_BERNOULLI_PROBIT) return fail(AGP_ERR_UNSUPPORTED, "unsupported likelihood kind %d", p->lik.kind);
   if (p->parametrization != AGP_NONCENTERED && p->parametrization != AGP_CENTERED) return fail(AGP_ERR_INVALID, "unknown parametrization");
   st.M = p->M;
@@ -798,14 +877,7 @@ static int32_t resolve_params(const agp_svgp_params* p, SvgpState& st) {
   st.centered = p->parametrization == AGP_CENTERED;
   st.mean_const = p->mean_const;
   st.jitter = p->jitter;
-  memset(&st.kp, 0, sizeof st.kp);
-  st.kp.kind = p->kernel.kind;
-  st.kp.D = p->D;
-  st.kp.M = p->M;
-  st.kp.ard = p->kernel.n_scale != 1;
-  st.kp.variance = p->kernel.variance;
-  st.kp.c = p->kernel.linear_c;
-  for (int d = 0; d < p->D; d++) st.kp.s[d] = p->kernel.inv_lengthscale[p->kernel.n_scale == 1 ? 0 : d];
+  OK(fill_kernel_params(&p->kernel, p->D, p->M, st.kp));
   if (p->compute_dtype < AGP_COMPUTE_F64 || p->compute_dtype > AGP_COMPUTE_F32_TC_SOLVE) return fail(AGP_ERR_INVALID, "unknown compute_dtype %d", p->compute_dtype);
   st.f32 = p->compute_dtype != AGP_COMPUTE_F64;
   st.f32_tc_solve = p->compute_dtype == AGP_COMPUTE_F32_TC_SOLVE;
@@ -1002,15 +1074,20 @@ struct RedLayout {
     G = g + Mp;
     dZ = G + (int64_t)Mp * Mp;
     theta = round_up(dZ + (int64_t)Mp * D, 16);
-    total = theta + 2 + D;
+    total = theta + theta_size(D);
   }
 };
 
 // Points per launch group.  Larger chunks amortise launch gaps and wave tails (measured at C4: 2 waves 1988 ms/step,
 // 4 waves 1961, 8 waves 1948); the four M x chunk scratch matrices are capped at ~8 GB.
+// S7 from stored kernel values: plain stationary kinds, split S1 (AGP_KGRAD_FAST=0 restores the recomputing kernel for A/B measurements)
+static bool kgrad_fast(const SvgpState& st) {
+  static const bool off = getenv("AGP_KGRAD_FAST") && atoi(getenv("AGP_KGRAD_FAST")) == 0;  // tuning knob
+  return !off && !s1_fused() && st.kp.kind >= AGP_KERNEL_SE && st.kp.kind <= AGP_KERNEL_MATERN52;
+}
 static int64_t pick_chunk_cols(agp_ctx* c, int64_t count) {
   const int64_t wave = (int64_t)c->sms * 2 * BN;  // one full wave of column tiles at 2 CTAs / SM
-  const int64_t by_mem = (int64_t)8e9 / (4 * 8 * std::max(c->st.Mp, BM)) / wave;
+  const int64_t by_mem = (int64_t)12e9 / (6 * 8 * std::max(c->st.Mp, BM)) / wave;  // six M x chunk scratch matrices
   int64_t cap = std::min<int64_t>(8, std::max<int64_t>(2, by_mem)) * wave;
   if (const char* e = getenv("AGP_CHUNK_COLS")) cap = std::max<int64_t>(BN, round_up(atoll(e), BN));
   return std::min<int64_t>(cap, round_up(std::max<int64_t>(count, 1), 2 * BN));  // multiples of 128: the tcgen05 stages tile the points by 128
@@ -1042,6 +1119,10 @@ static int32_t ensure_sweep_workspace(agp_ctx* c, int64_t cols, bool grad) {
   if (grad) {
     OK(c->Ab.ensure((int64_t)Mp * cc));
     OK(c->As.ensure((int64_t)Mp * cc));
+    if (kgrad_fast(st)) {
+      OK(c->Kf.ensure((int64_t)Mp * cc));
+      OK(c->DKb.ensure((int64_t)Mp * cc));
+    }
     OK(c->gpart.ensure((cc / BN) * Mp));
     const int ntiles = nb * (nb + 1);
     // K-splits of the SYRK: about eight waves of CTAs so that the cheap diagonal tiles (3/8 and 7/8 of a full tile's MMAs)
@@ -1053,17 +1134,20 @@ static int32_t ensure_sweep_workspace(agp_ctx* c, int64_t cols, bool grad) {
     if (const char* e = getenv("AGP_SYRK_SPLIT")) c->nsplit = std::max(1, atoi(e));  // tuning knob
     OK(c->Gpart.ensure((int64_t)c->nsplit * MM));
     c->nslab = (int)std::max<int64_t>((cc + 2047) / 2048, (Mp + 2047) / 2048);
-    OK(c->kpart.ensure((int64_t)c->nslab * Mp * (2 * D + 3)));
+    OK(c->kpart.ensure((int64_t)c->nslab * Mp * kgrad_stride(D)));
     DevBuf* w[] = {&c->W1, &c->W2, &c->W3, &c->W4};
     for (DevBuf* b : w) OK(b->ensure(MM));
   }
   return AGP_OK;
 }
 
-static int32_t run_kgrad(agp_ctx* c, const double* Kb, int64_t ld, const double* pts, int npts, int nslab) {
+static int32_t run_kgrad(agp_ctx* c, const double* Kb, int64_t ld, const double* pts, int npts, int nslab, const double* Kf = nullptr,
+                         const double* DK = nullptr) {
   const SvgpState& st = c->st;
   KgradArgs a{};
   a.Kb = Kb;
+  a.Kf = Kf;
+  a.DK = DK;
   a.ld = ld;
   a.pts = pts;
   a.npts = npts;
@@ -1071,22 +1155,28 @@ static int32_t run_kgrad(agp_ctx* c, const double* Kb, int64_t ld, const double*
   a.zn = c->zn.p;
   a.slab = 2048;
   a.part = c->kpart.p;
-  a.stride = 2 * st.D + 3;
+  a.stride = kgrad_stride(st.D);
   a.Mp = st.Mp;
   a.kp = st.kp;
   const int smem = 256 * (kuf_dp(st.D) + 2) * 8;
   const dim3 grid((st.M + 7) / 8, nslab);
 #define AGP_KGRAD_ONE(DM, KD)                                                                                        \
   {                                                                                                                \
-    if (smem > 48 * 1024) OK((ensure_smem<kgrad_kernel<DM, 1, KD>>(c, smem)));                                      \
-    kgrad_kernel<DM, 1, KD><<<grid, 256, smem, c->stream>>>(a);                                                   \
+    if (Kf && DK && KD <= AGP_KERNEL_MATERN52) {                                                                   \
+      if (smem > 48 * 1024) OK((ensure_smem<kgrad_kernel<DM, 1, AGP_KERNEL_SE, true>>(c, smem)));                  \
+      kgrad_kernel<DM, 1, AGP_KERNEL_SE, true><<<grid, 256, smem, c->stream>>>(a);                                 \
+    } else {                                                                                                       \
+      if (smem > 48 * 1024) OK((ensure_smem<kgrad_kernel<DM, 1, KD>>(c, smem)));                                    \
+      kgrad_kernel<DM, 1, KD><<<grid, 256, smem, c->stream>>>(a);                                                 \
+    }                                                                                                              \
   }
 #define AGP_KGRAD_LAUNCH(DM)                                          \
   switch (st.kp.kind) {                                               \
     case AGP_KERNEL_SE: AGP_KGRAD_ONE(DM, AGP_KERNEL_SE) break;       \
     case AGP_KERNEL_MATERN32: AGP_KGRAD_ONE(DM, AGP_KERNEL_MATERN32) break; \
     case AGP_KERNEL_MATERN52: AGP_KGRAD_ONE(DM, AGP_KERNEL_MATERN52) break; \
-    default: AGP_KGRAD_ONE(DM, AGP_KERNEL_LINEAR) break;              \
+    case AGP_KERNEL_LINEAR: AGP_KGRAD_ONE(DM, AGP_KERNEL_LINEAR) break; \
+    default: AGP_KGRAD_ONE(DM, AGP_KERNEL_COMPOSITE) break;           \
   }
   if (st.D <= 4) {
     AGP_KGRAD_LAUNCH(4)
@@ -1110,7 +1200,7 @@ static int32_t finish_kgrad(agp_ctx* c, int nslab, double zfac, double* dZ, doub
   a.part = c->kpart.p;
   a.nslab = nslab;
   a.Mp = st.Mp;
-  a.stride = 2 * st.D + 3;
+  a.stride = kgrad_stride(st.D);
   a.zs = c->zs.p;
   a.zfac = zfac;
   a.dZ = dZ;
@@ -1153,7 +1243,7 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
     if (grad) {
       OK(fill(c, c->gpart.p, (ldc / BN) * Mp, 0.0));
       OK(fill(c, c->Gpart.p, (int64_t)c->nsplit * MM, 0.0));
-      OK(fill(c, c->kpart.p, (int64_t)c->nslab * Mp * (2 * D + 3), 0.0));
+      OK(fill(c, c->kpart.p, (int64_t)c->nslab * Mp * kgrad_stride(D), 0.0));
     }
   }
   for (int64_t lo = 0; lo < count; lo += cols) {
@@ -1177,7 +1267,7 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
     t1.kp = st.kp;
     {
       ProfScope ps(c, PC_TRSM_FWD);
-      OK(launch_trsm<TR_KUF_FWD>(c, t1, tiles_n));
+      OK(launch_s1(c, t1, tiles_n, grad && kgrad_fast(st)));
     }
     // Float32 mode: point-major hi / lo planes of A, then C = A Bt on the tcgen05 path (f32sweep.cuh)
     const int64_t plane = (int64_t)Mp * ldc;  // floats per plane
@@ -1328,7 +1418,11 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
     // S7: contraction of Kb with the kernel derivatives
     {
       ProfScope ps(c, PC_KGRAD);
-      OK(run_kgrad(c, c->Ab.p, ldc, pts, npts, (npts + 2047) / 2048));
+      if (kgrad_fast(st)) {
+        OK(run_kgrad(c, c->Ab.p, ldc, pts, npts, (npts + 2047) / 2048, c->Kf.p, c->DKb.p));
+      } else {
+        OK(run_kgrad(c, c->Ab.p, ldc, pts, npts, (npts + 2047) / 2048));
+      }
     }
   }
   if (predict || !grad) return AGP_OK;
@@ -1489,15 +1583,15 @@ extern "C" int32_t agp_svgp_finish(agp_ctx* c, double* elbo_out, agp_svgp_grads*
   KCHECK();
   // Kuu part of dZ / dtheta: contraction with k(Z, Z); both arguments move -> zfac = 2
   const int nslab_z = (M + 2047) / 2048;
-  OK(fill(c, c->kpart.p, (int64_t)nslab_z * Mp * (2 * D + 3), 0.0));
+  OK(fill(c, c->kpart.p, (int64_t)nslab_z * Mp * kgrad_stride(D), 0.0));
   OK(run_kgrad(c, W4, Mp, c->z.p, M, nslab_z));
   OK(finish_kgrad(c, nslab_z, 2.0, dZ, theta));
   // outputs
-  std::vector<double> h_theta(2 + D), h_dZ((int64_t)Mp * D), h_vec(2 * (int64_t)Mp), h_g(Mp);
+  std::vector<double> h_theta(theta_size(D)), h_dZ((int64_t)Mp * D), h_vec(2 * (int64_t)Mp), h_g(Mp);
   std::vector<double> h_dLq;
   CU(cudaMemcpyAsync(h_scal.data(), red + rl.scal, sizeof(double) * rl.g, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(h_small.data(), small, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(h_theta.data(), theta, sizeof(double) * (2 + D), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(h_theta.data(), theta, sizeof(double) * theta_size(D), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(h_dZ.data(), dZ, sizeof(double) * Mp * D, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(h_g.data(), g, sizeof(double) * Mp, cudaMemcpyDeviceToHost, c->stream));
   if (st.centered) CU(cudaMemcpyAsync(h_vec.data(), c->vec64b.p, sizeof(double) * 2 * Mp, cudaMemcpyDeviceToHost, c->stream));
@@ -1534,6 +1628,7 @@ extern "C" int32_t agp_svgp_finish(agp_ctx* c, double* elbo_out, agp_svgp_grads*
       for (int d = 0; d < D; d++) go->dinv_lengthscale[d] = h_theta[2 + d] + (linear ? h_scal[SC_DS + d] : 0.0);
     }
   }
+  if (kernel_is_composite(st.kp.kind)) write_component_grads(st.kp, h_theta.data(), D, h_scal[SC_DKXX], go->dcomp_variance, go->dcomp_inv_lengthscale);
   if (go->dmean_const) *go->dmean_const = h_scal[SC_DMU] - (st.centered ? h_small[1] : 0.0);
   if (go->dlik_sigma2) *go->dlik_sigma2 = h_scal[SC_DS2];
   return AGP_OK;
@@ -1580,10 +1675,14 @@ extern "C" int32_t agp_svgp_elbo_grad(agp_ctx* c, agp_dataset* ds, int64_t offse
 }
 
 // Flat-vector form: [variance | inv_lengthscale (n_scale) | linear_c | mean_const | lik parameter |
-// Z (M*D, point-major) | m (M) | Lq (M*M, column-major)] in, the gradient in the same layout out.
+// Z (M*D, point-major) | m (M) | Lq (M*M, column-major) | kernel sums / products: component variances (n_components) |
+// component inverse lengthscales (n_components)] in, the gradient in the same layout out.
+static int flat_ncomp(const agp_svgp_params* p) {
+  return (kernel_is_composite(p->kernel.kind) && p->kernel.n_components >= 1 && p->kernel.n_components <= AGP_MAX_COMPONENTS && p->kernel.components) ? p->kernel.n_components : 0;
+}
 static int64_t flat_size(const agp_svgp_params* p) {
   if (!p || p->M < 1 || p->D < 1 || p->kernel.n_scale < 1) return 0;
-  return 4 + (int64_t)p->kernel.n_scale + (int64_t)p->M * p->D + p->M + (int64_t)p->M * p->M;
+  return 4 + (int64_t)p->kernel.n_scale + (int64_t)p->M * p->D + p->M + (int64_t)p->M * p->M + 2 * flat_ncomp(p);
 }
 extern "C" int32_t agp_svgp_flat_size(const agp_svgp_params* p, int64_t* n_out) {
   const int64_t n = flat_size(p);
@@ -1607,6 +1706,17 @@ extern "C" int32_t agp_svgp_elbo_grad_flat(agp_ctx* c, agp_dataset* ds, int64_t 
   p.m = p.Z + (int64_t)M * D;
   p.Lq = p.m + M;
   p.ldLq = M;
+  const int nc = flat_ncomp(tmpl);
+  agp_kernel_component comps[AGP_MAX_COMPONENTS];
+  const int64_t cbase = 4 + ns + (int64_t)M * D + M + (int64_t)M * M;
+  if (nc > 0) {
+    for (int i = 0; i < nc; i++) {
+      comps[i].kind = tmpl->kernel.components[i].kind;
+      comps[i].variance = f[cbase + i];
+      comps[i].inv_lengthscale = f[cbase + nc + i];
+    }
+    p.kernel.components = comps;
+  }
   if (!flat_grad) return agp_svgp_elbo(c, ds, offset, count, &p, num_data, global_batch, elbo_out);
   double* g = flat_grad;
   agp_svgp_grads go{};
@@ -1618,6 +1728,10 @@ extern "C" int32_t agp_svgp_elbo_grad_flat(agp_ctx* c, agp_dataset* ds, int64_t 
   go.dZ = g + 4 + ns;
   go.dm = go.dZ + (int64_t)M * D;
   go.dLq = go.dm + M;
+  if (nc > 0) {
+    go.dcomp_variance = g + cbase;
+    go.dcomp_inv_lengthscale = g + cbase + nc;
+  }
   return agp_svgp_elbo_grad(c, ds, offset, count, &p, num_data, global_batch, elbo_out, &go);
 }
 
@@ -1711,7 +1825,7 @@ static int32_t project_points(agp_ctx* c, const double* X_dev, int n, int ncols,
   t1.saa = c->saa.p;
   t1.sam = c->sam.p;
   t1.kp = st.kp;
-  OK(launch_trsm<TR_KUF_FWD>(c, t1, ncols / BN));
+  OK(launch_s1(c, t1, ncols / BN));
   EpiS2 e2{Cbuf, ldc, c->scc_part.p, ldc};
   OK((run_gemm<A_KM, B_KN>(c, st.nb, ncols / BN, c->Bt_rm.p, st.Mp, Abuf, ldc, st.Mp, KR_UPPER, TS_ALL, e2)));
   return AGP_OK;
@@ -1807,20 +1921,12 @@ extern "C" int32_t agp_kernel_matrix(agp_ctx* c, const agp_kernel* k, int32_t D,
                                      double* K_out) {
   if (!c || !k || !X1 || !K_out || n1 < 1 || D < 1) return fail(AGP_ERR_INVALID, "agp_kernel_matrix: bad arguments");
   if (D > MAXD) return fail(AGP_ERR_UNSUPPORTED, "input dimension %d > %d is not supported on device", D, MAXD);
-  if (k->kind < AGP_KERNEL_SE || k->kind > AGP_KERNEL_LINEAR) return fail(AGP_ERR_UNSUPPORTED, "unsupported kernel kind %d", k->kind);
-  if ((k->n_scale != 1 && k->n_scale != D) || !k->inv_lengthscale) return fail(AGP_ERR_INVALID, "kernel.n_scale must be 1 or D");
   const bool cross = X2 != nullptr;
   if (!cross) n2 = n1;
   if (n2 < 1 || n1 > AGP_MAX_COV_POINTS || n2 > AGP_MAX_COV_POINTS) return fail(AGP_ERR_INVALID, "agp_kernel_matrix: 1 <= n <= %lld", (long long)AGP_MAX_COV_POINTS);
   CU(cudaSetDevice(c->device));
   KernelParams kp;
-  memset(&kp, 0, sizeof kp);
-  kp.kind = k->kind;
-  kp.D = D;
-  kp.ard = k->n_scale != 1;
-  kp.variance = k->variance;
-  kp.c = k->linear_c;
-  for (int d = 0; d < D; d++) kp.s[d] = k->inv_lengthscale[k->n_scale == 1 ? 0 : d];
+  OK(fill_kernel_params(k, D, 0, kp));
   OK(c->px1.ensure(n1 * D));
   OK(c->pxs1.ensure(n1 * D));
   OK(c->pxn1.ensure(n1));

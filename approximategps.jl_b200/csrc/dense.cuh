@@ -49,7 +49,7 @@ __global__ void build_kuu_kernel(double* K, int Mp, const double* zs, const doub
       for (int d = 0; d < kp.D; d++) dot = fma(zs[(int64_t)lo * kp.D + d], zs[(int64_t)hi * kp.D + d], dot);
       u = u_from_dot(kp.kind, zn[lo], zn[hi], dot);
     }
-    v = kp.variance * kappa(kp.kind, u, kp.c);
+    v = kp.variance * kappa_kp(kp, u);
     if (a == b) v += jitter;
   }
   K[(int64_t)b * Mp + a] = v;
@@ -73,7 +73,7 @@ __global__ void cross_k_kernel(double* K, int64_t ld, const double* xs, const do
       for (int d = 0; d < kp.D; d++) dot = fma(xs[(int64_t)a * kp.D + d], ys[(int64_t)b * kp.D + d], dot);
       u = u_from_dot(kp.kind, xn[a], yn[b], dot);
     }
-    v = kp.variance * kappa(kp.kind, u, kp.c);
+    v = kp.variance * kappa_kp(kp, u);
   }
   K[(int64_t)b * ld + a] = v;
 }

@@ -11,6 +11,7 @@
 namespace agp {
 
 constexpr int MAXD = AGP_MAX_D;  // compile-time bound on the input dimension handled on device (include/agp.h)
+constexpr int MAXC = AGP_MAX_COMPONENTS;
 
 struct KernelParams {
   int kind;
@@ -20,7 +21,15 @@ struct KernelParams {
   double variance;
   double c;
   double s[MAXD];  // per-dimension input scale (ScaleTransform replicated, or ARDTransform)
+  // kind == AGP_KERNEL_SUM / AGP_KERNEL_PRODUCT: k = variance * F(u), F(u) = sum_c / prod_c  cv[c] kappa_{ckind[c]}(ca[c] u) with u the
+  // squared distance of the inputs scaled by s[] and ca[c] = (component inverse lengthscale)^2; f0 = F(0) (1 for the plain kinds)
+  int ncomp;
+  int ckind[MAXC];
+  double cv[MAXC];
+  double ca[MAXC];
+  double f0;
 };
+__host__ __device__ __forceinline__ bool kernel_is_composite(int kind) { return kind == AGP_KERNEL_SUM || kind == AGP_KERNEL_PRODUCT; }
 
 // Padded row width of the operands of the Kuf generator: Dq = D rounded up to 4 (one DMMA k-step); a padded row is
 // [v_0 .. v_{D-1}, 0.., |v|^2, 0] with Dq + 2 doubles (16-byte aligned rows).
@@ -67,6 +76,61 @@ __device__ __forceinline__ void kappa_and_du(int kind, double u, double c, doubl
 __device__ __forceinline__ double u_from_dot(int kind, double xn, double zn, double dot) {
   if (kind == AGP_KERNEL_LINEAR) return dot;
   return fmax(xn + zn - 2.0 * dot, 0.0);
+}
+
+// kappa for every kind, including sums / products of stationary components
+__device__ __forceinline__ double kappa_kp(const KernelParams& kp, double u) {
+  if (!kernel_is_composite(kp.kind)) return kappa(kp.kind, u, kp.c);
+  const bool sum = kp.kind == AGP_KERNEL_SUM;
+  double f = sum ? 0.0 : 1.0;
+  for (int c = 0; c < kp.ncomp; c++) {
+    const double kc = kp.cv[c] * kappa(kp.ckind[c], kp.ca[c] * u, 0.0);
+    f = sum ? f + kc : f * kc;
+  }
+  return f;
+}
+// F(u), dF/du and, per component, pc[c] = dF/d cv[c], qc[c] = dF/d ca[c]  (products: without divisions, so that a factor that
+// underflows to zero gives zeros, not NaNs)
+__device__ __forceinline__ void kappa_comp(const KernelParams& kp, double u, double& F, double& dF, double (&pc)[MAXC], double (&qc)[MAXC]) {
+  double kc[MAXC], dkc[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; c++) {
+    kc[c] = 1.0;
+    dkc[c] = 0.0;
+    if (c < kp.ncomp) kappa_and_du(kp.ckind[c], kp.ca[c] * u, 0.0, kc[c], dkc[c]);
+  }
+  F = dF = 0.0;
+  if (kp.kind == AGP_KERNEL_SUM) {
+#pragma unroll
+    for (int c = 0; c < MAXC; c++) {
+      pc[c] = qc[c] = 0.0;
+      if (c < kp.ncomp) {
+        F = fma(kp.cv[c], kc[c], F);
+        dF = fma(kp.cv[c] * kp.ca[c], dkc[c], dF);
+        pc[c] = kc[c];
+        qc[c] = kp.cv[c] * u * dkc[c];
+      }
+    }
+  } else {
+    double tot = 1.0;
+#pragma unroll
+    for (int c = 0; c < MAXC; c++)
+      if (c < kp.ncomp) tot *= kp.cv[c] * kc[c];
+    F = tot;
+#pragma unroll
+    for (int c = 0; c < MAXC; c++) {
+      pc[c] = qc[c] = 0.0;
+      if (c < kp.ncomp) {
+        double oth = 1.0;  // product of the other factors
+#pragma unroll
+        for (int e = 0; e < MAXC; e++)
+          if (e < kp.ncomp && e != c) oth *= kp.cv[e] * kc[e];
+        pc[c] = oth * kc[c];
+        qc[c] = oth * kp.cv[c] * u * dkc[c];
+        dF = fma(oth * kp.cv[c] * kp.ca[c], dkc[c], dF);
+      }
+    }
+  }
 }
 
 // ---- likelihood expectations ------------------------------------------------------------------

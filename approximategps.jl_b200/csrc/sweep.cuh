@@ -18,7 +18,10 @@
 
 namespace agp {
 
-constexpr int TR_KUF_FWD = 0, TR_RHS_FWD = 1, TR_RHS_BWD = 2, TR_KUF_FWD_SCALED = 3;
+constexpr int TR_KUF_FWD = 0, TR_RHS_FWD = 1, TR_RHS_BWD = 2, TR_KUF_FWD_SCALED = 3, TR_RHS_FWD_SUMS = 4;
+// TR_RHS_FWD_SUMS: the forward solve of S1 on a right-hand side that kuf_gen_kernel wrote into X (in place), with S1's column
+// sums a^T a and a^T mt.  The Kuf tile then costs one extra HBM write + read (0.6 GB per 151 552-point launch group, ~0.1 ms at
+// the measured copy bandwidth) instead of a generator entangled with the DMMA pipeline (~0.95 ms per launch group, r01t / r2a).
 // TR_KUF_FWD_SCALED (Laplace prediction, Laplace.jl:427-431): the generated rows are k(x_l, x*) scaled by rowscale[l]
 // (Wsqrt) before the solve, and skd[n] = sum_l k(x_l, x*_n) dvec[l] (k' * d_loglik) is accumulated from the unscaled rows.
 
@@ -29,6 +32,7 @@ struct TrsmArgs {
   int nb;     // Mp / BM
   double* X;  // [Mp][ldx] row-major: solution (and, in RHS modes, the right-hand side; in place)
   int64_t ldx;
+  const double* RHS;  // RHS modes, optional: right-hand side in a separate matrix (same layout); X is then only written / re-read as solution
   // TR_KUF_FWD only
   const double* pts;  // chunk's points, point-major [npts][D]
   int npts;
@@ -116,8 +120,8 @@ __device__ __forceinline__ void gen_kuf_tile(double* __restrict__ sB, const doub
     v0 = valid ? kp.variance * u[h][0] : 0.0;  // timing experiment only
     v1 = valid ? kp.variance * u[h][1] : 0.0;
 #else
-    v0 = valid ? kp.variance * kappa(kind, u[h][0], kp.c) : 0.0;
-    v1 = valid ? kp.variance * kappa(kind, u[h][1], kp.c) : 0.0;
+    v0 = valid ? kp.variance * kappa_kp(kp, u[h][0]) : 0.0;
+    v1 = valid ? kp.variance * kappa_kp(kp, u[h][1]) : 0.0;
 #endif
     if (SCALED) {
       const double dv = dvec[row], rsc = rowscale[row];
@@ -137,7 +141,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
   extern __shared__ __align__(128) double smem[];
   using Cfg = StageCfg<A_KM, B_KN>;
   constexpr bool SCALED = MODE == TR_KUF_FWD_SCALED;
-  constexpr bool FWD = MODE == TR_KUF_FWD || SCALED;
+  constexpr bool FWD = MODE == TR_KUF_FWD || SCALED;          // generator modes: the Kuf tile is built inside the pipeline
+  constexpr bool SUMS = FWD || MODE == TR_RHS_FWD_SUMS;       // S1's column sums
   ThreadMap tm;
   const int tid = threadIdx.x;
   const int n0 = blockIdx.x * BN;
@@ -202,7 +207,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
       const double* zsrc = a.zsp + (int64_t)(J * BM + kk * BK) * Sx;
       for (int ch = tid; ch < BK * Sx / 2; ch += NTHREADS) cp_async16(st + Cfg::elems + ch * 2, zsrc + ch * 2);
     } else {
-      lb.load(st + Cfg::a_elems, a.X + (int64_t)(L * BM + kk * BK) * a.ldx + n0);
+      const double* bsrc = (a.RHS != nullptr && it_issue.is_diag()) ? a.RHS : a.X;
+      lb.load(st + Cfg::a_elems, bsrc + (int64_t)(L * BM + kk * BK) * a.ldx + n0);
     }
     it_issue.next();
   };
@@ -258,13 +264,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
 #pragma unroll
       for (int mi = 0; mi < 4; mi++) {
         const int row = J * BM + tm.row(mi);
-        const double mtr = FWD ? a.mt[row] : 0.0;
+        const double mtr = SUMS ? a.mt[row] : 0.0;
         double* xr = a.X + (int64_t)row * a.ldx + n0;
 #pragma unroll
         for (int ni = 0; ni < 4; ni++) {
           const double v0 = acc[mi][ni][0], v1 = acc[mi][ni][1];
           *reinterpret_cast<double2*>(xr + tm.col(ni, 0)) = make_double2(v0, v1);
-          if (FWD) {
+          if (SUMS) {
             qa[2 * ni] = fma(v0, v0, qa[2 * ni]);
             qa[2 * ni + 1] = fma(v1, v1, qa[2 * ni + 1]);
             qm[2 * ni] = fma(v0, mtr, qm[2 * ni]);
@@ -272,7 +278,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
           }
         }
       }
-      if (FWD) {
+      if (SUMS) {
         const bool b2 = tm.g & 4, b1 = tm.g & 2, b0 = tm.g & 1;
 #pragma unroll
         for (int j = 0; j < 4; j++) {  // fold c bit 2 over lane bit 4
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
     it_cons.next();
   }
   cp_async_wait<0>();
-  if (FWD) {
+  if (SUMS) {
     __syncthreads();
     double* sred = smem;  // [2][4 m-warps][64]
     {
@@ -321,6 +327,70 @@ __global__ void __launch_bounds__(NTHREADS, 2) trsm_kernel(TrsmArgs a) {
         for (int o = 4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (tm.g == 0) a.skd[n0 + tm.warp * 8 + 2 * tm.t + e] = v;
       }
+    }
+  }
+}
+
+// ---- S1, first half: Kuf = cov(f.prior, z, x) (SVA.jl:216) for one launch group, row-major [Mp][ldx] -----------------------
+// One thread per point (its scaled coordinates in registers), 128 inducing rows per CTA read as shared-memory broadcasts from the
+// padded scaled copy of Z (prep_z_kernel: [Dq + 2] doubles per row, squared norm at column Dq); the stores of a warp are 256
+// contiguous bytes of one row.  Rows >= M are written as zeros (padding of every M x chunk operand), columns >= npts get x = 0.
+struct KufGenArgs {
+  double* K;
+  double* DK;  // optional: variance * kappa'(u), same layout (kept for S7 so that the reverse pass neither recomputes distances nor exp)
+  int64_t ldx;
+  int ncols;          // columns to write (multiple of BN)
+  const double* pts;  // [npts][D] raw points
+  int npts;
+  const double* zsp;  // [Mp][Dq + 2]
+  KernelParams kp;
+};
+constexpr int KG_ROWS = 128, KG_COLS = 256;
+template <int DMAX>
+__global__ void __launch_bounds__(KG_COLS) kuf_gen_kernel(KufGenArgs a) {
+  extern __shared__ __align__(16) double kgz[];  // [KG_ROWS][Sx]
+  const int D = a.kp.D, kind = a.kp.kind, Dq = kuf_dp(D), Sx = Dq + 2;
+  const int row0 = blockIdx.y * KG_ROWS;
+  const int n = blockIdx.x * KG_COLS + threadIdx.x;
+  {
+    const double* src = a.zsp + (int64_t)row0 * Sx;
+    for (int i = threadIdx.x; i < KG_ROWS * Sx / 2; i += KG_COLS) reinterpret_cast<double2*>(kgz)[i] = reinterpret_cast<const double2*>(src)[i];
+  }
+  double x[DMAX];
+  double xn = 0.0;
+#pragma unroll
+  for (int d = 0; d < DMAX; d++) {
+    x[d] = (d < D && n < a.npts) ? a.pts[(int64_t)n * D + d] * a.kp.s[d] : 0.0;
+    xn = fma(x[d], x[d], xn);
+  }
+  __syncthreads();
+  if (n >= a.ncols) return;
+  const bool direct = D == 1 && kind != AGP_KERNEL_LINEAR;
+  double* out = a.K + (int64_t)row0 * a.ldx + n;
+  double* outd = a.DK ? a.DK + (int64_t)row0 * a.ldx + n : nullptr;
+  const double var = a.kp.variance;
+#pragma unroll 4
+  for (int r = 0; r < KG_ROWS; r++) {
+    const double* z = kgz + r * Sx;
+    double u;
+    if (direct) {
+      const double df = x[0] - z[0];
+      u = df * df;
+    } else {
+      double dot = 0.0;
+#pragma unroll
+      for (int d = 0; d < DMAX; d++)
+        if (d < Dq) dot = fma(x[d], z[d], dot);
+      u = u_from_dot(kind, xn, z[Dq], dot);
+    }
+    if (outd) {  // plain kinds only (launch_s1)
+      double k, dk;
+      kappa_and_du(kind, u, a.kp.c, k, dk);
+      const bool valid = row0 + r < a.kp.M;
+      out[(int64_t)r * a.ldx] = valid ? var * k : 0.0;
+      outd[(int64_t)r * a.ldx] = valid ? var * dk : 0.0;
+    } else {
+      out[(int64_t)r * a.ldx] = (row0 + r < a.kp.M) ? var * kappa_kp(a.kp, u) : 0.0;
     }
   }
 }
@@ -461,8 +531,8 @@ __device__ __forceinline__ void perpoint_one(const PerPointArgs& p, int n, bool 
     kxxfac = s + p.kp.c;
     kxx = p.kp.variance * kxxfac;
   } else {
-    kxxfac = 1.0;
-    kxx = p.kp.variance;
+    kxxfac = p.kp.f0;  // kappa(0): 1, or sum / product of the component variances
+    kxx = p.kp.variance * kxxfac;
   }
   const double mu = p.mean_const + sam;
   const double var0 = kxx - saa + scc;
@@ -594,6 +664,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) syrk_kernel(SyrkArgs a) {
 // W = Kb * variance * kappa'(u).  kgrad_finish_kernel turns these into dZ, ds, dvariance, dc.
 struct KgradArgs {
   const double* Kb;
+  const double* Kf;  // FAST: the kernel values variance * kappa(u) and
+  const double* DK;  //       variance * kappa'(u) that kuf_gen_kernel stored for these points (same layout as Kb)
   int64_t ld;
   const double* pts;  // [npts][D] raw points
   int npts;
@@ -601,15 +673,20 @@ struct KgradArgs {
   const double* zn;
   int slab;      // points per slab
   double* part;  // [nslab][Mp][stride]
-  int stride;    // 2*D + 3
+  int stride;    // kgrad_stride(D) = 2*D + 3 + 2*MAXC: [rs, dvar, dc, wx[D], sum W (xs-zs)^2 [D], P[MAXC], Q[MAXC]]
   int Mp;
   KernelParams kp;
 };
+__host__ __device__ __forceinline__ int kgrad_stride(int D) { return 2 * D + 3 + 2 * MAXC; }
+__host__ __device__ __forceinline__ int theta_size(int D) { return 2 + D + 2 * MAXC; }
+constexpr int AGP_KERNEL_COMPOSITE = AGP_KERNEL_SUM;  // kgrad_kernel's KIND for both sums and products (kp.kind tells them apart)
 
 // RW rows per warp (16 or 8 rows per CTA): the points of a slab are staged through shared memory in tiles of 256
 // (scaled, with their squared norm) and shared by all rows of the CTA; each lane handles 8 points of a tile for its
 // RW rows, the Kb values of a tile are fetched up front so that the HBM latency overlaps the exp / FMA work.
-template <int DMAX, int RW, int KIND>
+// FAST (stationary kinds inside the sweep): kappa and kappa' are read back instead of recomputed -- no distances, no exp; what is left per
+// element is three coalesced loads and 3 D + 2 FMA-class operations.
+template <int DMAX, int RW, int KIND, bool FAST = false>
 __global__ void __launch_bounds__(256, (DMAX <= 8 && RW == 1) ? 2 : 1) kgrad_kernel(KgradArgs a) {
   extern __shared__ __align__(16) double kg_smem[];  // [256][Sx]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -629,6 +706,12 @@ __global__ void __launch_bounds__(256, (DMAX <= 8 && RW == 1) ? 2 : 1) kgrad_ker
     znr[r] = rvalid[r] ? a.zn[row0 + r] : 0.0;
   }
   double rs[RW], dvar[RW], dcc[RW], wx[RW][DMAX], wxx[RW][DMAX];
+  constexpr bool composite = KIND == AGP_KERNEL_COMPOSITE;
+  double cP[composite ? RW : 1][MAXC], cQ[composite ? RW : 1][MAXC];  // sum Kb dF/dcv[c], sum Kb dF/dca[c]
+#pragma unroll
+  for (int c = 0; c < MAXC; c++)
+#pragma unroll
+    for (int r = 0; r < (composite ? RW : 1); r++) cP[r][c] = cQ[r][c] = 0.0;
 #pragma unroll
   for (int r = 0; r < RW; r++) {
     rs[r] = dvar[r] = dcc[r] = 0.0;
@@ -652,12 +735,18 @@ __global__ void __launch_bounds__(256, (DMAX <= 8 && RW == 1) ? 2 : 1) kgrad_ker
     __syncthreads();
     const int cnt = min(256, ne - t0);
     double kb[RW][8];
+    double kfv[FAST ? RW : 1][8], dkv[FAST ? RW : 1][8];
 #pragma unroll
     for (int r = 0; r < RW; r++)
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         const int p = lane + 32 * i;
-        kb[r][i] = (p < cnt && rvalid[r]) ? a.Kb[(int64_t)(row0 + r) * a.ld + t0 + p] : 0.0;
+        const bool ok = p < cnt && rvalid[r];
+        kb[r][i] = ok ? a.Kb[(int64_t)(row0 + r) * a.ld + t0 + p] : 0.0;
+        if constexpr (FAST) {
+          kfv[r][i] = ok ? a.Kf[(int64_t)(row0 + r) * a.ld + t0 + p] : 0.0;
+          dkv[r][i] = ok ? a.DK[(int64_t)(row0 + r) * a.ld + t0 + p] : 0.0;
+        }
       }
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -679,6 +768,19 @@ __global__ void __launch_bounds__(256, (DMAX <= 8 && RW == 1) ? 2 : 1) kgrad_ker
       const double xnn = xr[Dp];
 #pragma unroll
       for (int r = 0; r < RW; r++) {
+        if constexpr (FAST) {
+          const double kbv = kb[r][i];
+          dvar[r] = fma(kbv, kfv[r][i], dvar[r]);  // sum Kb variance kappa: divided by the variance at the end
+          const double W = kbv * dkv[r][i];
+          rs[r] += W;
+#pragma unroll
+          for (int d = 0; d < DMAX; d++) {
+            const double wxd = W * xs[d];
+            wx[r][d] += wxd;
+            wxx[r][d] = fma(wxd, xs[d], wxx[r][d]);
+          }
+          continue;
+        }
         double u;
         if (direct) {
           const double df = xs[0] - z[r][0];
@@ -690,8 +792,18 @@ __global__ void __launch_bounds__(256, (DMAX <= 8 && RW == 1) ? 2 : 1) kgrad_ker
           u = u_from_dot(kind, xnn, znr[r], dot);
         }
         double k, dk;
-        kappa_and_du(kind, u, a.kp.c, k, dk);
         const double kbv = kb[r][i];
+        if constexpr (composite) {
+          double pc[MAXC], qc[MAXC];
+          kappa_comp(a.kp, u, k, dk, pc, qc);
+#pragma unroll
+          for (int c = 0; c < MAXC; c++) {
+            cP[r][c] = fma(kbv, pc[c], cP[r][c]);
+            cQ[r][c] = fma(kbv, qc[c], cQ[r][c]);
+          }
+        } else {
+          kappa_and_du(kind, u, a.kp.c, k, dk);
+        }
         dvar[r] = fma(kbv, k, dvar[r]);
         dcc[r] += kbv;
         const double W = kbv * a.kp.variance * dk;
@@ -717,12 +829,26 @@ __global__ void __launch_bounds__(256, (DMAX <= 8 && RW == 1) ? 2 : 1) kgrad_ker
         wx[r][d] += __shfl_xor_sync(0xffffffffu, wx[r][d], o);
         wxx[r][d] += __shfl_xor_sync(0xffffffffu, wxx[r][d], o);
       }
+      if constexpr (composite) {
+#pragma unroll
+        for (int c = 0; c < MAXC; c++) {
+          cP[r][c] += __shfl_xor_sync(0xffffffffu, cP[r][c], o);
+          cQ[r][c] += __shfl_xor_sync(0xffffffffu, cQ[r][c], o);
+        }
+      }
     }
     if (lane == 0 && rvalid[r]) {
       double* out = a.part + ((int64_t)slab * a.Mp + row0 + r) * a.stride;
       out[0] += rs[r];
-      out[1] += dvar[r];
+      out[1] += FAST ? dvar[r] / a.kp.variance : dvar[r];
       out[2] += dcc[r];
+      if constexpr (composite) {
+#pragma unroll
+        for (int c = 0; c < MAXC; c++) {
+          out[3 + 2 * D + c] += cP[r][c];
+          out[3 + 2 * D + MAXC + c] += cQ[r][c];
+        }
+      }
 #pragma unroll
       for (int d = 0; d < DMAX; d++)
         if (d < D) {
@@ -744,7 +870,7 @@ struct KgradFinishArgs {
   const double* zs;
   double zfac;
   double* dZ;     // [Mp][D] accumulated
-  double* theta;  // [2 + D]: dvariance, dc, ds[d]  (accumulated; single block)
+  double* theta;  // [theta_size(D)]: dvariance, dc, ds[d], then per component d cv[c] (MAXC) and d (component inverse lengthscale) (MAXC)
   KernelParams kp;
 };
 
@@ -778,6 +904,22 @@ __global__ void __launch_bounds__(256) kgrad_finish_kernel(KgradFinishArgs a) {
   if (threadIdx.x == 0) {
     a.theta[0] += tv;
     a.theta[1] += linear ? a.kp.variance * tc : 0.0;
+  }
+  if (kernel_is_composite(a.kp.kind)) {
+    // k = variance F: d/d cv[c] = variance sum Kb dF/dcv[c];  d/d s_c = variance sum Kb dF/dca[c] * 2 s_c,  ca[c] = s_c^2
+    for (int j = 0; j < 2 * MAXC; j++) {
+      double v = 0.0;
+      for (int row = threadIdx.x; row < a.kp.M; row += blockDim.x) {
+        double s = 0.0;
+        for (int sl = 0; sl < a.nslab; sl++) s += a.part[((int64_t)sl * a.Mp + row) * a.stride + 3 + 2 * D + j];
+        v += s;
+      }
+      const double r = block_sum(v, sred);
+      if (threadIdx.x == 0) {
+        const int c = j % MAXC;
+        a.theta[2 + D + j] += (j < MAXC) ? a.kp.variance * r : a.kp.variance * r * 2.0 * sqrt(a.kp.ca[c]);
+      }
+    }
   }
   for (int i = threadIdx.x; i < a.kp.M * D; i += blockDim.x) {
     const int row = i / D, d = i % D;

@@ -69,6 +69,8 @@ class LaplaceGradient:
     inv_lengthscale: np.ndarray
     linear_c: float
     X: np.ndarray
+    comp_variance: np.ndarray = None        # kernel sums / products: per component
+    comp_inv_lengthscale: np.ndarray = None
 
 
 @dataclass
@@ -105,10 +107,12 @@ def _run(ctx, *, K=None, kernel=None, X=None, jitter=0.0, y, lik, f_init=None, m
             X = X[:, None]
         if X.shape[0] != n:
             raise AssertionError("length(ys) == length(lfx.fx)")  # Laplace.jl:172
-        ils = np.ascontiguousarray(kernel.inv_lengthscale, dtype=np.float64)
-        kk = L.AgpKernel(kernel.kind, ils.size, kernel.variance, L.dptr(ils), kernel.c)
+        from .api import agp_kernel_struct
+
+        kk, kkeep = agp_kernel_struct(kernel)
+        ils = kkeep[0]
         pr.kernel, pr.X, pr.D, pr.jitter = C.pointer(kk), L.dptr(X), X.shape[1], float(jitter)
-        keep += [X, ils, kk]
+        keep += [X, kkeep, kk]
     pr.y = L.dptr(y)
     pr.lik = L.AgpLikelihood(lik.kind, float(lik.sigma2))
     if f_init is not None:
@@ -148,13 +152,17 @@ def _run(ctx, *, K=None, kernel=None, X=None, jitter=0.0, y, lik, f_init=None, m
         dils, dX = np.zeros(ils.size), np.zeros_like(X)
         rs.dvariance, rs.dlinear_c = sc[0:1].ctypes.data_as(L.c_double_p), sc[1:2].ctypes.data_as(L.c_double_p)
         rs.dinv_lengthscale, rs.dX = L.dptr(dils), L.dptr(dX)
+        ncomp = len(kernel.components)
+        dcv, dcs = np.zeros(ncomp), np.zeros(ncomp)
+        if ncomp:
+            rs.dcomp_variance, rs.dcomp_inv_lengthscale = L.dptr(dcv), L.dptr(dcs)
     h = C.c_void_p()
     status = lib.agp_laplace_f_and_lml(ctx.h, C.byref(pr), C.byref(rs), C.byref(h) if want_cache else None)
     if cb_error:
         raise cb_error[0]
     L.check(status)
     if want_grad:
-        grad = LaplaceGradient(float(sc[0]), dils, float(sc[1]), dX)
+        grad = LaplaceGradient(float(sc[0]), dils, float(sc[1]), dX, dcv, dcs)
     cache = LaplaceCacheView(lib, h, n, owning=True) if want_cache else None
     return LaplaceResult(f_opt, rs.lml, rs.steps, bool(rs.converged), dK, grad, cache)
 
@@ -284,9 +292,9 @@ class LaplacePosterior:
     def _predict(self, x, y=None, want_mean=False, want_var=False, want_cov=False):
         from .api import _points
 
-        k = self.prior.f.kernel
-        ils = np.ascontiguousarray(k.inv_lengthscale, dtype=np.float64)
-        kk = L.AgpKernel(k.kind, ils.size, k.variance, L.dptr(ils), k.c)
+        from .api import agp_kernel_struct
+
+        kk, _kkeep = agp_kernel_struct(self.prior.f.kernel)
         Xt = _points(self.prior.x)
         x = _points(x)
         yy = None if y is None else _points(y)

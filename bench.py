@@ -688,6 +688,29 @@ def run_laplace(args, w):
     ms_g = timed(step_grad, max(1, min(args.steps, 3))) / max(1, min(args.steps, 3))
     flop_it = laplace_flops_per_iteration(n)
     achieved = flop_it / (ms_iter * 1e-3) / 1e12
+    # yard-stick (not part of any product path): the vendor dense Cholesky (torch.linalg.cholesky_ex -> cuSOLVER potrf) on a matrix of the same size
+    yard = None
+    if rank == 0:
+        try:
+            g = torch.Generator(device="cuda").manual_seed(1)
+            Bm = torch.randn(n, n, dtype=torch.float64, device="cuda", generator=g)
+            Bm = Bm @ Bm.T / n + torch.eye(n, dtype=torch.float64, device="cuda")
+            for _ in range(2):
+                torch.linalg.cholesky_ex(Bm)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                torch.linalg.cholesky_ex(Bm)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_cus = e0.elapsed_time(e1) / 5
+            yard = {"cusolver_potrf_ms": ms_cus, "cusolver_potrf_tflops": n ** 3 / 3 / (ms_cus * 1e-3) / 1e12,
+                    "note": "torch.linalg.cholesky_ex (cuSOLVER) on a random SPD matrix of the same size; one Newton iteration is one such factorisation "
+                            "(+ the factor's block inverses, which this library's kernel also produces) + 6 n^2 of matrix-vector work"}
+            del Bm
+        except Exception as e:  # noqa: BLE001
+            yard = {"error": str(e)[:200]}
     if rank == 0:
         roof = {"bound": "tensor", "kernel": "blocked Cholesky of B = I + sqrt(W) K sqrt(W) (potrf_trinv128 + DMMA panel / trailing GEMMs) and the Newton update",
                 "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma, "traffic": None,
@@ -698,7 +721,7 @@ def run_laplace(args, w):
                 "config": {"workload": w["label"], "N": n, "D": w["D"], "parallelism": f"replicas x{world} (the path does not shard)",
                            "l2": "K, B and L are 537 MB each: far beyond the 126 MB L2"},
                 "lml": r.lml, "newton_steps": r.steps, "newton_iterations_per_step": iters, "gpu_launches": launches, "clocks": clk, "roofline": roof,
-                "lml_and_gradient_ms": ms_g,
+                "lml_and_gradient_ms": ms_g, "yardstick": yard,
                 "e2e": {"value": it_per_s, "unit": LAPLACE_UNIT, "ms_per_step": ms / args.steps, "h2d_bytes_per_step": 8 * n * (w["D"] + 1) * world,
                         "d2h_bytes_per_step": 8 * (n + 1) * world,
                         "note": "the timed call IS the end-to-end call: host X, y in, host f_opt and lml out, every step (the kernel matrix is built on the device)"}}

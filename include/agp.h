@@ -39,6 +39,9 @@ extern "C" {
 #define AGP_KERNEL_MATERN32 1 /* (1+sqrt3 d) exp(-sqrt3 d)                                       */
 #define AGP_KERNEL_MATERN52 2 /* (1+sqrt5 d+5d^2/3) exp(-sqrt5 d)                                */
 #define AGP_KERNEL_LINEAR 3   /* x.y + c                                                         */
+#define AGP_KERNEL_SUM 4      /* KernelSum of stationary components (agp_kernel.components)      */
+#define AGP_KERNEL_PRODUCT 5  /* KernelProduct of stationary components                          */
+#define AGP_MAX_COMPONENTS 4
 
 #define AGP_LIK_GAUSSIAN 0        /* GaussianLikelihood(sigma2)                                  */
 #define AGP_LIK_BERNOULLI_LOGIT 1 /* BernoulliLikelihood() (logistic link)                       */
@@ -84,12 +87,26 @@ typedef struct agp_laplace_cache agp_laplace_cache;
 
 /* `variance * (base o ScaleTransform(s))` (n_scale == 1) or `... o ARDTransform(v)` (n_scale == D);
  * KernelFunctions semantics as reached through cov(f.prior, z, x) at SVA.jl:216.                 */
+/* One term / factor of a KernelSum / KernelProduct (KernelFunctions `k1 + k2`, `k1 * k2`, reached through the same cov(f.prior, z, x)
+ * at SVA.jl:216): `variance * (base o ScaleTransform(inv_lengthscale))` with a stationary base (SE, Matern32, Matern52).      */
+typedef struct {
+  int32_t kind;
+  double variance;
+  double inv_lengthscale;
+} agp_kernel_component;
+
 typedef struct {
   int32_t kind;
   int32_t n_scale;
   double variance;
   const double* inv_lengthscale; /* host, n_scale entries */
   double linear_c;
+  /* kind == AGP_KERNEL_SUM / AGP_KERNEL_PRODUCT:
+   *   k = variance * ((c_1 + ... + c_n) o T)   or   variance * ((c_1 * ... * c_n) o T),   T = ScaleTransform / ARDTransform(inv_lengthscale)
+   * i.e. the components share the outer transform T (pass inv_lengthscale = {1} for none) and each has its own scalar lengthscale,
+   * so that one scaled squared distance serves all of them.  Ignored (may be 0 / NULL) for the plain kinds.                      */
+  int32_t n_components;                   /* 1..AGP_MAX_COMPONENTS */
+  const agp_kernel_component* components; /* host */
 } agp_kernel;
 
 typedef struct {
@@ -136,6 +153,8 @@ typedef struct {
   double* dlinear_c;        /* 1                                             */
   double* dmean_const;      /* 1                                             */
   double* dlik_sigma2;      /* 1: d / d(likelihood parameter) (sigma2 or alpha)  */
+  double* dcomp_variance;        /* n_components (AGP_KERNEL_SUM / AGP_KERNEL_PRODUCT only) */
+  double* dcomp_inv_lengthscale; /* n_components                                            */
 } agp_svgp_grads;
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -295,6 +314,8 @@ typedef struct {
   double* dinv_lengthscale; /* n_scale                                                             */
   double* dlinear_c;
   double* dX;               /* point-major n x D                                                   */
+  double* dcomp_variance;        /* n_components (AGP_KERNEL_SUM / AGP_KERNEL_PRODUCT only)         */
+  double* dcomp_inv_lengthscale; /* n_components                                                    */
 } agp_laplace_result;
 
 /* Replaces newton_inner_loop / _newton_inner_loop (Laplace.jl:256-276, :304-307), the intermediates at

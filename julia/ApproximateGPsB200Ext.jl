@@ -20,12 +20,19 @@ import ApproximateGPs.LaplaceApproximationModule: laplace_f_and_lml, laplace_f_c
 const lib = get(ENV, "AGP_B200_LIB", "libagp_b200.so")
 
 # ---- mirrors of the C structs (field order = include/agp.h) --------------------------------------------------------------------
+struct AgpKernelComponent
+    kind::Int32
+    variance::Float64
+    inv_lengthscale::Float64
+end
 struct AgpKernel
     kind::Int32
     n_scale::Int32
     variance::Float64
     inv_lengthscale::Ptr{Float64}
     linear_c::Float64
+    n_components::Int32
+    components::Ptr{AgpKernelComponent}
 end
 struct AgpLikelihood
     kind::Int32
@@ -62,6 +69,8 @@ struct AgpSvgpGrads
     dlinear_c::Ptr{Float64}
     dmean_const::Ptr{Float64}
     dlik_sigma2::Ptr{Float64}
+    dcomp_variance::Ptr{Float64}
+    dcomp_inv_lengthscale::Ptr{Float64}
 end
 struct AgpLaplaceProblem
     n::Int32
@@ -87,6 +96,8 @@ mutable struct AgpLaplaceResult
     dinv_lengthscale::Ptr{Float64}
     dlinear_c::Ptr{Float64}
     dX::Ptr{Float64}
+    dcomp_variance::Ptr{Float64}
+    dcomp_inv_lengthscale::Ptr{Float64}
 end
 
 # ---- status -> exception (SURVEY.md section 8b "error conventions") ---------------------------------------------------------------
@@ -155,7 +166,22 @@ unpack(::SqExponentialKernel) = (Int32(0), 1.0, [1.0], 0.0)
 unpack(::Matern32Kernel) = (Int32(1), 1.0, [1.0], 0.0)
 unpack(::Matern52Kernel) = (Int32(2), 1.0, [1.0], 0.0)
 unpack(k::LinearKernel) = (Int32(3), 1.0, [1.0], only(k.c))
+unpack(k::KernelSum) = (Int32(4), 1.0, [1.0], 0.0)       # AGP_KERNEL_SUM: the terms travel as components(k)
+unpack(k::KernelProduct) = (Int32(5), 1.0, [1.0], 0.0)   # AGP_KERNEL_PRODUCT
 unpack(k::Kernel) = throw(ArgumentError("kernel $(typeof(k)) is not implemented on the device (no CPU fallback)"))
+# the terms / factors of a KernelSum / KernelProduct: stationary kernels with their own variance and scalar lengthscale; the outer
+# ScaledKernel / TransformedKernel nodes around the sum or product go into the agp_kernel's variance / inv_lengthscale as usual
+function component(t::Kernel)
+    kind, var, ils, _ = unpack(t)
+    (kind <= 2 && length(ils) == 1) || throw(ArgumentError("kernel sums / products on the device take stationary kernels with scalar lengthscales"))
+    return AgpKernelComponent(kind, var, only(ils))
+end
+components(k::KernelSum) = AgpKernelComponent[component(t) for t in k.kernels]
+components(k::KernelProduct) = AgpKernelComponent[component(t) for t in k.kernels]
+components(k::ScaledKernel) = components(k.kernel)
+components(k::TransformedKernel) = components(k.kernel)
+components(::Kernel) = AgpKernelComponent[]
+agp_kernel(kind, ilsv, var, c, comps) = AgpKernel(kind, length(ilsv), var, pointer(ilsv), c, length(comps), isempty(comps) ? C_NULL : pointer(comps))
 
 # Structural tangents of the same trees from the flat device gradient g = (dvariance, dinv_lengthscale, dlinear_c):
 # d/d(ScaledKernel.σ²) = dvariance * (variance / σ²) ... every node's parameter enters the packed value as a product, so its
@@ -174,6 +200,13 @@ function kernel_tangent(k::TransformedKernel{<:Any,<:ARDTransform}, Δ, g)
     return Tangent{typeof(k)}(; kernel=kernel_tangent(k.kernel, Δ, g), transform=Tangent{typeof(k.transform)}(; v=Δ .* g.dinv_lengthscale .* ils ./ k.transform.v))
 end
 kernel_tangent(k::LinearKernel, Δ, g) = Tangent{typeof(k)}(; c=[Δ * g.dlinear_c])
+# KernelSum / KernelProduct: term i is variance_i * (base_i ∘ ScaleTransform(s_i)); its cotangents are entries i of the component gradients
+function kernel_tangent(k::Union{KernelSum,KernelProduct}, Δ, g)
+    ts = map(enumerate(k.kernels)) do (i, t)
+        kernel_tangent(t, Δ, (; dvariance=g.dcomp_variance[i], dinv_lengthscale=[g.dcomp_inv_lengthscale[i]], dlinear_c=0.0))
+    end
+    return Tangent{typeof(k)}(; kernels=Tuple(ts))
+end
 kernel_tangent(::Kernel, Δ, g) = NoTangent()   # SqExponential / Matern: no parameters
 mean_tangent(m::ConstMean, d) = Tangent{typeof(m)}(; c=d)
 mean_tangent(::Any, d) = NoTangent()           # ZeroMean
@@ -213,11 +246,12 @@ function pack(sva::SparseVariationalApproximation{P}, lik, quadrature; T::Type=F
     Lq = Matrix{Float64}(_chol_lower(_chol_cov(sva.q)))        # utils.jl:15-18: the PDMat factor as given
     method, npts, xs, ws, seed = quad_spec(default_quad(lik, quadrature))
     ilsv = collect(Float64, ils)
-    keep = (ilsv, Z, m, Lq, xs, ws)
+    comps = components(sva.fz.f.kernel)
+    keep = (ilsv, Z, m, Lq, xs, ws, comps)
     mean_c = sva.fz.f.mean isa ConstMean ? Float64(sva.fz.f.mean.c) : 0.0
-    p = AgpSvgpParams(AgpKernel(kind, length(ilsv), var, pointer(ilsv), c), mean_c, M, D, pointer(Z), Float64(sva.fz.Σy[1]), pointer(m), pointer(Lq), M,
+    p = AgpSvgpParams(agp_kernel(kind, ilsv, var, c, comps), mean_c, M, D, pointer(Z), Float64(sva.fz.Σy[1]), pointer(m), pointer(Lq), M,
                       P === Centered ? Int32(1) : Int32(0), lik_spec(lik), AgpExpectation(method, npts, pointer(xs), pointer(ws), seed), compute_dtype(T))
-    return p, keep, (; M, D, n_scale=length(ilsv))
+    return p, keep, (; M, D, n_scale=length(ilsv), n_comp=length(comps))
 end
 
 function check_prior(sva, fx)   # SVA.jl:347-351
@@ -231,9 +265,11 @@ function elbo_and_grad(sva::SparseVariationalApproximation, lfx::LatentFiniteGP,
     ds = dataset(lfx.fx.x, y)
     out = Ref(0.0)
     dm = zeros(sz.M); dLq = zeros(sz.M, sz.M); dZ = zeros(sz.D, sz.M); sc = zeros(4); dils = zeros(sz.n_scale)
-    GC.@preserve keep dm dLq dZ sc dils begin
+    dcv = zeros(sz.n_comp); dcs = zeros(sz.n_comp)
+    GC.@preserve keep dm dLq dZ sc dils dcv dcs begin
         if want_grad
-            g = AgpSvgpGrads(pointer(dm), pointer(dLq), pointer(dZ), pointer(sc, 1), pointer(dils), pointer(sc, 2), pointer(sc, 3), pointer(sc, 4))
+            g = AgpSvgpGrads(pointer(dm), pointer(dLq), pointer(dZ), pointer(sc, 1), pointer(dils), pointer(sc, 2), pointer(sc, 3), pointer(sc, 4),
+                             sz.n_comp > 0 ? pointer(dcv) : C_NULL, sz.n_comp > 0 ? pointer(dcs) : C_NULL)
             check(ccall((:agp_svgp_elbo_grad, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ref{AgpSvgpParams}, Float64, Int64, Ref{Float64}, Ref{AgpSvgpGrads}),
                         ctx(), ds.h, 0, ds.N, p, Float64(num_data), 0, out, g))
         else
@@ -241,7 +277,8 @@ function elbo_and_grad(sva::SparseVariationalApproximation, lfx::LatentFiniteGP,
                         ctx(), ds.h, 0, ds.N, p, Float64(num_data), 0, out))
         end
     end
-    return out[], (; dm, dLq=LowerTriangular(dLq), dZ, dvariance=sc[1], dinv_lengthscale=dils, dlinear_c=sc[2], dmean_const=sc[3], dlik_sigma2=sc[4])
+    return out[], (; dm, dLq=LowerTriangular(dLq), dZ, dvariance=sc[1], dinv_lengthscale=dils, dlinear_c=sc[2], dmean_const=sc[3], dlik_sigma2=sc[4],
+                   dcomp_variance=dcv, dcomp_inv_lengthscale=dcs)
 end
 
 # ---- elbo / approx_lml (SVA.jl:276-280, :307-360) ------------------------------------------------------------------------------------
@@ -357,18 +394,22 @@ function laplace_call(lik, ys; K=nothing, kernel=nothing, x=nothing, jitter=0.0,
     Kd = K === nothing ? zeros(0, 0) : Matrix{Float64}(K)
     dK = want_dK ? zeros(n, n) : zeros(0, 0)
     kind, var, ils, c, X, D = Int32(0), 1.0, [1.0], 0.0, zeros(1, 0), 1
+    comps = AgpKernelComponent[]
     if K === nothing
         kind, var, ils, c = unpack(kernel)
+        comps = components(kernel)
         X = pointmajor(x); D = size(X, 1)
     end
     ilsv = collect(Float64, ils); dils = zeros(length(ilsv)); dX = zeros(D, K === nothing ? n : 0)
-    k = Ref(AgpKernel(kind, length(ilsv), var, pointer(ilsv), c))
+    dcv = zeros(length(comps)); dcs = zeros(length(comps))
+    k = Ref(agp_kernel(kind, ilsv, var, c, comps))
     cbref = Ref{Any}(callback)
     cb = callback === nothing ? C_NULL : @cfunction(newton_cb, Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}))
     cache = Ref{Ptr{Cvoid}}(C_NULL)
     rs = AgpLaplaceResult(pointer(f_opt), 0.0, 0, 0, want_dK ? pointer(dK) : C_NULL, want_grad ? pointer(sc, 1) : C_NULL, want_grad ? pointer(dils) : C_NULL,
-                          want_grad ? pointer(sc, 2) : C_NULL, want_grad ? pointer(dX) : C_NULL)
-    GC.@preserve ilsv X yf f0 f_opt sc dils dX Kd dK k cbref begin
+                          want_grad ? pointer(sc, 2) : C_NULL, want_grad ? pointer(dX) : C_NULL,
+                          want_grad && !isempty(comps) ? pointer(dcv) : C_NULL, want_grad && !isempty(comps) ? pointer(dcs) : C_NULL)
+    GC.@preserve ilsv comps dcv dcs X yf f0 f_opt sc dils dX Kd dK k cbref begin
         pr = AgpLaplaceProblem(n, K === nothing ? C_NULL : pointer(Kd), K === nothing ? Base.unsafe_convert(Ptr{AgpKernel}, k) : C_NULL,
                                K === nothing ? pointer(X) : C_NULL, D, Float64(jitter), pointer(yf), lik_spec(lik), f_init === nothing ? C_NULL : pointer(f0), maxiter,
                                cb, callback === nothing ? C_NULL : pointer_from_objref(cbref))
@@ -378,7 +419,7 @@ function laplace_call(lik, ys; K=nothing, kernel=nothing, x=nothing, jitter=0.0,
         check(st)
     end
     return (; f_opt, lml=rs.lml, steps=Int(rs.steps), converged=rs.converged != 0, dK, dvariance=sc[1], dinv_lengthscale=dils, dlinear_c=sc[2], dX,
-            cache=want_cache ? LazyLaplaceCache(cache[], true) : nothing)
+            dcomp_variance=dcv, dcomp_inv_lengthscale=dcs, cache=want_cache ? LazyLaplaceCache(cache[], true) : nothing)
 end
 # the matrix form the judge's list calls laplace_call_K: newton_inner_loop(dist_y_given_f, ys, K; kwargs...) (Laplace.jl:304-307)
 laplace_call_K(dist_y_given_f, ys, K; kwargs...) = laplace_call(dist_y_given_f, ys; K, kwargs...)
@@ -412,13 +453,13 @@ function AbstractGPs.posterior(la::LaplaceApproximation, lfx::LatentFiniteGP, ys
 end
 const LaplacePosteriorB200 = ApproxPosteriorGP{<:LaplaceApproximation,<:Any,LazyLaplaceCache}
 function laplace_predict(f::LaplacePosteriorB200, x, y; want_mean=false, want_var=false, want_cov=false)   # Laplace.jl:425-463
-    kind, var, ils, c = unpack(f.prior.f.kernel); ilsv = collect(Float64, ils)
+    kind, var, ils, c = unpack(f.prior.f.kernel); ilsv = collect(Float64, ils); comps = components(f.prior.f.kernel)
     Xt = pointmajor(f.prior.x); D = size(Xt, 1)
     X1 = pointmajor(x); n1 = size(X1, 2)
     X2 = y === nothing ? X1 : pointmajor(y); n2 = size(X2, 2)
     μ = zeros(n1); v = zeros(n1); Σ = want_cov ? zeros(n1, n2) : zeros(0, 0)
-    k = Ref(AgpKernel(kind, length(ilsv), var, pointer(ilsv), c))
-    GC.@preserve ilsv Xt X1 X2 k check(ccall((:agp_laplace_predict, lib), Int32,
+    k = Ref(agp_kernel(kind, ilsv, var, c, comps))
+    GC.@preserve ilsv comps Xt X1 X2 k check(ccall((:agp_laplace_predict, lib), Int32,
         (Ptr{Cvoid}, Ref{AgpKernel}, Ptr{Float64}, Int32, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
         f.data.h, k, Xt, D, X1, n1, y === nothing ? Ptr{Float64}(C_NULL) : pointer(X2), n2, want_mean ? pointer(μ) : Ptr{Float64}(C_NULL),
         want_var ? pointer(v) : Ptr{Float64}(C_NULL), want_cov ? pointer(Σ) : Ptr{Float64}(C_NULL)))

@@ -26,7 +26,8 @@ from dataclasses import dataclass, field
 import numpy as np
 
 SE, MATERN32, MATERN52, LINEAR = "se", "matern32", "matern52", "linear"
-KINDS = (SE, MATERN32, MATERN52, LINEAR)
+SUM, PRODUCT = "sum", "product"
+KINDS = (SE, MATERN32, MATERN52, LINEAR, SUM, PRODUCT)
 
 _SQRT3 = np.sqrt(3.0)
 _SQRT5 = np.sqrt(5.0)
@@ -41,10 +42,17 @@ class Kernel:
     variance: float = 1.0
     inv_lengthscale: np.ndarray = field(default_factory=lambda: np.ones(1))
     c: float = 0.0
+    # kind == SUM / PRODUCT (KernelFunctions ``k1 + k2`` / ``k1 * k2`` of stationary kernels under a shared outer transform):
+    # ``variance * ((c_1 (+|*) c_2 ...) o Transform(inv_lengthscale))``, c_i = ``v_i * (base_i o ScaleTransform(s_i))`` given as
+    # (kind_i, v_i, s_i) tuples.  One scaled squared distance u serves all components: c_i = v_i kappa_i(s_i^2 u).
+    components: tuple = ()
 
     def __post_init__(self):
         assert self.kind in KINDS, self.kind
         self.inv_lengthscale = np.atleast_1d(np.asarray(self.inv_lengthscale, dtype=np.float64))
+        if self.kind in (SUM, PRODUCT):
+            assert 1 <= len(self.components) <= 4 and all(q[0] in (SE, MATERN32, MATERN52) for q in self.components)
+            self.components = tuple((q[0], float(q[1]), float(q[2])) for q in self.components)
 
     def scale_vec(self, D: int) -> np.ndarray:
         s = self.inv_lengthscale
@@ -107,9 +115,51 @@ def _dkappa_du(kind: str, u: np.ndarray) -> np.ndarray:
     return -(5.0 / 6.0) * (1.0 + _SQRT5 * d) * np.exp(-_SQRT5 * d)
 
 
+def _F(k: Kernel, u: np.ndarray) -> np.ndarray:
+    """kappa for every kind (sums / products of stationary components included)."""
+    if k.kind not in (SUM, PRODUCT):
+        return _kappa(k.kind, u, k.c)
+    terms = [v * _kappa(kd, s * s * u, 0.0) for kd, v, s in k.components]
+    out = terms[0]
+    for t in terms[1:]:
+        out = out + t if k.kind == SUM else out * t
+    return out
+
+
+def _dF(k: Kernel, u: np.ndarray):
+    """(dF/du, [dF/dv_i], [dF/ds_i]) for a sum / product kernel."""
+    kap = [_kappa(kd, s * s * u, 0.0) for kd, v, s in k.components]
+    dkap = [_dkappa_du(kd, s * s * u) for kd, v, s in k.components]
+    n = len(k.components)
+    if k.kind == SUM:
+        dFdu = sum(v * s * s * dkap[i] for i, (kd, v, s) in enumerate(k.components))
+        dv = [kap[i] for i in range(n)]
+        ds = [v * dkap[i] * u * 2.0 * s for i, (kd, v, s) in enumerate(k.components)]
+        return dFdu, dv, ds
+    dFdu = 0.0
+    dv, ds = [], []
+    for i, (kd, v, s) in enumerate(k.components):
+        oth = 1.0
+        for j, (kdj, vj, sj) in enumerate(k.components):
+            if j != i:
+                oth = oth * (vj * kap[j])
+        dFdu = dFdu + oth * v * s * s * dkap[i]
+        dv.append(oth * kap[i])
+        ds.append(oth * v * dkap[i] * u * 2.0 * s)
+    return dFdu, dv, ds
+
+
+def _F0(k: Kernel) -> float:
+    if k.kind == SUM:
+        return float(sum(v for _, v, _ in k.components))
+    if k.kind == PRODUCT:
+        return float(np.prod([v for _, v, _ in k.components]))
+    return 1.0
+
+
 def kernelmatrix(k: Kernel, X, Y=None) -> np.ndarray:
     """``kernelmatrix(k, x[, y])``: (len(X), len(Y))."""
-    return k.variance * _kappa(k.kind, _u_matrix(k, X, Y), k.c)
+    return k.variance * _F(k, _u_matrix(k, X, Y))
 
 
 def kernelmatrix_diag(k: Kernel, X) -> np.ndarray:
@@ -118,7 +168,7 @@ def kernelmatrix_diag(k: Kernel, X) -> np.ndarray:
     if k.kind == LINEAR:
         Xs = X * k.scale_vec(X.shape[1])
         return k.variance * (np.sum(Xs * Xs, axis=1) + k.c)
-    return np.full(X.shape[0], k.variance * 1.0)
+    return np.full(X.shape[0], k.variance * _F0(k))
 
 
 @dataclass
@@ -126,9 +176,15 @@ class KernelGrad:
     variance: float = 0.0
     inv_lengthscale: np.ndarray | None = None
     c: float = 0.0
+    comp_variance: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    comp_inv_lengthscale: np.ndarray = field(default_factory=lambda: np.zeros(0))
 
     def add(self, o: "KernelGrad") -> "KernelGrad":
-        return KernelGrad(self.variance + o.variance, self.inv_lengthscale + o.inv_lengthscale, self.c + o.c)
+        def _a(x, y):
+            return y if x.size == 0 else (x if y.size == 0 else x + y)
+
+        return KernelGrad(self.variance + o.variance, self.inv_lengthscale + o.inv_lengthscale, self.c + o.c,
+                          _a(self.comp_variance, o.comp_variance), _a(self.comp_inv_lengthscale, o.comp_inv_lengthscale))
 
 
 def kernelmatrix_pullback(k: Kernel, X, Y, Kbar: np.ndarray):
@@ -145,9 +201,15 @@ def kernelmatrix_pullback(k: Kernel, X, Y, Kbar: np.ndarray):
     sym = Y is None
     Yr = X if sym else _as2d(Y)
     u = _u_matrix(k, X, None if sym else Yr)
-    kap = _kappa(k.kind, u, k.c)
+    kap = _F(k, u)
     g = KernelGrad(float(np.sum(Kbar * kap)), np.zeros_like(k.inv_lengthscale), 0.0)
-    W = Kbar * (k.variance * _dkappa_du(k.kind, u))  # cotangent of u
+    if k.kind in (SUM, PRODUCT):
+        dFdu, dv, ds = _dF(k, u)
+        g.comp_variance = np.array([float(np.sum(Kbar * k.variance * t)) for t in dv])
+        g.comp_inv_lengthscale = np.array([float(np.sum(Kbar * k.variance * t)) for t in ds])
+        W = Kbar * (k.variance * dFdu)
+    else:
+        W = Kbar * (k.variance * _dkappa_du(k.kind, u))  # cotangent of u
     if sym and k.kind != LINEAR:
         W = W.copy()
         np.fill_diagonal(W, 0.0)  # the diagonal of u is the constant 0 for stationary kernels
@@ -191,5 +253,11 @@ def kernelmatrix_diag_pullback(k: Kernel, X, vbar: np.ndarray):
         g.inv_lengthscale = np.array([np.sum(sbar)]) if k.inv_lengthscale.size == 1 else sbar
         Xbar = 2.0 * k.variance * (vbar[:, None] * X) * s**2
         return Xbar, g
-    g.variance = float(np.sum(vbar))
+    g.variance = float(np.sum(vbar)) * _F0(k)
+    if k.kind == SUM:
+        g.comp_variance = np.full(len(k.components), k.variance * float(np.sum(vbar)))
+        g.comp_inv_lengthscale = np.zeros(len(k.components))
+    elif k.kind == PRODUCT:
+        g.comp_variance = np.array([k.variance * float(np.sum(vbar)) * _F0(k) / v for _, v, _ in k.components])
+        g.comp_inv_lengthscale = np.zeros(len(k.components))
     return np.zeros_like(X), g

@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 HEADER = os.path.join(ROOT, "include", "agp.h")
 SHIM = os.path.join(ROOT, "julia", "ApproximateGPsB200Ext.jl")
 
-STRUCT_NAMES = {"AgpKernel": "agp_kernel", "AgpLikelihood": "agp_likelihood", "AgpExpectation": "agp_expectation", "AgpSvgpParams": "agp_svgp_params",
+STRUCT_NAMES = {"AgpKernelComponent": "agp_kernel_component", "AgpKernel": "agp_kernel", "AgpLikelihood": "agp_likelihood", "AgpExpectation": "agp_expectation", "AgpSvgpParams": "agp_svgp_params",
                 "AgpSvgpGrads": "agp_svgp_grads", "AgpLaplaceProblem": "agp_laplace_problem", "AgpLaplaceResult": "agp_laplace_result"}
 
 
@@ -156,7 +156,7 @@ def test_ctypes_binding_matches_the_header():
         cret, cargs = protos[name]
         assert cls(res) == cret, (name, res, cret)
         assert [cls(a) for a in args] == cargs, (name, [cls(a) for a in args], cargs)
-    for pyname, cname in (("AgpKernel", "agp_kernel"), ("AgpLikelihood", "agp_likelihood"), ("AgpExpectation", "agp_expectation"), ("AgpSvgpParams", "agp_svgp_params"),
+    for pyname, cname in (("AgpKernelComponent", "agp_kernel_component"), ("AgpKernel", "agp_kernel"), ("AgpLikelihood", "agp_likelihood"), ("AgpExpectation", "agp_expectation"), ("AgpSvgpParams", "agp_svgp_params"),
                           ("AgpSvgpGrads", "agp_svgp_grads"), ("AgpLaplaceProblem", "agp_laplace_problem"), ("AgpLaplaceResult", "agp_laplace_result")):
         fields = getattr(L, pyname)._fields_
         assert [f[0] for f in fields] == [n for n, _ in cstructs[cname]], (pyname,)

@@ -272,3 +272,56 @@ def test_third_party_pin_scikit_learn_kernels_and_gpr():
     s = osv.SVGP(k, X, mq, np.linalg.cholesky(S), jitter=1e-10, centered=True)
     val = osv.elbo(s, X, y, ol.Likelihood("gaussian", s2), ol.Expectation())
     assert abs(val - gpr.log_marginal_likelihood_value_) < 1e-5
+
+
+@pytest.mark.parametrize("op", ["sum", "product"])
+@pytest.mark.parametrize("centered", [False, True])
+def test_kernel_sum_product_gradient_vs_finite_differences(op, centered):
+    """KernelSum / KernelProduct of stationary components under a shared ARD transform (KernelFunctions `k1 + k2`, `k1 * k2`, public through
+    `@reexport using AbstractGPs`, src/ApproximateGPs.jl:5): the oracle's hand-derived reverse pass against 5-point finite differences
+    of its own forward pass, for every kernel parameter (outer variance, outer ARD scales, component variances and lengthscales) and Z."""
+    p = make_problem(seed=11, kind="se", N=60, M=7, D=3, lik="poisson_exp", centered=centered, ard=True)
+    comps = (("se", 0.7, 1.3), ("matern32", 1.1, 0.6), ("matern52", 0.4, 2.0))
+    _, lik, ex = oracle_objects(p)
+
+    def build(variance, inv, comps, Z):
+        k = ok.Kernel(op, variance, inv, 0.0, comps)
+        return osv.SVGP(k, Z, p["m"], p["A"], jitter=1e-6, centered=centered)
+
+    def val(variance=p["variance"], inv=p["inv"], comps=comps, Z=p["Z"]):
+        return osv.elbo(build(variance, inv, comps, Z), p["X"], p["y"], lik, ex, num_data=200)
+
+    _, g = osv.elbo_and_grad(build(p["variance"], p["inv"], comps, p["Z"]), p["X"], p["y"], lik, ex, num_data=200)
+    h = 1e-3
+    cf = np.array([1.0, -8.0, 8.0, -1.0]) / (12.0 * h)
+    steps = (-2, -1, 1, 2)
+
+    def fd(fn):
+        return float(np.dot(cf, [fn(d * h) for d in steps]))
+
+    def close(a, b):
+        assert abs(a - b) < 2e-6 * max(1.0, abs(b)), (a, b)
+
+    close(fd(lambda e: val(variance=p["variance"] + e)), g.kernel.variance)
+    for d in range(3):
+        close(fd(lambda e: val(inv=p["inv"] + e * np.eye(3)[d])), g.kernel.inv_lengthscale[d])
+    for i in range(3):
+        def with_v(e, i=i):
+            c2 = list(comps)
+            c2[i] = (comps[i][0], comps[i][1] + e, comps[i][2])
+            return val(comps=tuple(c2))
+
+        def with_s(e, i=i):
+            c2 = list(comps)
+            c2[i] = (comps[i][0], comps[i][1], comps[i][2] + e)
+            return val(comps=tuple(c2))
+
+        close(fd(with_v), g.kernel.comp_variance[i])
+        close(fd(with_s), g.kernel.comp_inv_lengthscale[i])
+    E = np.zeros_like(p["Z"])
+    E[2, 1] = 1.0
+    close(fd(lambda e: val(Z=p["Z"] + e * E)), g.Z[2, 1])
+    # a one-component sum is the plain kernel
+    k1 = ok.Kernel("sum", 1.3, p["inv"], 0.0, (("matern52", 1.0, 1.0),))
+    k0 = ok.Kernel("matern52", 1.3, p["inv"])
+    assert np.allclose(ok.kernelmatrix(k1, p["X"], p["Z"]), ok.kernelmatrix(k0, p["X"], p["Z"]), rtol=0, atol=1e-15)
