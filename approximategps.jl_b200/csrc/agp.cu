@@ -532,12 +532,23 @@ static int32_t launch_s1(agp_ctx* c, const TrsmArgs& t1_in, int tiles_n, bool ke
   g.zsp = t1.zsp;
   g.kp = t1.kp;
   const int D = t1.kp.D;
-  const int smem = KG_ROWS * (kuf_dp(D) + 2) * (int)sizeof(double);
+  const int smem = 0;  // static: KG_ROWS x (DMAX + 2) doubles (34 KB at DMAX = 32)
   const dim3 grid((g.ncols + KG_COLS - 1) / KG_COLS, t1.nb * BM / KG_ROWS);
-  if (D <= 4) kuf_gen_kernel<4><<<grid, KG_COLS, smem, c->stream>>>(g);
-  else if (D <= 8) kuf_gen_kernel<8><<<grid, KG_COLS, smem, c->stream>>>(g);
-  else if (D <= 16) kuf_gen_kernel<16><<<grid, KG_COLS, smem, c->stream>>>(g);
-  else kuf_gen_kernel<32><<<grid, KG_COLS, smem, c->stream>>>(g);
+#define AGP_KGEN_D(KD)                                                                   \
+  {                                                                                      \
+    if (D <= 4) kuf_gen_kernel<4, KD><<<grid, KG_COLS, smem, c->stream>>>(g);            \
+    else if (D <= 8) kuf_gen_kernel<8, KD><<<grid, KG_COLS, smem, c->stream>>>(g);       \
+    else if (D <= 16) kuf_gen_kernel<16, KD><<<grid, KG_COLS, smem, c->stream>>>(g);     \
+    else kuf_gen_kernel<32, KD><<<grid, KG_COLS, smem, c->stream>>>(g);                  \
+  }
+  switch (t1.kp.kind) {
+    case AGP_KERNEL_SE: AGP_KGEN_D(AGP_KERNEL_SE) break;
+    case AGP_KERNEL_MATERN32: AGP_KGEN_D(AGP_KERNEL_MATERN32) break;
+    case AGP_KERNEL_MATERN52: AGP_KGEN_D(AGP_KERNEL_MATERN52) break;
+    case AGP_KERNEL_LINEAR: AGP_KGEN_D(AGP_KERNEL_LINEAR) break;
+    default: AGP_KGEN_D(AGP_KERNEL_SUM) break;
+  }
+#undef AGP_KGEN_D
   LAUNCHED(c);
   KCHECK();
   return launch_trsm<TR_RHS_FWD_SUMS>(c, t1, tiles_n);

@@ -72,6 +72,76 @@ __device__ __forceinline__ void kappa_and_du(int kind, double u, double c, doubl
   k = (1.0 + r + (5.0 / 3.0) * u) * e;
   dk = -(5.0 / 6.0) * (1.0 + r) * e;
 }
+// exp(x) for x <= 0 (the stationary covariance functions only ever need a decaying exponential): table-driven,
+//   x = (64 q + j) ln2/64 + r,  |r| <= ln2/128,  exp(x) = 2^q T[j] (1 + p(r)),  p = degree-6 Taylor of expm1 (|r|^7/5040 < 3e-20)
+// 13 FP64-pipe instructions against ~25 of the CUDA library routine (which spends the rest on the x > 0 / overflow paths this
+// caller cannot reach).  Used by kuf_gen_kernel, which is bound by the FP64 pipe (8 FMAs of distance + the exponential per element),
+// not by HBM.  Error against mpmath over [-708, 0]: below 1 ulp (exact emulation of this
+// operation sequence, and tests/test_gpu_svgp.py::test_kernel_function_values on the device).  x < -708 (result < 1e-307) returns 0.  -DAGP_NO_FAST_EXP restores exp().
+__device__ const double c_exp2_tab[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+__device__ __forceinline__ double exp_nonpos(double x) {
+#ifdef AGP_NO_FAST_EXP
+  return exp(x);
+#else
+  const double t = fma(x, 0x1.71547652b82fep+6, 0x1.8p52);  // low mantissa bits of t = k = round(64 x / ln2) (two's complement)
+  const double kd = t - 0x1.8p52;
+  double r = fma(-kd, 0x1.62e42fef00000p-7, x);  // exact: the high part of ln2/64 has 20 trailing zero bits, |k| < 2^17
+  r = fma(-kd, 0x1.473de6af278edp-40, r);
+  const int ki = __double2loint(t);
+  const double tj = __ldg(c_exp2_tab + (ki & 63));
+  double p = fma(r, 1.0 / 720.0, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p * r, r, r);  // expm1(r)
+  const double v = fma(tj, p, tj);
+  const double res = __hiloint2double(__double2hiint(v) + ((ki >> 6) << 20), __double2loint(v));
+  return x < -708.0 ? 0.0 : res;
+#endif
+}
+
+
+// kappa (and d kappa / d u) with the table-driven exponential: the stand-alone Kuf generator of S1
+__device__ __forceinline__ void kappa_and_du_gen(int kind, double u, double c, double& k, double& dk) {
+  if (kind == AGP_KERNEL_SE) {
+    k = exp_nonpos(-0.5 * u);
+    dk = -0.5 * k;
+    return;
+  }
+  if (kind == AGP_KERNEL_LINEAR) {
+    k = u + c;
+    dk = 1.0;
+    return;
+  }
+  const double d = sqrt(u);
+  if (kind == AGP_KERNEL_MATERN32) {
+    const double r = 1.7320508075688772 * d;
+    const double e = exp_nonpos(-r);
+    k = (1.0 + r) * e;
+    dk = -1.5 * e;
+    return;
+  }
+  const double r = 2.23606797749979 * d;
+  const double e = exp_nonpos(-r);
+  k = (1.0 + r + (5.0 / 3.0) * u) * e;
+  dk = -(5.0 / 6.0) * (1.0 + r) * e;
+}
 // combine |xs|^2, |zs|^2 and xs.zs into u (Distances.jl: GEMM form with max(., 0) for D > 1)
 __device__ __forceinline__ double u_from_dot(int kind, double xn, double zn, double dot) {
   if (kind == AGP_KERNEL_LINEAR) return dot;

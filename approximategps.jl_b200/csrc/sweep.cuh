@@ -346,15 +346,21 @@ struct KufGenArgs {
   KernelParams kp;
 };
 constexpr int KG_ROWS = 128, KG_COLS = 256;
-template <int DMAX>
+template <int DMAX, int KIND>  // KIND: compile-time covariance function (AGP_KERNEL_SUM stands for sums and products: a.kp.kind tells them apart)
 __global__ void __launch_bounds__(KG_COLS) kuf_gen_kernel(KufGenArgs a) {
-  extern __shared__ __align__(16) double kgz[];  // [KG_ROWS][Sx]
-  const int D = a.kp.D, kind = a.kp.kind, Dq = kuf_dp(D), Sx = Dq + 2;
+  // z rows re-padded to DMAX + 2 doubles ([0, DMAX): coordinates, zeros beyond D; [DMAX]: squared norm) so that the distance is DMAX
+  // unpredicated FMAs fed by 16-byte shared-memory broadcasts; the kernel is bound by instruction issue (r2k: 85 instructions per element
+  // before this layout), not by HBM or the FP64 pipe
+  constexpr int SZ = DMAX + 2;
+  __shared__ __align__(16) double kgz[KG_ROWS * SZ];
+  constexpr int kind = KIND;
+  const int D = a.kp.D, Dq = kuf_dp(D), Sx = Dq + 2;
   const int row0 = blockIdx.y * KG_ROWS;
   const int n = blockIdx.x * KG_COLS + threadIdx.x;
-  {
-    const double* src = a.zsp + (int64_t)row0 * Sx;
-    for (int i = threadIdx.x; i < KG_ROWS * Sx / 2; i += KG_COLS) reinterpret_cast<double2*>(kgz)[i] = reinterpret_cast<const double2*>(src)[i];
+  for (int i = threadIdx.x; i < KG_ROWS * SZ; i += KG_COLS) {
+    const int r = i / SZ, d = i - r * SZ;
+    const double* src = a.zsp + (int64_t)(row0 + r) * Sx;
+    kgz[i] = d < D ? src[d] : (d == DMAX ? src[Dq] : 0.0);
   }
   double x[DMAX];
   double xn = 0.0;
@@ -369,9 +375,10 @@ __global__ void __launch_bounds__(KG_COLS) kuf_gen_kernel(KufGenArgs a) {
   double* out = a.K + (int64_t)row0 * a.ldx + n;
   double* outd = a.DK ? a.DK + (int64_t)row0 * a.ldx + n : nullptr;
   const double var = a.kp.variance;
+  const int rvalid = max(0, min(KG_ROWS, a.kp.M - row0));  // rows >= M are padding: zeros
+  const double* z = kgz;
 #pragma unroll 4
-  for (int r = 0; r < KG_ROWS; r++) {
-    const double* z = kgz + r * Sx;
+  for (int r = 0; r < rvalid; r++, z += SZ, out += a.ldx) {
     double u;
     if (direct) {
       const double df = x[0] - z[0];
@@ -379,18 +386,30 @@ __global__ void __launch_bounds__(KG_COLS) kuf_gen_kernel(KufGenArgs a) {
     } else {
       double dot = 0.0;
 #pragma unroll
-      for (int d = 0; d < DMAX; d++)
-        if (d < Dq) dot = fma(x[d], z[d], dot);
-      u = u_from_dot(kind, xn, z[Dq], dot);
+      for (int d = 0; d < DMAX; d += 2) {
+        const double2 zz = *reinterpret_cast<const double2*>(z + d);
+        dot = fma(x[d], zz.x, dot);
+        dot = fma(x[d + 1], zz.y, dot);
+      }
+      u = u_from_dot(kind, xn, z[DMAX], dot);
     }
-    if (outd) {  // plain kinds only (launch_s1)
-      double k, dk;
-      kappa_and_du(kind, u, a.kp.c, k, dk);
-      const bool valid = row0 + r < a.kp.M;
-      out[(int64_t)r * a.ldx] = valid ? var * k : 0.0;
-      outd[(int64_t)r * a.ldx] = valid ? var * dk : 0.0;
+    if constexpr (kind == AGP_KERNEL_SUM) {
+      *out = var * kappa_kp(a.kp, u);
     } else {
-      out[(int64_t)r * a.ldx] = (row0 + r < a.kp.M) ? var * kappa_kp(a.kp, u) : 0.0;
+      double k, dk;
+      kappa_and_du_gen(kind, u, a.kp.c, k, dk);
+      *out = var * k;
+      if (outd) {
+        *outd = var * dk;
+        outd += a.ldx;
+      }
+    }
+  }
+  for (int r = rvalid; r < KG_ROWS; r++, out += a.ldx) {
+    *out = 0.0;
+    if (outd) {
+      *outd = 0.0;
+      outd += a.ldx;
     }
   }
 }

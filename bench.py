@@ -365,8 +365,8 @@ def setup_dist(args):
         sys.stdout.flush()
         _JSON_OUT = os.fdopen(os.dup(1), "w")
         os.dup2(2, 1)
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "INFO"  # (an inherited VERSION / WARN level would hide the communicator setup)
     import torch
     import torch.distributed as dist
 

@@ -3,8 +3,8 @@
 G=${1:-8}
 cd "$(dirname "$0")/.." && mkdir -p gpurun_out
 run() { # workload, steps, warmup, extra
-  if [ "$G" = "1" ]; then timeout 1500 python bench.py --gpus 1 --workload $1 --steps $2 --warmup $3 $4
-  else timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $G --workload $1 --steps $2 --warmup $3 $4; fi
+  if [ "$G" = "1" ]; then timeout 1200 python bench.py --gpus 1 --workload $1 --steps $2 --warmup $3 $4
+  else timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $G --workload $1 --steps $2 --warmup $3 $4; fi
 }
 run c5 1 1 "$2" > gpurun_out/r2_bench_c5_${G}gpu.json 2> gpurun_out/r2_bench_c5_${G}gpu.err
 run c5mb 3 3 "$2" > gpurun_out/r2_bench_c5mb_${G}gpu.json 2> gpurun_out/r2_bench_c5mb_${G}gpu.err
