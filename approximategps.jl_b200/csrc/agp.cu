@@ -522,8 +522,9 @@ static int32_t launch_s1(agp_ctx* c, const TrsmArgs& t1_in, int tiles_n, bool ke
   if (s1_fused()) return launch_trsm<TR_KUF_FWD>(c, t1_in, tiles_n);
   TrsmArgs t1 = t1_in;
   KufGenArgs g{};
+  // (SqExponential: kappa' = -kappa / 2, S7 needs only Kuf itself: one matrix written here instead of two)
   g.K = keep ? c->Kf.p : t1.X;
-  g.DK = keep ? c->DKb.p : nullptr;
+  g.DK = (keep && t1.kp.kind != AGP_KERNEL_SE) ? c->DKb.p : nullptr;
   if (keep) t1.RHS = c->Kf.p;
   g.ldx = t1.ldx;
   g.ncols = tiles_n * BN;
@@ -1132,7 +1133,7 @@ static int32_t ensure_sweep_workspace(agp_ctx* c, int64_t cols, bool grad) {
     OK(c->As.ensure((int64_t)Mp * cc));
     if (kgrad_fast(st)) {
       OK(c->Kf.ensure((int64_t)Mp * cc));
-      OK(c->DKb.ensure((int64_t)Mp * cc));
+      if (st.kp.kind != AGP_KERNEL_SE) OK(c->DKb.ensure((int64_t)Mp * cc));
     }
     OK(c->gpart.ensure((cc / BN) * Mp));
     const int ntiles = nb * (nb + 1);
@@ -1169,17 +1170,34 @@ static int32_t run_kgrad(agp_ctx* c, const double* Kb, int64_t ld, const double*
   a.stride = kgrad_stride(st.D);
   a.Mp = st.Mp;
   a.kp = st.kp;
-  const int smem = 256 * (kuf_dp(st.D) + 2) * 8;
   const dim3 grid((st.M + 7) / 8, nslab);
+  if (Kf) {  // stationary kinds inside the sweep: stream the stored kernel values (kgrad_stream_kernel)
+    const bool se = st.kp.kind == AGP_KERNEL_SE;
+#define AGP_KSTREAM(DM)                                                                              \
+  {                                                                                                  \
+    const int sm = KfTile<DM>::value * (DM + 2) * 8;                                                 \
+    if (se) {                                                                                        \
+      OK((ensure_smem<kgrad_stream_kernel<DM, true>>(c, sm)));                                       \
+      kgrad_stream_kernel<DM, true><<<grid, 256, sm, c->stream>>>(a);                                \
+    } else {                                                                                         \
+      OK((ensure_smem<kgrad_stream_kernel<DM, false>>(c, sm)));                                      \
+      kgrad_stream_kernel<DM, false><<<grid, 256, sm, c->stream>>>(a);                               \
+    }                                                                                                \
+  }
+    if (st.D <= 4) AGP_KSTREAM(4)
+    else if (st.D <= 8) AGP_KSTREAM(8)
+    else if (st.D <= 16) AGP_KSTREAM(16)
+    else AGP_KSTREAM(32)
+#undef AGP_KSTREAM
+    LAUNCHED(c);
+    KCHECK();
+    return AGP_OK;
+  }
+  const int smem = 256 * (kuf_dp(st.D) + 2) * 8;
 #define AGP_KGRAD_ONE(DM, KD)                                                                                        \
   {                                                                                                                \
-    if (Kf && DK && KD <= AGP_KERNEL_MATERN52) {                                                                   \
-      if (smem > 48 * 1024) OK((ensure_smem<kgrad_kernel<DM, 1, AGP_KERNEL_SE, true>>(c, smem)));                  \
-      kgrad_kernel<DM, 1, AGP_KERNEL_SE, true><<<grid, 256, smem, c->stream>>>(a);                                 \
-    } else {                                                                                                       \
-      if (smem > 48 * 1024) OK((ensure_smem<kgrad_kernel<DM, 1, KD>>(c, smem)));                                    \
-      kgrad_kernel<DM, 1, KD><<<grid, 256, smem, c->stream>>>(a);                                                 \
-    }                                                                                                              \
+    if (smem > 48 * 1024) OK((ensure_smem<kgrad_kernel<DM, 1, KD>>(c, smem)));                                      \
+    kgrad_kernel<DM, 1, KD><<<grid, 256, smem, c->stream>>>(a);                                                   \
   }
 #define AGP_KGRAD_LAUNCH(DM)                                          \
   switch (st.kp.kind) {                                               \
@@ -1430,7 +1448,7 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
     {
       ProfScope ps(c, PC_KGRAD);
       if (kgrad_fast(st)) {
-        OK(run_kgrad(c, c->Ab.p, ldc, pts, npts, (npts + 2047) / 2048, c->Kf.p, c->DKb.p));
+        OK(run_kgrad(c, c->Ab.p, ldc, pts, npts, (npts + 2047) / 2048, c->Kf.p, st.kp.kind != AGP_KERNEL_SE ? c->DKb.p : nullptr));
       } else {
         OK(run_kgrad(c, c->Ab.p, ldc, pts, npts, (npts + 2047) / 2048));
       }

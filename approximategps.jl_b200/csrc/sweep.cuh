@@ -703,9 +703,7 @@ constexpr int AGP_KERNEL_COMPOSITE = AGP_KERNEL_SUM;  // kgrad_kernel's KIND for
 // RW rows per warp (16 or 8 rows per CTA): the points of a slab are staged through shared memory in tiles of 256
 // (scaled, with their squared norm) and shared by all rows of the CTA; each lane handles 8 points of a tile for its
 // RW rows, the Kb values of a tile are fetched up front so that the HBM latency overlaps the exp / FMA work.
-// FAST (stationary kinds inside the sweep): kappa and kappa' are read back instead of recomputed -- no distances, no exp; what is left per
-// element is three coalesced loads and 3 D + 2 FMA-class operations.
-template <int DMAX, int RW, int KIND, bool FAST = false>
+template <int DMAX, int RW, int KIND>
 __global__ void __launch_bounds__(256, (DMAX <= 8 && RW == 1) ? 2 : 1) kgrad_kernel(KgradArgs a) {
   extern __shared__ __align__(16) double kg_smem[];  // [256][Sx]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -754,18 +752,12 @@ __global__ void __launch_bounds__(256, (DMAX <= 8 && RW == 1) ? 2 : 1) kgrad_ker
     __syncthreads();
     const int cnt = min(256, ne - t0);
     double kb[RW][8];
-    double kfv[FAST ? RW : 1][8], dkv[FAST ? RW : 1][8];
 #pragma unroll
     for (int r = 0; r < RW; r++)
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         const int p = lane + 32 * i;
-        const bool ok = p < cnt && rvalid[r];
-        kb[r][i] = ok ? a.Kb[(int64_t)(row0 + r) * a.ld + t0 + p] : 0.0;
-        if constexpr (FAST) {
-          kfv[r][i] = ok ? a.Kf[(int64_t)(row0 + r) * a.ld + t0 + p] : 0.0;
-          dkv[r][i] = ok ? a.DK[(int64_t)(row0 + r) * a.ld + t0 + p] : 0.0;
-        }
+        kb[r][i] = (p < cnt && rvalid[r]) ? a.Kb[(int64_t)(row0 + r) * a.ld + t0 + p] : 0.0;
       }
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -787,19 +779,6 @@ __global__ void __launch_bounds__(256, (DMAX <= 8 && RW == 1) ? 2 : 1) kgrad_ker
       const double xnn = xr[Dp];
 #pragma unroll
       for (int r = 0; r < RW; r++) {
-        if constexpr (FAST) {
-          const double kbv = kb[r][i];
-          dvar[r] = fma(kbv, kfv[r][i], dvar[r]);  // sum Kb variance kappa: divided by the variance at the end
-          const double W = kbv * dkv[r][i];
-          rs[r] += W;
-#pragma unroll
-          for (int d = 0; d < DMAX; d++) {
-            const double wxd = W * xs[d];
-            wx[r][d] += wxd;
-            wxx[r][d] = fma(wxd, xs[d], wxx[r][d]);
-          }
-          continue;
-        }
         double u;
         if (direct) {
           const double df = xs[0] - z[r][0];
@@ -859,7 +838,7 @@ __global__ void __launch_bounds__(256, (DMAX <= 8 && RW == 1) ? 2 : 1) kgrad_ker
     if (lane == 0 && rvalid[r]) {
       double* out = a.part + ((int64_t)slab * a.Mp + row0 + r) * a.stride;
       out[0] += rs[r];
-      out[1] += FAST ? dvar[r] / a.kp.variance : dvar[r];
+      out[1] += dvar[r];
       out[2] += dcc[r];
       if constexpr (composite) {
 #pragma unroll
@@ -876,6 +855,100 @@ __global__ void __launch_bounds__(256, (DMAX <= 8 && RW == 1) ? 2 : 1) kgrad_ker
           out[3 + D + d] += (kind == AGP_KERNEL_LINEAR) ? z[r][d] * wx[r][d] : fma(z[r][d], fma(z[r][d], rs[r], -2.0 * wx[r][d]), wxx[r][d]);
         }
     }
+  }
+}
+
+// S7 inside the sweep for the stationary kinds: kappa (and, for the Matern kinds, kappa') are READ BACK from what kuf_gen_kernel stored for
+// these points instead of being recomputed -- no distances, no exp.  What is left per element is two or three streamed loads and 3 D + 3
+// FMA-class operations, so the kernel is organised as a stream: the scaled points of half a slab are staged in shared memory once (two block
+// barriers per KF_TILE points instead of two per 256), every warp then walks its row with the loads of the next 128 points in flight while it
+// accumulates the current ones.  SqExponential: kappa' = -kappa / 2, only Kf is read.  Output layout = kgrad_kernel's.
+template <int DMAX>
+struct KfTile {
+  static constexpr int value = DMAX <= 8 ? 1024 : (DMAX <= 16 ? 512 : 256);  // points staged at a time: value * (DMAX + 2) * 8 bytes <= 80 KB
+};
+template <int DMAX, bool SE>
+__global__ void __launch_bounds__(256, DMAX <= 8 ? 2 : 1) kgrad_stream_kernel(KgradArgs a) {
+  extern __shared__ __align__(16) double kf_smem[];  // [KF_TILE][Sx]
+  constexpr int TILE = KfTile<DMAX>::value, U = 4;   // a lane owns U points of a 32 U-point chunk
+  constexpr int Sx = DMAX + 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  const int slab = blockIdx.y;
+  const int D = a.kp.D;
+  const bool rvalid = row < a.kp.M;
+  const int nb = slab * a.slab, ne = min(a.npts, nb + a.slab);
+  const double* kbr = a.Kb + (int64_t)row * a.ld;
+  const double* kfr = a.Kf + (int64_t)row * a.ld;
+  const double* dkr = SE ? nullptr : a.DK + (int64_t)row * a.ld;
+  double rs = 0.0, dvar = 0.0, wx[DMAX], wxx[DMAX];
+#pragma unroll
+  for (int d = 0; d < DMAX; d++) wx[d] = wxx[d] = 0.0;
+  for (int t0 = nb; t0 < ne; t0 += TILE) {
+    const int cnt = min(TILE, ne - t0);
+    __syncthreads();  // the previous tile is no longer read
+    for (int p = threadIdx.x; p < TILE; p += 256) {
+      double* xr = kf_smem + p * Sx;
+#pragma unroll
+      for (int d = 0; d < DMAX; d++) xr[d] = (d < D && p < cnt) ? a.pts[(int64_t)(t0 + p) * D + d] * a.kp.s[d] : 0.0;
+    }
+    __syncthreads();
+    if (!rvalid) continue;
+    double kb[2][U], kf[2][U], dk[2][U];
+    auto fetch = [&](int buf, int c0) {
+#pragma unroll
+      for (int i = 0; i < U; i++) {
+        const int p = c0 + lane + 32 * i;
+        const bool ok = p < cnt;
+        kb[buf][i] = ok ? kbr[t0 + p] : 0.0;
+        kf[buf][i] = ok ? kfr[t0 + p] : 0.0;
+        if (!SE) dk[buf][i] = ok ? dkr[t0 + p] : 0.0;
+      }
+    };
+    fetch(0, 0);
+    int buf = 0;
+    for (int c0 = 0; c0 < cnt; c0 += 32 * U, buf ^= 1) {
+      if (c0 + 32 * U < cnt) fetch(buf ^ 1, c0 + 32 * U);
+#pragma unroll
+      for (int i = 0; i < U; i++) {
+        const double* xr = kf_smem + (c0 + lane + 32 * i) * Sx;  // (rows >= cnt are zero and their cotangent was fetched as 0)
+        const double kbv = kb[buf][i];
+        dvar = fma(kbv, kf[buf][i], dvar);  // sum Kb variance kappa: divided by the variance at the end
+        const double W = SE ? -0.5 * (kbv * kf[buf][i]) : kbv * dk[buf][i];
+        rs += W;
+#pragma unroll
+        for (int d = 0; d < DMAX; d += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(xr + d);
+          const double w0 = W * v.x, w1 = W * v.y;
+          wx[d] += w0;
+          wxx[d] = fma(w0, v.x, wxx[d]);
+          wx[d + 1] += w1;
+          wxx[d + 1] = fma(w1, v.y, wxx[d + 1]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    dvar += __shfl_xor_sync(0xffffffffu, dvar, o);
+#pragma unroll
+    for (int d = 0; d < DMAX; d++) {
+      wx[d] += __shfl_xor_sync(0xffffffffu, wx[d], o);
+      wxx[d] += __shfl_xor_sync(0xffffffffu, wxx[d], o);
+    }
+  }
+  if (lane == 0 && rvalid) {
+    double* out = a.part + ((int64_t)slab * a.Mp + row) * a.stride;
+    out[0] += rs;
+    out[1] += dvar / a.kp.variance;
+#pragma unroll
+    for (int d = 0; d < DMAX; d++)
+      if (d < D) {
+        const double z = a.zs[(int64_t)row * D + d];
+        out[3 + d] += wx[d];
+        out[3 + D + d] += fma(z, fma(z, rs, -2.0 * wx[d]), wxx[d]);  // sum W (xs - zs)^2
+      }
   }
 }
 

@@ -631,7 +631,14 @@ def run_svgp(args, w):
         if world == 1 and not args.no_cpu_baseline:
             cores = host_threads()
             n_s = min(65536, n_local)
-            Xs, ys = (Xh[:n_s].numpy(), yh[:n_s].numpy()) if Xh is not None else gen_rows(w, 0, n_s, wvec)
+            if Xh is not None:
+                Xs, ys = Xh[:n_s].numpy(), yh[:n_s].numpy()
+            elif on_device:  # the resident data set was generated on the device: regenerate the same rows there (block-seeded) and fetch them
+                Xs_d, ys_d = gen_rows_device(w, 0, n_s, wvec, dev)
+                Xs, ys = Xs_d.cpu().numpy(), ys_d.cpu().numpy()
+                del Xs_d, ys_d
+            else:
+                Xs, ys = gen_rows(w, 0, n_s, wvec)
             pps, times, (ref, rg) = time_oracle(w, Z, m, A, Xs, ys, 3, num_data)
             line["cpu_baseline"] = {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"rows [0,{n_s}) of the same workload, median of 3 runs ({sum(times):.1f} s total), NumPy/SciPy OpenBLAS threads={cores}",
