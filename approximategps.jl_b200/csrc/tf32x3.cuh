@@ -72,16 +72,41 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, one 128 x 128 x 8 TF32 MMA issued by the calling thread
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem]^T, one 128 x 128 x 8 TF32 MMA.  The issuing warp walks its loops convergently and `leader` (one elected
+// lane) predicates the instruction itself: with a divergent `if (lane == 0)` around the loop the compiler wraps every uniform-datapath
+// instruction (descriptor arithmetic, the MMA, the commit) in an ELECT / BRA.U.ANY retry loop -- 13 instructions and ~95 cycles per MMA,
+// measured on the INT8 engine that shares this structure (profiles/r2q_i8emu_v0.jsonl -> v1).
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pred(uint32_t bar, uint32_t leader) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.b32 q, %1, 0;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(bar),
+      "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t r;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(r));
+  return r;
 }
 // 32 consecutive accumulator columns of this thread's TMEM lane
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
@@ -144,7 +169,11 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
 tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl, const __grid_constant__ CUtensorMap mBh,
                    const __grid_constant__ CUtensorMap mBl, Args g, Epi epi) {
   extern __shared__ uint8_t t5_smem_raw[];
-  const int tile_m = blockIdx.x, tile_n = blockIdx.y, z = blockIdx.z;
+  // launch grid = (m tiles, n tiles, z); the tiles are walked with n as the FAST index: the n-tile CTAs that share an A row tile (the
+  // streamed operand: two planes of 128 x K floats) run together and read it from HBM once, through L2.  With m fast every n tile streamed
+  // all of A again -- 8 x 1.24 GB per launch at C4, i.e. the stage was DRAM-bound (1.5 of its 1.8 ms).
+  const int lin = blockIdx.x + gridDim.x * blockIdx.y;
+  const int tile_n = lin % gridDim.y, tile_m = lin / gridDim.y, z = blockIdx.z;
   if (g.lower_only && tile_n > tile_m) return;
   int kb = 0, ke = g.K;
   if (g.kmode == KM_FROM_N) kb = tile_n * TN;
@@ -218,8 +247,10 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && nk > 0) {
-      // ---- MMA issuer: group gi accumulates GROUP_KB k-blocks into TMEM buffer gi & 1, starting from zero ------------------
+    if (nk > 0) {
+      // ---- MMA issuer (whole warp, uniform control flow; one elected lane issues): group gi accumulates GROUP_KB k-blocks into TMEM
+      //      buffer gi & 1, starting from zero ----------------------------------------------------------------------------------------
+      const uint32_t leader = elect_one();
       constexpr uint32_t idesc = make_idesc(AMN, BMN);
       constexpr uint32_t a_step = AMN ? 1024 : UK * 4, b_step = BMN ? 1024 : UK * 4;  // bytes per k-step of 8
       int i = 0;
@@ -240,14 +271,14 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constan
           for (int k = 0; k < TK / UK; k++) {
             const uint64_t ah = make_desc(st + k * a_step, AMN, g.mn), al = make_desc(st + TILE_BYTES + k * a_step, AMN, g.mn);
             const uint64_t bh = make_desc(st + 2 * TILE_BYTES + k * b_step, BMN, g.mn), bl = make_desc(st + 3 * TILE_BYTES + k * b_step, BMN, g.mn);
-            tc_mma_tf32(dcol, al, bh, idesc, first ? 0u : 1u);  // the small terms first
-            tc_mma_tf32(dcol, ah, bl, idesc, 1);
-            tc_mma_tf32(dcol, ah, bh, idesc, 1);
+            tc_mma_tf32(dcol, al, bh, idesc, first ? 0u : 1u, leader);  // the small terms first
+            tc_mma_tf32(dcol, ah, bl, idesc, 1, leader);
+            tc_mma_tf32(dcol, ah, bh, idesc, 1, leader);
             first = false;
           }
-          tc_commit(empty_bar(s));  // the stage may be refilled once these MMAs have read it
+          tc_commit_pred(empty_bar(s), leader);  // the stage may be refilled once these MMAs have read it
         }
-        tc_commit(tfull_bar(buf));  // this group's partial sums are complete
+        tc_commit_pred(tfull_bar(buf), leader);  // this group's partial sums are complete
       }
     }
   } else {
