@@ -173,6 +173,7 @@ struct agp_ctx {
   DevBuf gpart, Gpart, kpart, red, small, ghbuf;
   // Float32 mode: hi | lo FP32 planes (each DevBuf holds both: 2 x count floats = count doubles)
   DevBuf fA, fC, fAb, fAs, fBtc, fBtr, fLi;
+  DevBuf qAb, sAb, qLi, sLi;  // Float32 mode, S5 on the INT8 tensor path: 4 slice planes of Ab (point-major) and of Linv^T, their scales
   int* d_flags = nullptr;  // [0] potrf info, [1] domain flag
   SvgpState st;
   ncclComm_t comm = nullptr;
@@ -246,7 +247,7 @@ extern "C" int32_t agp_ctx_destroy(agp_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   DevBuf* bufs[] = {&c->z, &c->zs, &c->zn, &c->zsp, &c->mvec, &c->mt, &c->Lq, &c->Kw, &c->Lk, &c->Lt, &c->Ut, &c->Bt_cm, &c->Bt_rm,
                     &c->W1, &c->W2, &c->W3, &c->W4, &c->vec64, &c->vec64b, &c->A, &c->C, &c->Ab, &c->As, &c->Kf, &c->DKb, &c->saa, &c->sam,
-                    &c->scc_part, &c->dmu, &c->dv, &c->sc_part, &c->gpart, &c->Gpart, &c->kpart, &c->red, &c->small, &c->ghbuf, &c->fA, &c->fC, &c->fAb, &c->fAs, &c->fBtc, &c->fBtr, &c->fLi,
+                    &c->scc_part, &c->dmu, &c->dv, &c->sc_part, &c->gpart, &c->Gpart, &c->kpart, &c->red, &c->small, &c->ghbuf, &c->fA, &c->fC, &c->fAb, &c->fAs, &c->fBtc, &c->fBtr, &c->fLi, &c->qAb, &c->sAb, &c->qLi, &c->sLi,
                     &c->mu_out, &c->var_out, &c->px1, &c->px2, &c->pxs1, &c->pxn1, &c->pxs2, &c->pxn2, &c->pcov};
   for (DevBuf* b : bufs) b->release();
   lap_release(c);
@@ -958,7 +959,18 @@ static int32_t prepare_f32_operands(agp_ctx* c) {
   OK(launch_trsm<TR_RHS_FWD>(c, a, Mp / BN));
   OK(transpose(c, c->W1.p, c->W2.p, Mp, Mp));
   OK(split(c->W2.p, c->fLi));
+  // ... and as four INT8 slice planes per row j with a power-of-two row scale: the B operand of the INT8 S5 (f32sweep.cuh EpiE5)
+  OK(c->qLi.ensure((i8e::S5_NS * MM + 7) / 8));
+  OK(c->sLi.ensure(Mp));
+  i8e::slice_rows_kernel<i8e::S5_NS><<<(Mp + 7) / 8, 256, 0, c->stream>>>(c->W2.p, Mp, Mp, Mp, reinterpret_cast<signed char*>(c->qLi.p), Mp, MM, c->sLi.p);
+  LAUNCHED(c);
+  KCHECK();
   return AGP_OK;
+}
+// Float32 mode's reverse-pass solve: "i8" (default) = 4-slice INT8 product with the explicit inverse; "fp64" = the FP64 DMMA triangular solve
+static bool f32_s5_i8() {
+  static const bool off = getenv("AGP_F32_S5") && strcmp(getenv("AGP_F32_S5"), "fp64") == 0;  // tuning knob
+  return !off;
 }
 
 // Uploads the parameters and builds every once-per-step operand: zs, zn, Kuu, Lk, Lt, Ut, mt, Bt.
@@ -1126,6 +1138,8 @@ static int32_t ensure_sweep_workspace(agp_ctx* c, int64_t cols, bool grad) {
     if (grad) {
       OK(c->fAb.ensure((int64_t)Mp * cc));
       OK(c->fAs.ensure((int64_t)Mp * cc));
+      OK(c->qAb.ensure(((int64_t)i8e::S5_NS * Mp * cc + 7) / 8));
+      OK(c->sAb.ensure(cc));
     }
   }
   if (grad) {
@@ -1379,6 +1393,26 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
         t5::EpiF5 e5{c->Ab.p, ldc};
         t5::Args g{Mp, t5::KM_FROM_N, 0, 0, t5::MnDesc()};
         OK((launch_t5<false, false>(c, grid5, fAb, plane, Mp, ncols, reinterpret_cast<float*>(c->fLi.p), MMf, Mp, Mp, g, e5)));
+      } else if (f32_s5_i8()) {
+        // Kb = Lk^-T Ab as an exact-accumulation INT8 product with the explicit inverse: Ab (FP64, inducing-major, from the S4 epilogue) is
+        // cut into 4 slice planes per point (transpose_slice_kernel), the product overwrites Ab with Kb
+        ProfScope ps(c, PC_TRSM_BWD);
+        signed char* qAb = reinterpret_cast<signed char*>(c->qAb.p);
+        const int64_t pbytes = (int64_t)Mp * ldc;
+        i8e::transpose_slice_kernel<i8e::S5_NS><<<(ncols + 31) / 32, 256, 0, c->stream>>>(c->Ab.p, ldc, Mp, ncols, qAb, Mp, pbytes, c->sAb.p);
+        LAUNCHED(c);
+        KCHECK();
+        CUtensorMap ma, mb;
+        if (!i8e::make_map3(&ma, qAb, Mp, ncols, Mp, pbytes, i8e::EM, i8e::S5_NS) ||
+            !i8e::make_map3(&mb, reinterpret_cast<signed char*>(c->qLi.p), Mp, Mp, Mp, MM, i8e::S5_N, i8e::S5_NS))
+          return fail(AGP_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+        i8e::EpiE5 e5{c->Ab.p, ldc, c->sAb.p, c->sLi.p};
+        i8e::Args g8{Mp, i8e::KM_FROM_N, 0, 0};
+        constexpr int sm8 = i8e::Cfg<i8e::S5_NS, i8e::S5_N>::smem_bytes;
+        OK((ensure_smem<i8e::i8emu_gemm_kernel<i8e::EpiE5, i8e::S5_NS, i8e::S5_N>>(c, sm8)));
+        i8e::i8emu_gemm_kernel<i8e::EpiE5, i8e::S5_NS, i8e::S5_N><<<dim3(Mp / i8e::S5_N, ncols / i8e::EM, 1), i8e::E_THREADS, sm8, c->stream>>>(ma, mb, g8, e5);
+        LAUNCHED(c);
+        KCHECK();
       } else {
         // Kb = Lk^-T Ab stays the FP64 triangular solve, in place on the FP64 inducing-major matrix the S4 epilogue wrote
         TrsmArgs t5a{};

@@ -8,11 +8,13 @@
 //   S2  C[n][j]  = sum_{l >= j} A[n][l] Bt[l][j]          + per-point |c|^2                              (K-major x K-major)
 //   S4  T[n][i]  = sum_{j <= i} C[n][j] Bt[i][j];  Ab = dmu (x) mt + 2 dv (T - A),  As = dv A            (K-major x K-major)
 //   S6  G[i][j] += sum_n As[n][i] A[n][j]                 (MN-major x MN-major straight from the same planes, split over n)
-//   S5  Kb = Lk^-T Ab stays the FP64 DMMA solve by default: as a 3xTF32 product with the explicit inverse (AGP_F32_S5=tf32,
-//       Kb[n][j] = sum_{i >= j} Ab[n][i] Linv[i][j]) it is 4x faster, but its error is amplified by cond(Lk) into dZ / d theta
-//       (measured 1.7e-3 on dZ at the C4 twin, M = 1024 SqExponential: outside the 1e-4 budget).
+//   S5  Kb[n][j] = sum_{i >= j} Ab[n][i] Linv[i][j] with the explicit inverse.  As a 3xTF32 product (AGP_COMPUTE_F32_TC_SOLVE) its error is
+//       amplified by cond(Lk) into dZ / d theta (1.4e-4 at the C4 twin: outside the budget); the default is the same product on the INT8 tensor
+//       path with exact accumulation (i8emu.cuh, 5 slices = 35 bits: EpiE5 below), 2.1x faster than the FP64 DMMA solve it replaces
+//       (AGP_F32_S5=fp64 restores that one).
 #pragma once
 #include "tf32x3.cuh"
+#include "i8emu.cuh"
 
 namespace agp {
 namespace t5 {
@@ -172,4 +174,26 @@ struct EpiF6 {
 };
 
 }  // namespace t5
+
+// ---- S5 of the Float32 mode on the INT8 tensor path (i8emu.cuh, <5 slices, 64 columns>): Kb[n][j] = sum_{i >= j} Ab[n][i] Linv[i][j] ---------------
+// 35-bit fixed-point operands (relative to the row maximum) with EXACT accumulation: the reverse-pass solve through the explicit inverse loses
+// cond(Lk) ~ 1e3 to cancellation and another factor ~30 to the spread of magnitudes inside a row of Linv, which neither 22-bit TF32 operands
+// (1.4e-4 on dZ at the C4 twin) nor four slices (28 bits: 2.7e-4) can afford inside the 1e-4 budget.
+// Output: Kb (FP64, inducing-major [j][ldk]) for the FP64 kernel-gradient contraction, like EpiF5.
+namespace i8e {
+constexpr int S5_NS = 5, S5_N = 64;
+struct EpiE5 {
+  double* Kb;
+  int64_t ldk;
+  const double* sAb;  // per point
+  const double* sLi;  // per column j
+  __device__ __forceinline__ void operator()(int tm, int tn, int, int row, int c0, const double (&v)[32]) const {
+    const int n = tm * EM + row, j0 = tn * S5_N + c0;
+    const double sa = sAb[n] * (1.0 / 16384.0);
+    double* p = Kb + (int64_t)j0 * ldk + n;  // a warp's 32 rows (points) are 32 consecutive doubles
+#pragma unroll
+    for (int j = 0; j < 32; j++) p[(int64_t)j * ldk] = v[j] * sa * __ldg(sLi + j0 + j);
+  }
+};
+}  // namespace i8e
 }  // namespace agp

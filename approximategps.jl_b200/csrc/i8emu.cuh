@@ -31,17 +31,26 @@ using t5::tc_commit;
 using t5::tc_fence_after;
 using t5::tc_fence_before;
 
-constexpr int S = 7;     // slices per operand
+constexpr int S = 7;     // slices per operand of the FP64-accurate configuration (49 bits)
 constexpr int EM = 128;  // output rows per CTA = TMEM lanes
-constexpr int EN = 64;   // output columns per CTA (per accumulator group)
+constexpr int EN = 64;   // output columns per CTA (per accumulator group) of the S = 7 configuration: 7 x 64 = 448 TMEM columns
 constexpr int EK = 128;  // k per pipeline stage = one 128-byte swizzle row of int8
 constexpr int UK = 32;   // k of one tcgen05.mma.kind::i8
-constexpr int A_TILE = EM * EK, B_TILE = EN * EK;
-constexpr int A_SLOTS = 6;
-constexpr int B_STAGE = S * B_TILE;
+constexpr int A_TILE = EM * EK;
+constexpr int A_SLOTS = 4;
 constexpr int E_THREADS = 64 + 128;
-constexpr int SMEM_BYTES = A_SLOTS * A_TILE + 2 * B_STAGE + 1024 /* alignment slack */ + 256 /* barriers */;
 constexpr int TMEM_COLS = 512;
+// Configuration <NS slices, N columns>: NS * N <= 512 TMEM columns.  <7, 64>: FP64-accurate (2^-49); <4, 128>: 28 bits -- enough for the
+// Float32 mode's reverse-pass solve, whose 1e-4 budget 22-bit TF32 operands miss by the condition number -- at the full 64-cycle MMA rate.
+template <int NS, int N>
+struct Cfg {
+  static_assert(NS * N <= TMEM_COLS && N % 32 == 0, "accumulators must fit tensor memory");
+  static constexpr int b_tile = N * EK;
+  static constexpr int b_stage = NS * b_tile;
+  static constexpr int smem_bytes = A_SLOTS * A_TILE + 2 * b_stage + 1024 /* alignment slack */ + 256 /* barriers */;
+  static constexpr int products = NS * (NS + 1) / 2;
+};
+constexpr int B_TILE = Cfg<S, EN>::b_tile, B_STAGE = Cfg<S, EN>::b_stage, SMEM_BYTES = Cfg<S, EN>::smem_bytes;
 
 constexpr int KM_FULL = 0, KM_FROM_N = 1, KM_UPTO_N = 2, KM_SPLIT = 3;
 
@@ -53,16 +62,18 @@ struct Args {
 };
 
 // x = scale * sum_i q_i 2^{-7(i+1)}: inv_scale = 2^-e with |x| 2^-e < 1.  Every operation is exact in FP64.
-__host__ __device__ __forceinline__ void slice7(double x, double inv_scale, signed char (&q)[S]) {
+template <int NS>
+__host__ __device__ __forceinline__ void slice_n(double x, double inv_scale, signed char (&q)[NS]) {
   double t = x * inv_scale;
 #pragma unroll
-  for (int i = 0; i < S; i++) {
+  for (int i = 0; i < NS; i++) {
     t *= 128.0;
     const double qi = trunc(t);
     q[i] = (signed char)(int)qi;
     t -= qi;
   }
 }
+__host__ __device__ __forceinline__ void slice7(double x, double inv_scale, signed char (&q)[S]) { slice_n<S>(x, inv_scale, q); }
 // power-of-two scale of a row whose largest magnitude is mx: 2^e with mx 2^-e in [0.5, 1)
 __host__ __device__ __forceinline__ double pow2_scale(double mx) {
   if (!(mx > 0.0)) return 1.0;
@@ -107,14 +118,15 @@ __device__ __forceinline__ void tc_ld32_i(uint32_t taddr, int (&r)[32]) {
 __device__ __forceinline__ uint64_t kdesc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor: D = S32, A = B = signed 8 bit, K-major both, M = 128, N = 64, dense
-__host__ __device__ constexpr uint32_t idesc_i8() { return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(EN >> 3) << 17) | ((uint32_t)(EM >> 4) << 24); }
+// instruction descriptor: D = S32, A = B = signed 8 bit, K-major both, M = 128, N columns, dense
+__host__ __device__ constexpr uint32_t idesc_i8(int n = EN) { return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(EM >> 4) << 24); }
 
 // Epi: operator()(tile_m, tile_n, z, row, c0, const double (&v)[32]) -- a thread owns output row `row` (0..127 of the tile) and is called
 // for c0 = 0 and 32; v = sum_g acc_g 2^{-7g} (exact integers scaled by powers of two, summed in FP64); the functor applies
 // 2^-14 * scaleA[row] * scaleB[col] and whatever the stage needs.
-template <class Epi>
+template <class Epi, int NS = S, int EN = i8e::EN>
 __global__ void __launch_bounds__(E_THREADS, 1) i8emu_gemm_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB, Args g, Epi epi) {
+  constexpr int S = NS, B_TILE = Cfg<NS, EN>::b_tile, B_STAGE = Cfg<NS, EN>::b_stage;  // (shadow the FP64 configuration's constants)
   extern __shared__ uint8_t e_smem_raw[];
   // n-tile = fast grid index: the N / 64 CTAs that share an A row-tile (7 x 128 x K bytes) run together and read it from HBM once, through L2
   // (with the m-tile as the fast index every n-tile streamed all of A again: 16 x 1.1 GB per launch at the sweep's shape, i.e. DRAM-bound)
@@ -182,7 +194,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) i8emu_gemm_kernel(const __grid_c
   } else if (warp == 1) {
     if (nk > 0) {  // the whole warp walks the loops (uniform control flow); one elected lane issues
       const uint32_t leader = elect_one();
-      constexpr uint32_t idesc = idesc_i8();
+      constexpr uint32_t idesc = idesc_i8(EN);
       int ause = 0;
       for (int kb = 0; kb < nk; kb++) {
         const int buf = kb & 1;
@@ -218,7 +230,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) i8emu_gemm_kernel(const __grid_c
       tc_fence_after();
     }
 #pragma unroll 1
-    for (int half = 0; half < 2; half++) {
+    for (int half = 0; half < EN / 32; half++) {
       double v[32];
 #pragma unroll
       for (int j = 0; j < 32; j++) v[j] = 0.0;
@@ -245,10 +257,10 @@ __global__ void __launch_bounds__(E_THREADS, 1) i8emu_gemm_kernel(const __grid_c
 }
 
 // ---- host side: 3-D tensor map over slice planes [S][rows][ldk] of int8 (k contiguous); box = 128 k x box_rows rows x 1 slice ----------
-inline bool make_map3(CUtensorMap* map, const signed char* ptr, uint64_t k, uint64_t rows, uint64_t ldk, uint64_t plane_bytes, uint32_t box_rows) {
+inline bool make_map3(CUtensorMap* map, const signed char* ptr, uint64_t k, uint64_t rows, uint64_t ldk, uint64_t plane_bytes, uint32_t box_rows, int nslices = S) {
   t5::EncodeTiledFn fn = t5::encode_tiled_fn();
   if (!fn) return false;
-  cuuint64_t dims[3] = {k, rows, (cuuint64_t)S};
+  cuuint64_t dims[3] = {k, rows, (cuuint64_t)nslices};
   cuuint64_t strides[2] = {ldk, plane_bytes};
   cuuint32_t box[3] = {128, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
@@ -257,6 +269,7 @@ inline bool make_map3(CUtensorMap* map, const signed char* ptr, uint64_t k, uint
 }
 
 // slices of a row-major FP64 matrix [rows][ld] (k contiguous): one warp per row -- row maximum, power-of-two scale, S planes [S][rows][ldk]
+template <int NS = S>
 __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restrict__ in, int64_t ld, int rows, int k, signed char* __restrict__ planes, int64_t ldk,
                                                          int64_t plane_bytes, double* __restrict__ scale) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -269,10 +282,53 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
   const double sc = pow2_scale(mx), inv = 1.0 / sc;
   if (lane == 0) scale[row] = sc;
   for (int c = lane; c < (int)ldk; c += 32) {
-    signed char q[S];
-    slice7(c < k ? src[c] : 0.0, inv, q);
+    signed char q[NS];
+    slice_n<NS>(c < k ? src[c] : 0.0, inv, q);
 #pragma unroll
-    for (int i = 0; i < S; i++) planes[i * plane_bytes + (int64_t)row * ldk + c] = q[i];
+    for (int i = 0; i < NS; i++) planes[i * plane_bytes + (int64_t)row * ldk + c] = q[i];
+  }
+}
+
+// slices of the COLUMNS of a row-major FP64 matrix [rows][ld] (rows = k, columns = points), written point-major: planes [NS][cols][ldk] with
+// k contiguous, one power-of-two scale per point from the exact column maximum.  One CTA per 32 points: a first pass over the strip for the
+// maxima, a second one (an L2 hit: 32 x rows x 8 bytes) through a 32 x 32 shared-memory tile for the transposed, sliced stores.
+template <int NS>
+__global__ void __launch_bounds__(256) transpose_slice_kernel(const double* __restrict__ in, int64_t ld, int rows, int cols, signed char* __restrict__ planes,
+                                                              int64_t ldk, int64_t plane_bytes, double* __restrict__ scale) {
+  __shared__ double tile[32][33];
+  __shared__ double smx[8][32];
+  __shared__ double sinv[32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n0 = blockIdx.x * 32;
+  const bool cok = n0 + tx < cols;
+  double mx = 0.0;
+  for (int r = ty; r < rows; r += 8) mx = fmax(mx, cok ? fabs(in[(int64_t)r * ld + n0 + tx]) : 0.0);
+  smx[ty][tx] = mx;
+  __syncthreads();
+  if (ty == 0) {
+#pragma unroll
+    for (int j = 1; j < 8; j++) mx = fmax(mx, smx[j][tx]);
+    const double sc = pow2_scale(mx);
+    if (cok) scale[n0 + tx] = sc;
+    sinv[tx] = 1.0 / sc;
+  }
+  for (int r0 = 0; r0 < (int)ldk; r0 += 32) {
+    __syncthreads();  // (also publishes sinv on the first pass)
+    for (int j = ty; j < 32; j += 8) tile[j][tx] = (cok && r0 + j < rows) ? in[(int64_t)(r0 + j) * ld + n0 + tx] : 0.0;
+    __syncthreads();
+    // thread -> point ty * 4 + (tx >> 3), rows 4 (tx & 7) .. + 3: a warp stores 4 x 32 contiguous bytes per plane
+    const int n = ty * 4 + (tx >> 3), r4 = (tx & 7) * 4;
+    if (n0 + n < cols) {
+      const double inv = sinv[n];
+      signed char q[4][NS];
+#pragma unroll
+      for (int e = 0; e < 4; e++) slice_n<NS>(tile[r4 + e][n], inv, q[e]);
+#pragma unroll
+      for (int i = 0; i < NS; i++) {
+        const char4 v = make_char4(q[0][i], q[1][i], q[2][i], q[3][i]);
+        *reinterpret_cast<char4*>(planes + i * plane_bytes + (int64_t)(n0 + n) * ldk + r0 + r4) = v;
+      }
+    }
   }
 }
 

@@ -28,8 +28,11 @@ def test_tf32x3_engine():
 
 def test_i8emu_engine():
     rows = _run("i8emu_test")
-    cases = [r for r in rows if "case" in r]
+    cases = [r for r in rows if "rel_to_max" in r]
     assert len(cases) >= 5
     for r in cases:
         # error against the long-double reference, relative to the largest entry of the product: FP64-level
         assert r["rel_to_max"] < 2e-13, r
+    short = [r for r in rows if "rel_to_max_4slices" in r]
+    assert short and all(r["rel_to_max_4slices"] < 1e-7 for r in short)  # the 28-bit configuration
+    assert rows[-1]["ok"] is True
