@@ -160,6 +160,8 @@ struct agp_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;                // trailing updates of the blocked Cholesky (look-ahead), see blocked_cholesky
   cudaEvent_t ev_panel = nullptr, ev_trail = nullptr;
+  cudaStream_t stream_copy = nullptr;            // upload of the q.Sigma factor (M^2 doubles) behind the Kuu factorisation, see prepare_step
+  cudaEvent_t ev_copy = nullptr;
   int sms = 148;
   int64_t launches = 0;
   int64_t chunk_cols = 0;  // capacity of the per-chunk scratch (columns)
@@ -234,6 +236,8 @@ extern "C" int32_t agp_ctx_create(int32_t device, agp_ctx** out) {
   CU(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));
   CU(cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_trail, cudaEventDisableTiming));
+  CU(cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
   CU(cudaMalloc(&c->d_flags, 4 * sizeof(int)));
   CU(cudaMemset(c->d_flags, 0, 4 * sizeof(int)));
   *out = c;
@@ -256,6 +260,8 @@ extern "C" int32_t agp_ctx_destroy(agp_ctx* c) {
   if (c->ev_panel) cudaEventDestroy(c->ev_panel);
   if (c->ev_trail) cudaEventDestroy(c->ev_trail);
   if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+  if (c->stream_copy) cudaStreamDestroy(c->stream_copy);
   cudaStreamDestroy(c->stream);
   delete c;
   return AGP_OK;
@@ -1003,12 +1009,7 @@ static int32_t prepare_step(agp_ctx* c, const agp_svgp_params* p) {
   CU(cudaMemsetAsync(c->z.p, 0, sizeof(double) * Mp * D, c->stream));
   CU(cudaMemcpyAsync(c->z.p, p->Z, sizeof(double) * M * D, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->mvec.p, st.h_m.data(), sizeof(double) * Mp, cudaMemcpyHostToDevice, c->stream));
-  // Lq: straight from the caller's matrix into the leading M x M block (no host staging of M^2 doubles), then the strict
-  // upper triangle and the padding are zeroed on the device (LowerTriangular(A) view, utils.jl:18)
-  CU(cudaMemcpy2DAsync(c->Lq.p, sizeof(double) * Mp, p->Lq, sizeof(double) * ldq, sizeof(double) * M, M, cudaMemcpyHostToDevice, c->stream));
-  tril_pad_kernel<<<dim3((Mp + 127) / 128, Mp), 128, 0, c->stream>>>(c->Lq.p, M, Mp);
-  LAUNCHED(c);
-  KCHECK();
+  // (Lq is uploaded further down, on its own stream, behind the factorisation of Kuu)
   if (st.lp.method == AGP_EXPECT_GAUSS_HERMITE && st.lp.ngh > 0) {
     OK(c->ghbuf.ensure(2 * AGP_MAX_GH_POINTS));
     CU(cudaMemcpyAsync(c->ghbuf.p, p->expect.nodes, sizeof(double) * st.lp.ngh, cudaMemcpyHostToDevice, c->stream));
@@ -1028,6 +1029,16 @@ static int32_t prepare_step(agp_ctx* c, const agp_svgp_params* p) {
   OK(blocked_cholesky(c, c->Kw.p, c->Lk.p, c->Lt.p, c->Ut.p, nb, Mp, c->d_flags, M));
   OK(build_block_scaled(c, c->Lk.p, c->Lt.p, c->Ut.p, nb, Mp));
   // (the Cholesky status word is read together with the results: check_step_flags)
+  // Lq: straight from the caller's matrix into the leading M x M block (no host staging of M^2 doubles), then the strict upper triangle
+  // and the padding are zeroed on the device (LowerTriangular(A) view, utils.jl:18).  8 MB at M = 1024 from pageable host memory is
+  // ~0.8 ms: issued on its own stream AFTER the Kuu kernels have been queued, so that the copy runs under the factorisation (the
+  // replicated per-step work is what limits the 8-GPU efficiency of C4).
+  CU(cudaMemcpy2DAsync(c->Lq.p, sizeof(double) * Mp, p->Lq, sizeof(double) * ldq, sizeof(double) * M, M, cudaMemcpyHostToDevice, c->stream_copy));
+  tril_pad_kernel<<<dim3((Mp + 127) / 128, Mp), 128, 0, c->stream_copy>>>(c->Lq.p, M, Mp);
+  LAUNCHED(c);
+  KCHECK();
+  CU(cudaEventRecord(c->ev_copy, c->stream_copy));
+  CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
   if (!st.centered) {
     CU(cudaMemcpyAsync(c->mt.p, c->mvec.p, sizeof(double) * Mp, cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaMemcpyAsync(c->Bt_cm.p, c->Lq.p, sizeof(double) * MM, cudaMemcpyDeviceToDevice, c->stream));
@@ -1627,6 +1638,9 @@ extern "C" int32_t agp_svgp_finish(agp_ctx* c, double* elbo_out, agp_svgp_grads*
     OK((run_gemm<A_MK, B_KN>(c, nb, Mp / BN, W3, Mp, c->Bt_cm.p, Mp, Mp, KR_FULL, TS_ALL,
                              epi_store(W4, Mp, true, 1.0, 0.0, MASK_NONE, 0.0, c->vec64b.p + Mp, c->mt.p, 1.0))));
   }
+  // dLq_src (W3) is final from here on: its read-back (M^2 doubles, the largest output) goes to the copy stream below and runs under the
+  // Cholesky pullback and the Kuu part of the kernel gradient
+  if (go->dLq) CU(cudaEventRecord(c->ev_copy, c->stream));
   // W1 (row-major) = Lk-bar
   build_Lbar_kernel<<<dim3((Mp + 127) / 128, Mp), 128, 0, c->stream>>>(W2, W4, c->Lk.p, Mp, M, st.centered ? 1 : 0, W1);
   LAUNCHED(c);
@@ -1652,22 +1666,26 @@ extern "C" int32_t agp_svgp_finish(agp_ctx* c, double* elbo_out, agp_svgp_grads*
   // outputs
   std::vector<double> h_theta(theta_size(D)), h_dZ((int64_t)Mp * D), h_vec(2 * (int64_t)Mp), h_g(Mp);
   std::vector<double> h_dLq;
+  if (go->dLq) {
+    // issued before the small read-backs: a copy into pageable host memory holds the host until it is done, and by now every kernel of
+    // the epilogue is queued on the main stream
+    OK(c->A.ensure((int64_t)M * M));  // reuse chunk scratch as the staging area
+    CU(cudaStreamWaitEvent(c->stream_copy, c->ev_copy, 0));
+    finalize_dLq_kernel<<<dim3((M + 127) / 128, M), 128, 0, c->stream_copy>>>(dLq_src, c->Lq.p, M, Mp, st.centered ? 1 : 0, c->A.p);
+    LAUNCHED(c);
+    KCHECK();
+    CU(cudaMemcpyAsync(go->dLq, c->A.p, sizeof(double) * M * M, cudaMemcpyDeviceToHost, c->stream_copy));
+  }
   CU(cudaMemcpyAsync(h_scal.data(), red + rl.scal, sizeof(double) * rl.g, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(h_small.data(), small, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(h_theta.data(), theta, sizeof(double) * theta_size(D), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(h_dZ.data(), dZ, sizeof(double) * Mp * D, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(h_g.data(), g, sizeof(double) * Mp, cudaMemcpyDeviceToHost, c->stream));
   if (st.centered) CU(cudaMemcpyAsync(h_vec.data(), c->vec64b.p, sizeof(double) * 2 * Mp, cudaMemcpyDeviceToHost, c->stream));
-  if (go->dLq) {
-    OK(c->A.ensure((int64_t)M * M));  // reuse chunk scratch as the staging area
-    finalize_dLq_kernel<<<dim3((M + 127) / 128, M), 128, 0, c->stream>>>(dLq_src, c->Lq.p, M, Mp, st.centered ? 1 : 0, c->A.p);
-    LAUNCHED(c);
-    KCHECK();
-    CU(cudaMemcpyAsync(go->dLq, c->A.p, sizeof(double) * M * M, cudaMemcpyDeviceToHost, c->stream));
-  }
   int h_flags[4];
   CU(cudaMemcpyAsync(h_flags, c->d_flags, sizeof h_flags, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  if (go->dLq) CU(cudaStreamSynchronize(c->stream_copy));
 #if defined(AGP_EXP_NOGEN) || defined(AGP_EXP_NOEXP) || defined(AGP_EXP_WAIT2)
   h_flags[0] = h_flags[1] = 0;  // timing experiments (tools/s1_experiments.sh) produce garbage on purpose
 #endif
