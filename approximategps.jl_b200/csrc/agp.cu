@@ -1150,7 +1150,7 @@ static int32_t ensure_sweep_workspace(agp_ctx* c, int64_t cols, bool grad) {
       OK(c->fAb.ensure((int64_t)Mp * cc));
       OK(c->fAs.ensure((int64_t)Mp * cc));
       OK(c->qAb.ensure(((int64_t)i8e::S5_NS * Mp * cc + 7) / 8));
-      OK(c->sAb.ensure(cc));
+      OK(c->sAb.ensure(2 * cc));  // scales | column maxima
     }
   }
   if (grad) {
@@ -1396,6 +1396,10 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
           OK((launch_t5<false, false>(c, grid5, fC, plane, Mp, ncols, reinterpret_cast<float*>(c->fBtr.p), MMf, Mp, Mp, g, e4)));
         } else {
           t5::EpiF4<false> e4{fA, fA + plane, fAb, fAb + plane, fAs, fAs + plane, Mp, c->dmu.p, c->dv.p, c->mt.p, c->Ab.p, ldc};
+          if (f32_s5_i8()) {  // the column maxima of Ab ride along: the INT8 S5 slices without a pass of its own for them
+            CU(cudaMemsetAsync(c->sAb.p + ldc, 0, sizeof(double) * ncols, c->stream));
+            e4.abmax = c->sAb.p + ldc;
+          }
           OK((launch_t5<false, false>(c, grid5, fC, plane, Mp, ncols, reinterpret_cast<float*>(c->fBtr.p), MMf, Mp, Mp, g, e4)));
         }
       }
@@ -1410,7 +1414,7 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
         ProfScope ps(c, PC_TRSM_BWD);
         signed char* qAb = reinterpret_cast<signed char*>(c->qAb.p);
         const int64_t pbytes = (int64_t)Mp * ldc;
-        i8e::transpose_slice_kernel<i8e::S5_NS><<<(ncols + 31) / 32, 256, 0, c->stream>>>(c->Ab.p, ldc, Mp, ncols, qAb, Mp, pbytes, c->sAb.p);
+        i8e::transpose_slice_kernel<i8e::S5_NS><<<(ncols + 31) / 32, 256, 0, c->stream>>>(c->Ab.p, ldc, Mp, ncols, qAb, Mp, pbytes, c->sAb.p, c->sAb.p + ldc);
         LAUNCHED(c);
         KCHECK();
         CUtensorMap ma, mb;

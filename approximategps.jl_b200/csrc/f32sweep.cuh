@@ -112,13 +112,15 @@ struct EpiF4 {
   const double *dmu, *dv, *mt;
   double* Ab64;
   int64_t ldk;
+  double* abmax = nullptr;  // optional, per point: max_i |Ab[n][i]| (atomicMax over the column tiles; the scale of the INT8 slices of S5)
   struct State {
-    double dmu, dv;
+    double dmu, dv, mx;
   };
   __device__ __forceinline__ void begin(State& st, int tm, int, int, int row, int) const {
     const int n = tm * TM + row;
     st.dmu = dmu[n];
     st.dv = dv[n];
+    st.mx = 0.0;
   }
   __device__ __forceinline__ void operator()(State& st, int tm, int tn, int, int row, int c0, const double (&v)[32]) const {
     const int i0 = tn * TN + c0;
@@ -135,14 +137,20 @@ struct EpiF4 {
       for (int q = 0; q < 4; q++) {
         const double abv = fma(st.dmu, __ldg(mt + i0 + j + q), dv2 * (v[j + q] - a[q]));
         if (PLANES) ab[j + q] = (float)abv;
-        else p64[(int64_t)(j + q) * ldk] = abv;
+        else {
+          p64[(int64_t)(j + q) * ldk] = abv;
+          st.mx = fmax(st.mx, fabs(abv));
+        }
         as[j + q] = (float)(st.dv * a[q]);
       }
     }
     if (PLANES) store_split32(Abh + off, Abl + off, ab);
     store_split32(Ash + off, Asl + off, as);
   }
-  __device__ __forceinline__ void end(State&, int, int, int, int, int) const {}
+  __device__ __forceinline__ void end(State& st, int tm, int, int, int row, int) const {
+    // non-negative doubles order like their bit patterns
+    if (!PLANES && abmax) atomicMax(reinterpret_cast<unsigned long long*>(abmax) + tm * TM + row, (unsigned long long)__double_as_longlong(st.mx));
+  }
 };
 
 // ---- S5: Kb (FP64, inducing-major [j][ldk]) for the FP64 kernel-gradient contraction ---------------------------------------------

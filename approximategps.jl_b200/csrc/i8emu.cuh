@@ -292,9 +292,10 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
 // slices of the COLUMNS of a row-major FP64 matrix [rows][ld] (rows = k, columns = points), written point-major: planes [NS][cols][ldk] with
 // k contiguous, one power-of-two scale per point from the exact column maximum.  One CTA per 32 points: a first pass over the strip for the
 // maxima, a second one (an L2 hit: 32 x rows x 8 bytes) through a 32 x 32 shared-memory tile for the transposed, sliced stores.
+// colmax != nullptr: the column maxima are already known (the producing epilogue tracked them with atomicMax) and the first pass is skipped.
 template <int NS>
 __global__ void __launch_bounds__(256) transpose_slice_kernel(const double* __restrict__ in, int64_t ld, int rows, int cols, signed char* __restrict__ planes,
-                                                              int64_t ldk, int64_t plane_bytes, double* __restrict__ scale) {
+                                                              int64_t ldk, int64_t plane_bytes, double* __restrict__ scale, const double* __restrict__ colmax = nullptr) {
   __shared__ double tile[32][33];
   __shared__ double smx[8][32];
   __shared__ double sinv[32];
@@ -302,7 +303,11 @@ __global__ void __launch_bounds__(256) transpose_slice_kernel(const double* __re
   const int n0 = blockIdx.x * 32;
   const bool cok = n0 + tx < cols;
   double mx = 0.0;
-  for (int r = ty; r < rows; r += 8) mx = fmax(mx, cok ? fabs(in[(int64_t)r * ld + n0 + tx]) : 0.0);
+  if (colmax) {
+    if (ty == 0 && cok) mx = colmax[n0 + tx];
+  } else {
+    for (int r = ty; r < rows; r += 8) mx = fmax(mx, cok ? fabs(in[(int64_t)r * ld + n0 + tx]) : 0.0);
+  }
   smx[ty][tx] = mx;
   __syncthreads();
   if (ty == 0) {

@@ -534,3 +534,11 @@ print("RESULT" + json.dumps(out))
         for key in ("m", "Z", "ils"):
             assert rel_err(np.array(b[key]), np.array(a[key])) < 1e-10, (kind, key)
         assert abs(a["variance"] - b["variance"]) <= 1e-10 * max(1.0, abs(a["variance"]))
+
+
+@pytest.mark.parametrize("D,kind", [(12, "se"), (20, "matern52"), (32, "se"), (20, "linear")])
+def test_wide_inputs(agp, D, kind):
+    """Input dimensions beyond 8 take the DMAX = 16 / 32 instantiations of the Kuf generator and of the streaming kernel-gradient kernel
+    (BASELINE config 5 has D = 16; AGP_MAX_D = 32)."""
+    _run_case(agp, make_problem(seed=90 + D, kind=kind, N=1300, M=150, D=D, lik="gaussian" if kind == "linear" else "poisson_exp", ard=(D == 20),
+                                lengthscale=np.sqrt(D)), num_data=13000.0)
