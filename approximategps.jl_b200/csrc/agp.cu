@@ -175,7 +175,8 @@ struct agp_ctx {
   DevBuf gpart, Gpart, kpart, red, small, ghbuf;
   // Float32 mode: hi | lo FP32 planes (each DevBuf holds both: 2 x count floats = count doubles)
   DevBuf fA, fC, fAb, fAs, fBtc, fBtr, fLi;
-  DevBuf qAb, sAb, qLi, sLi;  // Float32 mode, S5 on the INT8 tensor path: 4 slice planes of Ab (point-major) and of Linv^T, their scales
+  DevBuf qAb, sAb, qLi, sLi;
+  DevBuf qK, sK, qLi7, sLi7, sxx_part;  // Float32 mode, forward solve on the INT8 tensor path: 7 slice planes of Kuf (point-major) and of Linv, scales, column-sum partials  // Float32 mode, S5 on the INT8 tensor path: 4 slice planes of Ab (point-major) and of Linv^T, their scales
   int* d_flags = nullptr;  // [0] potrf info, [1] domain flag
   SvgpState st;
   ncclComm_t comm = nullptr;
@@ -251,7 +252,7 @@ extern "C" int32_t agp_ctx_destroy(agp_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   DevBuf* bufs[] = {&c->z, &c->zs, &c->zn, &c->zsp, &c->mvec, &c->mt, &c->Lq, &c->Kw, &c->Lk, &c->Lt, &c->Ut, &c->Bt_cm, &c->Bt_rm,
                     &c->W1, &c->W2, &c->W3, &c->W4, &c->vec64, &c->vec64b, &c->A, &c->C, &c->Ab, &c->As, &c->Kf, &c->DKb, &c->saa, &c->sam,
-                    &c->scc_part, &c->dmu, &c->dv, &c->sc_part, &c->gpart, &c->Gpart, &c->kpart, &c->red, &c->small, &c->ghbuf, &c->fA, &c->fC, &c->fAb, &c->fAs, &c->fBtc, &c->fBtr, &c->fLi, &c->qAb, &c->sAb, &c->qLi, &c->sLi,
+                    &c->scc_part, &c->dmu, &c->dv, &c->sc_part, &c->gpart, &c->Gpart, &c->kpart, &c->red, &c->small, &c->ghbuf, &c->fA, &c->fC, &c->fAb, &c->fAs, &c->fBtc, &c->fBtr, &c->fLi, &c->qAb, &c->sAb, &c->qLi, &c->sLi, &c->qK, &c->sK, &c->qLi7, &c->sLi7, &c->sxx_part,
                     &c->mu_out, &c->var_out, &c->px1, &c->px2, &c->pxs1, &c->pxn1, &c->pxs2, &c->pxn2, &c->pcov};
   for (DevBuf* b : bufs) b->release();
   lap_release(c);
@@ -525,8 +526,9 @@ static bool s1_fused() {
 }
 // keep = true (reverse pass of a stationary kernel): Kuf goes to c->Kf and variance * kappa'(u) to c->DKb, the solve reads Kf and writes
 // t1.X; S7 then contracts the cotangent with the stored values (kgrad_kernel FAST) instead of recomputing distances and exp.
-static int32_t launch_s1(agp_ctx* c, const TrsmArgs& t1_in, int tiles_n, bool keep = false) {
-  if (s1_fused()) return launch_trsm<TR_KUF_FWD>(c, t1_in, tiles_n);
+// gen_only = true: only the generator runs (into c->Kf); the caller solves by other means (Float32 mode: INT8 product with the explicit inverse).
+static int32_t launch_s1(agp_ctx* c, const TrsmArgs& t1_in, int tiles_n, bool keep = false, bool gen_only = false) {
+  if (s1_fused() && !gen_only) return launch_trsm<TR_KUF_FWD>(c, t1_in, tiles_n);
   TrsmArgs t1 = t1_in;
   KufGenArgs g{};
   // (SqExponential: kappa' = -kappa / 2, S7 needs only Kuf itself: one matrix written here instead of two)
@@ -559,6 +561,7 @@ static int32_t launch_s1(agp_ctx* c, const TrsmArgs& t1_in, int tiles_n, bool ke
 #undef AGP_KGEN_D
   LAUNCHED(c);
   KCHECK();
+  if (gen_only) return AGP_OK;
   return launch_trsm<TR_RHS_FWD_SUMS>(c, t1, tiles_n);
 }
 
@@ -963,6 +966,12 @@ static int32_t prepare_f32_operands(agp_ctx* c) {
   a.ldx = Mp;
   a.kp = st.kp;
   OK(launch_trsm<TR_RHS_FWD>(c, a, Mp / BN));
+  // Linv itself (rows l, k = l' contiguous) as seven slice planes: the B operand of the INT8 forward solve (f32sweep.cuh EpiE1)
+  OK(c->qLi7.ensure((i8e::S * MM + 7) / 8));
+  OK(c->sLi7.ensure(Mp));
+  i8e::slice_rows_kernel<i8e::S><<<(Mp + 7) / 8, 256, 0, c->stream>>>(c->W1.p, Mp, Mp, Mp, reinterpret_cast<signed char*>(c->qLi7.p), Mp, MM, c->sLi7.p);
+  LAUNCHED(c);
+  KCHECK();
   OK(transpose(c, c->W1.p, c->W2.p, Mp, Mp));
   OK(split(c->W2.p, c->fLi));
   // ... and as four INT8 slice planes per row j with a power-of-two row scale: the B operand of the INT8 S5 (f32sweep.cuh EpiE5)
@@ -974,6 +983,11 @@ static int32_t prepare_f32_operands(agp_ctx* c) {
   return AGP_OK;
 }
 // Float32 mode's reverse-pass solve: "i8" (default) = 4-slice INT8 product with the explicit inverse; "fp64" = the FP64 DMMA triangular solve
+// Float32 mode's forward solve: "i8" (default) = 7-slice (FP64-accurate) INT8 product with the explicit inverse; "fp64" = the DMMA triangular solve
+static bool f32_s1_i8() {
+  static const bool off = getenv("AGP_F32_S1") && strcmp(getenv("AGP_F32_S1"), "fp64") == 0;  // tuning knob
+  return !off;
+}
 static bool f32_s5_i8() {
   static const bool off = getenv("AGP_F32_S5") && strcmp(getenv("AGP_F32_S5"), "fp64") == 0;  // tuning knob
   return !off;
@@ -1146,6 +1160,12 @@ static int32_t ensure_sweep_workspace(agp_ctx* c, int64_t cols, bool grad) {
   if (st.f32) {
     OK(c->fA.ensure((int64_t)Mp * cc));
     OK(c->fC.ensure((int64_t)Mp * cc));
+    if (f32_s1_i8() && Mp >= 768) {
+      OK(c->Kf.ensure((int64_t)Mp * cc));
+      OK(c->qK.ensure(((int64_t)i8e::S * Mp * cc + 7) / 8));
+      OK(c->sK.ensure(cc));
+      OK(c->sxx_part.ensure((int64_t)2 * (Mp / 32) * cc));  // saa partials | sam partials, one per 32 inducing rows
+    }
     if (grad) {
       OK(c->fAb.ensure((int64_t)Mp * cc));
       OK(c->fAs.ensure((int64_t)Mp * cc));
@@ -1319,7 +1339,32 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
     t1.saa = c->saa.p;
     t1.sam = c->sam.p;
     t1.kp = st.kp;
-    {
+    if (st.f32 && f32_s1_i8() && !s1_fused() && Mp >= 768) {  // (below M ~ 768 the DMMA solve is as fast: C2, M = 512: 11.5 against 12.0 ms)
+      // Float32 mode: A = Linv Kuf as an FP64-accurate INT8-slice product (i8emu.cuh, 7 slices): generator -> Kf (FP64, also S7's input),
+      // point-major slices with exact per-point scales, 28 exact slice products, column sums in the epilogue
+      ProfScope ps(c, PC_TRSM_FWD);
+      if (st.kp.kind != AGP_KERNEL_SE) OK(c->DKb.ensure((int64_t)Mp * ldc));  // (the generator also stores kappa' for the Matern kinds)
+      OK(launch_s1(c, t1, tiles_n, true, true));
+      signed char* qK = reinterpret_cast<signed char*>(c->qK.p);
+      const int64_t pbytes = (int64_t)Mp * ldc, MM8 = (int64_t)Mp * Mp;
+      i8e::transpose_slice_kernel<i8e::S><<<(ncols + 31) / 32, 256, 0, c->stream>>>(c->Kf.p, ldc, Mp, ncols, qK, Mp, pbytes, c->sK.p);
+      LAUNCHED(c);
+      KCHECK();
+      CUtensorMap ma, mb;
+      if (!i8e::make_map3(&ma, qK, Mp, ncols, Mp, pbytes, i8e::EM, i8e::S) ||
+          !i8e::make_map3(&mb, reinterpret_cast<signed char*>(c->qLi7.p), Mp, Mp, Mp, MM8, i8e::EN, i8e::S))
+        return fail(AGP_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+      const int nparts = Mp / 32;
+      i8e::EpiE1 e1{c->A.p, ldc, c->sK.p, c->sLi7.p, c->mt.p, c->sxx_part.p, c->sxx_part.p + (int64_t)nparts * ldc, ldc};
+      i8e::Args g8{Mp, i8e::KM_UPTO_N, 0, 0};
+      OK((ensure_smem<i8e::i8emu_gemm_kernel<i8e::EpiE1>>(c, i8e::SMEM_BYTES)));
+      i8e::i8emu_gemm_kernel<i8e::EpiE1><<<dim3(Mp / i8e::EN, ncols / i8e::EM, 1), i8e::E_THREADS, i8e::SMEM_BYTES, c->stream>>>(ma, mb, g8, e1);
+      LAUNCHED(c);
+      KCHECK();
+      i8e::colsum_reduce_kernel<<<(ncols + 255) / 256, 256, 0, c->stream>>>(c->sxx_part.p, nparts, ldc, ncols, c->saa.p, c->sam.p);
+      LAUNCHED(c);
+      KCHECK();
+    } else {
       ProfScope ps(c, PC_TRSM_FWD);
       OK(launch_s1(c, t1, tiles_n, grad && kgrad_fast(st)));
     }

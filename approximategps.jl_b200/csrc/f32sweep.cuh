@@ -189,6 +189,46 @@ struct EpiF6 {
 // (1.4e-4 on dZ at the C4 twin) nor four slices (28 bits: 2.7e-4) can afford inside the 1e-4 budget.
 // Output: Kb (FP64, inducing-major [j][ldk]) for the FP64 kernel-gradient contraction, like EpiF5.
 namespace i8e {
+// ---- S1's solve of the Float32 mode: A[n][l] = sum_{l' <= l} Kuf[n][l'] Linv[l][l'] with seven slices (FP64-accurate: the marginal variance
+// k(x,x) - a^T a + c^T c cancels to ~jitter, so a may not carry an FP32-sized error).  Writes A (FP64, inducing-major [l][ld]: a warp's 32 points are 32
+// consecutive doubles) and, per point and per 32 inducing rows, the partial column sums a^T a and a^T mt (summed in a fixed order afterwards).
+struct EpiE1 {
+  double* A;
+  int64_t ld;
+  const double* sK;   // per point
+  const double* sLi;  // per inducing row l
+  const double* mt;
+  double* saa_part;  // [Mp / 32][ldp]
+  double* sam_part;
+  int64_t ldp;
+  __device__ __forceinline__ void operator()(int tm, int tn, int, int row, int c0, const double (&v)[32]) const {
+    const int n = tm * EM + row, l0 = tn * EN + c0;
+    const double sk = sK[n] * (1.0 / 16384.0);
+    double* p = A + (int64_t)l0 * ld + n;
+    double pa = 0.0, pm = 0.0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      const double a = v[j] * sk * __ldg(sLi + l0 + j);
+      p[(int64_t)j * ld] = a;
+      pa = fma(a, a, pa);
+      pm = fma(a, __ldg(mt + l0 + j), pm);
+    }
+    saa_part[(int64_t)(l0 >> 5) * ldp + n] = pa;
+    sam_part[(int64_t)(l0 >> 5) * ldp + n] = pm;
+  }
+};
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const double* __restrict__ part, int nparts, int64_t ldp, int ncols, double* __restrict__ saa,
+                                                            double* __restrict__ sam) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= ncols) return;
+  double a = 0.0, m = 0.0;
+  for (int p = 0; p < nparts; p++) {
+    a += part[(int64_t)p * ldp + n];
+    m += part[(int64_t)(nparts + p) * ldp + n];
+  }
+  saa[n] = a;
+  sam[n] = m;
+}
 constexpr int S5_NS = 5, S5_N = 64;
 struct EpiE5 {
   double* Kb;

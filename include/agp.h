@@ -71,9 +71,9 @@ extern "C" {
 
 #define AGP_COMPUTE_F64 0 /* reference precision: every stage in Float64 (DMMA)                                   */
 #define AGP_COMPUTE_F32 1 /* "Float32 fast mode" (a Float32 GP in the reference, SVA.jl:59-62 is type-generic): S2 / S4 / S6 run as 3xTF32 split
-                           * products on the tcgen05 tensor path (partial sums carried over in Float64 every 64 k), the reverse-pass solve S5 as an
-                           * exact-accumulation INT8 product (5 slices of 7 bits, tcgen05.mma.kind::i8) with the explicit inverse; Kuf + forward solve,
-                           * per-point stage, reductions and the O(M^3) epilogue stay Float64.  Parity target 1e-4.          */
+                           * products on the tcgen05 tensor path (partial sums carried over in Float64 every 64 k), the two triangular solves as
+                           * exact-accumulation INT8 products with the explicit inverse (tcgen05.mma.kind::i8; forward: 7 slices of 7 bits =
+                           * Float64-accurate, reverse: 5); Kuf, per-point stage, reductions and the O(M^3) epilogue stay Float64.  Parity 1e-4. */
 #define AGP_COMPUTE_F32_TC_SOLVE 2 /* as AGP_COMPUTE_F32, with the reverse-pass solve Kb = Lk^-T Ab as a 3xTF32 product with the
                            * explicit inverse too (1.2x faster again; its error on dZ / d theta grows with cond(Lk): 1.4e-4 at
                            * the M = 1024 SqExponential twin of BASELINE config 4, below 1e-4 on the others)                */

@@ -3,9 +3,9 @@
 cd "$(dirname "$0")/.." && mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_f32.py tests/test_gpu_engines.py -m gpu -q -s > gpurun_out/r2v_f32tests.log 2>&1; grep -E "^\[f32|passed|failed|Error|error" gpurun_out/r2v_f32tests.log | cut -c1-330 | head -14
 python bench.py --dtype f32 --steps 3 --warmup 3 > gpurun_out/r2v_bench_c4_f32.json 2> gpurun_out/r2v_bench_c4_f32.err
-AGP_F32_S5=fp64 python bench.py --dtype f32 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2v_bench_c4_f32_s5fp64.json 2>/dev/null
+AGP_F32_S1=fp64 python bench.py --dtype f32 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2v_bench_c4_f32_s1fp64.json 2>/dev/null
 python bench.py --dtype f32 --workload c2 --steps 5 --warmup 3 > gpurun_out/r2v_bench_c2_f32.json 2>/dev/null
-for f in gpurun_out/r2v_bench_c4_f32.json gpurun_out/r2v_bench_c4_f32_s5fp64.json gpurun_out/r2v_bench_c2_f32.json; do python - "$f" <<'PY'
+for f in gpurun_out/r2v_bench_c4_f32.json gpurun_out/r2v_bench_c4_f32_s1fp64.json gpurun_out/r2v_bench_c2_f32.json; do python - "$f" <<'PY'
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
