@@ -1079,7 +1079,10 @@ static int32_t prepare_step(agp_ctx* c, const agp_svgp_params* p) {
     OK(launch_trsm<TR_RHS_FWD>(c, a, Mp / BN));
     OK(transpose(c, c->Bt_rm.p, c->Bt_cm.p, Mp, Mp));
   }
-  if (st.f32) OK(prepare_f32_operands(c));
+  {
+    static const bool f64_s1_i8 = getenv("AGP_F64_S1") && strcmp(getenv("AGP_F64_S1"), "i8") == 0;
+    if (st.f32 || (f64_s1_i8 && Mp >= 768)) OK(prepare_f32_operands(c));
+  }
   st.valid = true;
   return AGP_OK;
 }
@@ -1160,17 +1163,20 @@ static int32_t ensure_sweep_workspace(agp_ctx* c, int64_t cols, bool grad) {
   if (st.f32) {
     OK(c->fA.ensure((int64_t)Mp * cc));
     OK(c->fC.ensure((int64_t)Mp * cc));
-    if (f32_s1_i8() && Mp >= 768) {
-      OK(c->Kf.ensure((int64_t)Mp * cc));
-      OK(c->qK.ensure(((int64_t)i8e::S * Mp * cc + 7) / 8));
-      OK(c->sK.ensure(cc));
-      OK(c->sxx_part.ensure((int64_t)2 * (Mp / 32) * cc));  // saa partials | sam partials, one per 32 inducing rows
-    }
     if (grad) {
       OK(c->fAb.ensure((int64_t)Mp * cc));
       OK(c->fAs.ensure((int64_t)Mp * cc));
       OK(c->qAb.ensure(((int64_t)i8e::S5_NS * Mp * cc + 7) / 8));
       OK(c->sAb.ensure(2 * cc));  // scales | column maxima
+    }
+  }
+  {
+    static const bool f64_s1_i8 = getenv("AGP_F64_S1") && strcmp(getenv("AGP_F64_S1"), "i8") == 0;
+    if ((st.f32 || f64_s1_i8) && f32_s1_i8() && Mp >= 768) {
+      OK(c->Kf.ensure((int64_t)Mp * cc));
+      OK(c->qK.ensure(((int64_t)i8e::S * Mp * cc + 7) / 8));
+      OK(c->sK.ensure(cc));
+      OK(c->sxx_part.ensure((int64_t)2 * (Mp / 32) * cc));  // saa partials | sam partials, one per 32 inducing rows
     }
   }
   if (grad) {
@@ -1339,7 +1345,8 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
     t1.saa = c->saa.p;
     t1.sam = c->sam.p;
     t1.kp = st.kp;
-    if (st.f32 && f32_s1_i8() && !s1_fused() && Mp >= 768) {  // (below M ~ 768 the DMMA solve is as fast: C2, M = 512: 11.5 against 12.0 ms)
+    static const bool f64_s1_i8 = getenv("AGP_F64_S1") && strcmp(getenv("AGP_F64_S1"), "i8") == 0;  // experiment: the same solve in the Float64 mode
+    if ((st.f32 || f64_s1_i8) && f32_s1_i8() && !s1_fused() && Mp >= 768) {  // (below M ~ 768 the DMMA solve is as fast: C2, M = 512: 11.5 against 12.0 ms)
       // Float32 mode: A = Linv Kuf as an FP64-accurate INT8-slice product (i8emu.cuh, 7 slices): generator -> Kf (FP64, also S7's input),
       // point-major slices with exact per-point scales, 28 exact slice products, column sums in the epilogue
       ProfScope ps(c, PC_TRSM_FWD);
