@@ -972,6 +972,14 @@ static int32_t prepare_f32_operands(agp_ctx* c) {
   i8e::slice_rows_kernel<i8e::S><<<(Mp + 7) / 8, 256, 0, c->stream>>>(c->W1.p, Mp, Mp, Mp, reinterpret_cast<signed char*>(c->qLi7.p), Mp, MM, c->sLi7.p);
   LAUNCHED(c);
   KCHECK();
+  if (getenv("AGP_DEBUG_LINV")) {  // development aid: the largest entry of the explicit inverse (what the fixed-point slices are relative to)
+    std::vector<double> h(Mp);
+    CU(cudaMemcpyAsync(h.data(), c->sLi7.p, sizeof(double) * Mp, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    double mx = 0.0;
+    for (int i = 0; i < st.M; i++) mx = std::max(mx, h[i]);
+    fprintf(stderr, "[agp] M = %d: pow2 bound of max |Linv| = %.3g\n", st.M, mx);
+  }
   OK(transpose(c, c->W1.p, c->W2.p, Mp, Mp));
   OK(split(c->W2.p, c->fLi));
   // ... and as four INT8 slice planes per row j with a power-of-two row scale: the B operand of the INT8 S5 (f32sweep.cuh EpiE5)
@@ -1328,7 +1336,8 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
   }
   for (int64_t lo = 0; lo < count; lo += cols) {
     const int npts = (int)std::min<int64_t>(cols, count - lo);
-    const int ncols = (int)round_up(npts, st.f32 ? 2 * BN : BN);  // Float32 mode: the tcgen05 stages tile the points by 128
+    static const bool f64_i8_exp = getenv("AGP_F64_S1") && strcmp(getenv("AGP_F64_S1"), "i8") == 0;
+    const int ncols = (int)round_up(npts, (st.f32 || f64_i8_exp) ? 2 * BN : BN);  // Float32 mode: the tcgen05 stages tile the points by 128
     const int tiles_n = ncols / BN;
     const double* pts = X + lo * D;
     // S1: A = Lk^-1 Kuf
