@@ -1355,6 +1355,7 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
     t1.sam = c->sam.p;
     t1.kp = st.kp;
     static const bool f64_s1_i8 = getenv("AGP_F64_S1") && strcmp(getenv("AGP_F64_S1"), "i8") == 0;  // experiment: the same solve in the Float64 mode
+    bool a_planes_done = false;
     if ((st.f32 || f64_s1_i8) && f32_s1_i8() && !s1_fused() && Mp >= 768) {  // (below M ~ 768 the DMMA solve is as fast: C2, M = 512: 11.5 against 12.0 ms)
       // Float32 mode: A = Linv Kuf as an FP64-accurate INT8-slice product (i8emu.cuh, 7 slices): generator -> Kf (FP64, also S7's input),
       // point-major slices with exact per-point scales, 28 exact slice products, column sums in the epilogue
@@ -1372,6 +1373,12 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
         return fail(AGP_ERR_CUDA, "cuTensorMapEncodeTiled failed");
       const int nparts = Mp / 32;
       i8e::EpiE1 e1{c->A.p, ldc, c->sK.p, c->sLi7.p, c->mt.p, c->sxx_part.p, c->sxx_part.p + (int64_t)nparts * ldc, ldc};
+      if (st.f32) {  // the TF32 planes of A come straight from this epilogue
+        e1.Ah = reinterpret_cast<float*>(c->fA.p);
+        e1.Al = e1.Ah + (int64_t)Mp * ldc;
+        e1.ldf = Mp;
+        a_planes_done = true;
+      }
       i8e::Args g8{Mp, i8e::KM_UPTO_N, 0, 0};
       OK((ensure_smem<i8e::i8emu_gemm_kernel<i8e::EpiE1>>(c, i8e::SMEM_BYTES)));
       i8e::i8emu_gemm_kernel<i8e::EpiE1><<<dim3(Mp / i8e::EN, ncols / i8e::EM, 1), i8e::E_THREADS, i8e::SMEM_BYTES, c->stream>>>(ma, mb, g8, e1);
@@ -1393,7 +1400,7 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
     const int64_t MMf = (int64_t)Mp * Mp;
     const dim3 grid5(ncols / t5::TM, Mp / t5::TN, 1);
     if (st.f32) {
-      {
+      if (!a_planes_done) {
         ProfScope ps(c, PC_F32_AUX);
         t5::transpose_split_kernel<<<dim3(ncols / 32, Mp / 32), 256, 0, c->stream>>>(c->A.p, ldc, Mp, ncols, fA, fA + plane, Mp);
         LAUNCHED(c);

@@ -201,20 +201,25 @@ struct EpiE1 {
   double* saa_part;  // [Mp / 32][ldp]
   double* sam_part;
   int64_t ldp;
+  float* Ah = nullptr;  // optional: the point-major hi / lo TF32 planes of A that S2 / S4 / S6 read (32 consecutive floats per thread), so
+  float* Al = nullptr;  // that the transposing split pass over A is not needed
+  int64_t ldf = 0;
   __device__ __forceinline__ void operator()(int tm, int tn, int, int row, int c0, const double (&v)[32]) const {
     const int n = tm * EM + row, l0 = tn * EN + c0;
     const double sk = sK[n] * (1.0 / 16384.0);
     double* p = A + (int64_t)l0 * ld + n;
+    double a[32];
     double pa = 0.0, pm = 0.0;
 #pragma unroll
     for (int j = 0; j < 32; j++) {
-      const double a = v[j] * sk * __ldg(sLi + l0 + j);
-      p[(int64_t)j * ld] = a;
-      pa = fma(a, a, pa);
-      pm = fma(a, __ldg(mt + l0 + j), pm);
+      a[j] = v[j] * sk * __ldg(sLi + l0 + j);
+      p[(int64_t)j * ld] = a[j];
+      pa = fma(a[j], a[j], pa);
+      pm = fma(a[j], __ldg(mt + l0 + j), pm);
     }
     saa_part[(int64_t)(l0 >> 5) * ldp + n] = pa;
     sam_part[(int64_t)(l0 >> 5) * ldp + n] = pm;
+    if (Ah) t5::store_split32(Ah + (int64_t)n * ldf + l0, Al + (int64_t)n * ldf + l0, a);
   }
 };
 __global__ void __launch_bounds__(256) colsum_reduce_kernel(const double* __restrict__ part, int nparts, int64_t ldp, int ncols, double* __restrict__ saa,
