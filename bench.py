@@ -600,6 +600,8 @@ def run_svgp(args, w):
                                f"cuBLAS DGEMM 8192^3 {FP64_PEAK_TFLOPS_DGEMM}; MEASURED_PEAKS.json has no FP64 entry",
                 "kuf_trsm_stage": {"alg_tflops": kernels.get("trsm_kuf_fwd", {}).get("alg_tflops"), "frac_of_peak": kernels.get("trsm_kuf_fwd", {}).get("frac_of_peak")},
                 "profiled_pass": {"steps": psteps, "ms_per_step": ms_prof / psteps},
+                **({"note": "Float32 mode: the two triangular solves run on the INT8 tensor path and S2 / S4 / S6 on TF32; `achieved` and the fractions are "
+                            "FP64-equivalent throughput set against the FP64 DMMA peak for comparison with the Float64 line, not a utilisation"} if f32 else {}),
                 "whole_step": {"executed_tflops_per_gpu": exe_tf, "frac_of_fp64_peak_executed": exe_tf / peak_dmma,
                                "reference_equivalent_tflops_per_gpu": alg_tf,
                                "note": "executed = 5 M^2 + 6 M D flop per point (one SYRK serves the reference's two M x N . N x M products); "
