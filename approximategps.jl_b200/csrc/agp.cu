@@ -153,6 +153,7 @@ struct Prof {
 };
 
 static void lap_release(agp_ctx* c);
+static void chol_partition_release(agp_ctx* c);
 struct agp_ctx {
   Prof prof;
   void* lap = nullptr;  // LapWork (laplace_host.inc)
@@ -160,6 +161,14 @@ struct agp_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;                // trailing updates of the blocked Cholesky (look-ahead), see blocked_cholesky
   cudaEvent_t ev_panel = nullptr, ev_trail = nullptr;
+  cudaStream_t stream3 = nullptr;                // tile-level look-ahead of the blocked Cholesky: full-height panels / in-super-panel updates
+  // SM partition for large factorisations (green contexts, see chol_partition): the critical chain on its own 8 SMs
+  int part_state = 0;                            // 0 = not tried, 1 = in use, -1 = unavailable
+  CUgreenCtx part_chain = nullptr, part_bulk = nullptr;
+  cudaStream_t pstream_chain = nullptr, pstream_side = nullptr, pstream_trail = nullptr;
+  cudaEvent_t ev_enter = nullptr, ev_leave = nullptr;
+  int part_sms_chain = 0, part_sms_bulk = 0;
+  cudaEvent_t ev_diag = nullptr, ev_prow = nullptr, ev_side = nullptr, ev_prio[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t stream_copy = nullptr;            // upload of the q.Sigma factor (M^2 doubles) behind the Kuu factorisation, see prepare_step
   cudaEvent_t ev_copy = nullptr;
   int sms = 148;
@@ -235,8 +244,13 @@ extern "C" int32_t agp_ctx_create(int32_t device, agp_ctx** out) {
   CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
   CU(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));
+  CU(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prio_hi < prio_lo - 1 ? prio_hi + 1 : prio_hi));
   CU(cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_trail, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_diag, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_prow, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+  for (int i = 0; i < 4; i++) CU(cudaEventCreateWithFlags(&c->ev_prio[i], cudaEventDisableTiming));
   CU(cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
   CU(cudaMalloc(&c->d_flags, 4 * sizeof(int)));
@@ -261,6 +275,10 @@ extern "C" int32_t agp_ctx_destroy(agp_ctx* c) {
   if (c->ev_panel) cudaEventDestroy(c->ev_panel);
   if (c->ev_trail) cudaEventDestroy(c->ev_trail);
   if (c->stream2) cudaStreamDestroy(c->stream2);
+  for (cudaEvent_t e : {c->ev_diag, c->ev_prow, c->ev_side, c->ev_prio[0], c->ev_prio[1], c->ev_prio[2], c->ev_prio[3]})
+    if (e) cudaEventDestroy(e);
+  if (c->stream3) cudaStreamDestroy(c->stream3);
+  chol_partition_release(c);
   if (c->ev_copy) cudaEventDestroy(c->ev_copy);
   if (c->stream_copy) cudaStreamDestroy(c->stream_copy);
   cudaStreamDestroy(c->stream);
@@ -497,9 +515,15 @@ template <auto Kernel>
 static int32_t ensure_smem(agp_ctx* c, int bytes) {
   static int granted[64] = {0};
   int& g = granted[c->device & 63];
-  if (g >= bytes) return AGP_OK;
-  CU(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  g = bytes;
+  if (g > bytes) return AGP_OK;  // g = granted bytes + 1
+  if (bytes > 0) CU(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  // Every kernel of this library asks for the maximum shared-memory carve-out.  The L1 / shared split of an SM can only change while the SM
+  // is empty: with the driver's per-kernel default a 2-stage GEMM tile (51 KB, two per SM) configures a smaller carve-out, and the 166 KB
+  // diagonal-block kernel of the blocked Cholesky -- the head of its critical chain -- then waits until some SM has drained completely
+  // (measured: 80 -> 165..270 us per diagonal kernel while a trailing update is in flight, profiles/r3g_chol_trace_v2.txt).
+  static const bool carve = !(getenv("AGP_CARVEOUT") && atoi(getenv("AGP_CARVEOUT")) == 0);  // A/B knob
+  if (carve) CU(cudaFuncSetAttribute(Kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  g = bytes + 1;
   return AGP_OK;
 }
 
@@ -645,7 +669,11 @@ struct StreamSwap {  // launch helpers use c->stream: point it at the second str
   StreamSwap(agp_ctx* c_, cudaStream_t s) : c(c_), saved(c_->stream) { c->stream = s; }
   ~StreamSwap() { c->stream = saved; }
 };
+static int32_t blocked_cholesky_v2(agp_ctx* c, double* Kw, double* L, double* Lt, double* Ut, int nb, int64_t ld, int* info, int nvalid);
 static int32_t blocked_cholesky(agp_ctx* c, double* Kw, double* L, double* Lt, double* Ut, int nb, int64_t ld, int* info, int nvalid) {
+  // AGP_CHOL_SCHED=1 selects the super-panel-level look-ahead of round 1 (kept for A/B measurements); the default is the tile-level one
+  static const int sched = getenv("AGP_CHOL_SCHED") ? atoi(getenv("AGP_CHOL_SCHED")) : 2;
+  if (sched == 2 && nb > 1) return blocked_cholesky_v2(c, Kw, L, Lt, Ut, nb, ld, info, nvalid);
   OK((ensure_smem<potrf_trinv128_kernel>(c, PT_SMEM_BYTES)));
   constexpr int OB = 4;  // inner blocks per super-panel
   static const bool lookahead = !(getenv("AGP_CHOL_LOOKAHEAD") && atoi(getenv("AGP_CHOL_LOOKAHEAD")) == 0);  // tuning knob
@@ -727,6 +755,271 @@ static int32_t blocked_cholesky(agp_ctx* c, double* Kw, double* L, double* Lt, d
       fprintf(stderr, "[chol trace] %-12s s=%2d t=%9.1f us\n", m.what, m.s, 1e3 * ms);
     }
     for (const Mark& m : marks) cudaEventDestroy(m.e);
+  }
+  return AGP_OK;
+}
+
+// ---- SM partition for the blocked Cholesky (CUDA green contexts) ---------------------------------------------------------
+// The chain of a large factorisation (diagonal-block kernel -> block row of the panel -> tile update -> next diagonal block) is a
+// sequence of one-CTA / sixteen-CTA launches whose latency is the critical path once few block rows are left.  Stream priorities give
+// those CTAs the first free slot, but not a quiet SM: next to a DMMA tile of the trailing update, which keeps the FP64 pipe of its SM
+// busy, the one-warp column loop of the diagonal kernel runs 1.5-3x slower (80 -> 120..270 us, profiles/r3i_chol_trace_v2.txt).  So
+// for nb >= 16 the device is split: 8 SMs (the smallest partition sm_100 allows) carry only the chain, the other 140 carry
+// the panel / update / trailing GEMMs.  Streams of the two green contexts synchronise through events like any others; the rest of the
+// library keeps using the primary context's streams (all 148 SMs).  If the driver refuses any step, the unpartitioned schedule is used.
+struct GreenApi {
+  CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
+  CUresult (*DeviceGetDevResource)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+  CUresult (*DevSmResourceSplitByCount)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int) = nullptr;
+  CUresult (*DevResourceGenerateDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+  CUresult (*GreenCtxCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+  CUresult (*GreenCtxDestroy)(CUgreenCtx) = nullptr;
+  CUresult (*GreenCtxStreamCreate)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+  bool ok = false;
+};
+static GreenApi& green_api() {
+  static GreenApi g;
+  static bool tried = false;
+  if (tried) return g;
+  tried = true;
+  auto get = [](const char* name, void** fn) {
+    cudaDriverEntryPointQueryResult q;
+    return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+  };
+  g.ok = get("cuDeviceGet", (void**)&g.DeviceGet) && get("cuDeviceGetDevResource", (void**)&g.DeviceGetDevResource) &&
+         get("cuDevSmResourceSplitByCount", (void**)&g.DevSmResourceSplitByCount) && get("cuDevResourceGenerateDesc", (void**)&g.DevResourceGenerateDesc) &&
+         get("cuGreenCtxCreate", (void**)&g.GreenCtxCreate) && get("cuGreenCtxDestroy", (void**)&g.GreenCtxDestroy) &&
+         get("cuGreenCtxStreamCreate", (void**)&g.GreenCtxStreamCreate);
+  return g;
+}
+static bool chol_partition(agp_ctx* c) {
+  if (c->part_state != 0) return c->part_state > 0;
+  c->part_state = -1;
+  if (getenv("AGP_CHOL_PARTITION") && atoi(getenv("AGP_CHOL_PARTITION")) == 0) return false;  // A/B knob
+  GreenApi& g = green_api();
+  if (!g.ok) return false;
+  CUdevice dev;
+  CUdevResource all, grp[1], rest;
+  unsigned int ngrp = 1;
+  CUdevResourceDesc d_chain, d_bulk;
+  if (g.DeviceGet(&dev, c->device) != CUDA_SUCCESS) return false;
+  if (g.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+  if (g.DevSmResourceSplitByCount(grp, &ngrp, &all, &rest, 0, 8) != CUDA_SUCCESS || ngrp < 1) return false;
+  if (grp[0].sm.smCount < 4 || rest.sm.smCount < all.sm.smCount / 2) return false;
+  if (g.DevResourceGenerateDesc(&d_chain, &grp[0], 1) != CUDA_SUCCESS || g.DevResourceGenerateDesc(&d_bulk, &rest, 1) != CUDA_SUCCESS) return false;
+  if (g.GreenCtxCreate(&c->part_chain, d_chain, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+  if (g.GreenCtxCreate(&c->part_bulk, d_bulk, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) {
+    chol_partition_release(c);
+    return false;
+  }
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  CUstream s1 = nullptr, s2 = nullptr, s3 = nullptr;
+  if (g.GreenCtxStreamCreate(&s1, c->part_chain, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS ||
+      g.GreenCtxStreamCreate(&s2, c->part_bulk, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS ||
+      g.GreenCtxStreamCreate(&s3, c->part_bulk, CU_STREAM_NON_BLOCKING, prio_lo) != CUDA_SUCCESS ||
+      cudaEventCreateWithFlags(&c->ev_enter, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_leave, cudaEventDisableTiming) != cudaSuccess) {
+    c->pstream_chain = (cudaStream_t)s1;
+    c->pstream_side = (cudaStream_t)s2;
+    c->pstream_trail = (cudaStream_t)s3;
+    chol_partition_release(c);
+    cudaGetLastError();
+    return false;
+  }
+  c->pstream_chain = (cudaStream_t)s1;
+  c->pstream_side = (cudaStream_t)s2;
+  c->pstream_trail = (cudaStream_t)s3;
+  c->part_sms_chain = (int)grp[0].sm.smCount;
+  c->part_sms_bulk = (int)rest.sm.smCount;
+  c->part_state = 1;
+  if (getenv("AGP_CHOL_TRACE")) fprintf(stderr, "[chol partition] chain %d SMs, GEMMs %d SMs\n", c->part_sms_chain, c->part_sms_bulk);
+  return true;
+}
+static void chol_partition_release(agp_ctx* c) {
+  for (cudaStream_t* st : {&c->pstream_chain, &c->pstream_side, &c->pstream_trail})
+    if (*st) {
+      cudaStreamSynchronize(*st);
+      cudaStreamDestroy(*st);
+      *st = nullptr;
+    }
+  for (cudaEvent_t* e : {&c->ev_enter, &c->ev_leave})
+    if (*e) {
+      cudaEventDestroy(*e);
+      *e = nullptr;
+    }
+  GreenApi& g = green_api();
+  for (CUgreenCtx* gc : {&c->part_chain, &c->part_bulk})
+    if (*gc) {
+      if (g.GreenCtxDestroy) g.GreenCtxDestroy(*gc);
+      *gc = nullptr;
+    }
+  c->part_state = -1;
+}
+
+// Tile-level look-ahead (round 2).  The schedule above keeps the whole chain diag(J) -> panel(J) -> update(J) on one stream, so that the
+// 128 x 128 diagonal kernel of block J+1 (one CTA, ~80 us) waits for two full-height GEMM launches it does not depend on, and the next
+// super-panel waits for all four of its block columns to receive the K = 512 update.  diag(J+1) needs only block row J+1: the panel tile
+// L[J+1,J] = Kw[J+1,J] inv(L_JJ)^T and the update of Kw[J+1,J+1].  So:
+//   main stream (highest priority): diag(J), row J+1 of the panel (2 CTAs), update of the (J+1,J+1) tile (2 CTAs; K = 512 from the whole
+//                                   previous super-panel when J+1 opens a new one), diag(J+1), ...
+//   side stream (middle priority):  rows >= J+2 of panel(J) and of the in-super-panel update, then -- at the end of a super-panel -- the
+//                                   K = 512 update of the next super-panel's block columns, one launch per column in the order in
+//                                   which the chain consumes them
+//   trail stream (lowest priority): the K = 512 update of all later columns (2-stage tiles, as before)
+// Every output tile is produced by the same k loop as in the one-stream schedule, so the factor is bit-identical to it.
+static int32_t blocked_cholesky_v2(agp_ctx* c, double* Kw, double* L, double* Lt, double* Ut, int nb, int64_t ld, int* info, int nvalid) {
+  OK((ensure_smem<potrf_trinv128_kernel>(c, PT_SMEM_BYTES)));
+  constexpr int OB = 4;  // inner blocks per super-panel
+  cudaStream_t sm = c->stream, ss = c->stream3, st = c->stream2;
+  cudaStream_t caller = c->stream;
+  const bool part = nb >= 16 && chol_partition(c);
+  if (part) {  // the chain and the GEMMs move to the two SM partitions; the caller's stream waits for them at the end
+    sm = c->pstream_chain;
+    ss = c->pstream_side;
+    st = c->pstream_trail;
+    CU(cudaEventRecord(c->ev_enter, caller));
+    CU(cudaStreamWaitEvent(sm, c->ev_enter, 0));
+    CU(cudaStreamWaitEvent(ss, c->ev_enter, 0));
+    CU(cudaStreamWaitEvent(st, c->ev_enter, 0));
+  }
+  StreamSwap chain_scope(c, sm);  // launch helpers use c->stream
+  auto at = [&](int r, int col) { return (int64_t)col * BM * ld + (int64_t)r * BM; };  // offset of block (r, col)
+  bool trail_pending = false, prio_pending = false;
+  int prio_cols = 0;
+  static const bool small_tiles = !(getenv("AGP_CHOL_SMALLTILES") && atoi(getenv("AGP_CHOL_SMALLTILES")) == 0);  // A/B knob: chain_gemm32_kernel
+  OK((ensure_smem<chain_gemm32_kernel>(c, 0)));  // carve-out preference only (static shared memory)
+  static const int t4 = getenv("AGP_CHOL_T4") ? atoi(getenv("AGP_CHOL_T4")) : 0;  // A/B knob: 4-stage trailing tiles while rem2 >= t4 (2-stage below)
+  // side-stream GEMMs as 2-stage tiles (51 KB): one finished CTA then leaves room for the 166 KB diagonal kernel on its SM (A/B knob)
+  static const bool side2 = getenv("AGP_CHOL_SIDE2") && atoi(getenv("AGP_CHOL_SIDE2")) != 0;
+  // development aid (AGP_CHOL_TRACE=1): device timestamps around every diagonal-block kernel of one large factorisation
+  static int trace_left = getenv("AGP_CHOL_TRACE") ? 3 : 0;  // the third large factorisation of the process (warm) is traced
+  if (trace_left > 0 && nb >= 32) trace_left--;
+  const bool trace = getenv("AGP_CHOL_TRACE") && trace_left == 0 && nb >= 32;
+  std::vector<cudaEvent_t> marks;
+  auto mark = [&]() {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, sm);
+    marks.push_back(e);
+  };
+  for (int J0 = 0; J0 < nb; J0 += OB) {
+    const int J1 = std::min(nb, J0 + OB), J2 = std::min(nb, J1 + OB);
+    for (int J = J0; J < J1; J++) {
+      mark();
+      potrf_trinv128_kernel<<<1, 256, PT_SMEM_BYTES, sm>>>(Kw + at(J, J), L + at(J, J), Lt + at(J, J), Ut + at(J, J), ld, J * BM, info,
+                                                           std::max(0, std::min(BM, nvalid - J * BM)));
+      mark();
+      LAUNCHED(c);
+      KCHECK();
+      if (J == nb - 1) break;
+      CU(cudaEventRecord(c->ev_diag, sm));
+      const int below = nb - 1 - J;  // block rows J+1 .. nb-1
+      // ---- main stream: block row J+1 ----
+      if (J > J0) CU(cudaStreamWaitEvent(sm, c->ev_side, 0));  // side(J-1): Kw[J+1, J] and Kw[J+1, J+1] carry update(J-1)
+      else if (prio_pending) CU(cudaStreamWaitEvent(sm, c->ev_prio[0], 0));  // K = 512 update of this super-panel's block columns
+      if (small_tiles) {
+        chain_gemm32_kernel<<<dim3(4, 4), 128, 0, sm>>>(Kw + at(J + 1, J), ld, Lt + at(J, J), ld, BM, 1, 0, L + at(J + 1, J), ld, 1.0, 0.0);
+        LAUNCHED(c);
+        KCHECK();
+      } else {
+        OK((run_gemm<A_KM, B_KN>(c, 1, 2, Kw + at(J + 1, J), ld, Lt + at(J, J), ld, BM, KR_FULL, TS_ALL, epi_store(L + at(J + 1, J), ld, false))));
+      }
+      CU(cudaEventRecord(c->ev_prow, sm));
+      if (J + 1 < J1) {
+        if (small_tiles) {
+          chain_gemm32_kernel<<<dim3(4, 4), 128, 0, sm>>>(L + at(J + 1, J), ld, L + at(J + 1, J), ld, BM, 0, 1, Kw + at(J + 1, J + 1), ld, -1.0, 1.0);
+          LAUNCHED(c);
+          KCHECK();
+        } else {
+          OK((run_gemm<A_KM, B_KN>(c, 1, 2, L + at(J + 1, J), ld, L + at(J + 1, J), ld, BM, KR_FULL, TS_ALL, epi_store(Kw + at(J + 1, J + 1), ld, false, -1.0, 1.0))));
+        }
+      }
+      // ---- side stream: rows >= J+2 of panel(J) and of the update of the remaining block columns (J, J1) ----
+      {
+        StreamSwap sw(c, ss);
+        CU(cudaStreamWaitEvent(ss, c->ev_diag, 0));
+        if (below > 1) {
+          if (side2) OK((run_gemm<A_KM, B_KN, 2>(c, below - 1, 2, Kw + at(J + 2, J), ld, Lt + at(J, J), ld, BM, KR_FULL, TS_ALL, epi_store(L + at(J + 2, J), ld, false))));
+          else OK((run_gemm<A_KM, B_KN>(c, below - 1, 2, Kw + at(J + 2, J), ld, Lt + at(J, J), ld, BM, KR_FULL, TS_ALL, epi_store(L + at(J + 2, J), ld, false))));
+          const int wcols = J1 - 1 - J;
+          if (wcols > 0) {
+            CU(cudaStreamWaitEvent(ss, c->ev_prow, 0));  // L[J+1, J] is an operand of column J+1's tiles
+            if (side2) OK((run_gemm<A_KM, B_KN, 2>(c, below - 1, 2 * wcols, L + at(J + 2, J), ld, L + at(J + 1, J), ld, BM, KR_FULL, TS_NBLK_LE1,
+                                                epi_store(Kw + at(J + 2, J + 1), ld, false, -1.0, 1.0))));
+            else OK((run_gemm<A_KM, B_KN>(c, below - 1, 2 * wcols, L + at(J + 2, J), ld, L + at(J + 1, J), ld, BM, KR_FULL, TS_NBLK_LE1,
+                                          epi_store(Kw + at(J + 2, J + 1), ld, false, -1.0, 1.0))));
+          }
+        }
+        CU(cudaEventRecord(c->ev_side, ss));
+      }
+    }
+    prio_pending = false;
+    const int rem = nb - J1;
+    if (rem <= 0) break;
+    const int K = (J1 - J0) * BM;
+    // ---- main stream: the diagonal block that opens the next super-panel.  L[J1, J0..J1-2] came from the side stream (the main stream
+    // has waited for side(J1-2) above), L[J1, J1-1] from the main stream itself.
+    if (trail_pending) CU(cudaStreamWaitEvent(sm, c->ev_trail, 0));
+    if (small_tiles) {
+      chain_gemm32_kernel<<<dim3(4, 4), 128, 0, sm>>>(L + at(J1, J0), ld, L + at(J1, J0), ld, K, 0, 1, Kw + at(J1, J1), ld, -1.0, 1.0);
+      LAUNCHED(c);
+      KCHECK();
+    } else {
+      OK((run_gemm<A_KM, B_KN>(c, 1, 2, L + at(J1, J0), ld, L + at(J1, J0), ld, K, KR_FULL, TS_ALL, epi_store(Kw + at(J1, J1), ld, false, -1.0, 1.0))));
+    }
+    // ---- trail stream: columns >= J2 (needs every row >= J2 of block columns [J0, J1): the side stream up to side(J1-1)) ----
+    const int rem2 = nb - J2;
+    // ---- side stream: block columns [J1, J2), one launch each ----
+    {
+      StreamSwap sw(c, ss);
+      CU(cudaStreamWaitEvent(ss, c->ev_prow, 0));  // L[J1, J1-1]
+      if (trail_pending) CU(cudaStreamWaitEvent(ss, c->ev_trail, 0));  // these columns were last written by the previous trailing update
+      prio_cols = J2 - J1;
+      // rows >= J1+1 of the block columns [J1, J2) in one launch (a single wave of tiles once few rows are left: the per-column launches
+      // tried first kept the side stream busy for four tile durations and the chain waited for side(J1) behind them)
+      if (rem > 1) {
+        if (side2) OK((run_gemm<A_KM, B_KN, 2>(c, rem - 1, 2 * prio_cols, L + at(J1 + 1, J0), ld, L + at(J1, J0), ld, K, KR_FULL, TS_NBLK_LE1, epi_store(Kw + at(J1 + 1, J1), ld, false, -1.0, 1.0))));
+        else OK((run_gemm<A_KM, B_KN>(c, rem - 1, 2 * prio_cols, L + at(J1 + 1, J0), ld, L + at(J1, J0), ld, K, KR_FULL, TS_NBLK_LE1, epi_store(Kw + at(J1 + 1, J1), ld, false, -1.0, 1.0))));
+      }
+      CU(cudaEventRecord(c->ev_prio[0], ss));
+      prio_pending = true;
+    }
+    if (rem2 > 0) {
+      StreamSwap sw(c, st);
+      CU(cudaStreamWaitEvent(st, c->ev_side, 0));  // recorded after side(J1-1); the side stream's later work is not waited for
+      // While many block rows are left the factorisation is bound by this GEMM, not by the chain: 4-stage tiles (29 against 24 TFLOP/s);
+      // later the chain is the critical path and 2-stage tiles (51 KB) let the diagonal kernel in as soon as one tile finishes.
+      if (rem2 >= t4)
+        OK((run_gemm<A_KM, B_KN>(c, rem2, 2 * rem2, L + at(J2, J0), ld, L + at(J2, J0), ld, K, KR_FULL, TS_NBLK_LE, epi_store(Kw + at(J2, J2), ld, false, -1.0, 1.0))));
+      else
+      OK((run_gemm<A_KM, B_KN, 2>(c, rem2, 2 * rem2, L + at(J2, J0), ld, L + at(J2, J0), ld, K, KR_FULL, TS_NBLK_LE, epi_store(Kw + at(J2, J2), ld, false, -1.0, 1.0))));
+      CU(cudaEventRecord(c->ev_trail, st));
+      trail_pending = true;
+    } else {
+      trail_pending = false;
+    }
+  }
+  CU(cudaEventRecord(c->ev_side, ss));
+  CU(cudaStreamWaitEvent(sm, c->ev_side, 0));
+  if (trail_pending) CU(cudaStreamWaitEvent(sm, c->ev_trail, 0));
+  if (part) {
+    CU(cudaEventRecord(c->ev_leave, sm));
+    CU(cudaStreamWaitEvent(caller, c->ev_leave, 0));
+  }
+  if (trace) {
+    mark();
+    trace_left = -1;
+    cudaStreamSynchronize(sm);
+    for (size_t i = 0; i + 1 < marks.size(); i += 2) {
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+      cudaEventElapsedTime(&t0, marks[0], marks[i]);
+      cudaEventElapsedTime(&t1, marks[i], marks[i + 1]);
+      cudaEventElapsedTime(&t2, marks[i + 1], marks[i + 2 < marks.size() ? i + 2 : i + 1]);
+      fprintf(stderr, "[chol trace v2] J=%2d diag starts %9.1f us, runs %6.1f us, then %6.1f us until the next diag starts\n", (int)(i / 2), 1e3 * t0, 1e3 * t1, 1e3 * t2);
+    }
+    for (cudaEvent_t e : marks) cudaEventDestroy(e);
   }
   return AGP_OK;
 }

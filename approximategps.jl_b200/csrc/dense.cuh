@@ -123,6 +123,82 @@ __device__ __forceinline__ void pt_potrf32(double* blk, int lane, double* rdiag,
     __syncwarp();  // column J is read (as row J's entries) by every later column
   }
 }
+// The same factorisation with the ROWS IN REGISTERS and a compact loop (round 2, second attempt at the critical path of C3): lane i owns
+// row i as x[k] = A[i][j + k] -- the window slides by one column per step, so that the pivot column is always x[0] and every register
+// index is a compile-time constant although the loop over j is not unrolled (~100 instructions, warm in the instruction cache after the
+// first step, unlike the 10 KB straight-line pt_potrf16).  Right-looking: after column j is scaled, x[k-1] <- x[k] - l_ij l_(j+k)j, where
+// l_(j+k)j is lane j+k's own l_ij, fetched with a shuffle whose source LANE is dynamic (allowed) while the source register is fixed.
+// Slots that slide past column 31 and the entries above the diagonal carry unused values.  Same pivot arithmetic as pt_potrf32.
+__device__ __forceinline__ void pt_potrf32r(double* blk, int lane, double* rdiag, int col0, int* info) {
+  double x[32];
+#pragma unroll
+  for (int c = 0; c < 32; c++) x[c] = blk[lane * PT_LD + c];
+#pragma unroll 1
+  for (int j = 0; j < 32; j++) {
+    const double v = x[0];
+    const double d = __shfl_sync(0xffffffffu, v, j);
+    if (lane == 0 && !(d > 0.0)) atomicCAS(info, 0, col0 + j + 1);
+    const double y = rsqrt(d);
+    const double s0 = d * y;
+    const double sq = fma(fma(-s0, s0, d), 0.5 * y, s0);
+    const double inv = fma(fma(-sq, y, 1.0), y, y);
+    const double l0 = v * inv;
+    const double lij = (lane == j) ? sq : fma(fma(-l0, sq, v), inv, l0);
+#pragma unroll
+    for (int k = 1; k < 16; k++) x[k - 1] = fma(-lij, __shfl_sync(0xffffffffu, lij, (j + k) & 31), x[k]);
+    if (j < 16) {  // columns j + 16 .. j + 31 exist only in the first half of the sweep
+#pragma unroll
+      for (int k = 16; k < 32; k++) x[k - 1] = fma(-lij, __shfl_sync(0xffffffffu, lij, (j + k) & 31), x[k]);
+    } else {
+      x[15] = 0.0;
+    }
+    if (lane >= j) blk[lane * PT_LD + j] = lij;  // rows above the diagonal keep the zero they were loaded with
+    if (lane == j) rdiag[j] = inv;
+  }
+  __syncwarp();
+}
+// Third form (the default): the sliding window of pt_potrf32r, but the scaled column reaches the other lanes through shared memory: every
+// lane publishes its l_ij in two doubled buffers (one shifted by an element, so that the 31 partners l_(j+1)j .. l_(j+31)j start at a 16-byte
+// aligned address whatever the parity of j) and reads them back as 16 broadcast LDS.128.  tools/potrf32_bench.cu, one warp alone, cycles per
+// column: shared-memory left-looking loop 853, sliding window with 62 SHFL 550, with 31 LDS.64 654, with 16 LDS.128 362; the pivot chain
+// alone (shuffle of the pivot, rsqrt, nine dependent FP64 operations, 31 DFMA) is 313 (profiles/r3b_potrf32_variants.jsonl).
+// buf: 128 doubles, 16-byte aligned.
+__device__ __forceinline__ void pt_potrf32w(double* blk, int lane, double* rdiag, int col0, int* info, double* buf) {
+  double x[32];
+#pragma unroll
+  for (int c = 0; c < 32; c++) x[c] = blk[lane * PT_LD + c];
+  double* bufe = buf;       // bufe[i] = l_i (i = 0..63, wraps around)
+  double* bufo = buf + 64;  // bufo[i] = l_(i+1)
+  const int lo = (lane + 31) & 31;
+#pragma unroll 1
+  for (int j = 0; j < 32; j++) {
+    const double v = x[0];
+    const double d = __shfl_sync(0xffffffffu, v, j);
+    if (lane == 0 && !(d > 0.0)) atomicCAS(info, 0, col0 + j + 1);
+    const double y = rsqrt(d);
+    const double s0 = d * y;
+    const double sq = fma(fma(-s0, s0, d), 0.5 * y, s0);
+    const double inv = fma(fma(-sq, y, 1.0), y, y);
+    const double l0 = v * inv;
+    const double lij = (lane == j) ? sq : fma(fma(-l0, sq, v), inv, l0);
+    bufe[lane] = lij;
+    bufe[lane + 32] = lij;
+    bufo[lo] = lij;
+    bufo[lo + 32] = lij;
+    __syncwarp();
+    const double2* b = reinterpret_cast<const double2*>(((j + 1) & 1) ? (bufo + j) : (bufe + j + 1));
+#pragma unroll
+    for (int k = 0; k < 15; k++) {
+      const double2 p = b[k];
+      x[2 * k] = fma(-lij, p.x, x[2 * k + 1]);
+      x[2 * k + 1] = fma(-lij, p.y, x[2 * k + 2]);
+    }
+    x[30] = fma(-lij, b[15].x, x[31]);
+    if (lane >= j) blk[lane * PT_LD + j] = lij;  // rows above the diagonal keep the zero they were loaded with
+    if (lane == j) rdiag[j] = inv;
+    __syncwarp();  // the exchange buffers are rewritten by the next step
+  }
+}
 // Cholesky of a 16 x 16 diagonal block by one warp with the ROWS IN REGISTERS (lane i < 16 owns row i; lanes 16..31 mirror them):
 // right-looking and fully unrolled, so that every register index is a compile-time constant.  The columns are kept UNSCALED while the
 // sweep runs (LDL^T style: K[i][k] -= K[i][j] K[k][j] / d_j), so that the per-column dependency chain is: broadcast of the pivot ->
@@ -272,7 +348,7 @@ __device__ long long pt_ticks[16];
 // of the factorisation and of the inverse are skipped (a 20 x 20 problem costs one 32-block instead of four).
 __global__ void __launch_bounds__(256) potrf_trinv128_kernel(const double* src, double* dstL, double* dstLt, double* dstUt, int64_t ld, int col0,
                                                              int* info, int nvalid) {
-  extern __shared__ double s[];  // [128][129] + scratch [64][65]
+  extern __shared__ __align__(16) double s[];  // [128][129] + scratch [64][65]
   constexpr int N = 128, LD = PT_LD;
   double* tb = s + N * LD;
   double* rdiag = tb + 64 * 65;  // 1 / L_jj
@@ -299,7 +375,13 @@ __global__ void __launch_bounds__(256) potrf_trinv128_kernel(const double* src, 
 #endif
   for (int o = 0; o < nact; o += PB) {
     if (warp == 0) {  // diagonal PB x PB block
+#ifdef AGP_PT_LL
       if (PB == 32) pt_potrf32(s + o * LD + o, lane, rdiag + o, col0 + o, info);
+#elif defined(AGP_PT_SHFL)
+      if (PB == 32) pt_potrf32r(s + o * LD + o, lane, rdiag + o, col0 + o, info);
+#else
+      if (PB == 32) pt_potrf32w(s + o * LD + o, lane, rdiag + o, col0 + o, info, tb);
+#endif
       else pt_potrf16(s + o * LD + o, lane, rdiag + o, col0 + o, info);
     }
     __syncthreads();
@@ -408,6 +490,75 @@ __global__ void __launch_bounds__(256) potrf_trinv128_kernel(const double* src, 
     dstUt[(int64_t)c * ld + r] = s[c * LD + r];
   }
   PT_TICK(9)
+}
+
+// ---- small-tile GEMM for the critical chain of the blocked Cholesky -----------------------------------------------------
+// Between two diagonal-block kernels the chain needs one 128 x 128 block row: L[J+1,J] = Kw[J+1,J] inv(L_JJ)^T and
+// Kw[J+1,J+1] -= L[J+1,J] L[J+1,J]^T (K = 512 from a whole super-panel when J+1 opens the next one).  As two 128 x 64 tiles of the
+// throughput GEMM each of these took ~20 us (two SMs busy, eight barrier-separated k-stages each); here the block is cut into sixteen
+// 32 x 32 tiles (one CTA of four warps each, 2 x 2 DMMA tiles per warp, k-chunks of 32 double-buffered with cp.async).  Same operand
+// conventions as gemm_kernel<A_KM, B_KN> (A(m,k) = A[m + k lda], B(k,n) = B[n + k ldb], C column-major) and the same ascending-k DMMA
+// accumulation and epilogue arithmetic per element, so the result is bit-identical to it.
+//   ktri:       B(k,n) = 0 for k > n (B = transpose of a lower-triangular inverse): a column tile stops at k = n0 + 32
+//   lower_only: tiles strictly above the diagonal are skipped (their content is never read)
+constexpr int CG_T = 32, CG_KC = 32, CG_LD = 36;  // 36 = 4 mod 16: conflict-free fragments
+__global__ void __launch_bounds__(128) chain_gemm32_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb, int K,
+                                                            int ktri, int lower_only, double* C, int64_t ldc, double alpha, double beta) {
+  __shared__ __align__(16) double sm[2][2][CG_KC * CG_LD];
+  const int m0 = blockIdx.x * CG_T, n0 = blockIdx.y * CG_T;
+  if (lower_only && n0 > m0) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wm = (warp & 1) * 16, wn = (warp >> 1) * 16;
+  const int kend = ktri ? min(K, n0 + CG_T) : K;
+  const int nch = kend / CG_KC;
+  auto load = [&](int buf, int k0) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int p = tid + 128 * j, k = p >> 4, c2 = (p & 15) * 2;
+      cp_async16(&sm[buf][0][k * CG_LD + c2], A + (int64_t)(k0 + k) * lda + m0 + c2);
+      cp_async16(&sm[buf][1][k * CG_LD + c2], B + (int64_t)(k0 + k) * ldb + n0 + c2);
+    }
+  };
+  double acc[2][2][2];
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+  load(0, 0);
+  cp_async_commit();
+  for (int ch = 0; ch < nch; ch++) {
+    if (ch + 1 < nch) load((ch + 1) & 1, (ch + 1) * CG_KC);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const double* sA = sm[ch & 1][0];
+    const double* sB = sm[ch & 1][1];
+#pragma unroll
+    for (int kk = 0; kk < CG_KC; kk += 4) {
+      double a[2], b[2];
+#pragma unroll
+      for (int mi = 0; mi < 2; mi++) a[mi] = sA[(kk + t) * CG_LD + wm + mi * 8 + g];
+#pragma unroll
+      for (int ni = 0; ni < 2; ni++) b[ni] = sB[(kk + t) * CG_LD + wn + ni * 8 + g];
+#pragma unroll
+      for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 2; ni++) dmma884(acc[mi][ni], a[mi], b[ni]);
+    }
+    __syncthreads();  // the buffer is refilled by the load issued in the next iteration
+  }
+#pragma unroll
+  for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+    for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int row = m0 + wm + mi * 8 + g, col = n0 + wn + ni * 8 + 2 * t + e;
+        double* p = C + (int64_t)col * ldc + row;
+        double v = alpha * acc[mi][ni][e];
+        if (beta != 0.0) v += beta * (*p);
+        *p = v;
+      }
 }
 
 // out = in^T for square n x n matrices with leading dimension ld (out != in)

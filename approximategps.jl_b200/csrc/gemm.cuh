@@ -15,6 +15,7 @@ constexpr int TS_ALL = 0;
 constexpr int TS_NBLK_LT = 1;  // column block (of BM) <  tile_m
 constexpr int TS_NBLK_GT = 2;  // column block (of BM) >  tile_m
 constexpr int TS_NBLK_LE = 3;  // column block (of BM) <= tile_m   (lower triangle incl. diagonal block)
+constexpr int TS_NBLK_LE1 = 4; // column block (of BM) <= tile_m + 1   (the same when the row tiles start one block below the column tiles)
 
 struct GemmArgs {
   const double* A;
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(GemmArgs g, Epi epi) 
   if (g.tmode == TS_NBLK_LT && !(nblk < tile_m)) return;
   if (g.tmode == TS_NBLK_GT && !(nblk > tile_m)) return;
   if (g.tmode == TS_NBLK_LE && !(nblk <= tile_m)) return;
+  if (g.tmode == TS_NBLK_LE1 && !(nblk <= tile_m + 1)) return;
   int kb = 0, ke = g.K;
   if (g.kmode == KR_LOWER) ke = min(g.K, (tile_m + 1) * BM);
   if (g.kmode == KR_UPPER) kb = tile_m * BM;
