@@ -517,12 +517,6 @@ static int32_t ensure_smem(agp_ctx* c, int bytes) {
   int& g = granted[c->device & 63];
   if (g > bytes) return AGP_OK;  // g = granted bytes + 1
   if (bytes > 0) CU(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  // Every kernel of this library asks for the maximum shared-memory carve-out.  The L1 / shared split of an SM can only change while the SM
-  // is empty: with the driver's per-kernel default a 2-stage GEMM tile (51 KB, two per SM) configures a smaller carve-out, and the 166 KB
-  // diagonal-block kernel of the blocked Cholesky -- the head of its critical chain -- then waits until some SM has drained completely
-  // (measured: 80 -> 165..270 us per diagonal kernel while a trailing update is in flight, profiles/r3g_chol_trace_v2.txt).
-  static const bool carve = !(getenv("AGP_CARVEOUT") && atoi(getenv("AGP_CARVEOUT")) == 0);  // A/B knob
-  if (carve) CU(cudaFuncSetAttribute(Kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   g = bytes + 1;
   return AGP_OK;
 }
@@ -764,7 +758,7 @@ static int32_t blocked_cholesky(agp_ctx* c, double* Kw, double* L, double* Lt, d
 // sequence of one-CTA / sixteen-CTA launches whose latency is the critical path once few block rows are left.  Stream priorities give
 // those CTAs the first free slot, but not a quiet SM: next to a DMMA tile of the trailing update, which keeps the FP64 pipe of its SM
 // busy, the one-warp column loop of the diagonal kernel runs 1.5-3x slower (80 -> 120..270 us, profiles/r3i_chol_trace_v2.txt).  So
-// for nb >= 16 the device is split: 8 SMs (the smallest partition sm_100 allows) carry only the chain, the other 140 carry
+// for nb >= 32 the device is split: 8 SMs (the smallest partition sm_100 allows) carry only the chain, the other 140 carry
 // the panel / update / trailing GEMMs.  Streams of the two green contexts synchronise through events like any others; the rest of the
 // library keeps using the primary context's streams (all 148 SMs).  If the driver refuses any step, the unpartitioned schedule is used.
 struct GreenApi {
@@ -873,7 +867,7 @@ static int32_t blocked_cholesky_v2(agp_ctx* c, double* Kw, double* L, double* Lt
   constexpr int OB = 4;  // inner blocks per super-panel
   cudaStream_t sm = c->stream, ss = c->stream3, st = c->stream2;
   cudaStream_t caller = c->stream;
-  const bool part = nb >= 16 && chol_partition(c);
+  const bool part = nb >= 32 && chol_partition(c);  // n >= 4096: below that the factorisation is a millisecond and the split is not worth a second set of streams
   if (part) {  // the chain and the GEMMs move to the two SM partitions; the caller's stream waits for them at the end
     sm = c->pstream_chain;
     ss = c->pstream_side;
@@ -888,9 +882,10 @@ static int32_t blocked_cholesky_v2(agp_ctx* c, double* Kw, double* L, double* Lt
   bool trail_pending = false, prio_pending = false;
   int prio_cols = 0;
   static const bool small_tiles = !(getenv("AGP_CHOL_SMALLTILES") && atoi(getenv("AGP_CHOL_SMALLTILES")) == 0);  // A/B knob: chain_gemm32_kernel
-  OK((ensure_smem<chain_gemm32_kernel>(c, 0)));  // carve-out preference only (static shared memory)
   static const int t4 = getenv("AGP_CHOL_T4") ? atoi(getenv("AGP_CHOL_T4")) : 0;  // A/B knob: 4-stage trailing tiles while rem2 >= t4 (2-stage below)
-  // side-stream GEMMs as 2-stage tiles (51 KB): one finished CTA then leaves room for the 166 KB diagonal kernel on its SM (A/B knob)
+  // A/B knobs kept from the measurements: 2-stage tiles (51 KB) for the side-stream / trailing GEMMs.  They were introduced so that one
+  // finished CTA leaves room for the 166 KB diagonal kernel; the traces showed that placement was never the problem (the diagonal kernel
+  // was slow because it SHARED its SM with DMMA tiles), and 4-stage tiles are 29 against 24 TFLOP/s, so both default to 4 stages.
   static const bool side2 = getenv("AGP_CHOL_SIDE2") && atoi(getenv("AGP_CHOL_SIDE2")) != 0;
   // development aid (AGP_CHOL_TRACE=1): device timestamps around every diagonal-block kernel of one large factorisation
   static int trace_left = getenv("AGP_CHOL_TRACE") ? 3 : 0;  // the third large factorisation of the process (warm) is traced
@@ -989,8 +984,6 @@ static int32_t blocked_cholesky_v2(agp_ctx* c, double* Kw, double* L, double* Lt
     if (rem2 > 0) {
       StreamSwap sw(c, st);
       CU(cudaStreamWaitEvent(st, c->ev_side, 0));  // recorded after side(J1-1); the side stream's later work is not waited for
-      // While many block rows are left the factorisation is bound by this GEMM, not by the chain: 4-stage tiles (29 against 24 TFLOP/s);
-      // later the chain is the critical path and 2-stage tiles (51 KB) let the diagonal kernel in as soon as one tile finishes.
       if (rem2 >= t4)
         OK((run_gemm<A_KM, B_KN>(c, rem2, 2 * rem2, L + at(J2, J0), ld, L + at(J2, J0), ld, K, KR_FULL, TS_NBLK_LE, epi_store(Kw + at(J2, J2), ld, false, -1.0, 1.0))));
       else

@@ -12,6 +12,7 @@
 // Zygote pullbacks.  The one structural difference: with M <= 128 the triangular solves go through the explicit inverse of the
 // Cholesky factor (a column per thread, no barriers), so that everything else is a small dense product parallel over its outputs.
 #pragma once
+#include "common.cuh"
 #include "kfun.cuh"
 
 namespace agp {
@@ -34,6 +35,7 @@ struct SmallArgs {
   double* ws;          // device workspace (small_ws_doubles)
   int want_grad;
   int ldb;             // min(count, SM_TILE) rounded up to 32
+  int64_t smem_doubles; // svgp_small_kernel<false>: doubles of dynamic shared memory handed to the first arrays of the carve-up
 };
 
 __host__ __device__ inline int64_t small_ws_doubles(int M, int D) {
@@ -66,6 +68,69 @@ __device__ __forceinline__ double sm_block_sum(double v, double* sred /* >= 33 *
   return sred[32];
 }
 
+// Small dense product on the FP64 tensor path (mma.sync.m8n8k4), all warps of the CTA.  The one-output-per-thread dot products this
+// replaces are bound by shared-memory instruction issue (two LDS per FMA: 10-14 us per 50 x 50 x 100 product on one SM); a DMMA needs
+// two LDS per 256 FMAs, which leaves the SM's FP64 rate as the bound (2 us for that product).
+//   C(i, j) = sum_k A(i, k) B(k, j),   A(i, k) = A[i * sai + k * sak],   B(k, j) = B[k * sbk + j * sbj],   out(i, j, value) for i < R, j < C
+// Output blocks of 16 x 16 (2 x 2 DMMA tiles sharing their fragments) are dealt to the warps round-robin; k runs in ascending quads.
+// Rows / columns of a padded block are clamped to the last valid one (their results are dropped); the last k-quad is masked.
+// Structural zeros of triangular operands shorten the k-range of a block (the operands also hold those zeros explicitly, so the sums
+// are the same as the full ones):  ta / tb = SM_TRI_LE: A(i, k) [B(k, j)] = 0 for k > i [k > j];  SM_TRI_GE: = 0 for k < i [k < j].
+// lower_out: blocks strictly above the diagonal are skipped.
+constexpr int SM_TRI_NONE = 0, SM_TRI_LE = 1, SM_TRI_GE = 2;
+template <class FO>
+__device__ __forceinline__ void sm_dmma_gemm(int R, int C, int K, const double* A, int sai, int sak, int ta, const double* B, int sbk, int sbj, int tb,
+                                             bool lower_out, FO out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5, g = lane >> 2, t = lane & 3;
+  const int tr = (R + 15) >> 4, tc = (C + 15) >> 4;
+  for (int p = warp; p < tr * tc; p += nw) {
+    const int i0 = (p % tr) * 16, j0 = (p / tr) * 16;
+    if (lower_out && j0 > i0 + 15) continue;
+    int kb = 0, ke = K;
+    if (ta == SM_TRI_LE) ke = min(ke, i0 + 16);
+    if (tb == SM_TRI_LE) ke = min(ke, j0 + 16);
+    if (ta == SM_TRI_GE) kb = max(kb, i0);
+    if (tb == SM_TRI_GE) kb = max(kb, j0);
+    kb &= ~3;
+    const int ia = min(i0 + g, R - 1), ib = min(i0 + 8 + g, R - 1), ja = min(j0 + g, C - 1), jb = min(j0 + 8 + g, C - 1);
+    double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c10[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+    const double* pa0 = A + ia * sai + (kb + t) * sak;
+    const double* pa1 = A + ib * sai + (kb + t) * sak;
+    const double* pb0 = B + (kb + t) * sbk + ja * sbj;
+    const double* pb1 = B + (kb + t) * sbk + jb * sbj;
+    const int kfull = kb + ((ke - kb) & ~3);
+    for (int k0 = kb; k0 < kfull; k0 += 4) {
+      const double a0 = *pa0, a1 = *pa1, b0 = *pb0, b1 = *pb1;
+      dmma884(c00, a0, b0);
+      dmma884(c01, a0, b1);
+      dmma884(c10, a1, b0);
+      dmma884(c11, a1, b1);
+      pa0 += 4 * sak;
+      pa1 += 4 * sak;
+      pb0 += 4 * sbk;
+      pb1 += 4 * sbk;
+    }
+    if (kfull < ke) {  // last, partial quad: clamp the address, mask the value
+      const bool kv = kfull + t < ke;
+      const int back = kv ? 0 : (kfull + t - (ke - 1));
+      const double a0 = kv ? *(pa0 - back * sak) : 0.0, a1 = kv ? *(pa1 - back * sak) : 0.0;
+      const double b0 = kv ? *(pb0 - back * sbk) : 0.0, b1 = kv ? *(pb1 - back * sbk) : 0.0;
+      dmma884(c00, a0, b0);
+      dmma884(c01, a0, b1);
+      dmma884(c10, a1, b0);
+      dmma884(c11, a1, b1);
+    }
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int ca = j0 + 2 * t + e, cb = ca + 8, ra = i0 + g, rb = ra + 8;
+      if (ra < R && ca < C) out(ra, ca, c00[e]);
+      if (ra < R && cb < C) out(ra, cb, c01[e]);
+      if (rb < R && ca < C) out(rb, ca, c10[e]);
+      if (rb < R && cb < C) out(rb, cb, c11[e]);
+    }
+  }
+}
+
 // development aid (-DAGP_SMALL_TIMING, tools/c1_phases.py): %globaltimer at the phase boundaries, returned behind the status words
 #ifdef AGP_SMALL_TIMING
 #define SM_TICK(k)                                                                    \
@@ -90,39 +155,34 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
   const int MM = M * M;
   // ---- workspace carve-up ------------------------------------------------------------------------------------------------------
   // ALLSMEM: every array lives in shared memory (32-bit shared addresses: the ~35 array pointers cost one register each and a
-  // phase -- "read what the previous phase wrote, one FMA chain, write" -- pays a shared-memory round trip instead of an L1 / L2
-  // one); otherwise (M too large for 227 KB) every array lives in the global workspace.
+  // phase -- "read what the previous phase wrote, one FMA chain, write" -- pays a shared-memory round trip instead of an L2 one:
+  // global stores write through and invalidate the L1 line, so data handed from thread to thread through the global workspace
+  // comes back from L2).  Otherwise (M too large for 227 KB; M = 50 with a 100-point tile needs 525 KB) the arrays are taken from
+  // shared memory in the order below -- the vectors, the operands of the column-by-column factorisation, the factors every product
+  // reads, the first per-point matrices -- until a.smem_doubles are used up, and from the global workspace after that.
   extern __shared__ __align__(16) double sm_pool[];
   double* w = ALLSMEM ? sm_pool : a.ws;
+  double* w_s = sm_pool;
+  int64_t s_left = ALLSMEM ? 0 : a.smem_doubles;
   auto take = [&](int n) -> double* {
+    const int n2 = (n + 1) & ~1;
+    if (!ALLSMEM && n2 <= s_left) {
+      double* p = w_s;
+      w_s += n2;
+      s_left -= n2;
+      return p;
+    }
     double* p = w;
-    w += (n + 1) & ~1;
+    w += n2;
     return p;
   };
   const int LDB = a.ldb;  // row length of the per-point matrices: the tile size rounded up to 32
   const int MB = M * LDB;
-  // vectors and the factorisation's operands first
+  // vectors first
   double* zs = take(M * D);  // scaled Z
   double* zn = take(M);
   double* mt = take(M);   // whitened mean
   double* ipiv = take(M);  // 1 / Lk_jj
-  double* Lk = take(MM);   // all M x M matrices column-major: X[i + j*M]
-  double* W1 = take(MM);   // (the residual rows Y of the inverse during the factorisation)
-  double* Li = take(MM);   // Lk^-1 (lower)
-  double* Bt = take(MM);
-  double* A = take(MB);    // per-point matrices [i][n], n contiguous (ld = LDB)
-  double* Cm = take(MB);
-  double* At = take(MB);   // A transposed, [n][i] (ld = M): the reduction over the points of G / g runs with i contiguous
-  double* Kuf = take(MB);
-  double* G = take(MM);
-  double* W2 = take(MM);
-  double* W3 = take(MM);
-  double* W4 = take(MM);
-  double* LiT = take(MM);  // transposed copies: coalesced access when the thread index runs over the column
-  double* LkT = take(MM);
-  double* Ab = take(MB);
-  double* DK = take(MB);
-  double* Lq = take(MM);
   double* xs = take(LDB * D);  // scaled points of the tile [n][D]
   double* xn = take(LDB);
   double* pdmu = take(LDB);
@@ -138,6 +198,24 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
   double* dcc = take(M);
   double* mbar = take(M);
   double* acc = take(64 + 2 * MAXD);  // scalar accumulators: [0] E [1] dmu [2] dkxx [3] ds2 [4] dc [8..8+D) ds_lin [8+MAXD .. ) theta
+  // the factorisation's operands, then the factors
+  double* Lk = take(MM);   // all M x M matrices column-major: X[i + j*M]
+  double* W1 = take(MM);   // (the residual rows Y of the inverse during the factorisation)
+  double* Li = take(MM);   // Lk^-1 (lower)
+  double* Bt = take(MM);
+  double* A = take(MB);    // per-point matrices [i][n], n contiguous (ld = LDB)
+  double* Cm = take(MB);
+  double* G = take(MM);
+  double* LiT = take(MM);  // transposed copies: coalesced access when the thread index runs over the column
+  double* W2 = take(MM);
+  double* W3 = take(MM);
+  double* W4 = take(MM);
+  double* LkT = take(MM);
+  double* Ab = take(MB);
+  double* At = take(MB);   // A transposed, [n][i] (ld = M): the reduction over the points of G / g runs with i contiguous
+  double* Kuf = take(MB);
+  double* DK = take(MB);
+  double* Lq = take(MM);
   const double* f = a.flat;
   const double* fZ = f + 4 + ns;
   const double* fm = fZ + M * D;
@@ -320,20 +398,14 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
       DK[l * LDB + n] = variance * dk;
     }
     __syncthreads();
-    for (int e = tid; e < M * nb; e += nt) {  // A = Li Kuf
-      const int i = e / nb, n = e % nb;
-      double s = 0.0;
-      for (int j = 0; j <= i; j++) s = fma(Li[i + j * M], Kuf[j * LDB + n], s);
-      A[i * LDB + n] = s;
-      At[n * M + i] = s;
-    }
+    // A = Li Kuf
+    sm_dmma_gemm(M, nb, M, Li, 1, M, SM_TRI_LE, Kuf, LDB, 1, SM_TRI_NONE, false, [&](int i, int n, double v) {
+      A[i * LDB + n] = v;
+      At[n * M + i] = v;
+    });
     __syncthreads();
-    for (int e = tid; e < M * nb; e += nt) {  // C = Bt^T A
-      const int j = e / nb, n = e % nb;
-      double s = 0.0;
-      for (int i = j; i < M; i++) s = fma(Bt[i + j * M], A[i * LDB + n], s);
-      Cm[j * LDB + n] = s;
-    }
+    // C = Bt^T A
+    sm_dmma_gemm(M, nb, M, Bt, M, 1, SM_TRI_GE, A, LDB, 1, SM_TRI_NONE, false, [&](int j, int n, double v) { Cm[j * LDB + n] = v; });
     __syncthreads();
     SM_TICK(5)
     // marginals + expected log-likelihood, one point per thread (all threads take part in the reductions)
@@ -385,41 +457,24 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
     __syncthreads();
     SM_TICK(6)
     if (!a.want_grad) continue;
-    for (int e = tid; e < M * nb; e += nt) {  // Ab = dmu (x) mt + 2 dv (Bt C - A)
-      const int i = e / nb, n = e % nb;
-      double s = 0.0;
-      for (int j = 0; j <= i; j++) s = fma(Bt[i + j * M], Cm[j * LDB + n], s);
-      Ab[i * LDB + n] = fma(pdmu[n], mt[i], 2.0 * pdv[n] * (s - A[i * LDB + n]));
-    }
+    // Ab = dmu (x) mt + 2 dv (Bt C - A)
+    sm_dmma_gemm(M, nb, M, Bt, 1, M, SM_TRI_LE, Cm, LDB, 1, SM_TRI_NONE, false,
+                 [&](int i, int n, double v) { Ab[i * LDB + n] = fma(pdmu[n], mt[i], 2.0 * pdv[n] * (v - A[i * LDB + n])); });
     __syncthreads();
-    for (int e = tid; e < M * nb; e += nt) {  // Kb = Li^T Ab  (into Cm)
-      const int j = e / nb, n = e % nb;
-      double s = 0.0;
-      for (int i = j; i < M; i++) s = fma(Li[i + j * M], Ab[i * LDB + n], s);
-      Cm[j * LDB + n] = s;
-    }
+    // (dv A)^T for the product behind G, in the layout of At; A itself is no longer needed
+    for (int e = tid; e < M * nb; e += nt) A[e] = pdv[e / M] * At[e];
+    // Kb = Li^T Ab  (into Cm)
+    sm_dmma_gemm(M, nb, M, Li, M, 1, SM_TRI_GE, Ab, LDB, 1, SM_TRI_NONE, false, [&](int j, int n, double v) { Cm[j * LDB + n] = v; });
+    __syncthreads();  // the scaled copy of A^T is complete
     SM_TICK(7)
-    // G += (dv A) A^T (lower), g += A dmu: one thread per output, i contiguous across the threads (rows of the transposed copy);
-    // independent of Kb, so no barrier is needed before
-    for (int e = tid; e < MM + M; e += nt) {
-      if (e < MM) {
-        const int i = e % M, j = e / M;
-        if (i >= j) {
-          double s0 = 0.0, s1 = 0.0;
-          int n = 0;
-          for (; n + 1 < nb; n += 2) {
-            s0 = fma(pdv[n] * At[n * M + i], At[n * M + j], s0);
-            s1 = fma(pdv[n + 1] * At[(n + 1) * M + i], At[(n + 1) * M + j], s1);
-          }
-          if (n < nb) s0 = fma(pdv[n] * At[n * M + i], At[n * M + j], s0);
-          G[e] += s0 + s1;
-        }
-      } else {
-        const int i = e - MM;
-        double s0 = 0.0;
-        for (int n = 0; n < nb; n++) s0 = fma(pdmu[n], At[n * M + i], s0);
-        g[i] += s0;
-      }
+    // G += (dv A) A^T (lower blocks), g += A dmu
+    sm_dmma_gemm(M, M, nb, A, 1, M, SM_TRI_NONE, At, M, 1, SM_TRI_NONE, true, [&](int i, int j, double v) {
+      if (i >= j) G[i + j * M] += v;
+    });
+    for (int i = tid; i < M; i += nt) {
+      double s0 = 0.0;
+      for (int n = 0; n < nb; n++) s0 = fma(pdmu[n], At[n * M + i], s0);
+      g[i] += s0;
     }
     __syncthreads();
     SM_TICK(8)
@@ -528,34 +583,15 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
   }
   __syncthreads();
   // W1 = P1 = Bt Bt^T - I
-  for (int e = tid; e < MM; e += nt) {
-    const int i = (int)(e % M), j = (int)(e / M);
-    double s = (i == j) ? -1.0 : 0.0;
-    const int kmax = min(i, j);
-    for (int k = 0; k <= kmax; k++) s = fma(Bt[i + k * M], Bt[j + k * M], s);
-    W1[e] = s;
-  }
+  sm_dmma_gemm(M, M, M, Bt, 1, M, SM_TRI_LE, Bt, M, 1, SM_TRI_LE, false, [&](int i, int j, double v) { W1[i + j * M] = (i == j) ? v - 1.0 : v; });
   __syncthreads();
   // W2 = Asum = mt g^T + 2 P1 G ;  W3 = Bt-bar = tril(2 G Bt) [- Bt]
-  for (int e = tid; e < MM; e += nt) {
-    const int i = (int)(e % M), j = (int)(e / M);
-    double s = 0.0, t = 0.0;
-    for (int k = 0; k < M; k++) s = fma(W1[i + k * M], G[k + j * M], s);
-    W2[e] = fma(mt[i], g[j], 2.0 * s);
-    if (i >= j) {
-      for (int k = j; k < M; k++) t = fma(G[i + k * M], Bt[k + j * M], t);
-      t = 2.0 * t - (centered ? Bt[e] : 0.0);
-    }
-    W3[e] = t;
-  }
+  sm_dmma_gemm(M, M, M, W1, 1, M, SM_TRI_NONE, G, 1, M, SM_TRI_NONE, false, [&](int i, int j, double v) { W2[i + j * M] = fma(mt[i], g[j], 2.0 * v); });
+  sm_dmma_gemm(M, M, M, G, 1, M, SM_TRI_NONE, Bt, 1, M, SM_TRI_GE, false,
+               [&](int i, int j, double v) { W3[i + j * M] = (i >= j) ? 2.0 * v - (centered ? Bt[i + j * M] : 0.0) : 0.0; });
   __syncthreads();
   // W4 = V = Li^T Asum
-  for (int e = tid; e < MM; e += nt) {
-    const int i = (int)(e % M), j = (int)(e / M);
-    double s = 0.0;
-    for (int k = i; k < M; k++) s = fma(LiT[i + k * M], W2[k + j * M], s);
-    W4[e] = s;
-  }
+  sm_dmma_gemm(M, M, M, LiT, 1, M, SM_TRI_GE, W2, 1, M, SM_TRI_NONE, false, [&](int i, int j, double v) { W4[i + j * M] = v; });
   double summbar = 0.0;
   if (centered) {
     // mbar = Li^T (g - mt)
@@ -569,20 +605,10 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
     for (int i = tid; i < M; i += nt) v += mbar[i];
     summbar = sm_block_sum(v, sred);
     // W1 = Y = Li^T Bt-bar  (P1 is no longer needed: Asum has been formed)
-    for (int e = tid; e < MM; e += nt) {
-      const int i = (int)(e % M), j = (int)(e / M);
-      double s = 0.0;
-      for (int k = max(i, j); k < M; k++) s = fma(LiT[i + k * M], W3[k + j * M], s);
-      W1[e] = s;
-    }
+    sm_dmma_gemm(M, M, M, LiT, 1, M, SM_TRI_GE, W3, 1, M, SM_TRI_GE, false, [&](int i, int j, double v) { W1[i + j * M] = v; });
     __syncthreads();
     // W2 = X2 = Y Bt^T + mbar mt^T   (Asum is no longer needed: V has been formed)
-    for (int e = tid; e < MM; e += nt) {
-      const int i = (int)(e % M), j = (int)(e / M);
-      double s = mbar[i] * mt[j];
-      for (int k = 0; k <= j; k++) s = fma(W1[i + k * M], Bt[j + k * M], s);
-      W2[e] = s;
-    }
+    sm_dmma_gemm(M, M, M, W1, 1, M, SM_TRI_NONE, Bt, M, 1, SM_TRI_LE, false, [&](int i, int j, double v) { W2[i + j * M] = fma(mbar[i], mt[j], v); });
   }
   __syncthreads();
   SM_TICK(12)
@@ -617,30 +643,13 @@ __global__ void __launch_bounds__(SM_THREADS, 1) svgp_small_kernel(SmallArgs a) 
   }
   __syncthreads();
   // W3 = Phi(Lk^T Lbar): lower, diagonal halved
-  for (int e = tid; e < MM; e += nt) {
-    const int i = (int)(e % M), j = (int)(e / M);
-    double s = 0.0;
-    if (i >= j) {
-      for (int k = i; k < M; k++) s = fma(LkT[i + k * M], G[k + j * M], s);
-      if (i == j) s *= 0.5;
-    }
-    W3[e] = s;
-  }
+  sm_dmma_gemm(M, M, M, LkT, 1, M, SM_TRI_GE, G, 1, M, SM_TRI_GE, false,
+               [&](int i, int j, double v) { W3[i + j * M] = (i > j) ? v : (i == j ? 0.5 * v : 0.0); });
   __syncthreads();
   // W4 = Y1 = Li^T Phi ;  W2 = Y2 = Li^T Y1^T ;  G = Kuu-bar = (Y2 + Y2^T) / 2
-  for (int e = tid; e < MM; e += nt) {
-    const int i = (int)(e % M), j = (int)(e / M);
-    double s = 0.0;
-    for (int k = max(i, j); k < M; k++) s = fma(LiT[i + k * M], W3[k + j * M], s);
-    W4[e] = s;
-  }
+  sm_dmma_gemm(M, M, M, LiT, 1, M, SM_TRI_GE, W3, 1, M, SM_TRI_GE, false, [&](int i, int j, double v) { W4[i + j * M] = v; });
   __syncthreads();
-  for (int e = tid; e < MM; e += nt) {
-    const int i = (int)(e % M), j = (int)(e / M);
-    double s = 0.0;
-    for (int k = i; k < M; k++) s = fma(LiT[i + k * M], W4[j + k * M], s);  // Y1^T[k][j] = Y1[j][k]
-    W2[e] = s;
-  }
+  sm_dmma_gemm(M, M, M, LiT, 1, M, SM_TRI_GE, W4, M, 1, SM_TRI_NONE, false, [&](int i, int j, double v) { W2[i + j * M] = v; });
   __syncthreads();
   for (int e = tid; e < MM; e += nt) {
     const int i = (int)(e % M), j = (int)(e / M);
