@@ -184,7 +184,20 @@ __global__ void __launch_bounds__(256) trsv_bwd_step_kernel(const double* L, con
 // ---- single-launch blocked triangular solves (one CTA per 128-block, flag-chained) ------------------------------
 // CTA J accumulates  b_J - sum_{L before J} (block J,L) x_L  as the x_L are published, applies the inverse diagonal
 // block and publishes x_J.  A CTA only ever waits for CTAs with a smaller block index, which the hardware schedules
-// first, so the chain cannot deadlock; `epoch` distinguishes successive solves without clearing the flags.
+// first -- made independent of the hardware's dispatch order by a ticket: a CTA takes its block index from an atomic counter when it
+// starts, so every block with a smaller index belongs to a CTA that is already running or done, whatever the occupancy and whichever
+// order the block scheduler uses; the CTA that draws the last ticket resets the counter for the next launch.  `epoch` distinguishes
+// successive solves without clearing the flags.
+__device__ __forceinline__ int trsv_ticket(int* ticket) {
+  __shared__ int s_ticket;
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(ticket, 1);
+    if (t == (int)gridDim.x - 1) atomicExch(ticket, 0);
+    s_ticket = t;
+  }
+  __syncthreads();
+  return s_ticket;
+}
 __device__ __forceinline__ void trsv_wait(volatile int* flag, int epoch) {
   if (threadIdx.x == 0) {
     while (*flag != epoch) {
@@ -201,10 +214,10 @@ __device__ __forceinline__ void trsv_publish(int* flag, int epoch) {
 
 // L x = b.  Linv: inverse diagonal blocks (column-major).  grid = nb, block = 256.
 __global__ void __launch_bounds__(256) trsv_fwd_chain_kernel(const double* L, const double* Linv, int64_t ld, const double* b, double* x, int* flags,
-                                                             int epoch) {
+                                                             int epoch, int* ticket) {
   __shared__ double xs[128];
   __shared__ double part[256];
-  const int J = blockIdx.x, tid = threadIdx.x, i = tid & 127, h = tid >> 7;
+  const int J = trsv_ticket(ticket), tid = threadIdx.x, i = tid & 127, h = tid >> 7;
   double acc = 0.0;
   for (int Lb = 0; Lb < J; Lb++) {
     // the block of L does not depend on x: fetch it before waiting
@@ -234,11 +247,11 @@ __global__ void __launch_bounds__(256) trsv_fwd_chain_kernel(const double* L, co
 
 // L^T x = b.  LinvT: inverse-transposed diagonal blocks.  Block J = nb-1-blockIdx.x waits for the blocks after it.
 __global__ void __launch_bounds__(256) trsv_bwd_chain_kernel(const double* L, const double* LinvT, int64_t ld, int nb, const double* b, double* x, int* flags,
-                                                             int epoch) {
+                                                             int epoch, int* ticket) {
   __shared__ double xs[128];
   __shared__ double part[256];
   __shared__ double colacc[128];
-  const int J = nb - 1 - blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, i = tid & 127, h = tid >> 7;
+  const int J = nb - 1 - trsv_ticket(ticket), tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, i = tid & 127, h = tid >> 7;
   if (tid < 128) colacc[tid] = 0.0;
   for (int Lb = nb - 1; Lb > J; Lb--) {
     // (block Lb,J)^T x_Lb: column c of the block is contiguous over the rows; one warp handles 16 columns.  The block does
