@@ -25,7 +25,7 @@ NONCENTERED, CENTERED = 0, 1
 POINT_MAJOR, FEATURE_MAJOR = 0, 1
 Y_F64, Y_F32, Y_I64, Y_U8 = range(4)
 HOST, DEVICE = 0, 1
-COMPUTE_F64, COMPUTE_F32, COMPUTE_F32_TC_SOLVE = 0, 1, 2
+COMPUTE_F64, COMPUTE_F32, COMPUTE_F32_TC_SOLVE, COMPUTE_F64_EMU = 0, 1, 2, 3
 
 c_double_p = C.POINTER(C.c_double)
 

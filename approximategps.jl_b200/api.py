@@ -523,13 +523,16 @@ class DeviceData:
 
 
 def _compute_dtype(dtype) -> int:
-    """None / "f64" / np.float64 -> AGP_COMPUTE_F64; "f32" / np.float32 -> AGP_COMPUTE_F32 (the Float32 fast mode)."""
+    """None / "f64" / np.float64 -> AGP_COMPUTE_F64; "f32" / np.float32 -> AGP_COMPUTE_F32 (the Float32 fast mode); "f64emu" ->
+    AGP_COMPUTE_F64_EMU (Float64 tolerance, the reverse pass's point-sum product as an FP64-accurate INT8-slice product)."""
     if dtype is None or dtype in ("f64", "float64", np.float64):
         return L.COMPUTE_F64
     if dtype in ("f32", "float32", np.float32):
         return L.COMPUTE_F32
     if dtype in ("f32_tc_solve",):
         return L.COMPUTE_F32_TC_SOLVE
+    if dtype in ("f64emu", "f64_emu"):
+        return L.COMPUTE_F64_EMU
     raise ValueError(f"ArgumentError: unsupported compute dtype {dtype!r}")
 
 

@@ -114,6 +114,7 @@ struct SvgpState {
   bool valid = false;
   bool sweep_pending = false;  // agp_svgp_sweep has filled the reduce buffer and agp_svgp_finish has not consumed it yet
   bool f32 = false;            // params.compute_dtype != AGP_COMPUTE_F64: S2 / S4 / S6 on the tcgen05 3xTF32 path (f32sweep.cuh)
+  bool f64_emu = false;        // AGP_COMPUTE_F64_EMU: S6 as an FP64-accurate INT8-slice product (i8emu.cuh), everything else as Float64
   bool f32_tc_solve = false;   // AGP_COMPUTE_F32_TC_SOLVE: the reverse-pass solve S5 as a 3xTF32 product with the explicit inverse as well
   int M = 0, Mp = 0, D = 0, nb = 0;
   int n_scale = 1;
@@ -154,6 +155,11 @@ struct Prof {
 
 static void lap_release(agp_ctx* c);
 static void chol_partition_release(agp_ctx* c);
+// AGP_F64_S6=i8 forces AGP_COMPUTE_F64_EMU (S6 as an FP64-accurate 7-slice INT8 product) on every Float64 evaluation of the process: A/B knob
+static bool f64_s6_i8() {
+  static const bool on = getenv("AGP_F64_S6") && strcmp(getenv("AGP_F64_S6"), "i8") == 0;
+  return on;
+}
 struct agp_ctx {
   Prof prof;
   void* lap = nullptr;  // LapWork (laplace_host.inc)
@@ -182,6 +188,7 @@ struct agp_ctx {
   DevBuf Kf, DKb;  // reverse pass, stationary kernels: Kuf and variance * kappa'(u) of the launch group, kept from S1 for S7
   // accumulators
   DevBuf gpart, Gpart, kpart, red, small, ghbuf;
+  DevBuf q6A, q6As, s6;  // Float64 mode, S6 on the INT8 tensor path (experiment knob AGP_F64_S6=i8): slice planes of A and As, [scales A | scales As | row maxima x 2]
   // Float32 mode: hi | lo FP32 planes (each DevBuf holds both: 2 x count floats = count doubles)
   DevBuf fA, fC, fAb, fAs, fBtc, fBtr, fLi;
   DevBuf qAb, sAb, qLi, sLi;
@@ -266,7 +273,7 @@ extern "C" int32_t agp_ctx_destroy(agp_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   DevBuf* bufs[] = {&c->z, &c->zs, &c->zn, &c->zsp, &c->mvec, &c->mt, &c->Lq, &c->Kw, &c->Lk, &c->Lt, &c->Ut, &c->Bt_cm, &c->Bt_rm,
                     &c->W1, &c->W2, &c->W3, &c->W4, &c->vec64, &c->vec64b, &c->A, &c->C, &c->Ab, &c->As, &c->Kf, &c->DKb, &c->saa, &c->sam,
-                    &c->scc_part, &c->dmu, &c->dv, &c->sc_part, &c->gpart, &c->Gpart, &c->kpart, &c->red, &c->small, &c->ghbuf, &c->fA, &c->fC, &c->fAb, &c->fAs, &c->fBtc, &c->fBtr, &c->fLi, &c->qAb, &c->sAb, &c->qLi, &c->sLi, &c->qK, &c->sK, &c->qLi7, &c->sLi7, &c->sxx_part,
+                    &c->scc_part, &c->dmu, &c->dv, &c->sc_part, &c->gpart, &c->Gpart, &c->kpart, &c->red, &c->small, &c->ghbuf, &c->q6A, &c->q6As, &c->s6, &c->fA, &c->fC, &c->fAb, &c->fAs, &c->fBtc, &c->fBtr, &c->fLi, &c->qAb, &c->sAb, &c->qLi, &c->sLi, &c->qK, &c->sK, &c->qLi7, &c->sLi7, &c->sxx_part,
                     &c->mu_out, &c->var_out, &c->px1, &c->px2, &c->pxs1, &c->pxn1, &c->pxs2, &c->pxn2, &c->pcov};
   for (DevBuf* b : bufs) b->release();
   lap_release(c);
@@ -1186,8 +1193,9 @@ static int32_t resolve_params(const agp_svgp_params* p, SvgpState& st) {
   st.mean_const = p->mean_const;
   st.jitter = p->jitter;
   OK(fill_kernel_params(&p->kernel, p->D, p->M, st.kp));
-  if (p->compute_dtype < AGP_COMPUTE_F64 || p->compute_dtype > AGP_COMPUTE_F32_TC_SOLVE) return fail(AGP_ERR_INVALID, "unknown compute_dtype %d", p->compute_dtype);
-  st.f32 = p->compute_dtype != AGP_COMPUTE_F64;
+  if (p->compute_dtype < AGP_COMPUTE_F64 || p->compute_dtype > AGP_COMPUTE_F64_EMU) return fail(AGP_ERR_INVALID, "unknown compute_dtype %d", p->compute_dtype);
+  st.f32 = p->compute_dtype == AGP_COMPUTE_F32 || p->compute_dtype == AGP_COMPUTE_F32_TC_SOLVE;
+  st.f64_emu = p->compute_dtype == AGP_COMPUTE_F64_EMU || f64_s6_i8();
   st.f32_tc_solve = p->compute_dtype == AGP_COMPUTE_F32_TC_SOLVE;
   st.lp.kind = p->lik.kind;
   st.lp.sigma2 = p->lik.sigma2;
@@ -1489,6 +1497,7 @@ static int32_t ensure_sweep_workspace(agp_ctx* c, int64_t cols, bool grad) {
     const int by_mem = (int)std::max<int64_t>(1, ((int64_t)512 << 20) / (MM * 8));
     c->nsplit = std::max(1, std::min(std::min(by_waves, by_mem), 32));
     if (const char* e = getenv("AGP_SYRK_SPLIT")) c->nsplit = std::max(1, atoi(e));  // tuning knob
+    if (st.f64_emu && !st.f32) c->nsplit = std::max<int>(c->nsplit, (int)((round_up(cc, 128) + 16383) / 16384));  // one slab of G per 16384 points
     OK(c->Gpart.ensure((int64_t)c->nsplit * MM));
     c->nslab = (int)std::max<int64_t>((cc + 2047) / 2048, (Mp + 2047) / 2048);
     OK(c->kpart.ensure((int64_t)c->nslab * Mp * kgrad_stride(D)));
@@ -1829,7 +1838,42 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
       OK(launch_trsm<TR_RHS_BWD>(c, t5a, tiles_n));
     }
     // S6: G += As A^T
-    {
+    if (st.f64_emu && Mp >= 768 && ncols >= 2048) {  // (at M = 512 the DMMA SYRK is as fast: C2 10.7 against 11.3 ms; C4 350 -> 250 ms, C5 minibatch 139 -> 74 ms)
+      // AGP_COMPUTE_F64_EMU: the FP64-accurate INT8 engine (i8emu.cuh) over the points of the launch group.  Operands are already K-major (points contiguous):
+      // row maxima -> power-of-two scales -> seven 7-bit slice planes each for As (A operand, 128-row tiles) and A (B operand, 64-row tiles); one slab of
+      // 16384 points per blockIdx.z (INT32 accumulators: 7 * 127^2 * 16384 < 2^31), partial G per slab, summed in a fixed order with the other slabs
+      ProfScope ps(c, PC_SYRK);
+      const int64_t ldk = round_up(ncols, 128), pbytes = (int64_t)Mp * ldk;
+      OK(c->q6A.ensure(((int64_t)i8e::S * pbytes + 7) / 8));
+      OK(c->q6As.ensure(((int64_t)i8e::S * pbytes + 7) / 8));
+      OK(c->s6.ensure(4 * (int64_t)Mp));
+      double* sA = c->s6.p;
+      double* sAs = c->s6.p + Mp;
+      unsigned long long* mx = reinterpret_cast<unsigned long long*>(c->s6.p + 2 * Mp);
+      CU(cudaMemsetAsync(mx, 0, sizeof(unsigned long long) * 2 * Mp, c->stream));
+      const int seg = 8192;
+      const dim3 gmx((ncols + seg - 1) / seg, Mp / 8);
+      i8e::rowmax_kernel<<<gmx, 256, 0, c->stream>>>(c->A.p, ldc, Mp, ncols, seg, mx);
+      i8e::rowmax_kernel<<<gmx, 256, 0, c->stream>>>(c->As.p, ldc, Mp, ncols, seg, mx + Mp);
+      signed char* qA = reinterpret_cast<signed char*>(c->q6A.p);
+      signed char* qAs = reinterpret_cast<signed char*>(c->q6As.p);
+      const dim3 gsl((unsigned)((ldk + 1023) / 1024), Mp);
+      i8e::slice_rows2d_kernel<i8e::S><<<gsl, 256, 0, c->stream>>>(c->A.p, ldc, ncols, qA, ldk, pbytes, mx, sA);
+      i8e::slice_rows2d_kernel<i8e::S><<<gsl, 256, 0, c->stream>>>(c->As.p, ldc, ncols, qAs, ldk, pbytes, mx + Mp, sAs);
+      c->launches += 4;
+      KCHECK();
+      CUtensorMap ma, mb;
+      if (!i8e::make_map3(&ma, qAs, ldk, Mp, ldk, pbytes, i8e::EM, i8e::S) || !i8e::make_map3(&mb, qA, ldk, Mp, ldk, pbytes, i8e::EN, i8e::S))
+        return fail(AGP_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+      const int kchunk = 16384, nz = (int)((ldk + kchunk - 1) / kchunk);
+      if (nz > c->nsplit) return fail(AGP_ERR_ALLOC, "S6 (INT8): %d slabs of G needed, %d allocated", nz, c->nsplit);
+      i8e::EpiE6 e6{c->Gpart.p, Mp, sAs, sA};
+      i8e::Args g8{(int)ldk, i8e::KM_SPLIT, kchunk, 1};
+      OK((ensure_smem<i8e::i8emu_gemm_kernel<i8e::EpiE6>>(c, i8e::SMEM_BYTES)));
+      i8e::i8emu_gemm_kernel<i8e::EpiE6><<<dim3(Mp / i8e::EN, Mp / i8e::EM, nz), i8e::E_THREADS, i8e::SMEM_BYTES, c->stream>>>(ma, mb, g8, e6);
+      LAUNCHED(c);
+      KCHECK();
+    } else {
       ProfScope ps(c, PC_SYRK);
       SyrkArgs s{};
       s.As = c->As.p;

@@ -337,5 +337,66 @@ __global__ void __launch_bounds__(256) transpose_slice_kernel(const double* __re
   }
 }
 
+// ---- operands of the Float64 mode's S6 (G += As A^T, k = the points of a launch group) ----------------------------------------------------
+// The matrices are [rows = inducing index][ld] with the points contiguous, i.e. already K-major; what slice_rows_kernel (one warp per row) cannot do
+// is a row of 1.5e5 points.  rowmax_kernel: grid (column segments, rows / 8), one warp per (row, segment), the maxima combined with atomicMax on
+// the bit patterns (non-negative doubles order like their bits).  slice_rows2d_kernel: grid (column blocks of 1024, rows), four consecutive
+// points per thread (char4 stores), scale from the finished row maximum; columns [k, ldk) are zero-filled.
+__global__ void __launch_bounds__(256) rowmax_kernel(const double* __restrict__ in, int64_t ld, int rows, int k, int seg, unsigned long long* __restrict__ mx) {
+  const int row = blockIdx.y * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int c0 = blockIdx.x * seg, c1 = min(k, c0 + seg);
+  const double* src = in + (int64_t)row * ld;
+  double m = 0.0;
+  for (int c = c0 + lane; c < c1; c += 32) m = fmax(m, fabs(src[c]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) atomicMax(mx + row, (unsigned long long)__double_as_longlong(m));
+}
+// Round-to-nearest (signed-digit) slicing: q_i = rint(t), residual in [-1/2, 1/2], so every digit after the first is a zero-mean quantity in
+// [-64, 64] and both the dropped residual and the dropped slice products (i + j >= NS) are unbiased -- over the 1.5e5 points of a launch group a
+// truncation bias adds up linearly, a rounding error like sqrt(n).  Needs |x| * inv_scale <= 1/2 (first digit <= 64), i.e. twice pow2_scale().
+template <int NS>
+__host__ __device__ __forceinline__ void slice_rn(double x, double inv_scale, signed char (&q)[NS]) {
+  double t = x * inv_scale;
+#pragma unroll
+  for (int i = 0; i < NS; i++) {
+    t *= 128.0;
+    const double qi = rint(t);
+    q[i] = (signed char)(int)qi;
+    t -= qi;
+  }
+}
+template <int NS>
+__global__ void __launch_bounds__(256) slice_rows2d_kernel(const double* __restrict__ in, int64_t ld, int k, signed char* __restrict__ planes, int64_t ldk,
+                                                           int64_t plane_bytes, const unsigned long long* __restrict__ mx, double* __restrict__ scale) {
+  const int row = blockIdx.y;
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
+  const double sc = 2.0 * pow2_scale(__longlong_as_double((long long)mx[row])), inv = 1.0 / sc;  // |x| / sc <= 1/2 (slice_rn)
+  if (blockIdx.x == 0 && threadIdx.x == 0) scale[row] = sc;
+  if (c >= (int)ldk) return;
+  const double* src = in + (int64_t)row * ld;
+  signed char q[4][NS];
+#pragma unroll
+  for (int e = 0; e < 4; e++) slice_rn<NS>(c + e < k ? src[c + e] : 0.0, inv, q[e]);
+#pragma unroll
+  for (int i = 0; i < NS; i++) *reinterpret_cast<char4*>(planes + i * plane_bytes + (int64_t)row * ldk + c) = make_char4(q[0][i], q[1][i], q[2][i], q[3][i]);
+}
+// G[z][row + col * Mp] += 2^-14 sA[row] sB[col] v   (A operand = As planes, B operand = A planes; lower tiles only; one slab of points per z)
+struct EpiE6 {
+  double* G;  // [nz][Mp * Mp], column-major slabs
+  int Mp;
+  const double* sA;
+  const double* sB;
+  __device__ __forceinline__ void operator()(int tm, int tn, int z, int row, int c0, const double (&v)[32]) const {
+    const int r = tm * EM + row;
+    const double f = sA[r] * (1.0 / 16384.0);
+    double* p = G + (int64_t)z * Mp * Mp + (int64_t)(tn * EN + c0) * Mp + r;
+    const double* sb = sB + tn * EN + c0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) p[(int64_t)j * Mp] += v[j] * (f * sb[j]);
+  }
+};
+
 }  // namespace i8e
 }  // namespace agp

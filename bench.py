@@ -486,7 +486,8 @@ def run_svgp(args, w):
     sva = agp.SparseVariationalApproximation(f(Z, w["jitter"]), agp.MvNormal(m, chol_lower=A))
     lik = {"gaussian": agp.GaussianLikelihood(0.01), "bernoulli_logit": agp.BernoulliLikelihood(), "poisson_exp": agp.PoissonLikelihood()}[w["lik"]]
     pk = agp.PackedParams(sva, lik, agp.GaussHermiteExpectation(20) if w["method"] == "gauss_hermite" else None, args.dtype)
-    f32 = args.dtype != "f64"
+    f32 = args.dtype in ("f32", "f32_tc_solve")
+    emu = args.dtype == "f64emu"
     G, gb = grad_struct(L, M, D)
     out = C.c_double()
     num_data = float(w.get("num_data", N_total))
@@ -620,7 +621,12 @@ def run_svgp(args, w):
                      "frac": pp_gbs / hbm_peak if pp_gbs else None,
                      "note": "two ~10 us launches per 151 552-point chunk (perpoint + fixed-order scalar reduce): launch-latency-bound, 0.1 % of the step; "
                              "the same kernel given one 1e7-point launch moves 5.0 TB/s (profiles/r02f_perpoint_standalone.jsonl)"}
-        line = {"metric": METRIC if not f32 else METRIC.replace("FP64", "Float32 fast mode: 3xTF32 tcgen05 stages, FP64 solve / reductions"), "value": value, "unit": UNIT,
+        metric = METRIC
+        if f32:
+            metric = METRIC.replace("FP64", "Float32 fast mode: 3xTF32 tcgen05 stages, FP64 solve / reductions")
+        if emu:
+            metric = METRIC.replace("FP64", "FP64 with S6 emulated FP64-accurately on the INT8 tensor path")
+        line = {"metric": metric, "value": value, "unit": UNIT,
                 "n_gpus": world, "steps": args.steps, "warmup": n_warm, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": args.dtype,
                 "data": "synthetic" + (" (generated on the device)" if on_device else ""),
@@ -891,7 +897,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the N > 1 sharded-vs-single-rank correctness evaluation")
-    ap.add_argument("--dtype", default="f64", choices=["f64", "f32", "f32_tc_solve"], help="f32: the Float32 fast mode (3xTF32 on tcgen05 for the GEMM-shaped sweep stages); "
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32", "f32_tc_solve", "f64emu"], help="f64emu: Float64 tolerance with S6 as an FP64-accurate INT8-slice product on tcgen05 (AGP_COMPUTE_F64_EMU; its own line, never the headline); f32: the Float32 fast mode (3xTF32 on tcgen05 for the GEMM-shaped sweep stages); "
                                                                              "reported as its own line, never as the Float64 headline")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])

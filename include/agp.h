@@ -78,6 +78,12 @@ extern "C" {
                            * explicit inverse too (1.2x faster again; its error on dZ / d theta grows with cond(Lk): 1.4e-4 at
                            * the M = 1024 SqExponential twin of BASELINE config 4, below 1e-4 on the others)                */
 
+#define AGP_COMPUTE_F64_EMU 3 /* Float64 results inside the Float64 tolerance (1e-10), with the reverse pass's point-sum product G += (dv A) A^T
+                           * formed by FP64-ACCURATE EMULATION on the INT8 tensor path: both operands cut into seven signed 7-bit slices per element
+                           * (round to nearest) under one power-of-two scale per inducing row, the 28 slice products accumulated exactly in INT32
+                           * (tcgen05.mma.kind::i8, tensor memory), recombined in Float64.  Every other stage as AGP_COMPUTE_F64.  Opt-in: the default
+                           * Float64 mode uses Float64 DMMA / FMA arithmetic only.                                                         */
+
 #define AGP_MAX_GH_POINTS 128
 #define AGP_MAX_D 32 /* compile-time bound of the device code (kfun.cuh MAXD): larger D is AGP_ERR_UNSUPPORTED */
 
@@ -139,7 +145,7 @@ typedef struct {
   int32_t parametrization;
   agp_likelihood lik;
   agp_expectation expect;
-  int32_t compute_dtype; /* AGP_COMPUTE_F64 (0, default) | AGP_COMPUTE_F32: arithmetic of elbo / elbo_grad; inputs and outputs stay Float64 */
+  int32_t compute_dtype; /* AGP_COMPUTE_F64 (0, default) | AGP_COMPUTE_F32 | AGP_COMPUTE_F32_TC_SOLVE | AGP_COMPUTE_F64_EMU: arithmetic of elbo / elbo_grad; inputs and outputs stay Float64 */
 } agp_svgp_params;
 
 /* Gradient of the ELBO (unit cotangent); every pointer is a caller-allocated host buffer or NULL.

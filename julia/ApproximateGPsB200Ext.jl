@@ -234,7 +234,10 @@ quad_spec(q::GPLikelihoods.MonteCarloExpectation) = (Int32(3), Int32(q.n_samples
 default_quad(lik, q::GPLikelihoods.DefaultExpectationMethod) = lik isa BernoulliLikelihood ? GPLikelihoods.GaussHermiteExpectation(20) : q
 default_quad(lik, q) = q
 
-compute_dtype(::Type{Float64}) = Int32(0)   # AGP_COMPUTE_F64
+# Opt-in: `ApproximateGPsB200Ext.F64_EMU[] = true` evaluates Float64 problems with AGP_COMPUTE_F64_EMU (Float64 tolerance; the reverse pass's
+# point-sum product as an FP64-accurate INT8-slice product on the tcgen05 tensor path) instead of AGP_COMPUTE_F64.
+const F64_EMU = Ref(false)
+compute_dtype(::Type{Float64}) = F64_EMU[] ? Int32(3) : Int32(0)   # AGP_COMPUTE_F64_EMU : AGP_COMPUTE_F64
 compute_dtype(::Type{Float32}) = Int32(1)   # AGP_COMPUTE_F32: the Float32 fast mode (a Float32 GP in the type-generic reference)
 
 # ---- agp_svgp_params of one (sva, likelihood, quadrature): the arrays the struct points into are returned for GC.@preserve -----------
