@@ -155,6 +155,11 @@ struct Prof {
 
 static void lap_release(agp_ctx* c);
 static void chol_partition_release(agp_ctx* c);
+// AGP_F64_EMU_S2=0 keeps S2 of AGP_COMPUTE_F64_EMU on the DMMA kernel (A/B knob)
+static bool f64_emu_s2() {
+  static const bool off = getenv("AGP_F64_EMU_S2") && atoi(getenv("AGP_F64_EMU_S2")) == 0;
+  return !off;
+}
 // AGP_F64_S6=i8 forces AGP_COMPUTE_F64_EMU (S6 as an FP64-accurate 7-slice INT8 product) on every Float64 evaluation of the process: A/B knob
 static bool f64_s6_i8() {
   static const bool on = getenv("AGP_F64_S6") && strcmp(getenv("AGP_F64_S6"), "i8") == 0;
@@ -188,6 +193,7 @@ struct agp_ctx {
   DevBuf Kf, DKb;  // reverse pass, stationary kernels: Kuf and variance * kappa'(u) of the launch group, kept from S1 for S7
   // accumulators
   DevBuf gpart, Gpart, kpart, red, small, ghbuf;
+  DevBuf qBt7, sBt7, sPm;  // AGP_COMPUTE_F64_EMU, S2: slices / scales of Bt^T (once per sweep), per-point scales of the point-major slices of A
   DevBuf q6A, q6As, s6;  // Float64 mode, S6 on the INT8 tensor path (experiment knob AGP_F64_S6=i8): slice planes of A and As, [scales A | scales As | row maxima x 2]
   // Float32 mode: hi | lo FP32 planes (each DevBuf holds both: 2 x count floats = count doubles)
   DevBuf fA, fC, fAb, fAs, fBtc, fBtr, fLi;
@@ -273,7 +279,7 @@ extern "C" int32_t agp_ctx_destroy(agp_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   DevBuf* bufs[] = {&c->z, &c->zs, &c->zn, &c->zsp, &c->mvec, &c->mt, &c->Lq, &c->Kw, &c->Lk, &c->Lt, &c->Ut, &c->Bt_cm, &c->Bt_rm,
                     &c->W1, &c->W2, &c->W3, &c->W4, &c->vec64, &c->vec64b, &c->A, &c->C, &c->Ab, &c->As, &c->Kf, &c->DKb, &c->saa, &c->sam,
-                    &c->scc_part, &c->dmu, &c->dv, &c->sc_part, &c->gpart, &c->Gpart, &c->kpart, &c->red, &c->small, &c->ghbuf, &c->q6A, &c->q6As, &c->s6, &c->fA, &c->fC, &c->fAb, &c->fAs, &c->fBtc, &c->fBtr, &c->fLi, &c->qAb, &c->sAb, &c->qLi, &c->sLi, &c->qK, &c->sK, &c->qLi7, &c->sLi7, &c->sxx_part,
+                    &c->scc_part, &c->dmu, &c->dv, &c->sc_part, &c->gpart, &c->Gpart, &c->kpart, &c->red, &c->small, &c->ghbuf, &c->q6A, &c->q6As, &c->s6, &c->qBt7, &c->sBt7, &c->sPm, &c->fA, &c->fC, &c->fAb, &c->fAs, &c->fBtc, &c->fBtr, &c->fLi, &c->qAb, &c->sAb, &c->qLi, &c->sLi, &c->qK, &c->sK, &c->qLi7, &c->sLi7, &c->sxx_part,
                     &c->mu_out, &c->var_out, &c->px1, &c->px2, &c->pxs1, &c->pxn1, &c->pxs2, &c->pxn2, &c->pcov};
   for (DevBuf* b : bufs) b->release();
   lap_release(c);
@@ -1457,7 +1463,7 @@ static int32_t ensure_sweep_workspace(agp_ctx* c, int64_t cols, bool grad) {
   OK(c->C.ensure((int64_t)Mp * cc));
   OK(c->saa.ensure(cc));
   OK(c->sam.ensure(cc));
-  OK(c->scc_part.ensure((int64_t)2 * nb * cc));  // (Float32 mode: one partial per 64-column half of a 128-column tile)
+  OK(c->scc_part.ensure((int64_t)(st.f64_emu ? 4 : 2) * nb * cc));  // (Float32 mode: one partial per 64-column half of a 128-column tile; emulated S2: one per 32 rows)
   OK(c->dmu.ensure(cc));
   OK(c->dv.ensure(cc));
   OK(c->sc_part.ensure((cc / 256 + 2) * NSC));
@@ -1629,10 +1635,18 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
       OK(fill(c, c->kpart.p, (int64_t)c->nslab * Mp * kgrad_stride(D), 0.0));
     }
   }
+  const bool emu_s2 = st.f64_emu && !st.f32 && f64_emu_s2() && Mp >= 768;
+  if (emu_s2) {  // slices of the rows of Bt^T (columns of Bt, contiguous in the column-major copy), one scale per column
+    OK(c->qBt7.ensure(((int64_t)i8e::S * MM + 7) / 8));
+    OK(c->sBt7.ensure(Mp));
+    i8e::slice_rows_kernel<i8e::S><<<(Mp + 7) / 8, 256, 0, c->stream>>>(c->Bt_cm.p, Mp, Mp, Mp, reinterpret_cast<signed char*>(c->qBt7.p), Mp, MM, c->sBt7.p);
+    LAUNCHED(c);
+    KCHECK();
+  }
   for (int64_t lo = 0; lo < count; lo += cols) {
     const int npts = (int)std::min<int64_t>(cols, count - lo);
     static const bool f64_i8_exp = getenv("AGP_F64_S1") && strcmp(getenv("AGP_F64_S1"), "i8") == 0;
-    const int ncols = (int)round_up(npts, (st.f32 || f64_i8_exp) ? 2 * BN : BN);  // Float32 mode: the tcgen05 stages tile the points by 128
+    const int ncols = (int)round_up(npts, (st.f32 || f64_i8_exp || st.f64_emu) ? 2 * BN : BN);  // Float32 mode: the tcgen05 stages tile the points by 128
     const int tiles_n = ncols / BN;
     const double* pts = X + lo * D;
     // S1: A = Lk^-1 Kuf
@@ -1705,6 +1719,27 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
       t5::EpiF2 e2{fC, fC + plane, Mp, c->scc_part.p, ldc};
       t5::Args g{Mp, t5::KM_FROM_N, 0, 0, t5::MnDesc()};
       OK((launch_t5<false, false>(c, grid5, fA, plane, Mp, ncols, reinterpret_cast<float*>(c->fBtc.p), MMf, Mp, Mp, g, e2)));
+    } else if (emu_s2 && ncols >= 2048) {
+      // AGP_COMPUTE_F64_EMU, S2: C[n][j] = sum_{l >= j} A[n][l] Bt[l][j] on the INT8 engine.  The point-major slice planes of A live in the
+      // buffer that S6 refills with its own planes later in this launch group.
+      ProfScope ps(c, PC_GEMM_BTA);
+      const int64_t pbytes = (int64_t)Mp * ldc;
+      OK(c->q6As.ensure(((int64_t)i8e::S * pbytes + 7) / 8));
+      OK(c->sPm.ensure(ldc));
+      signed char* qApm = reinterpret_cast<signed char*>(c->q6As.p);
+      i8e::transpose_slice_kernel<i8e::S><<<(ncols + 31) / 32, 256, 0, c->stream>>>(c->A.p, ldc, Mp, ncols, qApm, Mp, pbytes, c->sPm.p);
+      LAUNCHED(c);
+      KCHECK();
+      CUtensorMap ma, mb;
+      if (!i8e::make_map3(&ma, qApm, Mp, ncols, Mp, pbytes, i8e::EM, i8e::S) ||
+          !i8e::make_map3(&mb, reinterpret_cast<signed char*>(c->qBt7.p), Mp, Mp, Mp, MM, i8e::EN, i8e::S))
+        return fail(AGP_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+      i8e::EpiE2 e2{c->C.p, ldc, c->sPm.p, c->sBt7.p, c->scc_part.p, ldc};
+      i8e::Args g8{Mp, i8e::KM_FROM_N, 0, 0};
+      OK((ensure_smem<i8e::i8emu_gemm_kernel<i8e::EpiE2>>(c, i8e::SMEM_BYTES)));
+      i8e::i8emu_gemm_kernel<i8e::EpiE2><<<dim3(Mp / i8e::EN, ncols / i8e::EM, 1), i8e::E_THREADS, i8e::SMEM_BYTES, c->stream>>>(ma, mb, g8, e2);
+      LAUNCHED(c);
+      KCHECK();
     } else {
     // S2: C = Bt^T A  (A operand (m=j, k=l) = Bt[l][j] = Bt_rm[l*Mp + j]; nonzero for l >= j)
     EpiS2 e2{c->C.p, ldc, c->scc_part.p, ldc};
@@ -1719,7 +1754,7 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
     pp.sam = c->sam.p;
     pp.scc_part = c->scc_part.p;
     pp.ldp = ldc;
-    pp.nb = st.f32 ? 2 * nb : nb;
+    pp.nb = st.f32 ? 2 * nb : ((emu_s2 && ncols >= 2048) ? 4 * nb : nb);
     pp.pts = pts;
     pp.y = y ? y + lo : nullptr;
     pp.npts = npts;

@@ -234,6 +234,31 @@ __global__ void __launch_bounds__(256) colsum_reduce_kernel(const double* __rest
   saa[n] = a;
   sam[n] = m;
 }
+// ---- S2 of AGP_COMPUTE_F64_EMU: C[n][j] = sum_{l >= j} A[n][l] Bt[l][j] with seven slices (FP64-accurate).  A operand: point-major slices of A
+// with one scale per point (transpose_slice_kernel), B operand: the rows of Bt^T (= columns of Bt, contiguous in the column-major copy) with one
+// scale per column j.  Writes C (FP64, inducing-major [j][ld], as the DMMA kernel of S2 does) and, per point and per 32 inducing rows, the partial
+// column sums c^T c that the per-point stage adds up in a fixed order.
+struct EpiE2 {
+  double* C;
+  int64_t ld;
+  const double* sA;   // per point
+  const double* sBt;  // per column j
+  double* scc_part;   // [Mp / 32][ldp]
+  int64_t ldp;
+  __device__ __forceinline__ void operator()(int tm, int tn, int, int row, int c0, const double (&v)[32]) const {
+    const int n = tm * EM + row, j0 = tn * EN + c0;
+    const double sa = sA[n] * (1.0 / 16384.0);
+    double* p = C + (int64_t)j0 * ld + n;
+    double pc = 0.0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      const double cv = v[j] * sa * __ldg(sBt + j0 + j);
+      p[(int64_t)j * ld] = cv;
+      pc = fma(cv, cv, pc);
+    }
+    scc_part[(int64_t)(j0 >> 5) * ldp + n] = pc;
+  }
+};
 constexpr int S5_NS = 5, S5_N = 64;
 struct EpiE5 {
   double* Kb;

@@ -1,6 +1,6 @@
 """GPU parity of AGP_COMPUTE_F64_EMU against the FLOAT64 NumPy oracle at the FLOAT64 tolerance (1e-10): the reverse pass's point-sum product
-G += (dv A) A^T (S6, the pullback of the two M x N . N x M products behind SVA.jl:251) runs as an FP64-accurate INT8-slice product on the
-tcgen05 tensor path (csrc/i8emu.cuh: seven round-to-nearest 7-bit slices per element under one power-of-two scale per inducing row, 28 exact
+G += (dv A) A^T (S6, the pullback of the two M x N . N x M products behind SVA.jl:251) and the forward product C = Bt^T A (S2, `B' * A` of SVA.jl:251)
+run as FP64-accurate INT8-slice products on the tcgen05 tensor path (csrc/i8emu.cuh: seven round-to-nearest 7-bit slices per element under one power-of-two scale per inducing row, 28 exact
 slice products in INT32 tensor memory, Float64 recombination); every other stage is the Float64 mode's.  The mode is opt-in."""
 import os
 import sys
@@ -34,7 +34,10 @@ def _run(agp, p, num_data=None, expect_engine=True):
     label = f"f64emu {p['kind']} D={p['X'].shape[1]} M={len(p['m'])} N={len(p['y'])} cent={p['centered']} {p['lik']}/{p['method']}"
     print(f"\n[{label}] elbo={val:.10f} " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
     record_parity(label, errs, tol=TOL)
-    assert val == v64  # the forward pass is the Float64 mode's, bit for bit
+    if expect_engine:  # S2 (forward pass) runs on the engine too: the ELBO agrees with the Float64 mode's far inside the tolerance, not to the last bit
+        assert abs(val - v64) <= 1e-12 * abs(v64)
+    else:
+        assert val == v64
     assert np.all(np.triu(g.Lq, 1) == 0.0)
     if expect_engine:  # the INT8 product really ran: G, hence dLq, cannot agree with the DMMA result to the last bit
         assert not np.array_equal(g.Lq, g64.Lq)
