@@ -79,7 +79,7 @@ extern "C" {
                            * the M = 1024 SqExponential twin of BASELINE config 4, below 1e-4 on the others)                */
 
 #define AGP_COMPUTE_F64_EMU 3 /* Float64 results inside the Float64 tolerance (1e-10), with the reverse pass's point-sum product G += (dv A) A^T
-                           * formed by FP64-ACCURATE EMULATION on the INT8 tensor path: both operands cut into seven signed 7-bit slices per element
+                           * and the forward product C = Bt^T A (for M >= 768) formed by FP64-ACCURATE EMULATION on the INT8 tensor path: both operands cut into seven signed 7-bit slices per element
                            * (round to nearest) under one power-of-two scale per inducing row, the 28 slice products accumulated exactly in INT32
                            * (tcgen05.mma.kind::i8, tensor memory), recombined in Float64.  Every other stage as AGP_COMPUTE_F64.  Opt-in: the default
                            * Float64 mode uses Float64 DMMA / FMA arithmetic only.                                                         */
