@@ -1269,6 +1269,9 @@ static int32_t prepare_f32_operands(agp_ctx* c) {
   // Linv itself (rows l, k = l' contiguous) as seven slice planes: the B operand of the INT8 forward solve (f32sweep.cuh EpiE1)
   OK(c->qLi7.ensure((i8e::S * MM + 7) / 8));
   OK(c->sLi7.ensure(Mp));
+  static const bool i8_rn = getenv("AGP_I8_RN") && atoi(getenv("AGP_I8_RN")) != 0;  // experiment: round-to-nearest slices for the forward solve's operands
+  if (i8_rn) i8e::slice_rows_kernel<i8e::S, true><<<(Mp + 7) / 8, 256, 0, c->stream>>>(c->W1.p, Mp, Mp, Mp, reinterpret_cast<signed char*>(c->qLi7.p), Mp, MM, c->sLi7.p);
+  else
   i8e::slice_rows_kernel<i8e::S><<<(Mp + 7) / 8, 256, 0, c->stream>>>(c->W1.p, Mp, Mp, Mp, reinterpret_cast<signed char*>(c->qLi7.p), Mp, MM, c->sLi7.p);
   LAUNCHED(c);
   KCHECK();
@@ -1673,6 +1676,9 @@ static int32_t sweep_points(agp_ctx* c, const double* X, const double* y, int64_
       OK(launch_s1(c, t1, tiles_n, true, true));
       signed char* qK = reinterpret_cast<signed char*>(c->qK.p);
       const int64_t pbytes = (int64_t)Mp * ldc, MM8 = (int64_t)Mp * Mp;
+      static const bool i8_rn = getenv("AGP_I8_RN") && atoi(getenv("AGP_I8_RN")) != 0;
+      if (i8_rn) i8e::transpose_slice_kernel<i8e::S, true><<<(ncols + 31) / 32, 256, 0, c->stream>>>(c->Kf.p, ldc, Mp, ncols, qK, Mp, pbytes, c->sK.p);
+      else
       i8e::transpose_slice_kernel<i8e::S><<<(ncols + 31) / 32, 256, 0, c->stream>>>(c->Kf.p, ldc, Mp, ncols, qK, Mp, pbytes, c->sK.p);
       LAUNCHED(c);
       KCHECK();

@@ -73,6 +73,20 @@ __host__ __device__ __forceinline__ void slice_n(double x, double inv_scale, sig
     t -= qi;
   }
 }
+// Round-to-nearest (signed-digit) slicing: q_i = rint(t), residual in [-1/2, 1/2], so every digit after the first is a zero-mean quantity in
+// [-64, 64] and both the dropped residual and the dropped slice products (i + j >= NS) are unbiased -- over the 1.5e5 points of a launch group a
+// truncation bias adds up linearly, a rounding error like sqrt(n).  Needs |x| * inv_scale <= 1/2 (first digit <= 64), i.e. twice pow2_scale().
+template <int NS>
+__host__ __device__ __forceinline__ void slice_rn(double x, double inv_scale, signed char (&q)[NS]) {
+  double t = x * inv_scale;
+#pragma unroll
+  for (int i = 0; i < NS; i++) {
+    t *= 128.0;
+    const double qi = rint(t);
+    q[i] = (signed char)(int)qi;
+    t -= qi;
+  }
+}
 __host__ __device__ __forceinline__ void slice7(double x, double inv_scale, signed char (&q)[S]) { slice_n<S>(x, inv_scale, q); }
 // power-of-two scale of a row whose largest magnitude is mx: 2^e with mx 2^-e in [0.5, 1)
 __host__ __device__ __forceinline__ double pow2_scale(double mx) {
@@ -269,7 +283,7 @@ inline bool make_map3(CUtensorMap* map, const signed char* ptr, uint64_t k, uint
 }
 
 // slices of a row-major FP64 matrix [rows][ld] (k contiguous): one warp per row -- row maximum, power-of-two scale, S planes [S][rows][ldk]
-template <int NS = S>
+template <int NS = S, bool RN = false>
 __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restrict__ in, int64_t ld, int rows, int k, signed char* __restrict__ planes, int64_t ldk,
                                                          int64_t plane_bytes, double* __restrict__ scale) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -279,11 +293,12 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
   for (int c = lane; c < k; c += 32) mx = fmax(mx, fabs(src[c]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  const double sc = pow2_scale(mx), inv = 1.0 / sc;
+  const double sc = (RN ? 2.0 : 1.0) * pow2_scale(mx), inv = 1.0 / sc;
   if (lane == 0) scale[row] = sc;
   for (int c = lane; c < (int)ldk; c += 32) {
     signed char q[NS];
-    slice_n<NS>(c < k ? src[c] : 0.0, inv, q);
+    if (RN) slice_rn<NS>(c < k ? src[c] : 0.0, inv, q);
+    else slice_n<NS>(c < k ? src[c] : 0.0, inv, q);
 #pragma unroll
     for (int i = 0; i < NS; i++) planes[i * plane_bytes + (int64_t)row * ldk + c] = q[i];
   }
@@ -293,7 +308,7 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
 // k contiguous, one power-of-two scale per point from the exact column maximum.  One CTA per 32 points: a first pass over the strip for the
 // maxima, a second one (an L2 hit: 32 x rows x 8 bytes) through a 32 x 32 shared-memory tile for the transposed, sliced stores.
 // colmax != nullptr: the column maxima are already known (the producing epilogue tracked them with atomicMax) and the first pass is skipped.
-template <int NS>
+template <int NS, bool RN = false>
 __global__ void __launch_bounds__(256) transpose_slice_kernel(const double* __restrict__ in, int64_t ld, int rows, int cols, signed char* __restrict__ planes,
                                                               int64_t ldk, int64_t plane_bytes, double* __restrict__ scale, const double* __restrict__ colmax = nullptr) {
   __shared__ double tile[32][33];
@@ -313,7 +328,7 @@ __global__ void __launch_bounds__(256) transpose_slice_kernel(const double* __re
   if (ty == 0) {
 #pragma unroll
     for (int j = 1; j < 8; j++) mx = fmax(mx, smx[j][tx]);
-    const double sc = pow2_scale(mx);
+    const double sc = (RN ? 2.0 : 1.0) * pow2_scale(mx);
     if (cok) scale[n0 + tx] = sc;
     sinv[tx] = 1.0 / sc;
   }
@@ -327,7 +342,10 @@ __global__ void __launch_bounds__(256) transpose_slice_kernel(const double* __re
       const double inv = sinv[n];
       signed char q[4][NS];
 #pragma unroll
-      for (int e = 0; e < 4; e++) slice_n<NS>(tile[r4 + e][n], inv, q[e]);
+      for (int e = 0; e < 4; e++) {
+        if (RN) slice_rn<NS>(tile[r4 + e][n], inv, q[e]);
+        else slice_n<NS>(tile[r4 + e][n], inv, q[e]);
+      }
 #pragma unroll
       for (int i = 0; i < NS; i++) {
         const char4 v = make_char4(q[0][i], q[1][i], q[2][i], q[3][i]);
@@ -352,20 +370,6 @@ __global__ void __launch_bounds__(256) rowmax_kernel(const double* __restrict__ 
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   if (lane == 0) atomicMax(mx + row, (unsigned long long)__double_as_longlong(m));
-}
-// Round-to-nearest (signed-digit) slicing: q_i = rint(t), residual in [-1/2, 1/2], so every digit after the first is a zero-mean quantity in
-// [-64, 64] and both the dropped residual and the dropped slice products (i + j >= NS) are unbiased -- over the 1.5e5 points of a launch group a
-// truncation bias adds up linearly, a rounding error like sqrt(n).  Needs |x| * inv_scale <= 1/2 (first digit <= 64), i.e. twice pow2_scale().
-template <int NS>
-__host__ __device__ __forceinline__ void slice_rn(double x, double inv_scale, signed char (&q)[NS]) {
-  double t = x * inv_scale;
-#pragma unroll
-  for (int i = 0; i < NS; i++) {
-    t *= 128.0;
-    const double qi = rint(t);
-    q[i] = (signed char)(int)qi;
-    t -= qi;
-  }
 }
 template <int NS>
 __global__ void __launch_bounds__(256) slice_rows2d_kernel(const double* __restrict__ in, int64_t ld, int k, signed char* __restrict__ planes, int64_t ldk,
