@@ -107,3 +107,25 @@ def test_reference_interface_objects_without_a_device():
         _check_laplace_inputs(lfx, np.ones(4))
     with pytest.raises(AssertionError):
         _check_laplace_inputs(agp.LatentGP(agp.GP(0.5, k), agp.BernoulliLikelihood(), 1e-8)(z), np.ones(5))
+
+
+def test_compute_dtype_selection_matches_the_header():
+    """The host mirror's dtype names map onto the header's AGP_COMPUTE_* values (include/agp.h); unknown names are an ArgumentError."""
+    import re
+
+    import numpy as np
+    import pytest
+
+    import agp_b200  # noqa: F401  (loads the package)
+    from agp_b200 import _lib as L
+    from agp_b200 import api
+
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "agp.h")).read()
+    vals = {name: int(v) for name, v in re.findall(r"#define (AGP_COMPUTE_[A-Z0-9_]+) (\d+)", hdr)}
+    assert vals == {"AGP_COMPUTE_F64": L.COMPUTE_F64, "AGP_COMPUTE_F32": L.COMPUTE_F32, "AGP_COMPUTE_F32_TC_SOLVE": L.COMPUTE_F32_TC_SOLVE,
+                    "AGP_COMPUTE_F64_EMU": L.COMPUTE_F64_EMU}
+    assert api._compute_dtype(None) == api._compute_dtype("f64") == api._compute_dtype(np.float64) == vals["AGP_COMPUTE_F64"]
+    assert api._compute_dtype("f32") == api._compute_dtype(np.float32) == vals["AGP_COMPUTE_F32"]
+    assert api._compute_dtype("f64emu") == vals["AGP_COMPUTE_F64_EMU"]
+    with pytest.raises(ValueError, match="ArgumentError"):
+        api._compute_dtype("bf16")
